@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- car-steps/sec of the batched CarEnv stepping path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference on all host cores
+
+A "step" is one CarEnv.step() of every env of the workload (one batched car-step with full 16-ray
+observations, reward, termination and same-step auto-reset).  Workload at any N: BASELINE.json configs[1]
+per GPU -- 4096 single-car envs on daytona.track, continuous actions, random policy (weak scaling).
+
+`value`   : whole-job car-steps/s, state and actions resident in HBM (rollout kernel, Philox actions on device,
+            observations of every step written to HBM), CUDA-event time on the launching stream, max over ranks.
+`e2e`     : the same metric through the CarEnv-facing host API (VectorEnv.step with numpy actions): host->device
+            copy of the actions and device->host copy of obs/reward/flags inside the timed region, every step.
+`roofline`: algorithmic bytes (832 B per car-step) / kernel duration vs measured HBM peak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_CAR_STEP = 832     # 83 state words read + written, 8 B action, 152 B obs, 4 B reward, 4 B flags
+METRIC = "car-steps/sec (16-ray sensors) at 4096-65536 envs, 1/2/4/8 B200 vs host CPU"
+UNIT = "car-steps/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# ----------------------------------------------------------------------------- Philox4x32-10 (same stream as the device)
+def philox_uniform2(seed: int, cars: np.ndarray, step: int):
+    """u0,u1 in [0,1) for (car, step): mirrors ncg::action_synthetic (csrc/ncg_car.cuh)."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c0 = cars.astype(np.uint64); c1 = np.full_like(c0, step); c2 = np.zeros_like(c0); c3 = np.zeros_like(c0)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        n0 = ((p1 >> np.uint64(32)) ^ c1 ^ k0) & mask
+        n1 = p1 & mask
+        n2 = ((p0 >> np.uint64(32)) ^ c3 ^ k1) & mask
+        n3 = p0 & mask
+        c0, c1, c2, c3 = n0, n1, n2, n3
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    to01 = lambda x: (x >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return to01(c0), to01(c1)
+
+
+def synthetic_actions(seed: int, cars: np.ndarray, step: int) -> np.ndarray:
+    u0, u1 = philox_uniform2(seed, cars, step)
+    return np.stack([np.float32(2.0) * u0 - np.float32(1.0), np.float32(2.0) * u1 - np.float32(1.0)], axis=1).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle = port of the reference)
+def _cpu_worker(args):
+    track, car_base, n_steps, seed, warm = args
+    from oracle import oracle as O
+    from nascargymnasium_b200 import track as T
+    env = O.OracleEnv(T.builtin_track_text(track))
+    env.reset()
+    cars = np.array([car_base], dtype=np.int64)
+    acts = [synthetic_actions(seed, cars, s) for s in range(warm + n_steps)]
+    for s in range(warm):
+        _, _, te, tr = env.step(acts[s])
+        if te or tr:
+            env.reset(fresh=False)
+    t0 = time.perf_counter()
+    for s in range(warm, warm + n_steps):
+        _, _, te, tr = env.step(acts[s])
+        if te or tr:
+            env.reset(fresh=False)
+    return n_steps, time.perf_counter() - t0
+
+
+def cpu_throughput(track: str, steps_per_proc: int, procs: int, seed: int = 0, warm: int = 600):
+    """car-steps/s of the oracle with `procs` independent single-car envs, one per process."""
+    jobs = [(track, i, steps_per_proc, seed, warm) for i in range(procs)]
+    if procs == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    from nascargymnasium_b200.engine import Engine
+    from nascargymnasium_b200.vector_env import NascarVectorEnv
+
+    E, C, track = args.envs, args.cars, args.track
+    N = E * C
+    K, Wm, T = args.steps, args.warmup, args.steps_per_launch
+    eng = Engine(E, C, tracks=[track], discrete=False, auto_reset=True, device=local)
+    eng.reset_host()
+    obs_roll = torch.empty((T, N, 38), dtype=torch.float32, device=dev)
+    rew_roll = torch.empty((T, N), dtype=torch.float32, device=dev)
+    done_roll = torch.empty((T, E), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def launch(n):
+        eng.rollout(n, seed=args.seed, mode=0, obs_rollout=obs_roll[:n].reshape(-1) if n != T else obs_roll.reshape(-1),
+                    reward_rollout=rew_roll[:n].reshape(-1) if n != T else rew_roll.reshape(-1),
+                    done_rollout=done_roll[:n].reshape(-1) if n != T else done_roll.reshape(-1))
+
+    # warm-up: W steps (at least 3 launches)
+    done = 0
+    for _ in range(max(3, (Wm + T - 1) // T)):
+        launch(T)
+        done += T
+    barrier()
+    eng.read_stats(reset=True)
+    launches0 = eng.launch_count
+    chunks = [T] * (K // T) + ([K % T] if K % T else [])
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in chunks]
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for (e0, e1), n in zip(ev, chunks):
+            flush.zero_()                         # L2 flush between timed launches (not inside the event pair)
+            e0.record()
+            launch(n)
+            e1.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    kern_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    gpu_launches = eng.launch_count - launches0
+    stats = eng.read_stats(reset=True)
+    assert stats["car_steps"] == N * K, (stats, N, K)
+    t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kern_ms_max = float(t.item())
+    value = world * N * K / (kern_ms_max / 1e3)
+
+    # ---- e2e: host buffers through the CarEnv-facing API, H2D + D2H every step
+    venv = NascarVectorEnv(num_envs=E, track_file=f"tracks/{track}.track", num_cars=C, device=local)
+    venv.reset()
+    Ke = args.e2e_steps
+    cars = np.arange(N, dtype=np.int64) + rank * N
+    acts = [synthetic_actions(args.seed, cars, s).reshape(E, C, 2) if C > 1 else synthetic_actions(args.seed, cars, s) for s in range(Ke + 5)]
+    for s in range(5):
+        venv.step(acts[s])
+    barrier()
+    l0 = venv.engine.launch_count
+    t0 = time.perf_counter()
+    for s in range(5, Ke + 5):
+        o, r, te, tr, info = venv.step(acts[s])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    gpu_launches += venv.engine.launch_count - l0
+    te2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te2, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * Ke / float(te2.item())
+    h2d = N * 2 * 4
+    d2h = N * 38 * 4 + N * 4 + 2 * E
+
+    peak, peak_src = measured_peak()
+    per_launch_s = (kern_ms / 1e3) / len(chunks)
+    achieved = ALGO_BYTES_PER_CAR_STEP * N * (K / len(chunks)) / per_launch_s / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": kern_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{E} batched {'single-car' if C == 1 else str(C) + '-car'} envs on {track}.track per GPU, continuous "
+                               f"actions ~ U[-1,1]^2 (Philox on device), 16-ray observations written every step, same-step auto-reset",
+                   "envs_per_gpu": E, "cars_per_env": C, "track": track, "steps_per_launch": T,
+                   "l2": "flushed (256 MiB memset) between timed launches; the working set itself is L2-resident by construction",
+                   "cars_per_warp": os.environ.get("NCG_CARS_PER_WARP", "auto")},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated"},
+        "gpu_launches": int(gpu_launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "ncg_step_kernel", "algorithmic_bytes_per_car_step": ALGO_BYTES_PER_CAR_STEP,
+                     "car_steps_per_launch": N * (K / len(chunks)), "avg_launch_ms": per_launch_s * 1e3},
+        "clocks": clk.summary(),
+        "counters": {k: int(v) if k != "return_sum" else float(v) for k, v in stats.items()},
+        "wall_s_timed_region": t_wall,
+    }
+    if rank == 0 and world == 1:
+        t0 = time.perf_counter()
+        v = cpu_throughput(track, args.cpu_steps, 1, seed=args.seed)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"1 single-car env on {track}.track, {args.cpu_steps} steps after 600 warm-up, same Philox action "
+                                          f"stream, oracle/ncg_oracle.cpp single thread ({time.perf_counter() - t0:.1f} s)"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: real box2d-py/gymnasium are not installable offline, so this
+    arm times the oracle port (oracle/ncg_oracle.cpp) with one process per host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    K, Wm = args.steps, args.warmup
+    # each "step" is a bounded sample: every core advances one single-car env by cpu_steps/ K ... keep total ~20-40 s
+    per_proc = max(200, min(args.cpu_steps, 40000))
+    t0 = time.perf_counter()
+    v = cpu_throughput(args.track, per_proc, cores, seed=args.seed)
+    dt = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": 1e3 * args.envs * args.cars / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64/f32", "data": "synthetic",
+        "config": {"workload": f"{args.envs} batched single-car envs on {args.track}.track per GPU, continuous actions ~ U[-1,1]^2",
+                   "envs_per_gpu": args.envs, "cars_per_env": args.cars, "track": args.track},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x 1 single-car env x {per_proc} steps after 600 warm-up ({dt:.1f} s wall); "
+                                   "box2d-py/gymnasium absent offline, so the oracle port stands in for the reference CarEnv"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=600)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--cars", type=int, default=1)
+    ap.add_argument("--track", default="daytona")
+    ap.add_argument("--steps-per-launch", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=500)
+    ap.add_argument("--cpu-steps", type=int, default=40000)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,489 @@
+// ncg_b200.cu -- kernels and the C ABI (include/ncg_b200.h) of the batched CarEnv stepping engine.
+//
+// Work decomposition (DESIGN.md "Kernels"): a warp owns G consecutive car records (G = 1, 2, 4 or 8).
+// The scalar phases of a car-step (dynamics, tyres, Box2D step, lap timer, reward) run one car per lane on
+// lanes < G; the sensor phase spreads the warp's G*16 rays over all 32 lanes.  A CTA owns whole envs, so the
+// env-level termination of a multi-car env is a shared-memory exchange behind one __syncthreads().
+// Records live in shared memory for the duration of a launch and move to/from HBM as coalesced 16-byte
+// accesses; in the multi-step rollout kernel the CTA's track table is staged into shared memory once with a
+// TMA bulk copy (cp.async.bulk + mbarrier) and stays resident across all T steps.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "ncg_car.cuh"
+
+using namespace ncg;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(NCG_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, contact_steps, toi_events, overflow; double return_sum; };
+
+struct KParams {
+    float* records; const float* blob; const long long* track_off;
+    int E, C, epb, discrete, reset_on_lap, auto_reset, contacts, stage, track_info;
+    const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
+    int T; unsigned long long seed; int mode; unsigned step_base;
+    float* obs_roll; float* rew_roll; uint8_t* done_roll;
+    DevStats* stats;
+};
+
+#define OBS_PAD 40
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS).
+__device__ __forceinline__ void tma_stage(float* dst, const float* src, unsigned bytes, unsigned long long* mbar) {
+    if (threadIdx.x == 0) {
+        unsigned mb = smem_u32(mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+    __syncthreads();
+    unsigned mb = smem_u32(mbar), ok = 0;
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(mb) : "memory");
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(320) ncg_step_kernel(KParams p) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned long long s_mbar;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cpc = p.epb * p.C;                      // car slots per CTA
+    float* s_rec = smem;                              // [cpc][128]
+    float* s_obs = s_rec + cpc * NCG_RECORD_WORDS;    // [cpc][OBS_PAD]
+    uint32_t* s_xf = (uint32_t*)(s_obs + cpc * OBS_PAD);
+    float* s_rew = (float*)(s_xf + cpc);
+    uint32_t* s_done = (uint32_t*)(s_rew + cpc);      // per car slot: bit0 terminated, bit1 truncated
+    float* s_track = smem + ((cpc * (NCG_RECORD_WORDS + OBS_PAD + 3) + 3) & ~3);   // 16-byte aligned for the TMA copy
+
+    const int env0 = blockIdx.x * p.epb;
+    const int n_env = min(p.epb, p.E - env0);
+    const int n_cars = n_env * p.C, car0 = env0 * p.C;
+    const int N = p.E * p.C;
+
+    // ---- records HBM -> shared (coalesced float4)
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
+        float4* dst = reinterpret_cast<float4*>(s_rec);
+        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    // ---- track table: staged by TMA when the whole CTA shares a track (rollout kernel), else read through L1/L2
+    const float* staged = nullptr;
+    if (p.stage) {
+        const float* g = p.blob + p.track_off[f2u(s_rec[NCG_R_TRACK])];
+        unsigned words = f2u(__ldg(g + TH_STAGE_WORDS));
+        tma_stage(s_track, g, words * 4u, &s_mbar);
+        staged = s_track;
+    }
+
+    const int slot = warp * G + lane;                 // car slot for the scalar phases
+    const bool active = lane < G && slot < n_cars;
+    float* R = s_rec + (active ? slot : 0) * NCG_RECORD_WORDS;
+    Counters cnt = {0, 0, 0, 0, 0};
+    unsigned long long episodes = 0; double ret_sum = 0.0;
+
+    for (int t = 0; t < p.T; ++t) {
+        float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
+        float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
+        // ---- A: scalar car phase
+        if (active) {
+            const float* g = p.blob + p.track_off[f2u(R[NCG_R_TRACK])];
+            Track T = track_view(staged ? staged : g, g);
+            float thr, brk, st;
+            const int gc = car0 + slot;
+            if (p.actions) {
+                if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
+                else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
+            } else action_synthetic(p.seed, (uint32_t)gc, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
+            uint32_t xf;
+            s_rew[slot] = car_step(R, T, thr, brk, st, p.contacts != 0, s_obs + slot * OBS_PAD, &xf, &cnt);
+            s_xf[slot] = xf;
+            if (p.track_info) {
+                uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
+                if (on_track(T, R[NCG_R_X], R[NCG_R_Y])) fl |= NCG_F_ON_TRACK;
+                R[NCG_R_FLAGS] = u2f(fl);
+            }
+        }
+        __syncwarp();
+        // ---- B: sensor phase, the warp's G*16 rays over 32 lanes
+        {
+            unsigned tests = 0;
+            for (int task = lane; task < G * 16; task += 32) {
+                int sl = warp * G + (task >> 4);
+                if (sl < n_cars) {
+                    const float* Rr = s_rec + sl * NCG_RECORD_WORDS;
+                    const float* g = p.blob + p.track_off[f2u(Rr[NCG_R_TRACK])];
+                    Track T = track_view(staged ? staged : g, g);
+                    float d = cast_ray(T, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests);
+                    s_obs[sl * OBS_PAD + 22 + (task & 15)] = sensor_obs(d);
+                }
+            }
+            cnt.ray_tests += tests;
+        }
+        if (p.C > 1) __syncthreads(); else __syncwarp();
+        // ---- C: env phase (every car of an env computes the same decision from the env's xf words)
+        bool done = false;
+        if (active) {
+            const int le = slot / p.C;
+            bool te, tr; int why;
+            env_decide(s_xf + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
+            float rew = s_rew[slot];
+            car_finish(R, rew);
+            rew_out[car0 + slot] = rew;
+            done = te || tr;
+            s_done[slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
+            if (slot % p.C == 0) {
+                const int ge = env0 + le;
+                if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
+                else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
+                if (done) ++episodes;
+            }
+            if (done) ret_sum += (double)R[NCG_R_CUM_REWARD];
+        }
+        __syncwarp();
+        // ---- D: observations shared -> HBM (coalesced), terminal observations of finished envs to final_obs
+        const bool do_reset = p.auto_reset != 0;
+        for (int i = lane; i < G * NCG_OBS_DIM; i += 32) {
+            int sl = warp * G + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
+            if (sl < n_cars) {
+                float v = s_obs[sl * OBS_PAD + k];
+                size_t o = (size_t)(car0 + sl) * NCG_OBS_DIM + k;
+                if (s_done[sl] && do_reset) { if (p.final_obs) p.final_obs[o] = v; }
+                else if (obs_out) obs_out[o] = v;
+            }
+        }
+        // ---- E: same-step auto-reset (CarPhysics.reset_car semantics) + reset observation
+        if (do_reset && __any_sync(0xffffffffu, active && done)) {
+            if (active && done) {
+                const float* g = p.blob + p.track_off[f2u(R[NCG_R_TRACK])];
+                Track T = track_view(staged ? staged : g, g);
+                reset_record(R, T, false, f2u(R[NCG_R_TRACK]));
+                observe_state(R, s_obs + slot * OBS_PAD);
+            }
+            __syncwarp();
+            unsigned tests = 0;
+            for (int task = lane; task < G * 16; task += 32) {
+                int sl = warp * G + (task >> 4);
+                if (sl < n_cars && s_done[sl]) {
+                    const float* Rr = s_rec + sl * NCG_RECORD_WORDS;
+                    const float* g = p.blob + p.track_off[f2u(Rr[NCG_R_TRACK])];
+                    Track T = track_view(staged ? staged : g, g);
+                    s_obs[sl * OBS_PAD + 22 + (task & 15)] = sensor_obs(cast_ray(T, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests));
+                }
+            }
+            cnt.ray_tests += tests;
+            __syncwarp();
+            for (int i = lane; i < G * NCG_OBS_DIM; i += 32) {
+                int sl = warp * G + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
+                if (sl < n_cars && s_done[sl] && obs_out) obs_out[(size_t)(car0 + sl) * NCG_OBS_DIM + k] = s_obs[sl * OBS_PAD + k];
+            }
+        }
+        if (p.C > 1) __syncthreads(); else __syncwarp();
+    }
+    // ---- records shared -> HBM
+    __syncthreads();
+    {
+        float4* dst = reinterpret_cast<float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
+        const float4* src = reinterpret_cast<const float4*>(s_rec);
+        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    // ---- counters
+    unsigned long long v[7] = {active ? (unsigned long long)p.T : 0ull, episodes, cnt.laps, cnt.ray_tests, cnt.contact_steps, cnt.toi_events, cnt.overflow};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(((unsigned long long*)p.stats) + k, x);
+    }
+    for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_down_sync(0xffffffffu, ret_sum, o);
+    if (lane == 0 && ret_sum != 0.0) atomicAdd(&p.stats->return_sum, ret_sum);
+}
+
+// reset of masked envs + their initial observation; one warp per car (rays over lanes)
+__global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const float* blob, const long long* track_off, int E, int C,
+                                                         const uint8_t* mask, const int* track_id, int fresh, float* obs) {
+    const int lane = threadIdx.x & 31;
+    const int car = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (car >= E * C) return;
+    const int env = car / C;
+    if (mask && !mask[env]) return;
+    float* R = records + (size_t)car * NCG_RECORD_WORDS;
+    __shared__ float s_obs[8][OBS_PAD];
+    float* so = s_obs[threadIdx.x >> 5];
+    uint32_t tid = track_id ? (uint32_t)track_id[env] : f2u(R[NCG_R_TRACK]);
+    const float* g = blob + track_off[tid];
+    Track T = track_view(g, g);
+    if (lane == 0) { reset_record(R, T, fresh != 0, tid); observe_state(R, so); }
+    __syncwarp();
+    if (obs) {
+        unsigned tests = 0;
+        if (lane < 16) so[22 + lane] = sensor_obs(cast_ray(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], lane, &tests));
+        __syncwarp();
+        for (int k = lane; k < NCG_OBS_DIM; k += 32) obs[(size_t)car * NCG_OBS_DIM + k] = so[k];
+    }
+}
+
+}  // namespace
+
+struct NcgHandle {
+    NcgConfig cfg; int N;
+    float* d_records = nullptr; float* d_blob = nullptr; long long* d_track_off = nullptr; int n_tracks = 0;
+    std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
+    std::vector<int> h_env_track; bool tracks_grouped = false;
+    DevStats* d_stats = nullptr;
+    bool was_reset = false;
+    unsigned step_base = 0;
+    int cars_per_warp = 1;
+    long long launches = 0;
+    // host-buffer path
+    cudaStream_t stream = nullptr;
+    void* d_actions = nullptr; float* d_obs = nullptr; float* d_final = nullptr; float* d_reward = nullptr; uint8_t* d_term = nullptr; uint8_t* d_trunc = nullptr;
+    uint8_t* d_mask = nullptr; int* d_tid = nullptr;
+    void* p_actions = nullptr; float* p_obs = nullptr; float* p_final = nullptr; float* p_reward = nullptr; uint8_t* p_flags = nullptr;
+};
+
+namespace {
+
+int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
+    const int C = h->cfg.cars_per_env, G = h->cars_per_warp;
+    int epb = (8 * G) / C; if (epb < 1) epb = 1;
+    const int cpc = epb * C;
+    const int warps = (cpc + G - 1) / G;
+    p.epb = epb;
+    size_t smem = (size_t)((cpc * (NCG_RECORD_WORDS + OBS_PAD + 3) + 3) & ~3) * 4;
+    if (p.stage) { unsigned mx = 0; for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx; smem += (size_t)mx * 4; }
+    const int grid = (h->cfg.num_envs + epb - 1) / epb;
+    void (*k)(KParams) = G == 1 ? ncg_step_kernel<1> : G == 2 ? ncg_step_kernel<2> : G == 4 ? ncg_step_kernel<4> : ncg_step_kernel<8>;
+    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, warps * 32, smem, s>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    return NCG_OK;
+}
+
+KParams base_params(NcgHandle* h) {
+    KParams p; memset(&p, 0, sizeof(p));
+    p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off;
+    p.E = h->cfg.num_envs; p.C = h->cfg.cars_per_env; p.discrete = h->cfg.discrete; p.reset_on_lap = h->cfg.reset_on_lap;
+    p.auto_reset = h->cfg.auto_reset; p.contacts = h->cfg.contacts; p.track_info = h->cfg.track_info; p.stats = h->d_stats; p.T = 1;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ncg_last_error(void) { return g_err.c_str(); }
+int ncg_version(void) { return 1; }
+
+int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
+    if (!cfg || !out) return fail(NCG_E_INVALID, "null argument");
+    if (cfg->cars_per_env < 1 || cfg->cars_per_env > NCG_MAX_CARS) return fail(NCG_E_INVALID, "Number of cars must be between 1 and 10");
+    if (cfg->num_envs < 1) return fail(NCG_E_INVALID, "num_envs must be >= 1");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NCG_E_INVALID, "no such CUDA device");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    NcgHandle* h = new NcgHandle();
+    h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
+    const char* g = getenv("NCG_CARS_PER_WARP");
+    int G = g ? atoi(g) : 0;
+    if (G != 1 && G != 2 && G != 4 && G != 8) G = h->N >= 148 * 64 * 4 ? 4 : (h->N >= 148 * 64 * 2 ? 2 : 1);
+    h->cars_per_warp = G;
+    size_t N = (size_t)h->N, E = (size_t)cfg->num_envs;
+    CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));
+    CUDA_TRY(cudaMemset(h->d_records, 0, N * NCG_RECORD_WORDS * 4));
+    CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(DevStats)));
+    CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(DevStats)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&h->d_actions, N * 8)); CUDA_TRY(cudaMalloc(&h->d_obs, N * NCG_OBS_DIM * 4)); CUDA_TRY(cudaMalloc(&h->d_final, N * NCG_OBS_DIM * 4));
+    CUDA_TRY(cudaMalloc(&h->d_reward, N * 4)); CUDA_TRY(cudaMalloc(&h->d_term, E)); CUDA_TRY(cudaMalloc(&h->d_trunc, E));
+    CUDA_TRY(cudaMalloc(&h->d_mask, E)); CUDA_TRY(cudaMalloc(&h->d_tid, E * 4));
+    CUDA_TRY(cudaMallocHost(&h->p_actions, N * 8)); CUDA_TRY(cudaMallocHost(&h->p_obs, N * NCG_OBS_DIM * 4)); CUDA_TRY(cudaMallocHost(&h->p_final, N * NCG_OBS_DIM * 4));
+    CUDA_TRY(cudaMallocHost(&h->p_reward, N * 4)); CUDA_TRY(cudaMallocHost(&h->p_flags, E * 8));
+    h->h_env_track.assign(E, 0);
+    *out = h;
+    return NCG_OK;
+}
+
+int ncg_destroy(NcgHandle* h) {
+    if (!h) return NCG_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats);
+    cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_final); cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_trunc);
+    cudaFree(h->d_mask); cudaFree(h->d_tid);
+    cudaFreeHost(h->p_actions); cudaFreeHost(h->p_obs); cudaFreeHost(h->p_final); cudaFreeHost(h->p_reward); cudaFreeHost(h->p_flags);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return NCG_OK;
+}
+
+int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offsets, int32_t n_tracks) {
+    if (!h || !h_blob || !h_offsets || n_tracks < 1) return fail(NCG_E_INVALID, "bad track upload");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (int i = 0; i <= n_tracks; ++i) if (h_offsets[i] % 4) return fail(NCG_E_INVALID, "track offsets must be multiples of 4 words");
+    cudaFree(h->d_blob); cudaFree(h->d_track_off); h->d_blob = nullptr; h->d_track_off = nullptr;
+    size_t words = (size_t)h_offsets[n_tracks];
+    CUDA_TRY(cudaMalloc(&h->d_blob, words * 4));
+    CUDA_TRY(cudaMemcpy(h->d_blob, h_blob, words * 4, cudaMemcpyHostToDevice));
+    h->h_track_off.assign(h_offsets, h_offsets + n_tracks + 1);
+    CUDA_TRY(cudaMalloc(&h->d_track_off, (n_tracks + 1) * sizeof(long long)));
+    CUDA_TRY(cudaMemcpy(h->d_track_off, h->h_track_off.data(), (n_tracks + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+    h->h_stage_words.clear();
+    for (int i = 0; i < n_tracks; ++i) { uint32_t w; memcpy(&w, h_blob + h_offsets[i] + TH_STAGE_WORDS, 4); h->h_stage_words.push_back(w); }
+    h->n_tracks = n_tracks;
+    return NCG_OK;
+}
+
+static void note_tracks(NcgHandle* h, const uint8_t* mask, const int32_t* tid) {
+    if (!tid) return;
+    for (int e = 0; e < h->cfg.num_envs; ++e) if (!mask || mask[e]) h->h_env_track[e] = tid[e];
+}
+
+int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id, int32_t fresh, float* d_obs, void* stream) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called before ncg_reset");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->was_reset && (d_env_mask || !fresh)) return fail(NCG_E_STATE, "the first reset must be a full fresh reset");
+    const int threads = 256, cars_per_block = threads / 32;
+    const int grid = (h->N + cars_per_block - 1) / cars_per_block;
+    ncg_reset_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(h->d_records, h->d_blob, h->d_track_off, h->cfg.num_envs, h->cfg.cars_per_env,
+                                                                d_env_mask, d_track_id, fresh, d_obs);
+    CUDA_TRY(cudaGetLastError());
+    ++h->launches;
+    h->was_reset = true;
+    if (d_track_id) h->tracks_grouped = false;   // device-side ids: grouping unknown, the rollout kernel will not stage
+    return NCG_OK;
+}
+
+int ncg_step(NcgHandle* h, const void* d_actions, float* d_obs, float* d_reward, uint8_t* d_terminated, uint8_t* d_truncated,
+             float* d_final_obs, void* stream) {
+    if (!h || !d_actions || !d_obs || !d_reward) return fail(NCG_E_INVALID, "null argument");
+    if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    KParams p = base_params(h);
+    p.actions = d_actions; p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated; p.final_obs = d_final_obs;
+    return launch_step(h, p, (cudaStream_t)stream);
+}
+
+int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float* d_obs_rollout, float* d_reward_rollout,
+                uint8_t* d_done_rollout, float* d_obs_last, void* stream) {
+    if (!h || steps < 1) return fail(NCG_E_INVALID, "bad rollout arguments");
+    if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    KParams p = base_params(h);
+    p.T = steps; p.seed = seed; p.mode = mode; p.step_base = h->step_base; p.auto_reset = 1;
+    p.obs_roll = d_obs_rollout; p.rew_roll = d_reward_rollout; p.done_roll = d_done_rollout; p.obs = d_obs_last; p.reward = nullptr;
+    if (!d_reward_rollout) { p.reward = h->d_reward; }
+    p.term = h->d_term; p.trunc = h->d_trunc;
+    const char* ns = getenv("NCG_NO_STAGE");
+    p.stage = (h->tracks_grouped && !(ns && atoi(ns))) ? 1 : 0;
+    h->step_base += (unsigned)steps;
+    return launch_step(h, p, (cudaStream_t)stream);
+}
+
+int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_track_id, int32_t fresh, float* h_obs) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t E = h->cfg.num_envs;
+    if (h_track_id) for (size_t e = 0; e < E; ++e) if ((!h_env_mask || h_env_mask[e]) && (h_track_id[e] < 0 || h_track_id[e] >= h->n_tracks)) return fail(NCG_E_INVALID, "track id out of range");
+    if (h_env_mask) CUDA_TRY(cudaMemcpyAsync(h->d_mask, h_env_mask, E, cudaMemcpyHostToDevice, h->stream));
+    if (h_track_id) CUDA_TRY(cudaMemcpyAsync(h->d_tid, h_track_id, E * 4, cudaMemcpyHostToDevice, h->stream));
+    int rc = ncg_reset(h, h_env_mask ? h->d_mask : nullptr, h_track_id ? h->d_tid : nullptr, fresh, h->d_obs, h->stream);
+    if (rc) return rc;
+    note_tracks(h, h_env_mask, h_track_id);
+    {   // the rollout kernel stages one track per CTA: that needs every CTA's envs on one track
+        const int C = h->cfg.cars_per_env, G = h->cars_per_warp; int epb = (8 * G) / C; if (epb < 1) epb = 1;
+        bool ok = true;
+        for (size_t e = 0; e < E && ok; ++e) if (h->h_env_track[e] != h->h_env_track[(e / epb) * epb]) ok = false;
+        h->tracks_grouped = ok;
+    }
+    if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, (size_t)h->N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return NCG_OK;
+}
+
+int ncg_step_host(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                  float* h_final_obs) {
+    if (!h || !h_actions || !h_obs || !h_reward || !h_terminated || !h_truncated) return fail(NCG_E_INVALID, "null argument");
+    if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const size_t N = h->N, E = h->cfg.num_envs, abytes = h->cfg.discrete ? N * 4 : N * 8;
+    memcpy(h->p_actions, h_actions, abytes);
+    CUDA_TRY(cudaMemcpyAsync(h->d_actions, h->p_actions, abytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = ncg_step(h, h->d_actions, h->d_obs, h->d_reward, h->d_term, h->d_trunc, h_final_obs ? h->d_final : nullptr, h->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->p_obs, h->d_obs, N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->p_reward, h->d_reward, N * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->p_flags, h->d_term, E, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->p_flags + E, h->d_trunc, E, cudaMemcpyDeviceToHost, h->stream));
+    if (h_final_obs) CUDA_TRY(cudaMemcpyAsync(h->p_final, h->d_final, N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memcpy(h_obs, h->p_obs, N * NCG_OBS_DIM * 4); memcpy(h_reward, h->p_reward, N * 4);
+    memcpy(h_terminated, h->p_flags, E); memcpy(h_truncated, h->p_flags + E, E);
+    if (h_final_obs) memcpy(h_final_obs, h->p_final, N * NCG_OBS_DIM * 4);
+    return NCG_OK;
+}
+
+int ncg_get_state(NcgHandle* h, float* d_records, void* stream) {
+    if (!h || !d_records) return fail(NCG_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(d_records, h->d_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return NCG_OK;
+}
+int ncg_set_state(NcgHandle* h, const float* d_records, void* stream) {
+    if (!h || !d_records) return fail(NCG_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(h->d_records, d_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    h->was_reset = true;
+    return NCG_OK;
+}
+int ncg_get_state_host(NcgHandle* h, float* h_records) {
+    if (!h || !h_records) return fail(NCG_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h_records, h->d_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyDeviceToHost));
+    return NCG_OK;
+}
+int ncg_set_state_host(NcgHandle* h, const float* h_records) {
+    if (!h || !h_records) return fail(NCG_E_INVALID, "null argument");
+    if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpy(h->d_records, h_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyHostToDevice));
+    for (int e = 0; e < h->cfg.num_envs; ++e) {
+        uint32_t t; memcpy(&t, h_records + (size_t)e * h->cfg.cars_per_env * NCG_RECORD_WORDS + NCG_R_TRACK, 4);
+        if ((int)t >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
+        h->h_env_track[e] = (int)t;
+    }
+    h->tracks_grouped = false;
+    h->was_reset = true;
+    return NCG_OK;
+}
+
+int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset) {
+    if (!h || !out) return fail(NCG_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DevStats s;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(&s, h->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
+    out->car_steps = s.car_steps; out->episodes = s.episodes; out->laps = s.laps; out->ray_tests = s.ray_tests;
+    out->contact_steps = s.contact_steps; out->toi_events = s.toi_events; out->overflow = s.overflow; out->return_sum = s.return_sum;
+    if (reset) CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(DevStats)));
+    return NCG_OK;
+}
+
+int64_t ncg_launch_count(NcgHandle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,1048 @@
+// ncg_car.cuh -- one car-step of NascarGymnasium's CarEnv for one car record, as run by one GPU thread
+// (scalar phases) plus the lane-cooperative ray phase.  float32 state and arithmetic.
+//
+// Reference path restated here (file:line in /root/reference/src):
+//   car.py:311-892 (engine, brake, drag, rolling, acceleration window, lateral force, damping, banking,
+//   steering, friction bookkeeping), tyre_manager.py:99-222, tyre.py:68-228, car_physics.py:341-441 and
+//   631-864 (step, banking lookup, collision listener), box2d-py b2World.Step (ncg_b2.cuh + World below),
+//   distance_sensor.py:71-117, lap_timer.py:95-273, car_env.py:575-676, 805-1158, 1544-1611.
+//
+// The same source is compiled for the device by nvcc (the product) and, for CPU-side debugging of the
+// scalar phases only, by tests/hostcheck (test infrastructure; never shipped, never a fallback).
+#pragma once
+#include "ncg_b2.cuh"
+
+namespace ncg {
+
+// ------------------------------------------------------------------ track table view
+// Blob layout is produced by nascargymnasium_b200/track.py::build_track_table.
+struct Track {
+    const float* hdr; const float* segs; const float* walls; const float* aabb;
+    const uint16_t* cells; const uint16_t* items;
+    int n_walls, n_segs, gnx, gny, has_bank;
+    float gx0, gy0, inv_cell, cell, ltot, min_lap, slx0, sly0, sldx, sldy, sllen2, slhalfw, half_ltot;
+};
+enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEGS, TH_OFF_WALLS, TH_OFF_AABB, TH_OFF_CELLS,
+       TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
+       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS };
+enum { SEG_STRIDE = 12, WALL_STRIDE = 8 };
+// `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
+NCG_HD Track track_view(const float* staged, const float* global) {
+    Track t; t.hdr = staged;
+    t.n_walls = (int)f2u(staged[TH_NWALLS]); t.n_segs = (int)f2u(staged[TH_NSEGS]);
+    t.gnx = (int)f2u(staged[TH_GNX]); t.gny = (int)f2u(staged[TH_GNY]); t.has_bank = (int)f2u(staged[TH_HASBANK]);
+    t.segs = staged + f2u(staged[TH_OFF_SEGS]); t.walls = staged + f2u(staged[TH_OFF_WALLS]);
+    t.cells = (const uint16_t*)(staged + f2u(staged[TH_OFF_CELLS])); t.items = (const uint16_t*)(staged + f2u(staged[TH_OFF_ITEMS]));
+    t.aabb = global + f2u(staged[TH_OFF_AABB]);
+    t.gx0 = staged[TH_GX0]; t.gy0 = staged[TH_GY0]; t.inv_cell = staged[TH_INVCELL]; t.cell = staged[TH_CELL];
+    t.ltot = staged[TH_LTOT]; t.min_lap = staged[TH_MINLAP]; t.slx0 = staged[TH_SLX0]; t.sly0 = staged[TH_SLY0];
+    t.sldx = staged[TH_SLDX]; t.sldy = staged[TH_SLDY]; t.sllen2 = staged[TH_SLLEN2]; t.slhalfw = staged[TH_SLHALFW];
+    t.half_ltot = staged[TH_HALF_LTOT];
+    return t;
+}
+NCG_HD void wall_get(const Track& T, int i, Xf* xf, Box* b) {
+    const float* w = T.walls + i * WALL_STRIDE;
+    xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[4]; b->hy = w[5];
+}
+NCG_HD float wall_angle(const Track& T, int i) { return T.walls[i * WALL_STRIDE + 6]; }
+NCG_HD AABB wall_fat(const Track& T, int i) { const float* a = T.aabb + i * 4; AABB r; r.lx = a[0]; r.ly = a[1]; r.ux = a[2]; r.uy = a[3]; return r; }
+
+// ------------------------------------------------------------------ the per-car Box2D world
+struct Contact { int wall; bool touching, enabled, toiFlag, island; int toiCount; float toi; Manifold m; };
+struct VCPoint { V2 rA; float ni, ti, nm, tm, bias; };
+struct VC { VCPoint p[2]; V2 normal; float K[4], nmat[4]; int pc, ci; };
+struct PC { V2 lp[2], localNormal, localPoint; int type, pc, wall; };
+
+struct World {
+    Xf xf; Sweep sweep; V2 v; float w; V2 force; float torque; float sleepTime, inv_dt0;
+    bool awake, proxyMoved, newFixture, overflow, stepComplete;
+    AABB fat;
+    int nc; Contact c[NCG_MAX_CONTACTS];
+    float wallAlpha[NCG_MAX_CONTACTS];          // alpha0 of the static sweeps of contacted walls (SolveTOI)
+    // CarCollisionListener (car_physics.py:693-864)
+    float impulse; bool hasKey; int na; int awall[NCG_MAX_ACTIVE]; float anx[NCG_MAX_ACTIVE], any[NCG_MAX_ACTIVE];
+    // solver
+    int ni; int isl[NCG_MAX_TOUCHING]; VC vc[NCG_MAX_TOUCHING]; PC pcs[NCG_MAX_TOUCHING];
+    V2 pc_c; float pc_a; V2 pv; float pw;
+    unsigned toi_events;
+};
+NCG_HD Box car_box() { Box b; b.hx = NCG_CAR_HALF_LENGTH; b.hy = NCG_CAR_HALF_WIDTH; return b; }
+#define NCG_INV_MASS (1.0f / NCG_CAR_MASS)
+#define NCG_INV_I (1.0f / NCG_CAR_MOI)
+
+NCG_HD void w_set_awake(World& W, bool flag) {
+    if (flag) { if (!W.awake) { W.awake = true; W.sleepTime = 0.0f; } }
+    else { W.awake = false; W.sleepTime = 0.0f; W.v = mk(0.0f, 0.0f); W.w = 0.0f; W.force = mk(0.0f, 0.0f); W.torque = 0.0f; }
+}
+NCG_HD void w_apply_force(World& W, V2 f, V2 point) { if (!W.awake) w_set_awake(W, true); W.force = W.force + f; W.torque += cross(point - W.sweep.c, f); }
+NCG_HD void w_apply_force_center(World& W, V2 f) { if (!W.awake) w_set_awake(W, true); W.force = W.force + f; }
+NCG_HD void w_apply_torque(World& W, float t) { if (!W.awake) w_set_awake(W, true); W.torque += t; }
+NCG_HD void w_sync_transform(World& W) { W.xf.q = rot(W.sweep.a); W.xf.p = W.sweep.c - mul(W.xf.q, mk(0.0f, 0.0f)); }
+NCG_HD void w_move_proxy(World& W, const AABB& aabb, V2 disp) {
+    if (aabb_contains(W.fat, aabb)) return;
+    AABB b = aabb;
+    b.lx -= NCG_B2_AABB_EXT; b.ly -= NCG_B2_AABB_EXT; b.ux += NCG_B2_AABB_EXT; b.uy += NCG_B2_AABB_EXT;
+    V2 d = NCG_B2_AABB_MULT * disp;
+    if (d.x < 0.0f) b.lx += d.x; else b.ux += d.x;
+    if (d.y < 0.0f) b.ly += d.y; else b.uy += d.y;
+    W.fat = b; W.proxyMoved = true;
+}
+NCG_HD void w_set_transform(World& W, V2 p, float angle) {
+    W.xf.q = rot(angle); W.xf.p = p;
+    W.sweep.c = mul(W.xf, mk(0.0f, 0.0f)); W.sweep.a = angle; W.sweep.c0 = W.sweep.c; W.sweep.a0 = angle;
+    w_move_proxy(W, box_aabb(car_box(), W.xf), mk(0.0f, 0.0f));
+}
+NCG_HD void w_sync_fixtures(World& W) {
+    Xf xf1; xf1.q = rot(W.sweep.a0); xf1.p = W.sweep.c0 - mul(xf1.q, mk(0.0f, 0.0f));
+    AABB a1 = box_aabb(car_box(), xf1), a2 = box_aabb(car_box(), W.xf);
+    AABB c; c.lx = fminb(a1.lx, a2.lx); c.ly = fminb(a1.ly, a2.ly); c.ux = fmaxb(a1.ux, a2.ux); c.uy = fmaxb(a1.uy, a2.uy);
+    w_move_proxy(W, c, W.xf.p - xf1.p);
+}
+NCG_HD void w_advance(World& W, float alpha) {
+    sweep_advance(W.sweep, alpha); W.sweep.c = W.sweep.c0; W.sweep.a = W.sweep.a0;
+    W.xf.q = rot(W.sweep.a); W.xf.p = W.sweep.c - mul(W.xf.q, mk(0.0f, 0.0f));
+}
+// listener callbacks
+NCG_HD void l_begin(World& W, int wall, V2 n) {
+    bool found = false;
+    for (int i = 0; i < W.na; ++i) if (W.awall[i] == wall) { W.anx[i] = n.x; W.any[i] = n.y; found = true; break; }
+    if (!found) { if (W.na < NCG_MAX_ACTIVE) { W.awall[W.na] = wall; W.anx[W.na] = n.x; W.any[W.na] = n.y; ++W.na; } else W.overflow = true; }
+    if (!W.hasKey) { W.hasKey = true; W.impulse = 0.0f; }
+}
+NCG_HD void l_end(World& W, int wall) {
+    for (int i = 0; i < W.na; ++i) if (W.awall[i] == wall) {
+        for (int j = i; j + 1 < W.na; ++j) { W.awall[j] = W.awall[j + 1]; W.anx[j] = W.anx[j + 1]; W.any[j] = W.any[j + 1]; }
+        --W.na; break;
+    }
+    if (W.na == 0) { W.impulse = 0.0f; W.hasKey = true; }
+}
+NCG_HD void l_post_solve(World& W, int count, float n0, float n1) {
+    if (count > 0) {
+        float total = n0; if (count > 1) total = total + n1;
+        if (W.hasKey) W.impulse = total > W.impulse ? total : W.impulse;
+    }
+}
+// b2Contact::Update
+NCG_HDN void w_update_contact(World& W, const Track& T, Contact& c) {
+    Manifold old = c.m;
+    c.enabled = true;
+    bool was = c.touching;
+    Xf xfB; Box bB; wall_get(T, c.wall, &xfB, &bB);
+    collide_boxes(&c.m, car_box(), W.xf, bB, xfB);
+    bool touching = c.m.pc > 0;
+    for (int i = 0; i < c.m.pc; ++i) {
+        c.m.ni[i] = 0.0f; c.m.ti[i] = 0.0f;
+        for (int j = 0; j < old.pc; ++j) if (old.key[j] == c.m.key[i]) { c.m.ni[i] = old.ni[j]; c.m.ti[i] = old.ti[j]; break; }
+    }
+    if (touching != was) w_set_awake(W, true);
+    c.touching = touching;
+    if (!was && touching) { V2 n, pts[2]; world_manifold(&n, pts, c.m, W.xf, xfB); l_begin(W, c.wall, n); }
+    if (was && !touching) l_end(W, c.wall);
+}
+// b2ContactManager::Collide
+NCG_HDN void w_collide(World& W, const Track& T) {
+    int i = 0;
+    while (i < W.nc) {
+        if (!W.awake) { ++i; continue; }
+        Contact& c = W.c[i];
+        if (!aabb_overlap(W.fat, wall_fat(T, c.wall))) {
+            if (c.touching) l_end(W, c.wall);
+            for (int j = i; j + 1 < W.nc; ++j) W.c[j] = W.c[j + 1];
+            --W.nc; continue;
+        }
+        w_update_contact(W, T, c);
+        ++i;
+    }
+}
+// b2ContactManager::FindNewContacts: pairs = walls whose fat AABB overlaps the car's, ascending wall index,
+// each head-inserted.  Candidates come from the uniform grid (cells overlapped by the car's fat AABB).
+NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
+    if (!W.proxyMoved) return;
+    W.proxyMoved = false;
+    int ix0 = (int)floorf((W.fat.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((W.fat.ux - T.gx0) * T.inv_cell);
+    int iy0 = (int)floorf((W.fat.ly - T.gy0) * T.inv_cell), iy1 = (int)floorf((W.fat.uy - T.gy0) * T.inv_cell);
+    ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
+    int found[NCG_MAX_CONTACTS]; int nf = 0;
+    for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
+        int cell = iy * T.gnx + ix;
+        int b = T.cells[cell], e = T.cells[cell + 1];
+        for (int k = b; k < e; ++k) {
+            int wi = T.items[k];
+            if (!aabb_overlap(W.fat, wall_fat(T, wi))) continue;
+            bool have = false;
+            for (int j = 0; j < W.nc; ++j) if (W.c[j].wall == wi) { have = true; break; }
+            for (int j = 0; j < nf && !have; ++j) if (found[j] == wi) have = true;
+            if (have) continue;
+            if (nf < NCG_MAX_CONTACTS) found[nf++] = wi; else W.overflow = true;
+        }
+    }
+    // ascending wall index, then head-insert one by one
+    for (int i = 1; i < nf; ++i) { int key = found[i], j = i - 1; while (j >= 0 && found[j] > key) { found[j + 1] = found[j]; --j; } found[j + 1] = key; }
+    for (int i = 0; i < nf; ++i) {
+        if (W.nc >= NCG_MAX_CONTACTS) { W.overflow = true; break; }
+        for (int j = W.nc; j > 0; --j) { W.c[j] = W.c[j - 1]; W.wallAlpha[j] = W.wallAlpha[j - 1]; }
+        Contact& c = W.c[0];
+        c.wall = found[i]; c.touching = false; c.enabled = true; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f;
+        c.m.pc = 0; c.m.type = FACE_A;
+        W.wallAlpha[0] = 0.0f;
+        ++W.nc;
+    }
+}
+// ---- b2ContactSolver over the island {car} + isl[]
+NCG_HDN void s_init(World& W, bool warm, float dtRatio) {
+    for (int i = 0; i < W.ni; ++i) {
+        Contact& c = W.c[W.isl[i]]; VC& vc = W.vc[i]; PC& pc = W.pcs[i];
+        vc.ci = W.isl[i]; vc.pc = c.m.pc;
+        for (int k = 0; k < 4; ++k) { vc.K[k] = 0.0f; vc.nmat[k] = 0.0f; }
+        pc.localNormal = c.m.localNormal; pc.localPoint = c.m.localPoint; pc.pc = c.m.pc; pc.type = c.m.type; pc.wall = c.wall;
+        for (int j = 0; j < c.m.pc; ++j) {
+            VCPoint& p = vc.p[j];
+            if (warm) { p.ni = dtRatio * c.m.ni[j]; p.ti = dtRatio * c.m.ti[j]; } else { p.ni = 0.0f; p.ti = 0.0f; }
+            p.rA = mk(0.0f, 0.0f); p.nm = 0.0f; p.tm = 0.0f; p.bias = 0.0f;
+            pc.lp[j] = c.m.lp[j];
+        }
+    }
+}
+NCG_HDN void s_init_velocity(World& W, const Track& T) {
+    const float mA = NCG_INV_MASS, iA = NCG_INV_I, restitution = NCG_WALL_RESTITUTION;   // max(0.1, 0.25)
+    for (int i = 0; i < W.ni; ++i) {
+        VC& vc = W.vc[i]; PC& pc = W.pcs[i]; Contact& c = W.c[vc.ci];
+        Xf xfB; Box bB; wall_get(T, pc.wall, &xfB, &bB);
+        V2 cA = W.pc_c; float aA = W.pc_a; V2 vA = W.pv; float wA = W.pw;
+        Xf xfA; xfA.q = rot(aA); xfA.p = cA - mul(xfA.q, mk(0.0f, 0.0f));
+        V2 pts[2]; world_manifold(&vc.normal, pts, c.m, xfA, xfB);
+        for (int j = 0; j < vc.pc; ++j) {
+            VCPoint& p = vc.p[j];
+            p.rA = pts[j] - cA;
+            float rnA = cross(p.rA, vc.normal);
+            float kNormal = mA + iA * rnA * rnA;
+            p.nm = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+            V2 tangent = cross(vc.normal, 1.0f);
+            float rtA = cross(p.rA, tangent);
+            float kTangent = mA + iA * rtA * rtA;
+            p.tm = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+            p.bias = 0.0f;
+            float vRel = dot(vc.normal, (-vA) - cross(wA, p.rA));
+            if (vRel < -NCG_B2_VEL_THRESHOLD) p.bias = -restitution * vRel;
+        }
+        if (vc.pc == 2) {
+            float rn1A = cross(vc.p[0].rA, vc.normal), rn2A = cross(vc.p[1].rA, vc.normal);
+            float k11 = mA + iA * rn1A * rn1A, k22 = mA + iA * rn2A * rn2A, k12 = mA + iA * rn1A * rn2A;
+            if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+                vc.K[0] = k11; vc.K[1] = k12; vc.K[2] = k12; vc.K[3] = k22;
+                float det = k11 * k22 - k12 * k12;
+                if (det != 0.0f) det = 1.0f / det;
+                vc.nmat[0] = det * k22; vc.nmat[2] = -det * k12; vc.nmat[1] = -det * k12; vc.nmat[3] = det * k11;
+            } else vc.pc = 1;
+        }
+    }
+}
+NCG_HDN void s_warm_start(World& W) {
+    const float mA = NCG_INV_MASS, iA = NCG_INV_I;
+    for (int i = 0; i < W.ni; ++i) {
+        VC& vc = W.vc[i];
+        V2 tangent = cross(vc.normal, 1.0f);
+        for (int j = 0; j < vc.pc; ++j) {
+            V2 P = vc.p[j].ni * vc.normal + vc.p[j].ti * tangent;
+            W.pw -= iA * cross(vc.p[j].rA, P);
+            W.pv = W.pv - mA * P;
+        }
+    }
+}
+NCG_HD void s_apply2(V2& vA, float& wA, const VC& vc, V2 x, V2 a) {
+    const float mA = NCG_INV_MASS, iA = NCG_INV_I;
+    V2 d = x - a; V2 P1 = d.x * vc.normal, P2 = d.y * vc.normal;
+    vA = vA - mA * (P1 + P2); wA -= iA * (cross(vc.p[0].rA, P1) + cross(vc.p[1].rA, P2));
+}
+NCG_HDN void s_solve_velocity(World& W) {
+    const float mA = NCG_INV_MASS, iA = NCG_INV_I;
+    const float friction = sqrtf(NCG_CAR_FRICTION * NCG_WALL_FRICTION);
+    for (int i = 0; i < W.ni; ++i) {
+        VC& vc = W.vc[i];
+        V2 vA = W.pv; float wA = W.pw;
+        V2 normal = vc.normal, tangent = cross(normal, 1.0f);
+        for (int j = 0; j < vc.pc; ++j) {
+            VCPoint& p = vc.p[j];
+            V2 dv = (-vA) - cross(wA, p.rA);
+            float vt = dot(dv, tangent) - 0.0f;
+            float lambda = p.tm * (-vt);
+            float maxF = friction * p.ni;
+            float ni = clampb(p.ti + lambda, -maxF, maxF);
+            lambda = ni - p.ti; p.ti = ni;
+            V2 P = lambda * tangent;
+            vA = vA - mA * P; wA -= iA * cross(p.rA, P);
+        }
+        if (vc.pc == 1) {
+            VCPoint& p = vc.p[0];
+            V2 dv = (-vA) - cross(wA, p.rA);
+            float vn = dot(dv, normal);
+            float lambda = -p.nm * (vn - p.bias);
+            float ni = fmaxb(p.ni + lambda, 0.0f);
+            lambda = ni - p.ni; p.ni = ni;
+            V2 P = lambda * normal;
+            vA = vA - mA * P; wA -= iA * cross(p.rA, P);
+        } else if (vc.pc == 2) {
+            VCPoint& c1 = vc.p[0]; VCPoint& c2 = vc.p[1];
+            V2 a = mk(c1.ni, c2.ni);
+            V2 dv1 = (-vA) - cross(wA, c1.rA), dv2 = (-vA) - cross(wA, c2.rA);
+            float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+            V2 b = mk(vn1 - c1.bias, vn2 - c2.bias);
+            b = b - mk(vc.K[0] * a.x + vc.K[2] * a.y, vc.K[1] * a.x + vc.K[3] * a.y);
+            for (;;) {
+                V2 x = -mk(vc.nmat[0] * b.x + vc.nmat[2] * b.y, vc.nmat[1] * b.x + vc.nmat[3] * b.y);
+                if (x.x >= 0.0f && x.y >= 0.0f) { s_apply2(vA, wA, vc, x, a); c1.ni = x.x; c2.ni = x.y; break; }
+                x.x = -c1.nm * b.x; x.y = 0.0f; vn2 = vc.K[1] * x.x + b.y;
+                if (x.x >= 0.0f && vn2 >= 0.0f) { s_apply2(vA, wA, vc, x, a); c1.ni = x.x; c2.ni = x.y; break; }
+                x.x = 0.0f; x.y = -c2.nm * b.y; vn1 = vc.K[2] * x.y + b.x;
+                if (x.y >= 0.0f && vn1 >= 0.0f) { s_apply2(vA, wA, vc, x, a); c1.ni = x.x; c2.ni = x.y; break; }
+                x.x = 0.0f; x.y = 0.0f; vn1 = b.x; vn2 = b.y;
+                if (vn1 >= 0.0f && vn2 >= 0.0f) { s_apply2(vA, wA, vc, x, a); c1.ni = x.x; c2.ni = x.y; break; }
+                break;
+            }
+        }
+        W.pv = vA; W.pw = wA;
+    }
+}
+NCG_HD void s_store_impulses(World& W) {
+    for (int i = 0; i < W.ni; ++i) { VC& vc = W.vc[i]; Manifold& m = W.c[vc.ci].m; for (int j = 0; j < vc.pc; ++j) { m.ni[j] = vc.p[j].ni; m.ti[j] = vc.p[j].ti; } }
+}
+NCG_HDN bool s_solve_position(World& W, const Track& T, float baumgarte, float okFactor) {
+    const float mA = NCG_INV_MASS, iA = NCG_INV_I;
+    float minSep = 0.0f;
+    for (int i = 0; i < W.ni; ++i) {
+        PC& pc = W.pcs[i];
+        Xf xfB; Box bB; wall_get(T, pc.wall, &xfB, &bB);
+        V2 cA = W.pc_c; float aA = W.pc_a;
+        for (int j = 0; j < pc.pc; ++j) {
+            Xf xfA; xfA.q = rot(aA); xfA.p = cA - mul(xfA.q, mk(0.0f, 0.0f));
+            V2 normal, point; float separation;
+            if (pc.type == FACE_A) {
+                normal = mul(xfA.q, pc.localNormal);
+                V2 planePoint = mul(xfA, pc.localPoint), clip = mul(xfB, pc.lp[j]);
+                separation = dot(clip - planePoint, normal) - NCG_B2_POLY_RADIUS - NCG_B2_POLY_RADIUS;
+                point = clip;
+            } else {
+                normal = mul(xfB.q, pc.localNormal);
+                V2 planePoint = mul(xfB, pc.localPoint), clip = mul(xfA, pc.lp[j]);
+                separation = dot(clip - planePoint, normal) - NCG_B2_POLY_RADIUS - NCG_B2_POLY_RADIUS;
+                point = clip; normal = -normal;
+            }
+            V2 rA = point - cA;
+            minSep = fminb(minSep, separation);
+            float C = clampb(baumgarte * (separation + NCG_B2_LINEAR_SLOP), -NCG_B2_MAX_LIN_CORR, 0.0f);
+            float rnA = cross(rA, normal);
+            float K = mA + iA * rnA * rnA;
+            float impulse = K > 0.0f ? -C / K : 0.0f;
+            V2 P = impulse * normal;
+            cA = cA - mA * P; aA -= iA * cross(rA, P);
+        }
+        W.pc_c = cA; W.pc_a = aA;
+    }
+    return minSep >= okFactor * NCG_B2_LINEAR_SLOP;
+}
+NCG_HD void s_report(World& W) {
+    for (int i = 0; i < W.ni; ++i) { VC& vc = W.vc[i]; l_post_solve(W, vc.pc, vc.p[0].ni, vc.pc > 1 ? vc.p[1].ni : 0.0f); }
+}
+NCG_HD void s_integrate(World& W, float h) {
+    V2 tr = h * W.pv;
+    if (dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION) { float ratio = NCG_B2_MAX_TRANSLATION / length(tr); W.pv = ratio * W.pv; }
+    float ro = h * W.pw;
+    if (ro * ro > NCG_B2_MAX_ROTATION * NCG_B2_MAX_ROTATION) { float ratio = NCG_B2_MAX_ROTATION / fabsf(ro); W.pw *= ratio; }
+    W.pc_c = W.pc_c + h * W.pv; W.pc_a += h * W.pw;
+}
+// b2World::Solve + b2Island::Solve
+NCG_HD void w_solve(World& W, const Track& T, float h, float dtRatio, bool contacts) {
+    if (W.awake) {
+        W.ni = 0;
+        if (contacts) for (int i = 0; i < W.nc; ++i) if (W.c[i].enabled && W.c[i].touching) { if (W.ni < NCG_MAX_TOUCHING) W.isl[W.ni++] = i; else W.overflow = true; }
+        W.pc_c = W.sweep.c; W.pc_a = W.sweep.a; W.pv = W.v; W.pw = W.w;
+        W.sweep.c0 = W.sweep.c; W.sweep.a0 = W.sweep.a;
+        W.pv = W.pv + h * (1.0f * mk(0.0f, 0.0f) + NCG_INV_MASS * W.force);
+        W.pw += h * NCG_INV_I * W.torque;
+        bool positionSolved;
+        if (W.ni > 0) {
+            s_init(W, true, dtRatio); s_init_velocity(W, T); s_warm_start(W);
+            for (int i = 0; i < NCG_VEL_ITERS; ++i) s_solve_velocity(W);
+            s_store_impulses(W);
+            s_integrate(W, h);
+            positionSolved = false;
+            for (int i = 0; i < NCG_POS_ITERS; ++i) if (s_solve_position(W, T, NCG_B2_BAUMGARTE, -3.0f)) { positionSolved = true; break; }
+        } else { s_integrate(W, h); positionSolved = true; }
+        W.sweep.c = W.pc_c; W.sweep.a = W.pc_a; W.v = W.pv; W.w = W.pw;
+        w_sync_transform(W);
+        if (W.ni > 0) s_report(W);
+        float minSleep = NCG_B2_MAXFLOAT;
+        if (W.w * W.w > NCG_B2_ANG_SLEEP_TOL * NCG_B2_ANG_SLEEP_TOL || dot(W.v, W.v) > NCG_B2_LIN_SLEEP_TOL * NCG_B2_LIN_SLEEP_TOL) { W.sleepTime = 0.0f; minSleep = 0.0f; }
+        else { W.sleepTime += h; minSleep = fminb(minSleep, W.sleepTime); }
+        if (minSleep >= NCG_B2_TIME_TO_SLEEP && positionSolved) w_set_awake(W, false);
+        w_sync_fixtures(W);
+    }
+    w_find_new_contacts(W, T);
+}
+// b2World::SolveTOI + b2Island::SolveTOI
+NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
+    W.sweep.alpha0 = 0.0f;
+    for (int i = 0; i < W.nc; ++i) { W.wallAlpha[i] = 0.0f; Contact& c = W.c[i]; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f; }
+    for (;;) {
+        int minC = -1; float minAlpha = 1.0f;
+        for (int i = 0; i < W.nc; ++i) {
+            Contact& c = W.c[i];
+            if (!c.enabled) continue;
+            if (c.toiCount > NCG_B2_MAX_SUBSTEPS) continue;
+            float alpha = 1.0f;
+            if (c.toiFlag) alpha = c.toi;
+            else {
+                if (!W.awake) continue;
+                float alpha0 = W.sweep.alpha0;
+                if (W.sweep.alpha0 < W.wallAlpha[i]) { alpha0 = W.wallAlpha[i]; sweep_advance(W.sweep, alpha0); }
+                else if (W.wallAlpha[i] < W.sweep.alpha0) { alpha0 = W.sweep.alpha0; W.wallAlpha[i] = alpha0; }
+                Xf xfB; Box bB; wall_get(T, c.wall, &xfB, &bB);
+                Sweep sB; sB.c0 = xfB.p; sB.c = xfB.p; sB.a0 = wall_angle(T, c.wall); sB.a = sB.a0; sB.alpha0 = W.wallAlpha[i];
+                int state; float t;
+                time_of_impact(&state, &t, car_box(), W.sweep, bB, sB, 1.0f);
+                if (state == TOI_TOUCHING) alpha = fminb(alpha0 + (1.0f - alpha0) * t, 1.0f); else alpha = 1.0f;
+                c.toi = alpha; c.toiFlag = true;
+            }
+            if (alpha < minAlpha) { minC = i; minAlpha = alpha; }
+        }
+        if (minC < 0 || 1.0f - 10.0f * NCG_B2_EPS < minAlpha) break;
+        Contact& mc = W.c[minC];
+        Sweep backup = W.sweep; float backupWall = W.wallAlpha[minC];
+        w_advance(W, minAlpha); W.wallAlpha[minC] = minAlpha;
+        w_update_contact(W, T, mc);
+        mc.toiFlag = false; ++mc.toiCount;
+        if (!mc.enabled || !mc.touching) { mc.enabled = false; W.sweep = backup; W.wallAlpha[minC] = backupWall; w_sync_transform(W); continue; }
+        w_set_awake(W, true);
+        W.ni = 0; W.isl[W.ni++] = minC; mc.island = true;
+        for (int i = 0; i < W.nc; ++i) {
+            Contact& c = W.c[i];
+            if (c.island) continue;
+            float bw = W.wallAlpha[i];
+            W.wallAlpha[i] = minAlpha;
+            w_update_contact(W, T, c);
+            if (!c.enabled || !c.touching) { W.wallAlpha[i] = bw; continue; }
+            if (W.ni < NCG_MAX_TOUCHING) { c.island = true; W.isl[W.ni++] = i; } else W.overflow = true;
+        }
+        float subDt = (1.0f - minAlpha) * stepDt;
+        W.pc_c = W.sweep.c; W.pc_a = W.sweep.a; W.pv = W.v; W.pw = W.w;
+        s_init(W, false, 1.0f);
+        for (int i = 0; i < 20; ++i) if (s_solve_position(W, T, NCG_B2_TOI_BAUMGARTE, -1.5f)) break;
+        W.sweep.c0 = W.pc_c; W.sweep.a0 = W.pc_a;
+        s_init_velocity(W, T);
+        for (int i = 0; i < NCG_VEL_ITERS; ++i) s_solve_velocity(W);
+        s_integrate(W, subDt);
+        W.sweep.c = W.pc_c; W.sweep.a = W.pc_a; W.v = W.pv; W.w = W.pw;
+        w_sync_transform(W);
+        s_report(W);
+        w_sync_fixtures(W);
+        for (int i = 0; i < W.nc; ++i) { W.c[i].toiFlag = false; W.c[i].island = false; }
+        w_find_new_contacts(W, T);
+        ++W.toi_events;
+    }
+}
+// b2World::Step
+NCG_HD void w_step(World& W, const Track& T, float dt, bool contacts) {
+    float inv_dt = 1.0f / dt;
+    float dtRatio = W.inv_dt0 * dt;
+    if (W.newFixture) { w_find_new_contacts(W, T); W.newFixture = false; }
+    if (contacts && W.nc > 0) w_collide(W, T);
+    w_solve(W, T, dt, dtRatio, contacts);
+    if (contacts && W.nc > 0) w_solve_toi(W, T, dt);
+    W.inv_dt0 = inv_dt;
+    W.force = mk(0.0f, 0.0f); W.torque = 0.0f;
+}
+
+// ------------------------------------------------------------------ record <-> World
+NCG_HD void w_load(World& W, const float* R) {
+    W.sweep.c = mk(R[NCG_R_X], R[NCG_R_Y]); W.sweep.a = R[NCG_R_ANGLE]; W.sweep.c0 = W.sweep.c; W.sweep.a0 = W.sweep.a; W.sweep.alpha0 = 0.0f;
+    w_sync_transform(W);
+    W.v = mk(R[NCG_R_VX], R[NCG_R_VY]); W.w = R[NCG_R_OMEGA]; W.force = mk(0.0f, 0.0f); W.torque = 0.0f;
+    W.sleepTime = R[NCG_R_SLEEP]; W.inv_dt0 = R[NCG_R_INV_DT0];
+    uint32_t fl = f2u(R[NCG_R_FLAGS]);
+    W.awake = (fl & NCG_F_AWAKE) != 0; W.proxyMoved = (fl & NCG_F_PROXY_MOVED) != 0; W.newFixture = (fl & NCG_F_NEW_FIXTURE) != 0;
+    W.hasKey = (fl & NCG_F_HAS_KEY) != 0; W.overflow = false; W.stepComplete = true; W.toi_events = 0;
+    W.fat.lx = R[NCG_R_FAT_LX]; W.fat.ly = R[NCG_R_FAT_LY]; W.fat.ux = R[NCG_R_FAT_UX]; W.fat.uy = R[NCG_R_FAT_UY];
+    uint32_t ncw = f2u(R[NCG_R_NCONTACT]);
+    W.nc = (int)(ncw & 255u); W.na = (int)((ncw >> 8) & 255u);
+    uint32_t tmask = (ncw >> 16) & 0xFFFu, pcw = f2u(R[NCG_R_MANIFOLD_PC]);
+    int k = 0;
+    for (int i = 0; i < W.nc; ++i) {
+        Contact& c = W.c[i];
+        uint32_t ww = f2u(R[NCG_R_CONTACT_WALL + (i >> 1)]);
+        c.wall = (int)((i & 1) ? (ww >> 16) : (ww & 0xFFFFu));
+        c.touching = ((tmask >> i) & 1u) != 0; c.enabled = true; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f;
+        c.m.pc = 0; c.m.type = FACE_A; c.m.localNormal = mk(0.0f, 0.0f); c.m.localPoint = mk(0.0f, 0.0f);
+        W.wallAlpha[i] = 0.0f;
+        if (c.touching && k < NCG_MAX_TOUCHING) {
+            const float* M = R + NCG_R_MANIFOLD + 6 * k;
+            c.m.pc = (int)((pcw >> (2 * k)) & 3u);
+            c.m.key[0] = f2u(M[0]); c.m.key[1] = f2u(M[1]); c.m.ni[0] = M[2]; c.m.ti[0] = M[3]; c.m.ni[1] = M[4]; c.m.ti[1] = M[5];
+            c.m.lp[0] = mk(0.0f, 0.0f); c.m.lp[1] = mk(0.0f, 0.0f);
+            ++k;
+        }
+    }
+    W.impulse = R[NCG_R_IMPULSE];
+    for (int i = 0; i < W.na; ++i) { W.awall[i] = (int)f2u(R[NCG_R_ACTIVE + 3 * i]); W.anx[i] = R[NCG_R_ACTIVE + 3 * i + 1]; W.any[i] = R[NCG_R_ACTIVE + 3 * i + 2]; }
+}
+NCG_HD void w_store(const World& W, float* R, uint32_t* flags) {
+    R[NCG_R_X] = W.sweep.c.x; R[NCG_R_Y] = W.sweep.c.y; R[NCG_R_ANGLE] = W.sweep.a; R[NCG_R_VX] = W.v.x; R[NCG_R_VY] = W.v.y; R[NCG_R_OMEGA] = W.w;
+    R[NCG_R_SLEEP] = W.sleepTime; R[NCG_R_INV_DT0] = W.inv_dt0;
+    uint32_t fl = *flags & ~(uint32_t)(NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE | NCG_F_HAS_KEY);
+    if (W.awake) fl |= NCG_F_AWAKE; if (W.proxyMoved) fl |= NCG_F_PROXY_MOVED; if (W.newFixture) fl |= NCG_F_NEW_FIXTURE;
+    if (W.hasKey) fl |= NCG_F_HAS_KEY; if (W.overflow) fl |= NCG_F_OVERFLOW;
+    *flags = fl;
+    R[NCG_R_FAT_LX] = W.fat.lx; R[NCG_R_FAT_LY] = W.fat.ly; R[NCG_R_FAT_UX] = W.fat.ux; R[NCG_R_FAT_UY] = W.fat.uy;
+    uint32_t tmask = 0, pcw = 0; int k = 0;
+    uint32_t ww[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < W.nc; ++i) {
+        const Contact& c = W.c[i];
+        ww[i >> 1] |= ((uint32_t)c.wall & 0xFFFFu) << ((i & 1) * 16);
+        if (c.touching && k < NCG_MAX_TOUCHING) {
+            tmask |= 1u << i; pcw |= ((uint32_t)c.m.pc & 3u) << (2 * k);
+            float* M = R + NCG_R_MANIFOLD + 6 * k;
+            M[0] = u2f(c.m.key[0]); M[1] = u2f(c.m.pc > 1 ? c.m.key[1] : 0u); M[2] = c.m.ni[0]; M[3] = c.m.ti[0];
+            M[4] = c.m.pc > 1 ? c.m.ni[1] : 0.0f; M[5] = c.m.pc > 1 ? c.m.ti[1] : 0.0f;
+            ++k;
+        } else if (c.touching) { *flags |= NCG_F_OVERFLOW; }
+    }
+    for (int i = 0; i < 6; ++i) R[NCG_R_CONTACT_WALL + i] = u2f(ww[i]);
+    R[NCG_R_NCONTACT] = u2f((uint32_t)W.nc | ((uint32_t)W.na << 8) | (tmask << 16));
+    R[NCG_R_MANIFOLD_PC] = u2f(pcw);
+    R[NCG_R_IMPULSE] = W.impulse;
+    for (int i = 0; i < W.na; ++i) { R[NCG_R_ACTIVE + 3 * i] = u2f((uint32_t)W.awall[i]); R[NCG_R_ACTIVE + 3 * i + 1] = W.anx[i]; R[NCG_R_ACTIVE + 3 * i + 2] = W.any[i]; }
+}
+
+// ------------------------------------------------------------------ tyres (tyre.py, tyre_manager.py)
+NCG_HD float tyre_grip(float T, float wear) {
+    float tg;
+    if (85.0f <= T && T <= 105.0f) tg = 1.5f;
+    else { float dev = T < 85.0f ? 85.0f - T : T - 105.0f; tg = fmaxf(0.8f, 1.5f - dev * 0.02f); }
+    return tg * (1.0f - (wear / 100.0f) * 0.5f);
+}
+NCG_HD float total_grip(const float* R) {
+    float tg = 0.0f, tw = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float l = R[NCG_R_TYRE_LOAD + i]; tg += tyre_grip(R[NCG_R_TYRE_TEMP + i], R[NCG_R_TYRE_WEAR + i]) * l; tw += l; }
+    return tw > 0.0f ? tg / tw : 0.0f;
+}
+NCG_HD void weight_transfer(float along, float alat, float speed, float* loads) {
+    float down = 0.0f;
+    if (speed > 50.0f) { float sf = (speed / 50.0f) * (speed / 50.0f); down = fminf(0.12f * sf * NCG_WEIGHT, 1.5f * NCG_WEIGHT); }
+    float base_front = NCG_WEIGHT * 0.5f + down * (1.0f - 0.6f), base_rear = NCG_WEIGHT * 0.5f + down * 0.6f;
+    float tew = NCG_WEIGHT + down;
+    float raw_long = along * tew * 0.02f;
+    float lt = raw_long > 0.0f ? fminf(raw_long, base_front * 0.95f) : fmaxf(raw_long, -(base_rear * 0.95f));
+    float front = base_front - lt, rear = base_rear + lt;
+    float raw_lat = alat * tew * 0.01f;
+    float ml = fminf(front / 2.0f - 200.0f, rear / 2.0f - 200.0f);
+    float latt = ml > 0.0f ? fmaxf(-ml, fminf(ml, raw_lat)) : 0.0f;
+    float raw[4] = {front / 2.0f - latt / 2.0f, front / 2.0f + latt / 2.0f, rear / 2.0f - latt / 2.0f, rear / 2.0f + latt / 2.0f};
+    float deficit = 0.0f, excess = 0.0f, con[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if (raw[i] < 50.0f) { con[i] = 50.0f; deficit += 50.0f - raw[i]; } else { con[i] = raw[i]; excess += raw[i] - 50.0f; } }
+    if (deficit > 0.0f && excess > 0.0f) {
+        float rf = deficit / excess;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) loads[i] = raw[i] >= 50.0f ? fmaxf(50.0f, con[i] - (con[i] - 50.0f) * rf) : con[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) loads[i] = con[i];
+    }
+}
+NCG_HD void tyre_update(float* T, float* wear, float load, float ff, float speed, float alat, float slip) {
+    const float dt = NCG_DT;
+    float ns = fminf(speed / NCG_CAR_MAX_SPEED, 2.0f);
+    float fp = fabsf(ff) * 0.040f * (1.0f + ns * ns);
+    float aero = speed > 50.0f ? speed * speed * 0.0002f : 0.0f;
+    float heat = (fp + aero) * dt / 125.0f;
+    float ce = 0.01f;
+    if (speed > 50.0f) ce *= (1.0f - fminf(0.8f, speed / 100.0f) * 0.5f);
+    float t = *T;
+    t += heat - (t - 25.0f) * ce * dt;
+    t = fmaxf(25.0f, fminf(120.0f, t));
+    *T = t;
+    float tm = (85.0f <= t && t <= 105.0f) ? 1.0f : (t > 105.0f ? 1.0f + (t - 105.0f) / 20.0f : 1.0f + (85.0f - t) / 30.0f);
+    float lm = fmaxf(0.5f, load / NCG_STATIC_TYRE_LOAD);
+    float wf = fmaxf(1.0f, t / 80.0f);
+    float sw = fminf(1.0f + (speed * 3.6f / 400.0f) * 3.0f, 3.0f);
+    float lg = fabsf(alat) / 9.81f;
+    float cw = lg > 2.0f ? fminf(1.0f + (lg - 2.0f) * 1.5f, 2.5f) : 1.0f;
+    float kw = fminf(1.0f + (fabsf(slip) / 45.0f) * 2.0f, 3.0f);
+    float wr = fabsf(ff) * 0.00001f * (tm * lm * wf * sw * cw * kw);
+    *wear = fminf(100.0f, *wear + wr * dt);
+}
+
+// friction forces for tyre heating: car.py:702-830
+NCG_HD void friction_forces(float* ff, const float* R, float driving, float throttle, float brake, float steer_angle, float sp) {
+    float rear, front;
+    if (throttle > 0.01f && sp > 50.0f) { float faf = fminf(0.3f, sp / 200.0f); rear = driving * (1.0f - faf); front = driving * faf / 2.0f; }
+    else { rear = throttle > 0.01f ? driving : 0.0f; front = 0.0f; }
+    float bf = 0.0f;
+    if (brake > 0.01f) { float base = NCG_CAR_MASS * 14.0f * brake / 4.0f; bf = sp <= 1.0f ? base * (0.05f + 0.95f * sp) : base; }
+    float rf = sp > 0.1f ? (0.015f * NCG_WEIGHT) / 4.0f : 0.0f;
+    ff[0] = ff[1] = front + bf + rf; ff[2] = ff[3] = rear / 2.0f + bf + rf;
+    if (sp < 2.0f) return;
+    float slip = R[NCG_R_SLIP], m = 1.0f;
+    if (slip > 5.0f) { float ex = slip - 5.0f; m = fminf(2.2f + 0.04f * ex * ex, 8.0f); }
+    float base = R[NCG_R_FLAT] * 0.05f * m;
+    float fl = base * 0.5f / 2.0f, rl = fl;
+    if (fabsf(steer_angle) > 0.01f && sp > 3.0f) {
+        int of = steer_angle < 0.0f ? 0 : 1, orr = of + 2, inf = 1 - of, inr = inf + 2;
+        ff[of] += fl * 1.5f + R[NCG_R_TYRE_LOAD + of] * 0.001f; ff[orr] += rl * 1.5f + R[NCG_R_TYRE_LOAD + orr] * 0.001f;
+        ff[inf] += fl * 0.5f; ff[inr] += rl * 0.5f;
+    } else { ff[0] += fl; ff[1] += fl; ff[2] += rl; ff[3] += rl; }
+}
+
+// chord-nearest segment (first strict minimum): car_physics.py:631-672 (banking) and car_env.py:1544-1611 (progress)
+NCG_HD void nearest_segment(const Track& T, float x, float y, float* banking, float* progress) {
+    float best = INFINITY; int bi = 0; float bcx = 0.0f, bcy = 0.0f;
+    for (int i = 0; i < T.n_segs; ++i) {
+        const float* s = T.segs + i * SEG_STRIDE;
+        float sx = s[0], sy = s[1], dx = s[4], dy = s[5], l2 = s[6], cx, cy;
+        if (l2 < 1e-6f) { cx = sx; cy = sy; }
+        else { float t = fmaxf(0.0f, fminf(1.0f, ((x - sx) * dx + (y - sy) * dy) / l2)); cx = sx + t * dx; cy = sy + t * dy; }
+        float d2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
+        if (d2 < best) { best = d2; bi = i; bcx = cx; bcy = cy; }
+    }
+    const float* s = T.segs + bi * SEG_STRIDE;
+    *banking = s[9];
+    float px = bcx - s[0], py = bcy - s[1];
+    *progress = s[8] + sqrtf(px * px + py * py);
+}
+// lap_timer.py:205-241
+NCG_HD bool on_startline(const Track& T, float x, float y) {
+    if (T.slhalfw < 0.0f) return false;
+    float d;
+    if (T.sllen2 < 1e-6f) { float ax = x - T.slx0, ay = y - T.sly0; d = sqrtf(ax * ax + ay * ay); }
+    else {
+        float t = fmaxf(0.0f, fminf(1.0f, ((x - T.slx0) * T.sldx + (y - T.sly0) * T.sldy) / T.sllen2));
+        float cx = T.slx0 + t * T.sldx, cy = T.sly0 + t * T.sldy;
+        d = sqrtf((x - cx) * (x - cx) + (y - cy) * (y - cy));
+    }
+    return d <= T.slhalfw;
+}
+// car_physics.py:470-524 (AABB query of +-0.5 m, TestPoint, corner distance)
+NCG_HDN bool on_track(const Track& T, float x, float y) {
+    const float radius = 0.5f;
+    AABB q; q.lx = x - radius; q.ly = y - radius; q.ux = x + radius; q.uy = y + radius;
+    int ix0 = (int)floorf((q.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((q.ux - T.gx0) * T.inv_cell);
+    int iy0 = (int)floorf((q.ly - T.gy0) * T.inv_cell), iy1 = (int)floorf((q.uy - T.gy0) * T.inv_cell);
+    ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
+    for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
+        int cell = iy * T.gnx + ix;
+        for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) {
+            int wi = T.items[k];
+            if (!aabb_overlap(q, wall_fat(T, wi))) continue;
+            Xf xf; Box b; wall_get(T, wi, &xf, &b);
+            V2 pl = mulT(xf.q, mk(x, y) - xf.p);
+            bool inside = true;
+            for (int i = 0; i < 4; ++i) if (dot(box_n(i), pl - box_v(b, i)) > 0.0f) { inside = false; break; }
+            if (inside) return false;
+            for (int i = 0; i < 4; ++i) { V2 v = mul(xf, box_v(b, i)); float dx = x - v.x, dy = y - v.y; if (sqrtf(dx * dx + dy * dy) < radius) return false; }
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ reset (car_env.py:316-535)
+// fresh: new Box2D world (CarPhysics.__init__); otherwise CarPhysics.reset_car + Car.reset on the existing world.
+NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id) {
+    uint32_t fl;
+    if (fresh) {
+        for (int i = 0; i < NCG_RECORD_WORDS; ++i) R[i] = 0.0f;
+        Xf xf; xf.p = mk(0.0f, 0.0f); xf.q = rot(0.0f);
+        AABB a = box_aabb(car_box(), xf);
+        R[NCG_R_FAT_LX] = a.lx - NCG_B2_AABB_EXT; R[NCG_R_FAT_LY] = a.ly - NCG_B2_AABB_EXT; R[NCG_R_FAT_UX] = a.ux + NCG_B2_AABB_EXT; R[NCG_R_FAT_UY] = a.uy + NCG_B2_AABB_EXT;
+        fl = NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE;
+    } else {
+        World W; w_load(W, R);
+        V2 p = mk(0.0f, 0.0f);
+        w_set_transform(W, p, W.sweep.a); w_set_transform(W, p, 0.0f);
+        W.v = mk(0.0f, 0.0f); W.w = 0.0f;     // SetLinearVelocity(0)/SetAngularVelocity(0) do not wake
+        W.na = 0; W.impulse = 0.0f; W.hasKey = false;
+        fl = f2u(R[NCG_R_FLAGS]) & (NCG_F_OVERFLOW);
+        w_store(W, R, &fl);
+        fl &= (NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE | NCG_F_OVERFLOW);
+        for (int i = NCG_R_RPM; i < NCG_R_USED; ++i) if (i != NCG_R_BANK) R[i] = 0.0f;
+    }
+    fl |= NCG_F_FIRST_STEP;
+    R[NCG_R_FLAGS] = u2f(fl);
+    R[NCG_R_RPM] = 1000.0f;
+    for (int i = 0; i < 4; ++i) { R[NCG_R_TYRE_TEMP + i] = 80.0f; R[NCG_R_TYRE_WEAR + i] = 0.0f; R[NCG_R_TYRE_LOAD + i] = NCG_STATIC_TYRE_LOAD; }
+    R[NCG_R_ACC_N] = u2f(0u); R[NCG_R_STUCK_STEPS] = u2f(0u); R[NCG_R_LAP_START] = u2f(0u); R[NCG_R_LAP_COUNT] = u2f(0u);
+    R[NCG_R_STEP] = u2f(0u); R[NCG_R_TRACK] = u2f(track_id);
+    float bank, prog; nearest_segment(T, R[NCG_R_X], R[NCG_R_Y], &bank, &prog);
+    R[NCG_R_PROGRESS_PREV] = prog; R[NCG_R_PREV_X] = R[NCG_R_X]; R[NCG_R_PREV_Y] = R[NCG_R_Y];
+}
+
+// ------------------------------------------------------------------ observation words 0..21 (car_env.py:891-946)
+NCG_HD float clip1(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+NCG_HD void observe_state(const float* R, float* obs) {
+    float vx = R[NCG_R_VX], vy = R[NCG_R_VY];
+    obs[0] = clip1(R[NCG_R_X] / 10000.0f, -1.0f, 1.0f); obs[1] = clip1(R[NCG_R_Y] / 10000.0f, -1.0f, 1.0f);
+    obs[2] = clip1(vx / 111.1f, -1.0f, 1.0f); obs[3] = clip1(vy / 111.1f, -1.0f, 1.0f);
+    obs[4] = clip1(sqrtf(vx * vx + vy * vy) / 111.1f, 0.0f, 1.0f);
+    obs[5] = clip1(R[NCG_R_ANGLE] / 3.14159265358979f, -1.0f, 1.0f); obs[6] = clip1(R[NCG_R_OMEGA] / 10.0f, -1.0f, 1.0f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        obs[7 + k] = clip1(R[NCG_R_TYRE_LOAD + k] / 29430.0f, 0.0f, 1.0f);
+        obs[11 + k] = clip1(R[NCG_R_TYRE_TEMP + k] / 200.0f, 0.0f, 1.0f);
+        obs[15 + k] = clip1(R[NCG_R_TYRE_WEAR + k] / 100.0f, 0.0f, 1.0f);
+    }
+    float ci = R[NCG_R_IMPULSE], ca = 0.0f;
+    if (ci < 100.0f) ci = 0.0f;
+    else if (((f2u(R[NCG_R_NCONTACT]) >> 8) & 255u) > 0) {
+        ca = atan2f(R[NCG_R_ACTIVE + 2], R[NCG_R_ACTIVE + 1]) - R[NCG_R_ANGLE];
+        while (ca > 3.14159265358979f) ca -= 6.28318530717959f;
+        while (ca < -3.14159265358979f) ca += 6.28318530717959f;
+    }
+    obs[19] = clip1(ci / 50000.0f, 0.0f, 1.0f); obs[20] = clip1(ca / 3.14159265358979f, -1.0f, 1.0f);
+    obs[21] = clip1(R[NCG_R_CUM_IMPACT] / 250000.0f, 0.0f, 1.0f);
+}
+
+// ------------------------------------------------------------------ the scalar car phase of one step
+// Runs CarPhysics.step and every per-car part of CarEnv._step_multi_car up to (not including) the env-level
+// termination.  Writes obs[0..21], returns the reward; *xflags gets NCG_X_* bits for the env phase.
+NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, float* obs,
+                       uint32_t* xflags, Counters* cnt) {
+    uint32_t fl = f2u(R[NCG_R_FLAGS]);
+    uint32_t xf = 0;
+    const bool dis_pre = (fl & NCG_F_DISABLED) != 0;
+    uint32_t laps_pre = f2u(R[NCG_R_LAP_COUNT]);
+    if (dis_pre) { xf |= NCG_X_DIS_PRE; thr_in = 0.0f; brk_in = 0.0f; steer_in = 0.0f; }
+    if (laps_pre >= 1u) xf |= NCG_X_LAP_PRE;
+    // ---- Car.set_inputs + update_physics (car.py:241-387)
+    float throttle = fmaxf(0.0f, fminf(1.0f, thr_in)), brake = fmaxf(0.0f, fminf(1.0f, brk_in));
+    float steer = fmaxf(-1.0f, fminf(1.0f, steer_in));
+    float delta = steer * 0.78539816339744831f;
+    World W; w_load(W, R);
+    {   // rpm :311-327
+        float rpm = R[NCG_R_RPM];
+        float diff = (1000.0f + 800.0f * throttle) - rpm;
+        rpm += diff * fminf(1.0f, NCG_DT * 3000.0f / fabsf(diff + 0.1f));
+        R[NCG_R_RPM] = fmaxf(600.0f, fminf(9500.0f, rpm));
+    }
+    {   // engine :389-449
+        float cs = length(W.v);
+        float r = fmaxf(1000.0f, fminf(9000.0f, R[NCG_R_RPM]));
+        float tf = r <= 5500.0f ? 0.7f + 0.3f * (r - 1000.0f) / 4500.0f : 1.0f - 0.6f * (r - 5500.0f) / 3500.0f;
+        float tlf = (NCG_CAR_MAX_TORQUE * tf) * throttle * 7.5f / 0.35f;
+        float ef;
+        if (cs > 12.0f) {
+            float plf = (NCG_CAR_MAX_POWER * throttle) / cs;
+            if (cs <= 25.0f) {
+                float ns = (cs - 12.0f) / 13.0f;
+                float b = fmaxf(0.05f, fminf(0.75f, 1.0f - expf(-2.0f * ns)));
+                ef = tlf * (1.0f - b) + plf * b;
+            } else ef = tlf * 0.25f + plf * 0.75f;
+        } else ef = tlf;
+        float grip = total_grip(R);
+        float sf = 1.0f - fminf(0.4f, fabsf(delta) * 1.5f);
+        ef = fminf(ef, NCG_WEIGHT * grip * sf);
+        V2 fwd = mul(W.xf.q, mk(1.0f, 0.0f));
+        float ff[4]; friction_forces(ff, R, fminf(2000.0f, fabsf(ef) / 2.0f), throttle, brake, delta, cs);
+        V2 rear = mul(W.xf, mk(-NCG_CAR_WHEELBASE / 2.0f, 0.0f));
+        w_apply_force(W, mk(ef * fwd.x, ef * fwd.y), rear);
+        // brake :451-469
+        if (brake > 0.01f) {
+            float bsf = 1.0f - fminf(0.3f, fabsf(delta) * 1.5f);
+            float bforce = NCG_CAR_MASS * 14.0f * bsf * brake;
+            float sp = length(W.v);
+            if (sp > 0.1f) {
+                w_apply_force_center(W, mk(bforce * (-W.v.x / sp), bforce * (-W.v.y / sp)));
+                friction_forces(ff, R, 0.0f, throttle, brake, delta, sp);
+            }
+        }
+        // drag :471-484, rolling :486-500
+        float sp = length(W.v);
+        if (sp > 0.1f) {
+            float mag = NCG_DRAG_CONSTANT * sp * sp;
+            w_apply_force_center(W, mk(mag * (-W.v.x / sp), mag * (-W.v.y / sp)));
+            float rr = 0.015f * NCG_WEIGHT;
+            w_apply_force_center(W, mk(rr * (-W.v.x / sp), rr * (-W.v.y / sp)));
+        }
+        // acceleration window :832-892
+        float along, alat;
+        {
+            float ax = (W.v.x - R[NCG_R_PREV_VX]) / NCG_DT, ay = (W.v.y - R[NCG_R_PREV_VY]) / NCG_DT;
+            V2 f = mul(W.xf.q, mk(1.0f, 0.0f)), l = mul(W.xf.q, mk(0.0f, 1.0f));
+            float lo = fmaxf(-12.0f, fminf(12.0f, ax * f.x + ay * f.y));
+            float la = fmaxf(-12.0f, fminf(12.0f, ax * l.x + ay * l.y));
+            int n = (int)f2u(R[NCG_R_ACC_N]);
+            if (n == 10) { for (int i = 0; i < 18; ++i) R[NCG_R_ACC + i] = R[NCG_R_ACC + i + 2]; n = 9; }
+            R[NCG_R_ACC + 2 * n] = lo; R[NCG_R_ACC + 2 * n + 1] = la; ++n;
+            R[NCG_R_ACC_N] = u2f((uint32_t)n);
+            float s0 = 0.0f, s1 = 0.0f;
+            for (int i = 0; i < n; ++i) { s0 += R[NCG_R_ACC + 2 * i]; s1 += R[NCG_R_ACC + 2 * i + 1]; }
+            along = s0 / (float)n; alat = s1 / (float)n;
+            R[NCG_R_PREV_VX] = W.v.x; R[NCG_R_PREV_VY] = W.v.y;
+        }
+        // tyres :354-357
+        {
+            float loads[4]; weight_transfer(along, alat, sp, loads);
+            float slip_prev = R[NCG_R_SLIP];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                R[NCG_R_TYRE_LOAD + i] = loads[i];
+                tyre_update(&R[NCG_R_TYRE_TEMP + i], &R[NCG_R_TYRE_WEAR + i], loads[i], ff[i], sp, alat, slip_prev);
+            }
+        }
+        // lateral alignment force :635-700
+        if (sp > 0.05f) {
+            V2 f = mul(W.xf.q, mk(1.0f, 0.0f));
+            float vnx = W.v.x / sp, vny = W.v.y / sp;
+            float cp = vnx * f.y - vny * f.x, dp = vnx * f.x + vny * f.y;
+            R[NCG_R_SLIP] = fabsf(atan2f(fabsf(cp), dp)) * 57.295779513082323f;
+            float cfx = (f.x * sp - W.v.x) * (NCG_CAR_MASS * 5.0f), cfy = (f.y * sp - W.v.y) * (NCG_CAR_MASS * 5.0f);
+            float g2 = total_grip(R);
+            float mf = fminf(30000.0f * g2, NCG_WEIGHT * g2);
+            float fm = sqrtf(cfx * cfx + cfy * cfy);
+            if (fm > mf) { float sc = mf / fm; cfx *= sc; cfy *= sc; fm = mf; }
+            R[NCG_R_FLAT] = fm;
+            w_apply_force_center(W, mk(cfx, cfy));
+        }
+        // angular damping :502-507
+        w_apply_torque(W, -W.w * NCG_CAR_MASS * 4.0f);
+        // banking :509-566
+        float bank = R[NCG_R_BANK];
+        if (!(fabsf(bank) < 0.1f) && !(sp < 1.0f)) {
+            float la = NCG_CAR_MASS * 9.81f * sinf(fabsf(bank * 0.017453292519943295f)) * 0.3f;
+            if (!(fabsf(la) < 1.0f) && sp > 5.0f) {
+                float sg = bank < 0.0f ? -1.0f : 1.0f;
+                w_apply_force_center(W, mk((-(W.v.y / sp)) * la * sg, (W.v.x / sp) * la * sg));
+            }
+        }
+        // steering :568-584
+        if (fabsf(delta) > 0.01f && sp > 0.1f) {
+            float dav = sp * tanf(delta) / NCG_CAR_WHEELBASE;
+            w_apply_torque(W, (dav - W.w) * NCG_CAR_MASS * 0.8f);
+        }
+    }
+    // ---- b2World.Step (car_physics.py:363)
+    w_step(W, T, NCG_DT, contacts);
+    w_store(W, R, &fl);
+    if (W.overflow) cnt->overflow++;
+    if (W.nc > 0) { int nt = 0; for (int i = 0; i < W.nc; ++i) nt += W.c[i].touching ? 1 : 0; if (nt) cnt->contact_steps++; }
+    cnt->toi_events += W.toi_events;
+    const float x = W.sweep.c.x, y = W.sweep.c.y;
+    const float speed = length(W.v);
+    // banking refresh + progress (one segment scan serves both)
+    float bank_new, progress;
+    nearest_segment(T, x, y, &bank_new, &progress);
+    R[NCG_R_BANK] = T.has_bank ? bank_new : 0.0f;
+    if (speed > R[NCG_R_MAX_SPEED]) R[NCG_R_MAX_SPEED] = speed;
+    // ---- _run_single_physics_step (car_env.py:581-638)
+    bool disabled = dis_pre, jd = false;
+    uint32_t stuck = f2u(R[NCG_R_STUCK_STEPS]);
+    if (!dis_pre) {
+        float ci = W.impulse;
+        if (ci > 50000.0f) { if (!disabled) { disabled = true; jd = true; } }
+        if (ci > 100.0f) R[NCG_R_CUM_IMPACT] += ci;
+        if (R[NCG_R_CUM_IMPACT] > 250000.0f) { if (!disabled) { disabled = true; jd = true; } }
+        if (speed < 0.5f) stuck += 1u; else { stuck = 0u; fl &= ~(uint32_t)NCG_F_STUCK_POS; }
+    }
+    if (disabled) xf |= NCG_X_DIS_MID;
+    // ---- LapTimer.update (lap_timer.py:95-203) with the pre-increment clock
+    uint32_t step_pre = f2u(R[NCG_R_STEP]);
+    {
+        bool has_pos = (fl & NCG_F_HAS_POS) != 0;
+        float lx = R[NCG_R_LAP_X], ly = R[NCG_R_LAP_Y];
+        if (has_pos) { float dx = x - lx, dy = y - ly; float d = sqrtf(dx * dx + dy * dy); if (d < 50.0f) R[NCG_R_ODO] += d; }
+        if (has_pos && T.slhalfw >= 0.0f) {
+            bool now = on_startline(T, x, y), before = on_startline(T, lx, ly);
+            if (now && !before) {
+                if (fl & NCG_F_CROSSED) {
+                    uint32_t lap_steps = step_pre - f2u(R[NCG_R_LAP_START]);
+                    if (lap_steps >= NCG_MIN_LAP_STEPS && !(R[NCG_R_ODO] < T.min_lap)) {
+                        float lt = (float)lap_steps / 60.0f;
+                        R[NCG_R_LAST_LAP] = lt;
+                        if (!(fl & NCG_F_HAS_BEST) || lt < R[NCG_R_BEST_LAP]) { R[NCG_R_BEST_LAP] = lt; fl |= NCG_F_HAS_BEST; }
+                        fl |= NCG_F_HAS_LAST;
+                        R[NCG_R_LAP_START] = u2f(step_pre);
+                        R[NCG_R_LAP_COUNT] = u2f(laps_pre + 1u); R[NCG_R_ODO] = 0.0f;
+                        xf |= NCG_X_COMPLETED; cnt->laps++;
+                    }
+                } else { fl |= NCG_F_CROSSED; R[NCG_R_LAP_START] = u2f(step_pre); R[NCG_R_ODO] = 0.0f; }
+            }
+        }
+        R[NCG_R_LAP_X] = x; R[NCG_R_LAP_Y] = y; fl |= NCG_F_HAS_POS;
+    }
+    if (f2u(R[NCG_R_LAP_COUNT]) >= 1u) xf |= NCG_X_LAP_MID;
+    R[NCG_R_STEP] = u2f(step_pre + 1u);
+    // ---- _check_and_disable_cars (car_env.py:805-888)
+    if (!disabled) {
+        if (speed < 0.5f && stuck > 0u) {
+            if (!(fl & NCG_F_STUCK_POS)) { fl |= NCG_F_STUCK_POS; R[NCG_R_STUCK_X] = x; R[NCG_R_STUCK_Y] = y; }
+            float dx = x - R[NCG_R_STUCK_X], dy = y - R[NCG_R_STUCK_Y];
+            float moved = sqrtf(dx * dx + dy * dy);
+            if (stuck >= NCG_STUCK_STEPS) { if (moved < 1.0f || stuck >= NCG_STUCK_EXT_STEPS) { disabled = true; jd = true; } }
+        } else { stuck = 0u; fl &= ~(uint32_t)NCG_F_STUCK_POS; }
+    }
+    R[NCG_R_STUCK_STEPS] = u2f(stuck);
+    // ---- observation words 0..21 (before the end-of-step impulse reset)
+    observe_state(R, obs);
+    // ---- reward (car_env.py:980-1113)
+    float reward = 0.0f;
+    if (!(disabled && !jd)) {
+        float r = jd ? 10.0f : 0.0f;
+        if (!disabled) { r -= 0.05f; if (fabsf(W.impulse) > 0.0f) r -= 0.5f; }
+        {
+            float dx = x - R[NCG_R_PREV_X], dy = y - R[NCG_R_PREV_Y];
+            r += sqrtf(dx * dx + dy * dy) * 0.15f;
+            R[NCG_R_PREV_X] = x; R[NCG_R_PREV_Y] = y;
+        }
+        if (!(fl & NCG_F_FIRST_STEP)) {
+            float dl = progress - R[NCG_R_PROGRESS_PREV];
+            if (dl > T.half_ltot) dl -= T.ltot; else if (dl < -T.half_ltot) dl += T.ltot;
+            if (dl < 0.0f) {
+                float back = R[NCG_R_BACK] + fabsf(dl);
+                R[NCG_R_BACK] = back;
+                if (back > 200.0f) { if (!disabled) { disabled = true; jd = true; } }
+                if (back > 25.0f) {
+                    fl |= NCG_F_BACK_ACTIVE;
+                    float nb = fmaxf(0.0f, back - 25.0f) - fmaxf(0.0f, R[NCG_R_BACK_PREV] - 25.0f);
+                    if (nb > 0.0f) r -= nb * 0.05f;
+                }
+            } else { R[NCG_R_BACK] = 0.0f; R[NCG_R_BACK_PREV] = 0.0f; fl &= ~(uint32_t)NCG_F_BACK_ACTIVE; }
+            R[NCG_R_PROGRESS_PREV] = progress;
+        } else { R[NCG_R_PROGRESS_PREV] = progress; fl &= ~(uint32_t)NCG_F_FIRST_STEP; }
+        if (!disabled) R[NCG_R_BACK_PREV] = R[NCG_R_BACK];
+        reward = r;
+    }
+    if (disabled) { fl |= NCG_F_DISABLED; xf |= NCG_X_DIS_POST; }
+    if (jd) xf |= NCG_X_JUST_DISABLED;
+    if (R[NCG_R_CUM_REWARD] < -250.0f) xf |= NCG_X_LOW_REWARD;
+    R[NCG_R_FLAGS] = u2f(fl);
+    *xflags = xf;
+    return reward;
+}
+
+// ------------------------------------------------------------------ env phase (car_env.py:672-676, 1115-1158, 773-797)
+// xf[0..C) are the cars' NCG_X_* words of this step, step_after the env clock after its increment.
+// reason: 0 none, 1 all_cars_disabled, 2 all_active_cars_low_reward, 3 time_limit, 4 truncated.
+NCG_HD void env_decide(const uint32_t* xf, int C, bool reset_on_lap, uint32_t step_after, bool* term, bool* trunc, int* reason) {
+    // _lap_reset_pending: evaluated when car i's timer fires, i.e. with cars j<=i already stepped and j>i not yet
+    bool pending = false;
+    if (reset_on_lap) {
+        for (int i = 0; i < C; ++i) {
+            if (!(xf[i] & NCG_X_COMPLETED)) continue;
+            int active = 0; bool all = true;
+            for (int j = 0; j < C; ++j) {
+                bool dis = j <= i ? (xf[j] & NCG_X_DIS_MID) != 0 : (xf[j] & NCG_X_DIS_PRE) != 0;
+                bool lap = j <= i ? (xf[j] & NCG_X_LAP_MID) != 0 : (xf[j] & NCG_X_LAP_PRE) != 0;
+                if (dis) continue;
+                ++active; if (!lap) all = false;
+            }
+            if (active > 0 && all) pending = true;
+        }
+    }
+    bool te = false, tr = false; int why = 0;
+    int nd = 0, active = 0, below = 0;
+    for (int i = 0; i < C; ++i) { if (xf[i] & NCG_X_DIS_POST) ++nd; else { ++active; if (xf[i] & NCG_X_LOW_REWARD) ++below; } }
+    if (nd >= C) { te = true; why = 1; }
+    else if (active > 0 && below == active) { te = true; why = 2; }
+    else if (reset_on_lap && step_after >= NCG_TERMINATE_STEPS) { te = true; why = 3; }
+    else if (step_after >= NCG_TRUNCATE_STEPS) { tr = true; why = 4; }
+    if (pending) te = true;
+    *term = te; *trunc = tr; *reason = why;
+}
+// per-car end of step: cumulative reward (float32, as numpy 2 accumulates it), listener impulse reset
+NCG_HD void car_finish(float* R, float reward) {
+    R[NCG_R_CUM_REWARD] = R[NCG_R_CUM_REWARD] + reward;
+    R[NCG_R_IMPULSE] = 0.0f;
+    R[NCG_R_FLAGS] = u2f(f2u(R[NCG_R_FLAGS]) | NCG_F_HAS_KEY);
+}
+
+// ------------------------------------------------------------------ one sensor ray (distance_sensor.py:71-117)
+// Returns the hit distance in metres (250 if nothing is hit).  Uniform-grid DDA over the wall boxes; each
+// candidate is tested with b2PolygonShape::RayCast's arithmetic, the minimum entry fraction wins.
+NCG_HD float ray_box_fraction(const float* w, V2 P1, V2 P2, float maxFraction) {
+    Rot q; q.c = w[2]; q.s = w[3];
+    V2 pos = mk(w[0], w[1]);
+    Box b; b.hx = w[4]; b.hy = w[5];
+    V2 p1 = mulT(q, P1 - pos), p2 = mulT(q, P2 - pos), d = p2 - p1;
+    float lower = 0.0f, upper = maxFraction; int index = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        V2 n = box_n(i);
+        float num = dot(n, box_v(b, i) - p1), den = dot(n, d);
+        if (den == 0.0f) { if (num < 0.0f) return -1.0f; }
+        else {
+            if (den < 0.0f && num < lower * den) { lower = num / den; index = i; }
+            else if (den > 0.0f && num < upper * den) { upper = num / den; }
+        }
+        if (upper < lower) return -1.0f;
+    }
+    return index >= 0 ? lower : -1.0f;
+}
+NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, unsigned* tests) {
+    float phi = -(float)i * 0.39269908169872414f + angle;
+    float dx = cosf(phi), dy = sinf(phi);
+    V2 P1 = mk(px, py), P2 = mk(px + dx * 250.0f, py + dy * 250.0f);
+    float best = 1.0f;
+    unsigned nt = 0;
+    // grid coordinates of the origin
+    float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
+    int ix = (int)floorf(gx), iy = (int)floorf(gy);
+    if (ix < 0 || iy < 0 || ix >= T.gnx || iy >= T.gny) {
+        for (int wi = 0; wi < T.n_walls; ++wi) { float fr = ray_box_fraction(T.walls + wi * WALL_STRIDE, P1, P2, best); ++nt; if (fr >= 0.0f) best = fr; }
+    } else {
+        // Amanatides-Woo in units of ray fraction (t in [0,1] <-> 250 m)
+        float ddx = P2.x - P1.x, ddy = P2.y - P1.y;
+        int sx = ddx > 0.0f ? 1 : -1, sy = ddy > 0.0f ? 1 : -1;
+        float tdx = ddx != 0.0f ? T.cell / fabsf(ddx) : INFINITY, tdy = ddy != 0.0f ? T.cell / fabsf(ddy) : INFINITY;
+        float fx = gx - (float)ix, fy = gy - (float)iy;
+        float tmx = ddx != 0.0f ? (ddx > 0.0f ? (1.0f - fx) : fx) * tdx : INFINITY;
+        float tmy = ddy != 0.0f ? (ddy > 0.0f ? (1.0f - fy) : fy) * tdy : INFINITY;
+        int last0 = -1, last1 = -1;
+        for (;;) {
+            int cell = iy * T.gnx + ix;
+            int b = T.cells[cell], e = T.cells[cell + 1];
+            for (int k = b; k < e; ++k) {
+                int wi = T.items[k];
+                if (wi == last0 || wi == last1) continue;
+                last1 = last0; last0 = wi;
+                float fr = ray_box_fraction(T.walls + wi * WALL_STRIDE, P1, P2, best); ++nt;
+                if (fr >= 0.0f) best = fr;
+            }
+            float texit = fminf(tmx, tmy);
+            if (best <= texit || texit >= 1.0f) break;
+            if (tmx < tmy) { ix += sx; tmx += tdx; if (ix < 0 || ix >= T.gnx) break; }
+            else { iy += sy; tmy += tdy; if (iy < 0 || iy >= T.gny) break; }
+        }
+    }
+    *tests += nt;
+    return best < 1.0f ? best * 250.0f : 250.0f;
+}
+NCG_HD float sensor_obs(float dist) { float n = dist / 250.0f; return n < 0.0f ? 0.0f : (n > 1.0f ? 1.0f : n); }
+
+// ------------------------------------------------------------------ Philox4x32-10 (synthetic actions)
+NCG_HD void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+NCG_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// raw action -> [throttle, brake, steer] (base_env.py:201-252)
+NCG_HD void action_continuous(float tb, float steer, float* thr, float* brk, float* st) {
+    if (tb >= 0.0f) { *thr = tb; *brk = 0.0f; } else { *thr = 0.0f; *brk = -tb; }
+    *st = steer;
+}
+NCG_HD void action_discrete(int a, float* thr, float* brk, float* st) {
+    float tb = a == 1 ? 1.0f : (a == 2 ? -1.0f : 0.0f), s = a == 3 ? -1.0f : (a == 4 ? 1.0f : 0.0f);
+    action_continuous(tb, s, thr, brk, st);
+}
+NCG_HD void action_synthetic(uint64_t seed, uint32_t car, uint32_t step, int mode, bool discrete, float* thr, float* brk, float* st) {
+    uint32_t r[4]; philox4x32(car, step, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    if (discrete) { action_discrete((int)(r[0] % 5u), thr, brk, st); return; }
+    float a0 = u01(r[0]), a1 = u01(r[1]);
+    if (mode == 0) action_continuous(2.0f * a0 - 1.0f, 2.0f * a1 - 1.0f, thr, brk, st);
+    else action_continuous(0.2f + 0.8f * a0, -0.2f + 0.8f * a1, thr, brk, st);
+}
+
+}  // namespace ncg

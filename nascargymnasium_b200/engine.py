@@ -1,0 +1,252 @@
+"""ctypes binding of ``libncg_b200.so`` (the C ABI in ``include/ncg_b200.h``) exchanging PyTorch tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every number is produced by the CUDA
+library.  There is no CPU fallback: a missing library or a missing GPU raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import layout as L
+from . import track as T
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "libncg_b200.so")
+_CSRC = os.path.join(_PKG, "csrc")
+_SOURCES = ("ncg_b200.cu", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class NcgError(RuntimeError):
+    pass
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(_CSRC, s) for s in _SOURCES] + [os.path.join(_PKG, "..", "include", "ncg_b200.h")]
+    have_src = all(os.path.exists(s) for s in srcs)
+    if os.path.exists(_SO) and not force:
+        if not have_src or all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
+            return _SO
+    if not have_src:
+        raise NcgError("CUDA sources missing and no prebuilt libncg_b200.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO + ".tmp", os.path.join(_CSRC, "ncg_b200.cu")]
+    subprocess.check_call(cmd)
+    os.replace(_SO + ".tmp", _SO)
+    return _SO
+
+
+class _Config(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("num_envs", ctypes.c_int32), ("cars_per_env", ctypes.c_int32),
+                ("discrete", ctypes.c_int32), ("reset_on_lap", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
+                ("contacts", ctypes.c_int32), ("track_info", ctypes.c_int32)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("car_steps", ctypes.c_uint64), ("episodes", ctypes.c_uint64), ("laps", ctypes.c_uint64),
+                ("ray_tests", ctypes.c_uint64), ("contact_steps", ctypes.c_uint64), ("toi_events", ctypes.c_uint64),
+                ("overflow", ctypes.c_uint64), ("return_sum", ctypes.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_upload_tracks", "ncg_reset", "ncg_step",
+           "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
+           "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count")
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library (built in-tree).  Raises NcgError when it is missing: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise NcgError(f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). nascargymnasium_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(_SO)
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64
+    lib.ncg_last_error.restype = ctypes.c_char_p
+    lib.ncg_create.argtypes = [ctypes.POINTER(_Config), ctypes.POINTER(vp)]
+    lib.ncg_destroy.argtypes = [vp]
+    lib.ncg_upload_tracks.argtypes = [vp, vp, vp, i32]
+    lib.ncg_reset.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.ncg_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ncg_rollout.argtypes = [vp, i32, u64, i32, vp, vp, vp, vp, vp]
+    lib.ncg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.ncg_reset_host.argtypes = [vp, vp, vp, i32, vp]
+    lib.ncg_get_state.argtypes = [vp, vp, vp]
+    lib.ncg_set_state.argtypes = [vp, vp, vp]
+    lib.ncg_get_state_host.argtypes = [vp, vp]
+    lib.ncg_set_state_host.argtypes = [vp, vp]
+    lib.ncg_read_stats.argtypes = [vp, ctypes.POINTER(Stats), i32]
+    lib.ncg_launch_count.argtypes = [vp]
+    lib.ncg_launch_count.restype = ctypes.c_int64
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc == 0:
+        return
+    msg = load_library().ncg_last_error().decode()
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -3:
+        raise RuntimeError(msg)
+    raise NcgError(f"ncg error {rc}: {msg}")
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """E environments x C cars stepped on one B200.  Thin, explicit wrapper over the C ABI."""
+
+    def __init__(self, num_envs: int, cars_per_env: int = 1, tracks: Sequence[str] = ("nascar",), discrete: bool = False,
+                 reset_on_lap: bool = False, auto_reset: bool = True, contacts: bool = True, device: int = 0,
+                 track_info: bool = False):
+        lib = load_library()
+        self._lib = lib
+        self.num_envs, self.cars_per_env = int(num_envs), int(cars_per_env)
+        self.num_cars = self.num_envs * self.cars_per_env
+        self.discrete, self.device = bool(discrete), int(device)
+        cfg = _Config(device, num_envs, cars_per_env, int(discrete), int(reset_on_lap), int(auto_reset), int(contacts), int(track_info))
+        h = ctypes.c_void_p()
+        _check(lib.ncg_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        self.track_names = [T.track_name_of(t) for t in tracks]
+        self.tables = [T.get_track_table(t) for t in tracks]
+        blobs = [t.blob for t in self.tables]
+        offs = np.zeros(len(blobs) + 1, dtype=np.int64)
+        offs[1:] = np.cumsum([len(b) for b in blobs])
+        blob = np.ascontiguousarray(np.concatenate(blobs), dtype=np.float32)
+        _check(lib.ncg_upload_tracks(h, _np_ptr(blob), _np_ptr(offs), len(blobs)))
+
+    # ------------------------------------------------------------------ torch (device tensor) path
+    def _torch(self):
+        import torch
+        return torch
+
+    def _stream(self):
+        torch = self._torch()
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _dev(self, t, dtype, numel, name):
+        torch = self._torch()
+        if t is None:
+            return None
+        if not t.is_cuda or t.device.index != self.device or t.dtype != dtype or not t.is_contiguous() or t.numel() != numel:
+            raise ValueError(f"{name}: expected a contiguous {dtype} CUDA tensor with {numel} elements on cuda:{self.device}")
+        return t
+
+    def reset(self, obs=None, env_mask=None, track_id=None, fresh: bool = True):
+        torch = self._torch()
+        E, N = self.num_envs, self.num_cars
+        self._dev(obs, torch.float32, N * 38, "obs")
+        self._dev(env_mask, torch.uint8, E, "env_mask")
+        self._dev(track_id, torch.int32, E, "track_id")
+        _check(self._lib.ncg_reset(self._h, self._ptr(env_mask), self._ptr(track_id), int(fresh), self._ptr(obs), self._stream()))
+
+    def step(self, actions, obs, reward, terminated, truncated, final_obs=None):
+        torch = self._torch()
+        E, N = self.num_envs, self.num_cars
+        self._dev(actions, torch.int32 if self.discrete else torch.float32, N if self.discrete else N * 2, "actions")
+        self._dev(obs, torch.float32, N * 38, "obs")
+        self._dev(reward, torch.float32, N, "reward")
+        self._dev(terminated, torch.uint8, E, "terminated")
+        self._dev(truncated, torch.uint8, E, "truncated")
+        self._dev(final_obs, torch.float32, N * 38, "final_obs")
+        _check(self._lib.ncg_step(self._h, self._ptr(actions), self._ptr(obs), self._ptr(reward), self._ptr(terminated),
+                                  self._ptr(truncated), self._ptr(final_obs), self._stream()))
+
+    def rollout(self, steps: int, seed: int = 0, mode: int = 0, obs_rollout=None, reward_rollout=None, done_rollout=None,
+                obs_last=None):
+        torch = self._torch()
+        E, N = self.num_envs, self.num_cars
+        self._dev(obs_rollout, torch.float32, steps * N * 38, "obs_rollout")
+        self._dev(reward_rollout, torch.float32, steps * N, "reward_rollout")
+        self._dev(done_rollout, torch.uint8, steps * E, "done_rollout")
+        self._dev(obs_last, torch.float32, N * 38, "obs_last")
+        _check(self._lib.ncg_rollout(self._h, steps, seed, mode, self._ptr(obs_rollout), self._ptr(reward_rollout),
+                                     self._ptr(done_rollout), self._ptr(obs_last), self._stream()))
+
+    def get_state(self, out=None):
+        torch = self._torch()
+        if out is None:
+            out = torch.empty((self.num_cars, L.RECORD_WORDS), dtype=torch.float32, device=f"cuda:{self.device}")
+        _check(self._lib.ncg_get_state(self._h, self._ptr(out), self._stream()))
+        return out
+
+    def set_state(self, records):
+        torch = self._torch()
+        self._dev(records, torch.float32, self.num_cars * L.RECORD_WORDS, "records")
+        _check(self._lib.ncg_set_state(self._h, self._ptr(records), self._stream()))
+
+    # ------------------------------------------------------------------ host (numpy) path
+    def reset_host(self, env_mask: Optional[np.ndarray] = None, track_id: Optional[np.ndarray] = None, fresh: bool = True):
+        obs = np.empty((self.num_cars, 38), dtype=np.float32)
+        if env_mask is not None:
+            env_mask = np.ascontiguousarray(env_mask, dtype=np.uint8)
+        if track_id is not None:
+            track_id = np.ascontiguousarray(track_id, dtype=np.int32)
+        _check(self._lib.ncg_reset_host(self._h, _np_ptr(env_mask), _np_ptr(track_id), int(fresh), _np_ptr(obs)))
+        return obs
+
+    def step_host(self, actions: np.ndarray, want_final: bool = False):
+        N, E = self.num_cars, self.num_envs
+        actions = np.ascontiguousarray(actions, dtype=np.int32 if self.discrete else np.float32)
+        if actions.size != (N if self.discrete else 2 * N):
+            raise ValueError("actions: wrong number of elements")
+        obs = np.empty((N, 38), dtype=np.float32)
+        rew = np.empty(N, dtype=np.float32)
+        te = np.empty(E, dtype=np.uint8)
+        tr = np.empty(E, dtype=np.uint8)
+        fin = np.empty((N, 38), dtype=np.float32) if want_final else None
+        _check(self._lib.ncg_step_host(self._h, _np_ptr(actions), _np_ptr(obs), _np_ptr(rew), _np_ptr(te), _np_ptr(tr), _np_ptr(fin)))
+        return obs, rew, te, tr, fin
+
+    def get_state_host(self) -> np.ndarray:
+        out = np.empty((self.num_cars, L.RECORD_WORDS), dtype=np.float32)
+        _check(self._lib.ncg_get_state_host(self._h, _np_ptr(out)))
+        return out
+
+    def set_state_host(self, records: np.ndarray) -> None:
+        records = np.ascontiguousarray(records, dtype=np.float32)
+        if records.size != self.num_cars * L.RECORD_WORDS:
+            raise ValueError("records: wrong number of elements")
+        _check(self._lib.ncg_set_state_host(self._h, _np_ptr(records)))
+
+    def read_stats(self, reset: bool = False) -> dict:
+        s = Stats()
+        _check(self._lib.ncg_read_stats(self._h, ctypes.byref(s), int(reset)))
+        return s.as_dict()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.ncg_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ncg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -267,10 +267,10 @@ _libm.cosf.argtypes = [ctypes.c_float]
 
 
 def wall_boxes(track: Track) -> np.ndarray:
-    """(n,6) float32 [px,py,c,s,hx,hy]: what Box2D stores for each static wall
+    """(n,7) float32 [px,py,c,s,hx,hy,angle]: what Box2D stores for each static wall
     body (``_create_wall_body_from_line`` :293-315 then b2Body/b2Rot float32)."""
     lines = wall_lines(track)
-    out = np.zeros((len(lines), 6), dtype=np.float32)
+    out = np.zeros((len(lines), 7), dtype=np.float32)
     for i, (x1, y1, x2, y2) in enumerate(lines):
         cx = (x1 + x2) / 2
         cy = (y1 + y2) / 2
@@ -282,6 +282,7 @@ def wall_boxes(track: Track) -> np.ndarray:
         out[i, 3] = _libm.sinf(float(angle))
         out[i, 4] = np.float32(length / 2)
         out[i, 5] = np.float32(K.WALL_THICKNESS / 2)
+        out[i, 6] = angle
     return out
 
 
@@ -290,7 +291,7 @@ def wall_boxes(track: Track) -> np.ndarray:
 # ----------------------------------------------------------------------------
 MAX_SEGS = 16
 SEG_STRIDE = 12          # floats per segment row
-WALL_STRIDE = 8          # floats per wall row  [px,py,c,s,hx,hy,0,0]
+WALL_STRIDE = 8          # floats per wall row  [px,py,c,s,hx,hy,angle,0]
 HDR_WORDS = 32
 GRID_CELL = 32.0
 POLY_RADIUS = 0.01       # b2_polygonRadius
@@ -301,6 +302,7 @@ H_NWALLS, H_NSEGS, H_GNX, H_GNY, H_HASBANK, H_WORDS, H_OFF_SEGS, H_OFF_WALLS, H_
     H_OFF_ITEMS, H_NITEMS = range(12)
 H_GX0, H_GY0, H_INVCELL, H_CELL, H_LTOT, H_MINLAP, H_SLX0, H_SLY0, H_SLDX, H_SLDY, H_SLLEN2, H_SLHALFW, \
     H_HALF_LTOT = range(12, 25)
+H_STAGE_WORDS = 25       # words [0, H_STAGE_WORDS) are what a CTA stages into shared memory (all but the AABBs)
 
 
 def _wall_corners(b: np.ndarray) -> np.ndarray:
@@ -326,7 +328,7 @@ def wall_fat_aabbs(b: np.ndarray) -> np.ndarray:
 
 def _obb_overlaps_cell(bx, cell_lo, cell_hi, margin):
     """SAT test: oriented wall box (inflated by margin) vs axis-aligned cell."""
-    px, py, c, s, hx, hy = [float(v) for v in bx]
+    px, py, c, s, hx, hy = [float(v) for v in bx[:6]]
     hx += margin
     hy += margin
     ccx, ccy = 0.5 * (cell_lo[0] + cell_hi[0]), 0.5 * (cell_lo[1] + cell_hi[1])
@@ -349,7 +351,7 @@ def _obb_overlaps_cell(bx, cell_lo, cell_hi, margin):
 class TrackTable:
     """Everything the engine (and the tests) need about one track."""
     track: Track
-    boxes: np.ndarray        # (n,6) f32
+    boxes: np.ndarray        # (n,7) f32 [px,py,c,s,hx,hy,angle]
     fat_aabb: np.ndarray     # (n,4) f32
     segs: np.ndarray         # (MAX_SEGS, SEG_STRIDE) f32
     seg64: np.ndarray        # (nseg, 6) f64 [sx,sy,ex,ey,banking,0] for the oracle
@@ -426,12 +428,12 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
 
     off_segs = HDR_WORDS
     off_walls = off_segs + MAX_SEGS * SEG_STRIDE
-    off_aabb = off_walls + pad4(n * WALL_STRIDE)
-    off_cells = off_aabb + pad4(n * 4)
+    off_cells = off_walls + pad4(n * WALL_STRIDE)
     cells_words = pad4((len(cell_start) + 1) // 2)
     off_items = off_cells + cells_words
     items_words = pad4((len(items) + 1) // 2)
-    total = off_items + items_words
+    off_aabb = off_items + items_words          # broad-phase only: kept in global memory, not staged
+    total = off_aabb + pad4(n * 4)
     blob = np.zeros(total, dtype=np.float32)
     hi = blob.view(np.int32)
     hi[H_NWALLS] = n
@@ -446,6 +448,7 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     hi[H_OFF_CELLS] = off_cells
     hi[H_OFF_ITEMS] = off_items
     hi[H_NITEMS] = len(items)
+    hi[H_STAGE_WORDS] = off_aabb
     blob[H_GX0] = x0
     blob[H_GY0] = y0
     blob[H_INVCELL] = 1.0 / cell
@@ -463,7 +466,7 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
         blob[H_SLHALFW] = -1.0
     blob[off_segs:off_segs + MAX_SEGS * SEG_STRIDE] = segs.reshape(-1)
     wrows = np.zeros((n, WALL_STRIDE), dtype=np.float32)
-    wrows[:, :6] = boxes
+    wrows[:, :7] = boxes
     blob[off_walls:off_walls + n * WALL_STRIDE] = wrows.reshape(-1)
     blob[off_aabb:off_aabb + n * 4] = fat.reshape(-1)
     cs16 = np.zeros(cells_words * 2, dtype=np.uint16)

@@ -1,0 +1,62 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the product's per-car device code (ncg_car.cuh) for the host so the
+// scalar phases can be compared with the oracle on a machine without a GPU.  This library is never shipped,
+// never loaded by nascargymnasium_b200 and is not a fallback: the product path is the CUDA build only.
+#include "../../nascargymnasium_b200/csrc/ncg_car.cuh"
+
+using namespace ncg;
+
+extern "C" {
+
+// One env of C cars: records [C][128], actions [C][3] (throttle, brake, steer), obs [C][38], reward [C].
+void hc_env_step(const float* blob, float* records, int C, const float* act3, int contacts, int reset_on_lap, float* obs,
+                 float* reward, int* terminated, int* truncated, int* reason, unsigned long long* counters) {
+    Track T = track_view(blob, blob);
+    Counters cnt = {0, 0, 0, 0, 0};
+    uint32_t xf[NCG_MAX_CARS];
+    for (int i = 0; i < C; ++i) {
+        float* R = records + i * NCG_RECORD_WORDS;
+        reward[i] = car_step(R, T, act3[i * 3], act3[i * 3 + 1], act3[i * 3 + 2], contacts != 0, obs + i * 38, &xf[i], &cnt);
+        unsigned tests = 0;
+        for (int k = 0; k < 16; ++k) obs[i * 38 + 22 + k] = sensor_obs(cast_ray(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, &tests));
+        cnt.ray_tests += tests;
+    }
+    bool te, tr; int why;
+    env_decide(xf, C, reset_on_lap != 0, f2u(records[NCG_R_STEP]), &te, &tr, &why);
+    for (int i = 0; i < C; ++i) car_finish(records + i * NCG_RECORD_WORDS, reward[i]);
+    *terminated = te; *truncated = tr; *reason = why;
+    if (counters) { counters[0] = cnt.ray_tests; counters[1] = cnt.contact_steps; counters[2] = cnt.toi_events; counters[3] = cnt.overflow; counters[4] = cnt.laps; }
+}
+
+void hc_env_reset(const float* blob, float* records, int C, int fresh, int track_id, float* obs) {
+    Track T = track_view(blob, blob);
+    for (int i = 0; i < C; ++i) {
+        float* R = records + i * NCG_RECORD_WORDS;
+        reset_record(R, T, fresh != 0, (uint32_t)track_id);
+        if (obs) {
+            observe_state(R, obs + i * 38);
+            unsigned tests = 0;
+            for (int k = 0; k < 16; ++k) obs[i * 38 + 22 + k] = sensor_obs(cast_ray(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, &tests));
+        }
+    }
+}
+
+// brute-force sensor (all walls) for checking the grid traversal
+void hc_sensors_brute(const float* blob, float x, float y, float angle, float* out16) {
+    Track T = track_view(blob, blob);
+    for (int i = 0; i < 16; ++i) {
+        float phi = -(float)i * 0.39269908169872414f + angle;
+        V2 P1 = mk(x, y), P2 = mk(x + cosf(phi) * 250.0f, y + sinf(phi) * 250.0f);
+        float best = 1.0f;
+        for (int wi = 0; wi < T.n_walls; ++wi) { float fr = ray_box_fraction(T.walls + wi * WALL_STRIDE, P1, P2, best); if (fr >= 0.0f) best = fr; }
+        out16[i] = best < 1.0f ? best * 250.0f : 250.0f;
+    }
+}
+void hc_sensors_grid(const float* blob, float x, float y, float angle, float* out16, unsigned* tests) {
+    Track T = track_view(blob, blob);
+    for (int i = 0; i < 16; ++i) out16[i] = cast_ray(T, x, y, angle, i, tests);
+}
+int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }
+void hc_synthetic_action(unsigned long long seed, unsigned car, unsigned step, int mode, int discrete, float* out3) {
+    action_synthetic(seed, car, step, mode, discrete != 0, out3, out3 + 1, out3 + 2);
+}
+}

@@ -1,0 +1,72 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle on teacher-forced single steps."""
+import numpy as np
+import pytest
+
+from nascargymnasium_b200 import layout as L
+from nascargymnasium_b200 import track as T
+from tests import parity_util as P
+
+pytestmark = pytest.mark.gpu
+
+TRACKS = list(T.BUILTIN_TRACK_NAMES)
+
+
+def _engine(n, tracks, **kw):
+    from nascargymnasium_b200.engine import Engine
+    return Engine(n, 1, tracks=tracks, auto_reset=False, **kw)
+
+
+def test_reset_observation_matches_oracle():
+    from oracle import oracle as O
+    eng = _engine(len(TRACKS), TRACKS)
+    obs = eng.reset_host(track_id=np.arange(len(TRACKS), dtype=np.int32))
+    for i, name in enumerate(TRACKS):
+        want = O.OracleEnv(T.builtin_track_text(name)).reset()[0]
+        assert np.abs(obs[i] - want).max() < 1e-6, name
+    eng.close()
+
+
+@pytest.mark.parametrize("track,kind,seed", [("nascar", "drive", 0), ("martinsville", "drive", 1), ("daytona", "drive", 2),
+                                             ("talladega", "random", 3), ("michigan", "drive", 4), ("nascar2", "drive", 5),
+                                             ("trioval", "full", 6), ("nascar_banked", "drive", 7)])
+def test_teacher_forced_single_steps(track, kind, seed):
+    recs, act3, raws, exp = P.collect_cases(track, 300, kind=kind, seed=seed)
+    n = len(recs)
+    eng = _engine(n, [track])
+    eng.reset_host()
+    eng.set_state_host(recs)
+    obs, rew, te, tr, _ = eng.step_host(np.array(raws, dtype=np.float32))
+    got = eng.get_state_host()
+    bad, report = P.check_cases(got, obs, rew, te, tr, exp, label=track)
+    contact = int((exp["touching"] > 0).sum())
+    print(f"{track}: {n} cases, {contact} with touching contacts, {bad} mismatches")
+    assert bad == 0, report
+    eng.close()
+
+
+def test_discrete_actions():
+    recs, act3, raws, exp = P.collect_cases("martinsville", 200, kind="random", seed=11, discrete=True)
+    eng = _engine(len(recs), ["martinsville"], discrete=True)
+    eng.reset_host()
+    eng.set_state_host(recs)
+    obs, rew, te, tr, _ = eng.step_host(np.array(raws, dtype=np.int32))
+    bad, report = P.check_cases(eng.get_state_host(), obs, rew, te, tr, exp, label="discrete")
+    assert bad == 0, report
+    eng.close()
+
+
+def test_free_running_rollout_stays_close():
+    """No teacher forcing: 600 steps of the same action stream; discrete events must agree, floats stay close."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(5)
+    orc = O.OracleEnv(T.builtin_track_text("nascar"))
+    orc.reset()
+    eng = _engine(1, ["nascar"])
+    eng.reset_host()
+    for i in range(600):
+        a = [float(rng.uniform(0.2, 1.0)), float(rng.uniform(-0.1, 0.1))]
+        oo, ro, teo, tro = orc.step([a])
+        og, rg, teg, trg, _ = eng.step_host(np.array([a], dtype=np.float32))
+        assert bool(teg[0]) == teo and bool(trg[0]) == tro
+        assert np.abs(og[0] - oo[0]).max() < 5e-3, (i, np.abs(og[0] - oo[0]).argmax())
+    eng.close()
