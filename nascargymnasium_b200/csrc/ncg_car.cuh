@@ -17,21 +17,22 @@ namespace ncg {
 // ------------------------------------------------------------------ track table view
 // Blob layout is produced by nascargymnasium_b200/track.py::build_track_table.
 struct Track {
-    const float* hdr; const float* segs; const float* walls; const float* aabb;
+    const float* hdr; const float* segs; const double* seg64; const float* walls; const float* aabb;
     const uint16_t* cells; const uint16_t* items;
     int n_walls, n_segs, gnx, gny, has_bank;
     float gx0, gy0, inv_cell, cell, ltot, min_lap, slx0, sly0, sldx, sldy, sllen2, slhalfw, half_ltot;
 };
 enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEGS, TH_OFF_WALLS, TH_OFF_AABB, TH_OFF_CELLS,
        TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
-       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS };
-enum { SEG_STRIDE = 12, WALL_STRIDE = 8 };
+       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64 };
+enum { SEG_STRIDE = 12, WALL_STRIDE = 8, SEG64_STRIDE = 5 };
 // `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
 NCG_HD Track track_view(const float* staged, const float* global) {
     Track t; t.hdr = staged;
     t.n_walls = (int)f2u(staged[TH_NWALLS]); t.n_segs = (int)f2u(staged[TH_NSEGS]);
     t.gnx = (int)f2u(staged[TH_GNX]); t.gny = (int)f2u(staged[TH_GNY]); t.has_bank = (int)f2u(staged[TH_HASBANK]);
     t.segs = staged + f2u(staged[TH_OFF_SEGS]); t.walls = staged + f2u(staged[TH_OFF_WALLS]);
+    t.seg64 = (const double*)(staged + f2u(staged[TH_OFF_SEG64]));
     t.cells = (const uint16_t*)(staged + f2u(staged[TH_OFF_CELLS])); t.items = (const uint16_t*)(staged + f2u(staged[TH_OFF_ITEMS]));
     t.aabb = global + f2u(staged[TH_OFF_AABB]);
     t.gx0 = staged[TH_GX0]; t.gy0 = staged[TH_GY0]; t.inv_cell = staged[TH_INVCELL]; t.cell = staged[TH_CELL];
@@ -593,17 +594,45 @@ NCG_HD void friction_forces(float* ff, const float* R, float driving, float thro
     } else { ff[0] += fl; ff[1] += fl; ff[2] += rl; ff[3] += rl; }
 }
 
-// chord-nearest segment (first strict minimum): car_physics.py:631-672 (banking) and car_env.py:1544-1611 (progress)
+// chord-nearest segment (first strict minimum): car_physics.py:631-672 (banking) and car_env.py:1544-1611 (progress).
+// The reference does this search in float64.  Tracks whose last segment overshoots the start (closure gaps of
+// SURVEY App. F) have two chords that coincide to ~1e-14 m near the start line, and the reference's answer there
+// hangs on float64 digits -- so a float32 scan picks the winner only when it is clear-cut, and otherwise the
+// search is redone in float64 with the reference's exact expressions.
+NCG_HDN void nearest_segment64(const Track& T, float xf, float yf, float* banking, float* progress) {
+    const double x = (double)xf, y = (double)yf;
+    double best = INFINITY; int bi = 0; double bcx = 0.0, bcy = 0.0;
+    for (int i = 0; i < T.n_segs; ++i) {
+        const double* s = T.seg64 + i * SEG64_STRIDE;
+        double sx = s[0], sy = s[1], dx = s[2] - s[0], dy = s[3] - s[1];
+        double l2 = dx * dx + dy * dy, cx, cy;
+        if (l2 < 1e-6) { cx = sx; cy = sy; }
+        else {
+            double t = ((x - sx) * dx + (y - sy) * dy) / l2;
+            t = t > 1.0 ? 1.0 : t; t = t < 0.0 ? 0.0 : t;
+            cx = sx + t * dx; cy = sy + t * dy;
+        }
+        double d2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
+        if (d2 < best) { best = d2; bi = i; bcx = cx; bcy = cy; }
+    }
+    const double* s = T.seg64 + bi * SEG64_STRIDE;
+    *banking = T.segs[bi * SEG_STRIDE + 9];
+    *progress = (float)(s[4] + sqrt((bcx - s[0]) * (bcx - s[0]) + (bcy - s[1]) * (bcy - s[1])));
+}
 NCG_HD void nearest_segment(const Track& T, float x, float y, float* banking, float* progress) {
-    float best = INFINITY; int bi = 0; float bcx = 0.0f, bcy = 0.0f;
+    float best = INFINITY, second = INFINITY; int bi = 0; float bcx = 0.0f, bcy = 0.0f;
     for (int i = 0; i < T.n_segs; ++i) {
         const float* s = T.segs + i * SEG_STRIDE;
         float sx = s[0], sy = s[1], dx = s[4], dy = s[5], l2 = s[6], cx, cy;
         if (l2 < 1e-6f) { cx = sx; cy = sy; }
         else { float t = fmaxf(0.0f, fminf(1.0f, ((x - sx) * dx + (y - sy) * dy) / l2)); cx = sx + t * dx; cy = sy + t * dy; }
         float d2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
-        if (d2 < best) { best = d2; bi = i; bcx = cx; bcy = cy; }
+        if (d2 < best) { second = best; best = d2; bi = i; bcx = cx; bcy = cy; }
+        else if (d2 < second) second = d2;
     }
+    // float32 projection error is ~1e-4 m at these coordinates: demand a clear margin in distance, else go to float64
+    float db = sqrtf(best), ds = sqrtf(second);
+    if (ds - db < 2e-3f + 1e-4f * ds) { nearest_segment64(T, x, y, banking, progress); return; }
     const float* s = T.segs + bi * SEG_STRIDE;
     *banking = s[9];
     float px = bcx - s[0], py = bcy - s[1];
@@ -976,8 +1005,17 @@ NCG_HD float ray_box_fraction(const float* w, V2 P1, V2 P2, float maxFraction) {
     return index >= 0 ? lower : -1.0f;
 }
 NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, unsigned* tests) {
-    float phi = -(float)i * 0.39269908169872414f + angle;
-    float dx = cosf(phi), dy = sinf(phi);
+    // direction = heading rotated by -i*22.5 deg.  The reference evaluates cos/sin(theta - i*pi/8) in float64
+    // (distance_sensor.py:95-103); rotating the float32 heading by a constant table keeps the axis-aligned rays
+    // of the start pose (theta = 0) exactly axis-aligned, as they are in float64, instead of 4e-8 rad off.
+    const float kc[16] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.0f, -0.38268343236508977f,
+                          -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f, -0.70710678118654752f,
+                          -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+    const float ks[16] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f,
+                          -0.70710678118654752f, -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f,
+                          0.92387953251128674f, 1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+    float ca = cosf(angle), sa = sinf(angle);
+    float dx = ca * kc[i] - sa * ks[i], dy = sa * kc[i] + ca * ks[i];
     V2 P1 = mk(px, py), P2 = mk(px + dx * 250.0f, py + dy * 250.0f);
     float best = 1.0f;
     unsigned nt = 0;

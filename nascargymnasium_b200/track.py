@@ -303,6 +303,8 @@ H_NWALLS, H_NSEGS, H_GNX, H_GNY, H_HASBANK, H_WORDS, H_OFF_SEGS, H_OFF_WALLS, H_
 H_GX0, H_GY0, H_INVCELL, H_CELL, H_LTOT, H_MINLAP, H_SLX0, H_SLY0, H_SLDX, H_SLDY, H_SLLEN2, H_SLHALFW, \
     H_HALF_LTOT = range(12, 25)
 H_STAGE_WORDS = 25       # words [0, H_STAGE_WORDS) are what a CTA stages into shared memory (all but the AABBs)
+H_OFF_SEG64 = 26         # float64 rows [sx,sy,ex,ey,cum_chord] per segment (tie-exact nearest-segment search)
+SEG64_STRIDE = 5
 
 
 def _wall_corners(b: np.ndarray) -> np.ndarray:
@@ -427,7 +429,8 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
         return (nwords + 3) // 4 * 4
 
     off_segs = HDR_WORDS
-    off_walls = off_segs + MAX_SEGS * SEG_STRIDE
+    off_seg64 = off_segs + MAX_SEGS * SEG_STRIDE               # even word offset => 8-byte aligned doubles
+    off_walls = off_seg64 + pad4(MAX_SEGS * SEG64_STRIDE * 2)
     off_cells = off_walls + pad4(n * WALL_STRIDE)
     cells_words = pad4((len(cell_start) + 1) // 2)
     off_items = off_cells + cells_words
@@ -449,6 +452,7 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     hi[H_OFF_ITEMS] = off_items
     hi[H_NITEMS] = len(items)
     hi[H_STAGE_WORDS] = off_aabb
+    hi[H_OFF_SEG64] = off_seg64
     blob[H_GX0] = x0
     blob[H_GY0] = y0
     blob[H_INVCELL] = 1.0 / cell
@@ -465,6 +469,12 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     else:
         blob[H_SLHALFW] = -1.0
     blob[off_segs:off_segs + MAX_SEGS * SEG_STRIDE] = segs.reshape(-1)
+    s64 = np.zeros((MAX_SEGS, SEG64_STRIDE), dtype=np.float64)
+    cum64 = 0.0
+    for i, sg in enumerate(segs_src):
+        s64[i] = [sg.start[0], sg.start[1], sg.end[0], sg.end[1], cum64]
+        cum64 += math.sqrt((sg.end[0] - sg.start[0]) ** 2 + (sg.end[1] - sg.start[1]) ** 2)     # car_env.py:1594-1600
+    blob[off_seg64:off_seg64 + MAX_SEGS * SEG64_STRIDE * 2] = s64.reshape(-1).view(np.float32)
     wrows = np.zeros((n, WALL_STRIDE), dtype=np.float32)
     wrows[:, :7] = boxes
     blob[off_walls:off_walls + n * WALL_STRIDE] = wrows.reshape(-1)

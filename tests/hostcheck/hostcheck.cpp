@@ -44,11 +44,9 @@ void hc_env_reset(const float* blob, float* records, int C, int fresh, int track
 void hc_sensors_brute(const float* blob, float x, float y, float angle, float* out16) {
     Track T = track_view(blob, blob);
     for (int i = 0; i < 16; ++i) {
-        float phi = -(float)i * 0.39269908169872414f + angle;
-        V2 P1 = mk(x, y), P2 = mk(x + cosf(phi) * 250.0f, y + sinf(phi) * 250.0f);
-        float best = 1.0f;
-        for (int wi = 0; wi < T.n_walls; ++wi) { float fr = ray_box_fraction(T.walls + wi * WALL_STRIDE, P1, P2, best); if (fr >= 0.0f) best = fr; }
-        out16[i] = best < 1.0f ? best * 250.0f : 250.0f;
+        Track B = T; B.gnx = 0; B.gny = 0;   // an empty grid sends cast_ray down its all-walls path
+        unsigned tests = 0;
+        out16[i] = cast_ray(B, x, y, angle, i, &tests);
     }
 }
 void hc_sensors_grid(const float* blob, float x, float y, float angle, float* out16, unsigned* tests) {
