@@ -54,6 +54,35 @@ __device__ __forceinline__ void tma_stage(float* dst, const float* src, unsigned
     }
 }
 
+// same-track reset of one record + observation words 0..21 (kept out of line: it runs once per episode)
+__device__ __noinline__ void reset_in_place(float* R, const Track& T, float* obs) {
+    reset_record(R, T, false, f2u(R[NCG_R_TRACK]));
+    observe_state(R, obs);
+}
+
+// Sensor phase: lane <-> (car of this warp, ray).  `only_done`: cast only for cars that were just reset.
+template <int G>
+__device__ __forceinline__ unsigned sensor_phase(const KParams& p, const float* s_rec, float* s_obs, const Track& Tw, bool warp_uniform,
+                                                 const float* staged, int warp, int lane, int n_cars, bool only_done, const uint32_t* s_done) {
+    unsigned tests = 0;
+#pragma unroll 1
+    for (int task = lane; task < G * 16; task += 32) {
+        const int sl = warp * G + (task >> 4);
+        if (sl < n_cars && (!only_done || s_done[sl])) {
+            const float* Rr = s_rec + sl * NCG_RECORD_WORDS;
+            float d;
+            if (warp_uniform) d = cast_ray(Tw, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests);
+            else {
+                const float* g = p.blob + p.track_off[f2u(Rr[NCG_R_TRACK])];
+                const Track T = track_view(staged ? staged : g, g);
+                d = cast_ray(T, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests);
+            }
+            s_obs[sl * OBS_PAD + 22 + (task & 15)] = sensor_obs(d);
+        }
+    }
+    return tests;
+}
+
 template <int G>
 __global__ void __launch_bounds__(320) ncg_step_kernel(KParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -93,14 +122,18 @@ __global__ void __launch_bounds__(320) ncg_step_kernel(KParams p) {
     float* R = s_rec + (active ? slot : 0) * NCG_RECORD_WORDS;
     Counters cnt = {0, 0, 0, 0, 0};
     unsigned long long episodes = 0; double ret_sum = 0.0;
+    // track views are fixed for the launch (auto-reset keeps an env on its track): build them once
+    const int wslot0 = min(warp * G, max(n_cars - 1, 0));
+    const uint32_t my_tid = f2u(s_rec[(active ? slot : wslot0) * NCG_RECORD_WORDS + NCG_R_TRACK]);
+    const bool warp_uniform = __all_sync(0xffffffffu, my_tid == f2u(s_rec[wslot0 * NCG_RECORD_WORDS + NCG_R_TRACK]));
+    const float* gblob = p.blob + p.track_off[my_tid];
+    const Track T = track_view(staged ? staged : gblob, gblob);
 
     for (int t = 0; t < p.T; ++t) {
         float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
         float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
         // ---- A: scalar car phase
         if (active) {
-            const float* g = p.blob + p.track_off[f2u(R[NCG_R_TRACK])];
-            Track T = track_view(staged ? staged : g, g);
             float thr, brk, st;
             const int gc = car0 + slot;
             if (p.actions) {
@@ -118,20 +151,7 @@ __global__ void __launch_bounds__(320) ncg_step_kernel(KParams p) {
         }
         __syncwarp();
         // ---- B: sensor phase, the warp's G*16 rays over 32 lanes
-        {
-            unsigned tests = 0;
-            for (int task = lane; task < G * 16; task += 32) {
-                int sl = warp * G + (task >> 4);
-                if (sl < n_cars) {
-                    const float* Rr = s_rec + sl * NCG_RECORD_WORDS;
-                    const float* g = p.blob + p.track_off[f2u(Rr[NCG_R_TRACK])];
-                    Track T = track_view(staged ? staged : g, g);
-                    float d = cast_ray(T, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests);
-                    s_obs[sl * OBS_PAD + 22 + (task & 15)] = sensor_obs(d);
-                }
-            }
-            cnt.ray_tests += tests;
-        }
+        cnt.ray_tests += sensor_phase<G>(p, s_rec, s_obs, T, warp_uniform, staged, warp, lane, n_cars, false, s_done);
         if (p.C > 1) __syncthreads(); else __syncwarp();
         // ---- C: env phase (every car of an env computes the same decision from the env's xf words)
         bool done = false;
@@ -166,24 +186,9 @@ __global__ void __launch_bounds__(320) ncg_step_kernel(KParams p) {
         }
         // ---- E: same-step auto-reset (CarPhysics.reset_car semantics) + reset observation
         if (do_reset && __any_sync(0xffffffffu, active && done)) {
-            if (active && done) {
-                const float* g = p.blob + p.track_off[f2u(R[NCG_R_TRACK])];
-                Track T = track_view(staged ? staged : g, g);
-                reset_record(R, T, false, f2u(R[NCG_R_TRACK]));
-                observe_state(R, s_obs + slot * OBS_PAD);
-            }
+            if (active && done) reset_in_place(R, T, s_obs + slot * OBS_PAD);
             __syncwarp();
-            unsigned tests = 0;
-            for (int task = lane; task < G * 16; task += 32) {
-                int sl = warp * G + (task >> 4);
-                if (sl < n_cars && s_done[sl]) {
-                    const float* Rr = s_rec + sl * NCG_RECORD_WORDS;
-                    const float* g = p.blob + p.track_off[f2u(Rr[NCG_R_TRACK])];
-                    Track T = track_view(staged ? staged : g, g);
-                    s_obs[sl * OBS_PAD + 22 + (task & 15)] = sensor_obs(cast_ray(T, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests));
-                }
-            }
-            cnt.ray_tests += tests;
+            cnt.ray_tests += sensor_phase<G>(p, s_rec, s_obs, T, warp_uniform, staged, warp, lane, n_cars, true, s_done);
             __syncwarp();
             for (int i = lane; i < G * NCG_OBS_DIM; i += 32) {
                 int sl = warp * G + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;

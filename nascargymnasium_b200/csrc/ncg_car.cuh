@@ -54,15 +54,19 @@ struct VCPoint { V2 rA; float ni, ti, nm, tm, bias; };
 struct VC { VCPoint p[2]; V2 normal; float K[4], nmat[4]; int pc, ci; };
 struct PC { V2 lp[2], localNormal, localPoint; int type, pc, wall; };
 
-struct World {
+// The car's b2Body plus the listener scalars: small enough to live in registers on the contact-free fast path.
+struct Body {
     Xf xf; Sweep sweep; V2 v; float w; V2 force; float torque; float sleepTime, inv_dt0;
-    bool awake, proxyMoved, newFixture, overflow, stepComplete;
+    bool awake, proxyMoved, newFixture, overflow;
     AABB fat;
+    float impulse; bool hasKey;          // CarCollisionListener.car_collision_impulses[car]
+};
+// Everything else Box2D keeps for a car that has broad-phase contacts; only the (rare) contact path builds it.
+struct World {
+    Body b;
     int nc; Contact c[NCG_MAX_CONTACTS];
     float wallAlpha[NCG_MAX_CONTACTS];          // alpha0 of the static sweeps of contacted walls (SolveTOI)
-    // CarCollisionListener (car_physics.py:693-864)
-    float impulse; bool hasKey; int na; int awall[NCG_MAX_ACTIVE]; float anx[NCG_MAX_ACTIVE], any[NCG_MAX_ACTIVE];
-    // solver
+    int na; int awall[NCG_MAX_ACTIVE]; float anx[NCG_MAX_ACTIVE], any[NCG_MAX_ACTIVE];   // active_collisions
     int ni; int isl[NCG_MAX_TOUCHING]; VC vc[NCG_MAX_TOUCHING]; PC pcs[NCG_MAX_TOUCHING];
     V2 pc_c; float pc_a; V2 pv; float pw;
     unsigned toi_events;
@@ -71,56 +75,80 @@ NCG_HD Box car_box() { Box b; b.hx = NCG_CAR_HALF_LENGTH; b.hy = NCG_CAR_HALF_WI
 #define NCG_INV_MASS (1.0f / NCG_CAR_MASS)
 #define NCG_INV_I (1.0f / NCG_CAR_MOI)
 
-NCG_HD void w_set_awake(World& W, bool flag) {
-    if (flag) { if (!W.awake) { W.awake = true; W.sleepTime = 0.0f; } }
-    else { W.awake = false; W.sleepTime = 0.0f; W.v = mk(0.0f, 0.0f); W.w = 0.0f; W.force = mk(0.0f, 0.0f); W.torque = 0.0f; }
+NCG_HD void b_set_awake(Body& B, bool flag) {
+    if (flag) { if (!B.awake) { B.awake = true; B.sleepTime = 0.0f; } }
+    else { B.awake = false; B.sleepTime = 0.0f; B.v = mk(0.0f, 0.0f); B.w = 0.0f; B.force = mk(0.0f, 0.0f); B.torque = 0.0f; }
 }
-NCG_HD void w_apply_force(World& W, V2 f, V2 point) { if (!W.awake) w_set_awake(W, true); W.force = W.force + f; W.torque += cross(point - W.sweep.c, f); }
-NCG_HD void w_apply_force_center(World& W, V2 f) { if (!W.awake) w_set_awake(W, true); W.force = W.force + f; }
-NCG_HD void w_apply_torque(World& W, float t) { if (!W.awake) w_set_awake(W, true); W.torque += t; }
-NCG_HD void w_sync_transform(World& W) { W.xf.q = rot(W.sweep.a); W.xf.p = W.sweep.c - mul(W.xf.q, mk(0.0f, 0.0f)); }
-NCG_HD void w_move_proxy(World& W, const AABB& aabb, V2 disp) {
-    if (aabb_contains(W.fat, aabb)) return;
+NCG_HD void b_apply_force(Body& B, V2 f, V2 point) { if (!B.awake) b_set_awake(B, true); B.force = B.force + f; B.torque += cross(point - B.sweep.c, f); }
+NCG_HD void b_apply_force_center(Body& B, V2 f) { if (!B.awake) b_set_awake(B, true); B.force = B.force + f; }
+NCG_HD void b_apply_torque(Body& B, float t) { if (!B.awake) b_set_awake(B, true); B.torque += t; }
+NCG_HD void b_sync_transform(Body& B) { B.xf.q = rot(B.sweep.a); B.xf.p = B.sweep.c - mul(B.xf.q, mk(0.0f, 0.0f)); }
+NCG_HD void b_move_proxy(Body& B, const AABB& aabb, V2 disp) {
+    if (aabb_contains(B.fat, aabb)) return;
     AABB b = aabb;
     b.lx -= NCG_B2_AABB_EXT; b.ly -= NCG_B2_AABB_EXT; b.ux += NCG_B2_AABB_EXT; b.uy += NCG_B2_AABB_EXT;
     V2 d = NCG_B2_AABB_MULT * disp;
     if (d.x < 0.0f) b.lx += d.x; else b.ux += d.x;
     if (d.y < 0.0f) b.ly += d.y; else b.uy += d.y;
-    W.fat = b; W.proxyMoved = true;
+    B.fat = b; B.proxyMoved = true;
 }
-NCG_HD void w_set_transform(World& W, V2 p, float angle) {
-    W.xf.q = rot(angle); W.xf.p = p;
-    W.sweep.c = mul(W.xf, mk(0.0f, 0.0f)); W.sweep.a = angle; W.sweep.c0 = W.sweep.c; W.sweep.a0 = angle;
-    w_move_proxy(W, box_aabb(car_box(), W.xf), mk(0.0f, 0.0f));
+NCG_HD void b_set_transform(Body& B, V2 p, float angle) {
+    B.xf.q = rot(angle); B.xf.p = p;
+    B.sweep.c = mul(B.xf, mk(0.0f, 0.0f)); B.sweep.a = angle; B.sweep.c0 = B.sweep.c; B.sweep.a0 = angle;
+    b_move_proxy(B, box_aabb(car_box(), B.xf), mk(0.0f, 0.0f));
 }
-NCG_HD void w_sync_fixtures(World& W) {
-    Xf xf1; xf1.q = rot(W.sweep.a0); xf1.p = W.sweep.c0 - mul(xf1.q, mk(0.0f, 0.0f));
-    AABB a1 = box_aabb(car_box(), xf1), a2 = box_aabb(car_box(), W.xf);
+NCG_HD void b_sync_fixtures(Body& B) {
+    Xf xf1; xf1.q = rot(B.sweep.a0); xf1.p = B.sweep.c0 - mul(xf1.q, mk(0.0f, 0.0f));
+    AABB a1 = box_aabb(car_box(), xf1), a2 = box_aabb(car_box(), B.xf);
     AABB c; c.lx = fminb(a1.lx, a2.lx); c.ly = fminb(a1.ly, a2.ly); c.ux = fmaxb(a1.ux, a2.ux); c.uy = fmaxb(a1.uy, a2.uy);
-    w_move_proxy(W, c, W.xf.p - xf1.p);
+    b_move_proxy(B, c, B.xf.p - xf1.p);
 }
-NCG_HD void w_advance(World& W, float alpha) {
-    sweep_advance(W.sweep, alpha); W.sweep.c = W.sweep.c0; W.sweep.a = W.sweep.a0;
-    W.xf.q = rot(W.sweep.a); W.xf.p = W.sweep.c - mul(W.xf.q, mk(0.0f, 0.0f));
+NCG_HD void b_advance(Body& B, float alpha) {
+    sweep_advance(B.sweep, alpha); B.sweep.c = B.sweep.c0; B.sweep.a = B.sweep.a0;
+    B.xf.q = rot(B.sweep.a); B.xf.p = B.sweep.c - mul(B.xf.q, mk(0.0f, 0.0f));
 }
+// integrate velocities (forces) -- b2Island::Solve prologue for a body with no joints, gravity or damping
+NCG_HD void b_integrate_velocity(Body& B, float h) {
+    B.v = B.v + h * (1.0f * mk(0.0f, 0.0f) + NCG_INV_MASS * B.force);
+    B.w += h * NCG_INV_I * B.torque;
+}
+// integrate positions with b2_maxTranslation / b2_maxRotation clamps, on (c, a, v, w)
+NCG_HD void integrate_position(V2& c, float& a, V2& v, float& w, float h) {
+    V2 tr = h * v;
+    if (dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION) { float ratio = NCG_B2_MAX_TRANSLATION / length(tr); v = ratio * v; }
+    float ro = h * w;
+    if (ro * ro > NCG_B2_MAX_ROTATION * NCG_B2_MAX_ROTATION) { float ratio = NCG_B2_MAX_ROTATION / fabsf(ro); w *= ratio; }
+    c = c + h * v; a += h * w;
+}
+// sleep bookkeeping at the end of b2Island::Solve
+NCG_HD void b_sleep(Body& B, float h, bool positionSolved) {
+    float minSleep = NCG_B2_MAXFLOAT;
+    if (B.w * B.w > NCG_B2_ANG_SLEEP_TOL * NCG_B2_ANG_SLEEP_TOL || dot(B.v, B.v) > NCG_B2_LIN_SLEEP_TOL * NCG_B2_LIN_SLEEP_TOL) { B.sleepTime = 0.0f; minSleep = 0.0f; }
+    else { B.sleepTime += h; minSleep = fminb(minSleep, B.sleepTime); }
+    if (minSleep >= NCG_B2_TIME_TO_SLEEP && positionSolved) b_set_awake(B, false);
+}
+#define w_set_awake(W, f) b_set_awake((W).b, f)
+#define w_sync_transform(W) b_sync_transform((W).b)
+#define w_sync_fixtures(W) b_sync_fixtures((W).b)
+#define w_advance(W, a) b_advance((W).b, a)
 // listener callbacks
 NCG_HD void l_begin(World& W, int wall, V2 n) {
     bool found = false;
     for (int i = 0; i < W.na; ++i) if (W.awall[i] == wall) { W.anx[i] = n.x; W.any[i] = n.y; found = true; break; }
-    if (!found) { if (W.na < NCG_MAX_ACTIVE) { W.awall[W.na] = wall; W.anx[W.na] = n.x; W.any[W.na] = n.y; ++W.na; } else W.overflow = true; }
-    if (!W.hasKey) { W.hasKey = true; W.impulse = 0.0f; }
+    if (!found) { if (W.na < NCG_MAX_ACTIVE) { W.awall[W.na] = wall; W.anx[W.na] = n.x; W.any[W.na] = n.y; ++W.na; } else W.b.overflow = true; }
+    if (!W.b.hasKey) { W.b.hasKey = true; W.b.impulse = 0.0f; }
 }
 NCG_HD void l_end(World& W, int wall) {
     for (int i = 0; i < W.na; ++i) if (W.awall[i] == wall) {
         for (int j = i; j + 1 < W.na; ++j) { W.awall[j] = W.awall[j + 1]; W.anx[j] = W.anx[j + 1]; W.any[j] = W.any[j + 1]; }
         --W.na; break;
     }
-    if (W.na == 0) { W.impulse = 0.0f; W.hasKey = true; }
+    if (W.na == 0) { W.b.impulse = 0.0f; W.b.hasKey = true; }
 }
 NCG_HD void l_post_solve(World& W, int count, float n0, float n1) {
     if (count > 0) {
         float total = n0; if (count > 1) total = total + n1;
-        if (W.hasKey) W.impulse = total > W.impulse ? total : W.impulse;
+        if (W.b.hasKey) W.b.impulse = total > W.b.impulse ? total : W.b.impulse;
     }
 }
 // b2Contact::Update
@@ -129,7 +157,7 @@ NCG_HDN void w_update_contact(World& W, const Track& T, Contact& c) {
     c.enabled = true;
     bool was = c.touching;
     Xf xfB; Box bB; wall_get(T, c.wall, &xfB, &bB);
-    collide_boxes(&c.m, car_box(), W.xf, bB, xfB);
+    collide_boxes(&c.m, car_box(), W.b.xf, bB, xfB);
     bool touching = c.m.pc > 0;
     for (int i = 0; i < c.m.pc; ++i) {
         c.m.ni[i] = 0.0f; c.m.ti[i] = 0.0f;
@@ -137,16 +165,16 @@ NCG_HDN void w_update_contact(World& W, const Track& T, Contact& c) {
     }
     if (touching != was) w_set_awake(W, true);
     c.touching = touching;
-    if (!was && touching) { V2 n, pts[2]; world_manifold(&n, pts, c.m, W.xf, xfB); l_begin(W, c.wall, n); }
+    if (!was && touching) { V2 n, pts[2]; world_manifold(&n, pts, c.m, W.b.xf, xfB); l_begin(W, c.wall, n); }
     if (was && !touching) l_end(W, c.wall);
 }
 // b2ContactManager::Collide
 NCG_HDN void w_collide(World& W, const Track& T) {
     int i = 0;
     while (i < W.nc) {
-        if (!W.awake) { ++i; continue; }
+        if (!W.b.awake) { ++i; continue; }
         Contact& c = W.c[i];
-        if (!aabb_overlap(W.fat, wall_fat(T, c.wall))) {
+        if (!aabb_overlap(W.b.fat, wall_fat(T, c.wall))) {
             if (c.touching) l_end(W, c.wall);
             for (int j = i; j + 1 < W.nc; ++j) W.c[j] = W.c[j + 1];
             --W.nc; continue;
@@ -158,10 +186,10 @@ NCG_HDN void w_collide(World& W, const Track& T) {
 // b2ContactManager::FindNewContacts: pairs = walls whose fat AABB overlaps the car's, ascending wall index,
 // each head-inserted.  Candidates come from the uniform grid (cells overlapped by the car's fat AABB).
 NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
-    if (!W.proxyMoved) return;
-    W.proxyMoved = false;
-    int ix0 = (int)floorf((W.fat.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((W.fat.ux - T.gx0) * T.inv_cell);
-    int iy0 = (int)floorf((W.fat.ly - T.gy0) * T.inv_cell), iy1 = (int)floorf((W.fat.uy - T.gy0) * T.inv_cell);
+    if (!W.b.proxyMoved) return;
+    W.b.proxyMoved = false;
+    int ix0 = (int)floorf((W.b.fat.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((W.b.fat.ux - T.gx0) * T.inv_cell);
+    int iy0 = (int)floorf((W.b.fat.ly - T.gy0) * T.inv_cell), iy1 = (int)floorf((W.b.fat.uy - T.gy0) * T.inv_cell);
     ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
     int found[NCG_MAX_CONTACTS]; int nf = 0;
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
@@ -169,18 +197,18 @@ NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
         int b = T.cells[cell], e = T.cells[cell + 1];
         for (int k = b; k < e; ++k) {
             int wi = T.items[k];
-            if (!aabb_overlap(W.fat, wall_fat(T, wi))) continue;
+            if (!aabb_overlap(W.b.fat, wall_fat(T, wi))) continue;
             bool have = false;
             for (int j = 0; j < W.nc; ++j) if (W.c[j].wall == wi) { have = true; break; }
             for (int j = 0; j < nf && !have; ++j) if (found[j] == wi) have = true;
             if (have) continue;
-            if (nf < NCG_MAX_CONTACTS) found[nf++] = wi; else W.overflow = true;
+            if (nf < NCG_MAX_CONTACTS) found[nf++] = wi; else W.b.overflow = true;
         }
     }
     // ascending wall index, then head-insert one by one
     for (int i = 1; i < nf; ++i) { int key = found[i], j = i - 1; while (j >= 0 && found[j] > key) { found[j + 1] = found[j]; --j; } found[j + 1] = key; }
     for (int i = 0; i < nf; ++i) {
-        if (W.nc >= NCG_MAX_CONTACTS) { W.overflow = true; break; }
+        if (W.nc >= NCG_MAX_CONTACTS) { W.b.overflow = true; break; }
         for (int j = W.nc; j > 0; --j) { W.c[j] = W.c[j - 1]; W.wallAlpha[j] = W.wallAlpha[j - 1]; }
         Contact& c = W.c[0];
         c.wall = found[i]; c.touching = false; c.enabled = true; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f;
@@ -344,22 +372,16 @@ NCG_HDN bool s_solve_position(World& W, const Track& T, float baumgarte, float o
 NCG_HD void s_report(World& W) {
     for (int i = 0; i < W.ni; ++i) { VC& vc = W.vc[i]; l_post_solve(W, vc.pc, vc.p[0].ni, vc.pc > 1 ? vc.p[1].ni : 0.0f); }
 }
-NCG_HD void s_integrate(World& W, float h) {
-    V2 tr = h * W.pv;
-    if (dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION) { float ratio = NCG_B2_MAX_TRANSLATION / length(tr); W.pv = ratio * W.pv; }
-    float ro = h * W.pw;
-    if (ro * ro > NCG_B2_MAX_ROTATION * NCG_B2_MAX_ROTATION) { float ratio = NCG_B2_MAX_ROTATION / fabsf(ro); W.pw *= ratio; }
-    W.pc_c = W.pc_c + h * W.pv; W.pc_a += h * W.pw;
-}
-// b2World::Solve + b2Island::Solve
-NCG_HD void w_solve(World& W, const Track& T, float h, float dtRatio, bool contacts) {
-    if (W.awake) {
+NCG_HD void s_integrate(World& W, float h) { integrate_position(W.pc_c, W.pc_a, W.pv, W.pw, h); }
+// b2World::Solve + b2Island::Solve for a car that has contacts in its list
+NCG_HDN void w_solve(World& W, const Track& T, float h, float dtRatio) {
+    Body& B = W.b;
+    if (B.awake) {
         W.ni = 0;
-        if (contacts) for (int i = 0; i < W.nc; ++i) if (W.c[i].enabled && W.c[i].touching) { if (W.ni < NCG_MAX_TOUCHING) W.isl[W.ni++] = i; else W.overflow = true; }
-        W.pc_c = W.sweep.c; W.pc_a = W.sweep.a; W.pv = W.v; W.pw = W.w;
-        W.sweep.c0 = W.sweep.c; W.sweep.a0 = W.sweep.a;
-        W.pv = W.pv + h * (1.0f * mk(0.0f, 0.0f) + NCG_INV_MASS * W.force);
-        W.pw += h * NCG_INV_I * W.torque;
+        for (int i = 0; i < W.nc; ++i) if (W.c[i].enabled && W.c[i].touching) { if (W.ni < NCG_MAX_TOUCHING) W.isl[W.ni++] = i; else B.overflow = true; }
+        B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
+        b_integrate_velocity(B, h);
+        W.pc_c = B.sweep.c; W.pc_a = B.sweep.a; W.pv = B.v; W.pw = B.w;
         bool positionSolved;
         if (W.ni > 0) {
             s_init(W, true, dtRatio); s_init_velocity(W, T); s_warm_start(W);
@@ -369,20 +391,16 @@ NCG_HD void w_solve(World& W, const Track& T, float h, float dtRatio, bool conta
             positionSolved = false;
             for (int i = 0; i < NCG_POS_ITERS; ++i) if (s_solve_position(W, T, NCG_B2_BAUMGARTE, -3.0f)) { positionSolved = true; break; }
         } else { s_integrate(W, h); positionSolved = true; }
-        W.sweep.c = W.pc_c; W.sweep.a = W.pc_a; W.v = W.pv; W.w = W.pw;
-        w_sync_transform(W);
+        B.sweep.c = W.pc_c; B.sweep.a = W.pc_a; B.v = W.pv; B.w = W.pw;
+        b_sync_transform(B);
         if (W.ni > 0) s_report(W);
-        float minSleep = NCG_B2_MAXFLOAT;
-        if (W.w * W.w > NCG_B2_ANG_SLEEP_TOL * NCG_B2_ANG_SLEEP_TOL || dot(W.v, W.v) > NCG_B2_LIN_SLEEP_TOL * NCG_B2_LIN_SLEEP_TOL) { W.sleepTime = 0.0f; minSleep = 0.0f; }
-        else { W.sleepTime += h; minSleep = fminb(minSleep, W.sleepTime); }
-        if (minSleep >= NCG_B2_TIME_TO_SLEEP && positionSolved) w_set_awake(W, false);
-        w_sync_fixtures(W);
+        b_sleep(B, h, positionSolved);
+        b_sync_fixtures(B);
     }
-    w_find_new_contacts(W, T);
 }
 // b2World::SolveTOI + b2Island::SolveTOI
 NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
-    W.sweep.alpha0 = 0.0f;
+    W.b.sweep.alpha0 = 0.0f;
     for (int i = 0; i < W.nc; ++i) { W.wallAlpha[i] = 0.0f; Contact& c = W.c[i]; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f; }
     for (;;) {
         int minC = -1; float minAlpha = 1.0f;
@@ -393,14 +411,14 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
             float alpha = 1.0f;
             if (c.toiFlag) alpha = c.toi;
             else {
-                if (!W.awake) continue;
-                float alpha0 = W.sweep.alpha0;
-                if (W.sweep.alpha0 < W.wallAlpha[i]) { alpha0 = W.wallAlpha[i]; sweep_advance(W.sweep, alpha0); }
-                else if (W.wallAlpha[i] < W.sweep.alpha0) { alpha0 = W.sweep.alpha0; W.wallAlpha[i] = alpha0; }
+                if (!W.b.awake) continue;
+                float alpha0 = W.b.sweep.alpha0;
+                if (W.b.sweep.alpha0 < W.wallAlpha[i]) { alpha0 = W.wallAlpha[i]; sweep_advance(W.b.sweep, alpha0); }
+                else if (W.wallAlpha[i] < W.b.sweep.alpha0) { alpha0 = W.b.sweep.alpha0; W.wallAlpha[i] = alpha0; }
                 Xf xfB; Box bB; wall_get(T, c.wall, &xfB, &bB);
                 Sweep sB; sB.c0 = xfB.p; sB.c = xfB.p; sB.a0 = wall_angle(T, c.wall); sB.a = sB.a0; sB.alpha0 = W.wallAlpha[i];
                 int state; float t;
-                time_of_impact(&state, &t, car_box(), W.sweep, bB, sB, 1.0f);
+                time_of_impact(&state, &t, car_box(), W.b.sweep, bB, sB, 1.0f);
                 if (state == TOI_TOUCHING) alpha = fminb(alpha0 + (1.0f - alpha0) * t, 1.0f); else alpha = 1.0f;
                 c.toi = alpha; c.toiFlag = true;
             }
@@ -408,11 +426,11 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
         }
         if (minC < 0 || 1.0f - 10.0f * NCG_B2_EPS < minAlpha) break;
         Contact& mc = W.c[minC];
-        Sweep backup = W.sweep; float backupWall = W.wallAlpha[minC];
+        Sweep backup = W.b.sweep; float backupWall = W.wallAlpha[minC];
         w_advance(W, minAlpha); W.wallAlpha[minC] = minAlpha;
         w_update_contact(W, T, mc);
         mc.toiFlag = false; ++mc.toiCount;
-        if (!mc.enabled || !mc.touching) { mc.enabled = false; W.sweep = backup; W.wallAlpha[minC] = backupWall; w_sync_transform(W); continue; }
+        if (!mc.enabled || !mc.touching) { mc.enabled = false; W.b.sweep = backup; W.wallAlpha[minC] = backupWall; w_sync_transform(W); continue; }
         w_set_awake(W, true);
         W.ni = 0; W.isl[W.ni++] = minC; mc.island = true;
         for (int i = 0; i < W.nc; ++i) {
@@ -422,17 +440,17 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
             W.wallAlpha[i] = minAlpha;
             w_update_contact(W, T, c);
             if (!c.enabled || !c.touching) { W.wallAlpha[i] = bw; continue; }
-            if (W.ni < NCG_MAX_TOUCHING) { c.island = true; W.isl[W.ni++] = i; } else W.overflow = true;
+            if (W.ni < NCG_MAX_TOUCHING) { c.island = true; W.isl[W.ni++] = i; } else W.b.overflow = true;
         }
         float subDt = (1.0f - minAlpha) * stepDt;
-        W.pc_c = W.sweep.c; W.pc_a = W.sweep.a; W.pv = W.v; W.pw = W.w;
+        W.pc_c = W.b.sweep.c; W.pc_a = W.b.sweep.a; W.pv = W.b.v; W.pw = W.b.w;
         s_init(W, false, 1.0f);
         for (int i = 0; i < 20; ++i) if (s_solve_position(W, T, NCG_B2_TOI_BAUMGARTE, -1.5f)) break;
-        W.sweep.c0 = W.pc_c; W.sweep.a0 = W.pc_a;
+        W.b.sweep.c0 = W.pc_c; W.b.sweep.a0 = W.pc_a;
         s_init_velocity(W, T);
         for (int i = 0; i < NCG_VEL_ITERS; ++i) s_solve_velocity(W);
         s_integrate(W, subDt);
-        W.sweep.c = W.pc_c; W.sweep.a = W.pc_a; W.v = W.pv; W.w = W.pw;
+        W.b.sweep.c = W.pc_c; W.b.sweep.a = W.pc_a; W.b.v = W.pv; W.b.w = W.pw;
         w_sync_transform(W);
         s_report(W);
         w_sync_fixtures(W);
@@ -441,28 +459,33 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
         ++W.toi_events;
     }
 }
-// b2World::Step
-NCG_HD void w_step(World& W, const Track& T, float dt, bool contacts) {
-    float inv_dt = 1.0f / dt;
-    float dtRatio = W.inv_dt0 * dt;
-    if (W.newFixture) { w_find_new_contacts(W, T); W.newFixture = false; }
-    if (contacts && W.nc > 0) w_collide(W, T);
-    w_solve(W, T, dt, dtRatio, contacts);
-    if (contacts && W.nc > 0) w_solve_toi(W, T, dt);
-    W.inv_dt0 = inv_dt;
-    W.force = mk(0.0f, 0.0f); W.torque = 0.0f;
-}
-
-// ------------------------------------------------------------------ record <-> World
-NCG_HD void w_load(World& W, const float* R) {
-    W.sweep.c = mk(R[NCG_R_X], R[NCG_R_Y]); W.sweep.a = R[NCG_R_ANGLE]; W.sweep.c0 = W.sweep.c; W.sweep.a0 = W.sweep.a; W.sweep.alpha0 = 0.0f;
-    w_sync_transform(W);
-    W.v = mk(R[NCG_R_VX], R[NCG_R_VY]); W.w = R[NCG_R_OMEGA]; W.force = mk(0.0f, 0.0f); W.torque = 0.0f;
-    W.sleepTime = R[NCG_R_SLEEP]; W.inv_dt0 = R[NCG_R_INV_DT0];
+// ------------------------------------------------------------------ record <-> Body / World
+NCG_HD void b_load(Body& B, const float* R) {
+    B.sweep.c = mk(R[NCG_R_X], R[NCG_R_Y]); B.sweep.a = R[NCG_R_ANGLE]; B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a; B.sweep.alpha0 = 0.0f;
+    b_sync_transform(B);
+    B.v = mk(R[NCG_R_VX], R[NCG_R_VY]); B.w = R[NCG_R_OMEGA]; B.force = mk(0.0f, 0.0f); B.torque = 0.0f;
+    B.sleepTime = R[NCG_R_SLEEP]; B.inv_dt0 = R[NCG_R_INV_DT0];
     uint32_t fl = f2u(R[NCG_R_FLAGS]);
-    W.awake = (fl & NCG_F_AWAKE) != 0; W.proxyMoved = (fl & NCG_F_PROXY_MOVED) != 0; W.newFixture = (fl & NCG_F_NEW_FIXTURE) != 0;
-    W.hasKey = (fl & NCG_F_HAS_KEY) != 0; W.overflow = false; W.stepComplete = true; W.toi_events = 0;
-    W.fat.lx = R[NCG_R_FAT_LX]; W.fat.ly = R[NCG_R_FAT_LY]; W.fat.ux = R[NCG_R_FAT_UX]; W.fat.uy = R[NCG_R_FAT_UY];
+    B.awake = (fl & NCG_F_AWAKE) != 0; B.proxyMoved = (fl & NCG_F_PROXY_MOVED) != 0; B.newFixture = (fl & NCG_F_NEW_FIXTURE) != 0;
+    B.hasKey = (fl & NCG_F_HAS_KEY) != 0; B.overflow = false;
+    B.fat.lx = R[NCG_R_FAT_LX]; B.fat.ly = R[NCG_R_FAT_LY]; B.fat.ux = R[NCG_R_FAT_UX]; B.fat.uy = R[NCG_R_FAT_UY];
+    B.impulse = R[NCG_R_IMPULSE];
+}
+NCG_HD void b_store(const Body& B, float* R, uint32_t* flags) {
+    R[NCG_R_X] = B.sweep.c.x; R[NCG_R_Y] = B.sweep.c.y; R[NCG_R_ANGLE] = B.sweep.a; R[NCG_R_VX] = B.v.x; R[NCG_R_VY] = B.v.y; R[NCG_R_OMEGA] = B.w;
+    R[NCG_R_SLEEP] = B.sleepTime; R[NCG_R_INV_DT0] = B.inv_dt0;
+    uint32_t fl = *flags & ~(uint32_t)(NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE | NCG_F_HAS_KEY);
+    if (B.awake) fl |= NCG_F_AWAKE;
+    if (B.proxyMoved) fl |= NCG_F_PROXY_MOVED;
+    if (B.newFixture) fl |= NCG_F_NEW_FIXTURE;
+    if (B.hasKey) fl |= NCG_F_HAS_KEY;
+    if (B.overflow) fl |= NCG_F_OVERFLOW;
+    *flags = fl;
+    R[NCG_R_FAT_LX] = B.fat.lx; R[NCG_R_FAT_LY] = B.fat.ly; R[NCG_R_FAT_UX] = B.fat.ux; R[NCG_R_FAT_UY] = B.fat.uy;
+    R[NCG_R_IMPULSE] = B.impulse;
+}
+NCG_HD void w_load_contacts(World& W, const float* R) {
+    W.toi_events = 0;
     uint32_t ncw = f2u(R[NCG_R_NCONTACT]);
     W.nc = (int)(ncw & 255u); W.na = (int)((ncw >> 8) & 255u);
     uint32_t tmask = (ncw >> 16) & 0xFFFu, pcw = f2u(R[NCG_R_MANIFOLD_PC]);
@@ -482,17 +505,9 @@ NCG_HD void w_load(World& W, const float* R) {
             ++k;
         }
     }
-    W.impulse = R[NCG_R_IMPULSE];
     for (int i = 0; i < W.na; ++i) { W.awall[i] = (int)f2u(R[NCG_R_ACTIVE + 3 * i]); W.anx[i] = R[NCG_R_ACTIVE + 3 * i + 1]; W.any[i] = R[NCG_R_ACTIVE + 3 * i + 2]; }
 }
-NCG_HD void w_store(const World& W, float* R, uint32_t* flags) {
-    R[NCG_R_X] = W.sweep.c.x; R[NCG_R_Y] = W.sweep.c.y; R[NCG_R_ANGLE] = W.sweep.a; R[NCG_R_VX] = W.v.x; R[NCG_R_VY] = W.v.y; R[NCG_R_OMEGA] = W.w;
-    R[NCG_R_SLEEP] = W.sleepTime; R[NCG_R_INV_DT0] = W.inv_dt0;
-    uint32_t fl = *flags & ~(uint32_t)(NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE | NCG_F_HAS_KEY);
-    if (W.awake) fl |= NCG_F_AWAKE; if (W.proxyMoved) fl |= NCG_F_PROXY_MOVED; if (W.newFixture) fl |= NCG_F_NEW_FIXTURE;
-    if (W.hasKey) fl |= NCG_F_HAS_KEY; if (W.overflow) fl |= NCG_F_OVERFLOW;
-    *flags = fl;
-    R[NCG_R_FAT_LX] = W.fat.lx; R[NCG_R_FAT_LY] = W.fat.ly; R[NCG_R_FAT_UX] = W.fat.ux; R[NCG_R_FAT_UY] = W.fat.uy;
+NCG_HD void w_store_contacts(World& W, float* R) {
     uint32_t tmask = 0, pcw = 0; int k = 0;
     uint32_t ww[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < W.nc; ++i) {
@@ -504,13 +519,69 @@ NCG_HD void w_store(const World& W, float* R, uint32_t* flags) {
             M[0] = u2f(c.m.key[0]); M[1] = u2f(c.m.pc > 1 ? c.m.key[1] : 0u); M[2] = c.m.ni[0]; M[3] = c.m.ti[0];
             M[4] = c.m.pc > 1 ? c.m.ni[1] : 0.0f; M[5] = c.m.pc > 1 ? c.m.ti[1] : 0.0f;
             ++k;
-        } else if (c.touching) { *flags |= NCG_F_OVERFLOW; }
+        } else if (c.touching) W.b.overflow = true;
     }
     for (int i = 0; i < 6; ++i) R[NCG_R_CONTACT_WALL + i] = u2f(ww[i]);
     R[NCG_R_NCONTACT] = u2f((uint32_t)W.nc | ((uint32_t)W.na << 8) | (tmask << 16));
     R[NCG_R_MANIFOLD_PC] = u2f(pcw);
-    R[NCG_R_IMPULSE] = W.impulse;
     for (int i = 0; i < W.na; ++i) { R[NCG_R_ACTIVE + 3 * i] = u2f((uint32_t)W.awall[i]); R[NCG_R_ACTIVE + 3 * i + 1] = W.anx[i]; R[NCG_R_ACTIVE + 3 * i + 2] = W.any[i]; }
+}
+// does any wall's fat AABB overlap the car's?  (what b2BroadPhase::UpdatePairs would turn into new contacts)
+NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
+    int ix0 = (int)floorf((fat.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((fat.ux - T.gx0) * T.inv_cell);
+    int iy0 = (int)floorf((fat.ly - T.gy0) * T.inv_cell), iy1 = (int)floorf((fat.uy - T.gy0) * T.inv_cell);
+    ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
+    for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
+        int cell = iy * T.gnx + ix;
+        for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) if (aabb_overlap(fat, wall_fat(T, T.items[k]))) return true;
+    }
+    return false;
+}
+// The general b2World::Step for a car with (or about to get) contacts.  `resume`: the fast path has already done
+// Collide (nothing to do) and Solve for a car whose contact list was empty, and found that the moved proxy now
+// overlaps a wall; continue from FindNewContacts.
+NCG_HDN void step_with_contacts(Body& B, float* R, const Track& T, float dt, bool resume, Counters* cnt) {
+    World W; W.b = B;
+    w_load_contacts(W, R);
+    float dtRatio = B.inv_dt0 * dt;
+    if (!resume) {
+        if (W.b.newFixture) { w_find_new_contacts(W, T); W.b.newFixture = false; }
+        w_collide(W, T);
+        w_solve(W, T, dt, dtRatio);
+    }
+    w_find_new_contacts(W, T);
+    w_solve_toi(W, T, dt);
+    w_store_contacts(W, R);
+    B = W.b;
+    int nt = 0; for (int i = 0; i < W.nc; ++i) nt += W.c[i].touching ? 1 : 0;
+    if (nt) cnt->contact_steps++;
+    cnt->toi_events += W.toi_events;
+}
+// b2World::Step
+NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts, Counters* cnt) {
+    const float inv_dt = 1.0f / dt;
+    const int nc = (int)(f2u(R[NCG_R_NCONTACT]) & 255u);
+    bool slow = contacts && nc > 0;
+    if (!slow && contacts && B.newFixture) {           // first Step of a fresh world: pairs of the initial proxy
+        if (any_wall_overlap(T, B.fat)) slow = true; else { B.newFixture = false; B.proxyMoved = false; }
+    }
+    if (slow) step_with_contacts(B, R, T, dt, false, cnt);
+    else {
+        if (B.awake) {                                 // b2Island::Solve of a lone body
+            B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
+            b_integrate_velocity(B, dt);
+            integrate_position(B.sweep.c, B.sweep.a, B.v, B.w, dt);
+            b_sync_transform(B);
+            b_sleep(B, dt, true);
+            b_sync_fixtures(B);
+        }
+        if (contacts && B.proxyMoved) {                // FindNewContacts
+            if (any_wall_overlap(T, B.fat)) step_with_contacts(B, R, T, dt, true, cnt);
+            else B.proxyMoved = false;
+        }
+    }
+    B.inv_dt0 = inv_dt;
+    B.force = mk(0.0f, 0.0f); B.torque = 0.0f;
 }
 
 // ------------------------------------------------------------------ tyres (tyre.py, tyre_manager.py)
@@ -684,13 +755,14 @@ NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id
         R[NCG_R_FAT_LX] = a.lx - NCG_B2_AABB_EXT; R[NCG_R_FAT_LY] = a.ly - NCG_B2_AABB_EXT; R[NCG_R_FAT_UX] = a.ux + NCG_B2_AABB_EXT; R[NCG_R_FAT_UY] = a.uy + NCG_B2_AABB_EXT;
         fl = NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE;
     } else {
-        World W; w_load(W, R);
+        Body B; b_load(B, R);
         V2 p = mk(0.0f, 0.0f);
-        w_set_transform(W, p, W.sweep.a); w_set_transform(W, p, 0.0f);
-        W.v = mk(0.0f, 0.0f); W.w = 0.0f;     // SetLinearVelocity(0)/SetAngularVelocity(0) do not wake
-        W.na = 0; W.impulse = 0.0f; W.hasKey = false;
+        b_set_transform(B, p, B.sweep.a); b_set_transform(B, p, 0.0f);
+        B.v = mk(0.0f, 0.0f); B.w = 0.0f;     // SetLinearVelocity(0)/SetAngularVelocity(0) do not wake
+        B.impulse = 0.0f; B.hasKey = false;
         fl = f2u(R[NCG_R_FLAGS]) & (NCG_F_OVERFLOW);
-        w_store(W, R, &fl);
+        b_store(B, R, &fl);
+        R[NCG_R_NCONTACT] = u2f(f2u(R[NCG_R_NCONTACT]) & ~0xFF00u);      // active_collisions.clear(); contacts persist
         fl &= (NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE | NCG_F_OVERFLOW);
         for (int i = NCG_R_RPM; i < NCG_R_USED; ++i) if (i != NCG_R_BANK) R[i] = 0.0f;
     }
@@ -744,7 +816,7 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
     float throttle = fmaxf(0.0f, fminf(1.0f, thr_in)), brake = fmaxf(0.0f, fminf(1.0f, brk_in));
     float steer = fmaxf(-1.0f, fminf(1.0f, steer_in));
     float delta = steer * 0.78539816339744831f;
-    World W; w_load(W, R);
+    Body W; b_load(W, R);
     {   // rpm :311-327
         float rpm = R[NCG_R_RPM];
         float diff = (1000.0f + 800.0f * throttle) - rpm;
@@ -771,14 +843,14 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
         V2 fwd = mul(W.xf.q, mk(1.0f, 0.0f));
         float ff[4]; friction_forces(ff, R, fminf(2000.0f, fabsf(ef) / 2.0f), throttle, brake, delta, cs);
         V2 rear = mul(W.xf, mk(-NCG_CAR_WHEELBASE / 2.0f, 0.0f));
-        w_apply_force(W, mk(ef * fwd.x, ef * fwd.y), rear);
+        b_apply_force(W, mk(ef * fwd.x, ef * fwd.y), rear);
         // brake :451-469
         if (brake > 0.01f) {
             float bsf = 1.0f - fminf(0.3f, fabsf(delta) * 1.5f);
             float bforce = NCG_CAR_MASS * 14.0f * bsf * brake;
             float sp = length(W.v);
             if (sp > 0.1f) {
-                w_apply_force_center(W, mk(bforce * (-W.v.x / sp), bforce * (-W.v.y / sp)));
+                b_apply_force_center(W, mk(bforce * (-W.v.x / sp), bforce * (-W.v.y / sp)));
                 friction_forces(ff, R, 0.0f, throttle, brake, delta, sp);
             }
         }
@@ -786,9 +858,9 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
         float sp = length(W.v);
         if (sp > 0.1f) {
             float mag = NCG_DRAG_CONSTANT * sp * sp;
-            w_apply_force_center(W, mk(mag * (-W.v.x / sp), mag * (-W.v.y / sp)));
+            b_apply_force_center(W, mk(mag * (-W.v.x / sp), mag * (-W.v.y / sp)));
             float rr = 0.015f * NCG_WEIGHT;
-            w_apply_force_center(W, mk(rr * (-W.v.x / sp), rr * (-W.v.y / sp)));
+            b_apply_force_center(W, mk(rr * (-W.v.x / sp), rr * (-W.v.y / sp)));
         }
         // acceleration window :832-892
         float along, alat;
@@ -828,31 +900,29 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
             float fm = sqrtf(cfx * cfx + cfy * cfy);
             if (fm > mf) { float sc = mf / fm; cfx *= sc; cfy *= sc; fm = mf; }
             R[NCG_R_FLAT] = fm;
-            w_apply_force_center(W, mk(cfx, cfy));
+            b_apply_force_center(W, mk(cfx, cfy));
         }
         // angular damping :502-507
-        w_apply_torque(W, -W.w * NCG_CAR_MASS * 4.0f);
+        b_apply_torque(W, -W.w * NCG_CAR_MASS * 4.0f);
         // banking :509-566
         float bank = R[NCG_R_BANK];
         if (!(fabsf(bank) < 0.1f) && !(sp < 1.0f)) {
             float la = NCG_CAR_MASS * 9.81f * sinf(fabsf(bank * 0.017453292519943295f)) * 0.3f;
             if (!(fabsf(la) < 1.0f) && sp > 5.0f) {
                 float sg = bank < 0.0f ? -1.0f : 1.0f;
-                w_apply_force_center(W, mk((-(W.v.y / sp)) * la * sg, (W.v.x / sp) * la * sg));
+                b_apply_force_center(W, mk((-(W.v.y / sp)) * la * sg, (W.v.x / sp) * la * sg));
             }
         }
         // steering :568-584
         if (fabsf(delta) > 0.01f && sp > 0.1f) {
             float dav = sp * tanf(delta) / NCG_CAR_WHEELBASE;
-            w_apply_torque(W, (dav - W.w) * NCG_CAR_MASS * 0.8f);
+            b_apply_torque(W, (dav - W.w) * NCG_CAR_MASS * 0.8f);
         }
     }
     // ---- b2World.Step (car_physics.py:363)
-    w_step(W, T, NCG_DT, contacts);
-    w_store(W, R, &fl);
+    body_step(W, R, T, NCG_DT, contacts, cnt);
+    b_store(W, R, &fl);
     if (W.overflow) cnt->overflow++;
-    if (W.nc > 0) { int nt = 0; for (int i = 0; i < W.nc; ++i) nt += W.c[i].touching ? 1 : 0; if (nt) cnt->contact_steps++; }
-    cnt->toi_events += W.toi_events;
     const float x = W.sweep.c.x, y = W.sweep.c.y;
     const float speed = length(W.v);
     // banking refresh + progress (one segment scan serves both)
@@ -985,24 +1055,31 @@ NCG_HD void car_finish(float* R, float reward) {
 // ------------------------------------------------------------------ one sensor ray (distance_sensor.py:71-117)
 // Returns the hit distance in metres (250 if nothing is hit).  Uniform-grid DDA over the wall boxes; each
 // candidate is tested with b2PolygonShape::RayCast's arithmetic, the minimum entry fraction wins.
+// b2PolygonShape::RayCast for a box, branch-free.  For the four box edges the generic dot(n_i, v_i - p1) and
+// dot(n_i, d) reduce exactly (x*0 = 0, x*1 = x, x*-1 = -x) to the expressions below, so every quotient is the
+// float32 value Box2D computes; the early exits of the reference loop are equivalent to testing at the end
+// because `lower` only grows and `upper` only shrinks.
 NCG_HD float ray_box_fraction(const float* w, V2 P1, V2 P2, float maxFraction) {
-    Rot q; q.c = w[2]; q.s = w[3];
-    V2 pos = mk(w[0], w[1]);
-    Box b; b.hx = w[4]; b.hy = w[5];
-    V2 p1 = mulT(q, P1 - pos), p2 = mulT(q, P2 - pos), d = p2 - p1;
-    float lower = 0.0f, upper = maxFraction; int index = -1;
+    const float c = w[2], s = w[3], hx = w[4], hy = w[5];
+    const float ax = P1.x - w[0], ay = P1.y - w[1], bx = P2.x - w[0], by = P2.y - w[1];
+    const float p1x = c * ax + s * ay, p1y = -s * ax + c * ay;
+    const float p2x = c * bx + s * by, p2y = -s * bx + c * by;
+    const float dx = p2x - p1x, dy = p2y - p1y;
+    const float num[4] = {-((-hy) - p1y), hx - p1x, hy - p1y, -((-hx) - p1x)};
+    const float den[4] = {-dy, dx, dy, -dx};
+    float lower = 0.0f, upper = maxFraction; bool hit = false, miss = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        V2 n = box_n(i);
-        float num = dot(n, box_v(b, i) - p1), den = dot(n, d);
-        if (den == 0.0f) { if (num < 0.0f) return -1.0f; }
-        else {
-            if (den < 0.0f && num < lower * den) { lower = num / den; index = i; }
-            else if (den > 0.0f && num < upper * den) { upper = num / den; }
-        }
-        if (upper < lower) return -1.0f;
+        const float q = num[i] / den[i];
+        const bool zero = den[i] == 0.0f;
+        const bool enter = den[i] < 0.0f && num[i] < lower * den[i];
+        const bool leave = den[i] > 0.0f && num[i] < upper * den[i];
+        miss = miss || (zero && num[i] < 0.0f);
+        lower = enter ? q : lower; hit = hit || enter;
+        upper = (!enter && leave) ? q : upper;
+        miss = miss || upper < lower;
     }
-    return index >= 0 ? lower : -1.0f;
+    return (hit && !miss) ? lower : -1.0f;
 }
 NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, unsigned* tests) {
     // direction = heading rotated by -i*22.5 deg.  The reference evaluates cos/sin(theta - i*pi/8) in float64
@@ -1040,7 +1117,12 @@ NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, un
                 int wi = T.items[k];
                 if (wi == last0 || wi == last1) continue;
                 last1 = last0; last0 = wi;
-                float fr = ray_box_fraction(T.walls + wi * WALL_STRIDE, P1, P2, best); ++nt;
+                const float* w = T.walls + wi * WALL_STRIDE;
+                // conservative reject: bounding circle (w[7] = radius + 1 cm) against the ray's line and extent
+                float cx = w[0] - px, cy = w[1] - py;
+                float along = cx * dx + cy * dy, perp = cx * dy - cy * dx;
+                if (fabsf(perp) > w[7] || along < -w[7] || along > best * 250.0f + w[7]) continue;
+                float fr = ray_box_fraction(w, P1, P2, best); ++nt;
                 if (fr >= 0.0f) best = fr;
             }
             float texit = fminf(tmx, tmy);

@@ -53,6 +53,33 @@ void hc_sensors_grid(const float* blob, float x, float y, float angle, float* ou
     Track T = track_view(blob, blob);
     for (int i = 0; i < 16; ++i) out16[i] = cast_ray(T, x, y, angle, i, tests);
 }
+// the generic b2PolygonShape::RayCast loop, kept here to prove the branch-free box version bit-identical
+static float ray_box_generic(const float* w, V2 P1, V2 P2, float maxFraction) {
+    Rot q; q.c = w[2]; q.s = w[3]; V2 pos = mk(w[0], w[1]); Box b; b.hx = w[4]; b.hy = w[5];
+    V2 p1 = mulT(q, P1 - pos), p2 = mulT(q, P2 - pos), d = p2 - p1;
+    float lower = 0.0f, upper = maxFraction; int index = -1;
+    for (int i = 0; i < 4; ++i) {
+        V2 n = box_n(i);
+        float num = dot(n, box_v(b, i) - p1), den = dot(n, d);
+        if (den == 0.0f) { if (num < 0.0f) return -1.0f; }
+        else {
+            if (den < 0.0f && num < lower * den) { lower = num / den; index = i; }
+            else if (den > 0.0f && num < upper * den) { upper = num / den; }
+        }
+        if (upper < lower) return -1.0f;
+    }
+    return index >= 0 ? lower : -1.0f;
+}
+// returns the number of walls on which the two implementations disagree (bitwise) for one ray
+int hc_ray_box_mismatches(const float* blob, float x1, float y1, float x2, float y2, float maxFraction) {
+    Track T = track_view(blob, blob); int bad = 0;
+    for (int wi = 0; wi < T.n_walls; ++wi) {
+        float a = ray_box_fraction(T.walls + wi * WALL_STRIDE, mk(x1, y1), mk(x2, y2), maxFraction);
+        float b = ray_box_generic(T.walls + wi * WALL_STRIDE, mk(x1, y1), mk(x2, y2), maxFraction);
+        if (f2u(a) != f2u(b)) ++bad;
+    }
+    return bad;
+}
 int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }
 void hc_synthetic_action(unsigned long long seed, unsigned car, unsigned step, int mode, int discrete, float* out3) {
     action_synthetic(seed, car, step, mode, discrete != 0, out3, out3 + 1, out3 + 2);
