@@ -15,7 +15,7 @@
  *   ncg_rollout                      the demo/random_demo.py loop shape (random actions, T steps) kept on device
  *   ncg_get_state / ncg_set_state    (no reference equivalent: Box2D state is not serialisable; used for
  *                                    teacher-forced parity tests and env checkpoints)
- *   ncg_get_field                    the per-car numbers behind CarEnv._get_multi_info (src/car_env.py:1160-1227)
+ *   (info dict)                      built lazily on the host from ncg_get_state records (src/car_env.py:1160-1227)
  *
  * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch tensor
  * storage), contiguous, on the handle's device; h_* are HOST pointers.  All work is enqueued on the
@@ -167,6 +167,15 @@ int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float*
 int ncg_step_host(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
                   uint8_t* h_truncated, float* h_final_obs);
 int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_track_id, int32_t fresh, float* h_obs);
+
+/* Zero-copy variant of ncg_step_host: ncg_host_buffers hands out the library's page-locked staging buffers (valid
+ * until ncg_destroy; actions float32[E*C*2] or int32[E*C], obs float32[E*C*38], reward float32[E*C], terminated and
+ * truncated uint8[E], final_obs float32[E*C*38]).  The caller writes actions into `actions`, calls ncg_step_pinned and
+ * reads the results in place; *any_done != 0 means at least one env finished (and, with want_final and auto_reset,
+ * final_obs holds the terminal observations of the finished envs). */
+int ncg_host_buffers(NcgHandle* h, void** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated,
+                     float** final_obs);
+int ncg_step_pinned(NcgHandle* h, int32_t want_final, int32_t* any_done);
 
 /* Raw records, NCG_RECORD_WORDS words per car, car-major; d_records float32[n_cars*128]. */
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream);

@@ -33,7 +33,7 @@ NCG_HD float fmaxb(float a, float b) { return a > b ? a : b; }
 NCG_HD float clampb(float a, float lo, float hi) { return fmaxb(lo, fminb(a, hi)); }
 
 struct Rot { float s, c; };
-NCG_HD Rot rot(float a) { Rot q; q.s = sinf(a); q.c = cosf(a); return q; }
+NCG_HD Rot rot(float a) { Rot q; sincosf(a, &q.s, &q.c); return q; }
 struct Xf { V2 p; Rot q; };
 NCG_HD V2 mul(Rot q, V2 v) { return mk(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
 NCG_HD V2 mulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }

@@ -257,6 +257,7 @@ struct NcgHandle {
     void* d_actions = nullptr; float* d_obs = nullptr; float* d_final = nullptr; float* d_reward = nullptr; uint8_t* d_term = nullptr; uint8_t* d_trunc = nullptr;
     uint8_t* d_mask = nullptr; int* d_tid = nullptr;
     void* p_actions = nullptr; float* p_obs = nullptr; float* p_final = nullptr; float* p_reward = nullptr; uint8_t* p_flags = nullptr;
+    void* d_pack = nullptr; void* p_pack = nullptr; size_t pack_bytes = 0;
 };
 
 namespace {
@@ -305,7 +306,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
     const char* g = getenv("NCG_CARS_PER_WARP");
     int G = g ? atoi(g) : 0;
-    if (G != 1 && G != 2 && G != 4 && G != 8) G = h->N >= 148 * 64 * 4 ? 4 : (h->N >= 148 * 64 * 2 ? 2 : 1);
+    if (G != 1 && G != 2 && G != 4 && G != 8) G = h->N >= 32768 ? 8 : (h->N >= 2048 ? 4 : (h->N >= 512 ? 2 : 1));   // measured: profiles/
     h->cars_per_warp = G;
     size_t N = (size_t)h->N, E = (size_t)cfg->num_envs;
     CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));
@@ -313,11 +314,13 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(DevStats)));
     CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(DevStats)));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&h->d_actions, N * 8)); CUDA_TRY(cudaMalloc(&h->d_obs, N * NCG_OBS_DIM * 4)); CUDA_TRY(cudaMalloc(&h->d_final, N * NCG_OBS_DIM * 4));
-    CUDA_TRY(cudaMalloc(&h->d_reward, N * 4)); CUDA_TRY(cudaMalloc(&h->d_term, E)); CUDA_TRY(cudaMalloc(&h->d_trunc, E));
+    // host path: results packed as obs | reward | terminated | truncated so one D2H copy brings a whole step back
+    h->pack_bytes = N * NCG_OBS_DIM * 4 + N * 4 + 2 * E;
+    CUDA_TRY(cudaMalloc(&h->d_actions, N * 8)); CUDA_TRY(cudaMalloc(&h->d_pack, h->pack_bytes)); CUDA_TRY(cudaMalloc(&h->d_final, N * NCG_OBS_DIM * 4));
+    h->d_obs = (float*)h->d_pack; h->d_reward = h->d_obs + N * NCG_OBS_DIM; h->d_term = (uint8_t*)(h->d_reward + N); h->d_trunc = h->d_term + E;
     CUDA_TRY(cudaMalloc(&h->d_mask, E)); CUDA_TRY(cudaMalloc(&h->d_tid, E * 4));
-    CUDA_TRY(cudaMallocHost(&h->p_actions, N * 8)); CUDA_TRY(cudaMallocHost(&h->p_obs, N * NCG_OBS_DIM * 4)); CUDA_TRY(cudaMallocHost(&h->p_final, N * NCG_OBS_DIM * 4));
-    CUDA_TRY(cudaMallocHost(&h->p_reward, N * 4)); CUDA_TRY(cudaMallocHost(&h->p_flags, E * 8));
+    CUDA_TRY(cudaMallocHost(&h->p_actions, N * 8)); CUDA_TRY(cudaMallocHost(&h->p_pack, h->pack_bytes)); CUDA_TRY(cudaMallocHost(&h->p_final, N * NCG_OBS_DIM * 4));
+    h->p_obs = (float*)h->p_pack; h->p_reward = h->p_obs + N * NCG_OBS_DIM; h->p_flags = (uint8_t*)(h->p_reward + N);
     h->h_env_track.assign(E, 0);
     *out = h;
     return NCG_OK;
@@ -327,9 +330,9 @@ int ncg_destroy(NcgHandle* h) {
     if (!h) return NCG_OK;
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats);
-    cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_final); cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_trunc);
+    cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
     cudaFree(h->d_mask); cudaFree(h->d_tid);
-    cudaFreeHost(h->p_actions); cudaFreeHost(h->p_obs); cudaFreeHost(h->p_final); cudaFreeHost(h->p_reward); cudaFreeHost(h->p_flags);
+    cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return NCG_OK;
@@ -420,6 +423,25 @@ int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_tra
     return NCG_OK;
 }
 
+// One step through the pinned staging buffers: actions are read from p_actions, results land in p_pack (and p_final
+// when an env finished).  *any_done tells the caller whether p_final holds terminal observations.
+static int step_pinned(NcgHandle* h, bool want_final, int* any_done) {
+    const size_t N = h->N, E = h->cfg.num_envs, abytes = h->cfg.discrete ? N * 4 : N * 8;
+    CUDA_TRY(cudaMemcpyAsync(h->d_actions, h->p_actions, abytes, cudaMemcpyHostToDevice, h->stream));
+    int rc = ncg_step(h, h->d_actions, h->d_obs, h->d_reward, h->d_term, h->d_trunc, want_final ? h->d_final : nullptr, h->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->p_pack, h->d_pack, h->pack_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    int done = 0;
+    for (size_t e = 0; e < 2 * E; ++e) done |= h->p_flags[e];
+    if (want_final && done && h->cfg.auto_reset) {
+        CUDA_TRY(cudaMemcpyAsync(h->p_final, h->d_final, N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    if (any_done) *any_done = done ? 1 : 0;
+    return NCG_OK;
+}
+
 int ncg_step_host(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
                   float* h_final_obs) {
     if (!h || !h_actions || !h_obs || !h_reward || !h_terminated || !h_truncated) return fail(NCG_E_INVALID, "null argument");
@@ -427,19 +449,31 @@ int ncg_step_host(NcgHandle* h, const void* h_actions, float* h_obs, float* h_re
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const size_t N = h->N, E = h->cfg.num_envs, abytes = h->cfg.discrete ? N * 4 : N * 8;
     memcpy(h->p_actions, h_actions, abytes);
-    CUDA_TRY(cudaMemcpyAsync(h->d_actions, h->p_actions, abytes, cudaMemcpyHostToDevice, h->stream));
-    int rc = ncg_step(h, h->d_actions, h->d_obs, h->d_reward, h->d_term, h->d_trunc, h_final_obs ? h->d_final : nullptr, h->stream);
+    int done = 0;
+    int rc = step_pinned(h, h_final_obs != nullptr, &done);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h->p_obs, h->d_obs, N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->p_reward, h->d_reward, N * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->p_flags, h->d_term, E, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaMemcpyAsync(h->p_flags + E, h->d_trunc, E, cudaMemcpyDeviceToHost, h->stream));
-    if (h_final_obs) CUDA_TRY(cudaMemcpyAsync(h->p_final, h->d_final, N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
     memcpy(h_obs, h->p_obs, N * NCG_OBS_DIM * 4); memcpy(h_reward, h->p_reward, N * 4);
     memcpy(h_terminated, h->p_flags, E); memcpy(h_truncated, h->p_flags + E, E);
-    if (h_final_obs) memcpy(h_final_obs, h->p_final, N * NCG_OBS_DIM * 4);
+    if (h_final_obs && done && h->cfg.auto_reset) memcpy(h_final_obs, h->p_final, N * NCG_OBS_DIM * 4);
     return NCG_OK;
+}
+
+int ncg_host_buffers(NcgHandle* h, void** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated, float** final_obs) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    if (actions) *actions = h->p_actions;
+    if (obs) *obs = h->p_obs;
+    if (reward) *reward = h->p_reward;
+    if (terminated) *terminated = h->p_flags;
+    if (truncated) *truncated = h->p_flags + h->cfg.num_envs;
+    if (final_obs) *final_obs = h->p_final;
+    return NCG_OK;
+}
+
+int ncg_step_pinned(NcgHandle* h, int32_t want_final, int32_t* any_done) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    return step_pinned(h, want_final != 0, any_done);
 }
 
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream) {

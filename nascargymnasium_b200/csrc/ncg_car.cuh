@@ -589,7 +589,7 @@ NCG_HD float tyre_grip(float T, float wear) {
     float tg;
     if (85.0f <= T && T <= 105.0f) tg = 1.5f;
     else { float dev = T < 85.0f ? 85.0f - T : T - 105.0f; tg = fmaxf(0.8f, 1.5f - dev * 0.02f); }
-    return tg * (1.0f - (wear / 100.0f) * 0.5f);
+    return tg * (1.0f - (wear * 0.01f) * 0.5f);
 }
 NCG_HD float total_grip(const float* R) {
     float tg = 0.0f, tw = 0.0f;
@@ -599,7 +599,7 @@ NCG_HD float total_grip(const float* R) {
 }
 NCG_HD void weight_transfer(float along, float alat, float speed, float* loads) {
     float down = 0.0f;
-    if (speed > 50.0f) { float sf = (speed / 50.0f) * (speed / 50.0f); down = fminf(0.12f * sf * NCG_WEIGHT, 1.5f * NCG_WEIGHT); }
+    if (speed > 50.0f) { float sf = (speed * 0.02f) * (speed * 0.02f); down = fminf(0.12f * sf * NCG_WEIGHT, 1.5f * NCG_WEIGHT); }
     float base_front = NCG_WEIGHT * 0.5f + down * (1.0f - 0.6f), base_rear = NCG_WEIGHT * 0.5f + down * 0.6f;
     float tew = NCG_WEIGHT + down;
     float raw_long = along * tew * 0.02f;
@@ -623,23 +623,23 @@ NCG_HD void weight_transfer(float along, float alat, float speed, float* loads) 
 }
 NCG_HD void tyre_update(float* T, float* wear, float load, float ff, float speed, float alat, float slip) {
     const float dt = NCG_DT;
-    float ns = fminf(speed / NCG_CAR_MAX_SPEED, 2.0f);
+    float ns = fminf(speed * (1.0f / NCG_CAR_MAX_SPEED), 2.0f);
     float fp = fabsf(ff) * 0.040f * (1.0f + ns * ns);
     float aero = speed > 50.0f ? speed * speed * 0.0002f : 0.0f;
-    float heat = (fp + aero) * dt / 125.0f;
+    float heat = (fp + aero) * (dt * (1.0f / 125.0f));
     float ce = 0.01f;
-    if (speed > 50.0f) ce *= (1.0f - fminf(0.8f, speed / 100.0f) * 0.5f);
+    if (speed > 50.0f) ce *= (1.0f - fminf(0.8f, speed * 0.01f) * 0.5f);
     float t = *T;
     t += heat - (t - 25.0f) * ce * dt;
     t = fmaxf(25.0f, fminf(120.0f, t));
     *T = t;
-    float tm = (85.0f <= t && t <= 105.0f) ? 1.0f : (t > 105.0f ? 1.0f + (t - 105.0f) / 20.0f : 1.0f + (85.0f - t) / 30.0f);
-    float lm = fmaxf(0.5f, load / NCG_STATIC_TYRE_LOAD);
-    float wf = fmaxf(1.0f, t / 80.0f);
-    float sw = fminf(1.0f + (speed * 3.6f / 400.0f) * 3.0f, 3.0f);
-    float lg = fabsf(alat) / 9.81f;
+    float tm = (85.0f <= t && t <= 105.0f) ? 1.0f : (t > 105.0f ? 1.0f + (t - 105.0f) * 0.05f : 1.0f + (85.0f - t) * (1.0f / 30.0f));
+    float lm = fmaxf(0.5f, load * (1.0f / NCG_STATIC_TYRE_LOAD));
+    float wf = fmaxf(1.0f, t * 0.0125f);
+    float sw = fminf(1.0f + (speed * (3.6f / 400.0f)) * 3.0f, 3.0f);
+    float lg = fabsf(alat) * (1.0f / 9.81f);
     float cw = lg > 2.0f ? fminf(1.0f + (lg - 2.0f) * 1.5f, 2.5f) : 1.0f;
-    float kw = fminf(1.0f + (fabsf(slip) / 45.0f) * 2.0f, 3.0f);
+    float kw = fminf(1.0f + (fabsf(slip) * (1.0f / 45.0f)) * 2.0f, 3.0f);
     float wr = fabsf(ff) * 0.00001f * (tm * lm * wf * sw * cw * kw);
     *wear = fminf(100.0f, *wear + wr * dt);
 }
@@ -647,10 +647,10 @@ NCG_HD void tyre_update(float* T, float* wear, float load, float ff, float speed
 // friction forces for tyre heating: car.py:702-830
 NCG_HD void friction_forces(float* ff, const float* R, float driving, float throttle, float brake, float steer_angle, float sp) {
     float rear, front;
-    if (throttle > 0.01f && sp > 50.0f) { float faf = fminf(0.3f, sp / 200.0f); rear = driving * (1.0f - faf); front = driving * faf / 2.0f; }
+    if (throttle > 0.01f && sp > 50.0f) { float faf = fminf(0.3f, sp * 0.005f); rear = driving * (1.0f - faf); front = driving * faf / 2.0f; }
     else { rear = throttle > 0.01f ? driving : 0.0f; front = 0.0f; }
     float bf = 0.0f;
-    if (brake > 0.01f) { float base = NCG_CAR_MASS * 14.0f * brake / 4.0f; bf = sp <= 1.0f ? base * (0.05f + 0.95f * sp) : base; }
+    if (brake > 0.01f) { float base = (NCG_CAR_MASS * 14.0f * 0.25f) * brake; bf = sp <= 1.0f ? base * (0.05f + 0.95f * sp) : base; }
     float rf = sp > 0.1f ? (0.015f * NCG_WEIGHT) / 4.0f : 0.0f;
     ff[0] = ff[1] = front + bf + rf; ff[2] = ff[3] = rear / 2.0f + bf + rf;
     if (sp < 2.0f) return;
@@ -696,7 +696,7 @@ NCG_HD void nearest_segment(const Track& T, float x, float y, float* banking, fl
         const float* s = T.segs + i * SEG_STRIDE;
         float sx = s[0], sy = s[1], dx = s[4], dy = s[5], l2 = s[6], cx, cy;
         if (l2 < 1e-6f) { cx = sx; cy = sy; }
-        else { float t = fmaxf(0.0f, fminf(1.0f, ((x - sx) * dx + (y - sy) * dy) / l2)); cx = sx + t * dx; cy = sy + t * dy; }
+        else { float t = fmaxf(0.0f, fminf(1.0f, ((x - sx) * dx + (y - sy) * dy) * s[7])); cx = sx + t * dx; cy = sy + t * dy; }
         float d2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
         if (d2 < best) { second = best; best = d2; bi = i; bcx = cx; bcy = cy; }
         else if (d2 < second) second = d2;
@@ -780,15 +780,15 @@ NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id
 NCG_HD float clip1(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 NCG_HD void observe_state(const float* R, float* obs) {
     float vx = R[NCG_R_VX], vy = R[NCG_R_VY];
-    obs[0] = clip1(R[NCG_R_X] / 10000.0f, -1.0f, 1.0f); obs[1] = clip1(R[NCG_R_Y] / 10000.0f, -1.0f, 1.0f);
-    obs[2] = clip1(vx / 111.1f, -1.0f, 1.0f); obs[3] = clip1(vy / 111.1f, -1.0f, 1.0f);
-    obs[4] = clip1(sqrtf(vx * vx + vy * vy) / 111.1f, 0.0f, 1.0f);
-    obs[5] = clip1(R[NCG_R_ANGLE] / 3.14159265358979f, -1.0f, 1.0f); obs[6] = clip1(R[NCG_R_OMEGA] / 10.0f, -1.0f, 1.0f);
+    obs[0] = clip1(R[NCG_R_X] * 1e-4f, -1.0f, 1.0f); obs[1] = clip1(R[NCG_R_Y] * 1e-4f, -1.0f, 1.0f);
+    obs[2] = clip1(vx * (1.0f / 111.1f), -1.0f, 1.0f); obs[3] = clip1(vy * (1.0f / 111.1f), -1.0f, 1.0f);
+    obs[4] = clip1(sqrtf(vx * vx + vy * vy) * (1.0f / 111.1f), 0.0f, 1.0f);
+    obs[5] = clip1(R[NCG_R_ANGLE] * (1.0f / 3.14159265358979f), -1.0f, 1.0f); obs[6] = clip1(R[NCG_R_OMEGA] * 0.1f, -1.0f, 1.0f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        obs[7 + k] = clip1(R[NCG_R_TYRE_LOAD + k] / 29430.0f, 0.0f, 1.0f);
-        obs[11 + k] = clip1(R[NCG_R_TYRE_TEMP + k] / 200.0f, 0.0f, 1.0f);
-        obs[15 + k] = clip1(R[NCG_R_TYRE_WEAR + k] / 100.0f, 0.0f, 1.0f);
+        obs[7 + k] = clip1(R[NCG_R_TYRE_LOAD + k] * (1.0f / 29430.0f), 0.0f, 1.0f);
+        obs[11 + k] = clip1(R[NCG_R_TYRE_TEMP + k] * 0.005f, 0.0f, 1.0f);
+        obs[15 + k] = clip1(R[NCG_R_TYRE_WEAR + k] * 0.01f, 0.0f, 1.0f);
     }
     float ci = R[NCG_R_IMPULSE], ca = 0.0f;
     if (ci < 100.0f) ci = 0.0f;
@@ -797,8 +797,8 @@ NCG_HD void observe_state(const float* R, float* obs) {
         while (ca > 3.14159265358979f) ca -= 6.28318530717959f;
         while (ca < -3.14159265358979f) ca += 6.28318530717959f;
     }
-    obs[19] = clip1(ci / 50000.0f, 0.0f, 1.0f); obs[20] = clip1(ca / 3.14159265358979f, -1.0f, 1.0f);
-    obs[21] = clip1(R[NCG_R_CUM_IMPACT] / 250000.0f, 0.0f, 1.0f);
+    obs[19] = clip1(ci * (1.0f / 50000.0f), 0.0f, 1.0f); obs[20] = clip1(ca * (1.0f / 3.14159265358979f), -1.0f, 1.0f);
+    obs[21] = clip1(R[NCG_R_CUM_IMPACT] * (1.0f / 250000.0f), 0.0f, 1.0f);
 }
 
 // ------------------------------------------------------------------ the scalar car phase of one step
@@ -826,13 +826,13 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
     {   // engine :389-449
         float cs = length(W.v);
         float r = fmaxf(1000.0f, fminf(9000.0f, R[NCG_R_RPM]));
-        float tf = r <= 5500.0f ? 0.7f + 0.3f * (r - 1000.0f) / 4500.0f : 1.0f - 0.6f * (r - 5500.0f) / 3500.0f;
-        float tlf = (NCG_CAR_MAX_TORQUE * tf) * throttle * 7.5f / 0.35f;
+        float tf = r <= 5500.0f ? 0.7f + (r - 1000.0f) * (0.3f / 4500.0f) : 1.0f - (r - 5500.0f) * (0.6f / 3500.0f);
+        float tlf = (NCG_CAR_MAX_TORQUE * tf) * throttle * (7.5f / 0.35f);
         float ef;
         if (cs > 12.0f) {
             float plf = (NCG_CAR_MAX_POWER * throttle) / cs;
             if (cs <= 25.0f) {
-                float ns = (cs - 12.0f) / 13.0f;
+                float ns = (cs - 12.0f) * (1.0f / 13.0f);
                 float b = fmaxf(0.05f, fminf(0.75f, 1.0f - expf(-2.0f * ns)));
                 ef = tlf * (1.0f - b) + plf * b;
             } else ef = tlf * 0.25f + plf * 0.75f;
@@ -850,22 +850,22 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
             float bforce = NCG_CAR_MASS * 14.0f * bsf * brake;
             float sp = length(W.v);
             if (sp > 0.1f) {
-                b_apply_force_center(W, mk(bforce * (-W.v.x / sp), bforce * (-W.v.y / sp)));
+                { float is = 1.0f / sp; b_apply_force_center(W, mk(bforce * (-W.v.x * is), bforce * (-W.v.y * is))); }
                 friction_forces(ff, R, 0.0f, throttle, brake, delta, sp);
             }
         }
         // drag :471-484, rolling :486-500
         float sp = length(W.v);
         if (sp > 0.1f) {
-            float mag = NCG_DRAG_CONSTANT * sp * sp;
-            b_apply_force_center(W, mk(mag * (-W.v.x / sp), mag * (-W.v.y / sp)));
+            float mag = NCG_DRAG_CONSTANT * sp * sp, is = 1.0f / sp;
+            b_apply_force_center(W, mk(mag * (-W.v.x * is), mag * (-W.v.y * is)));
             float rr = 0.015f * NCG_WEIGHT;
-            b_apply_force_center(W, mk(rr * (-W.v.x / sp), rr * (-W.v.y / sp)));
+            b_apply_force_center(W, mk(rr * (-W.v.x * is), rr * (-W.v.y * is)));
         }
         // acceleration window :832-892
         float along, alat;
         {
-            float ax = (W.v.x - R[NCG_R_PREV_VX]) / NCG_DT, ay = (W.v.y - R[NCG_R_PREV_VY]) / NCG_DT;
+            float ax = (W.v.x - R[NCG_R_PREV_VX]) * 60.0f, ay = (W.v.y - R[NCG_R_PREV_VY]) * 60.0f;
             V2 f = mul(W.xf.q, mk(1.0f, 0.0f)), l = mul(W.xf.q, mk(0.0f, 1.0f));
             float lo = fmaxf(-12.0f, fminf(12.0f, ax * f.x + ay * f.y));
             float la = fmaxf(-12.0f, fminf(12.0f, ax * l.x + ay * l.y));
@@ -891,7 +891,7 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
         // lateral alignment force :635-700
         if (sp > 0.05f) {
             V2 f = mul(W.xf.q, mk(1.0f, 0.0f));
-            float vnx = W.v.x / sp, vny = W.v.y / sp;
+            float is = 1.0f / sp; float vnx = W.v.x * is, vny = W.v.y * is;
             float cp = vnx * f.y - vny * f.x, dp = vnx * f.x + vny * f.y;
             R[NCG_R_SLIP] = fabsf(atan2f(fabsf(cp), dp)) * 57.295779513082323f;
             float cfx = (f.x * sp - W.v.x) * (NCG_CAR_MASS * 5.0f), cfy = (f.y * sp - W.v.y) * (NCG_CAR_MASS * 5.0f);
@@ -910,12 +910,12 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
             float la = NCG_CAR_MASS * 9.81f * sinf(fabsf(bank * 0.017453292519943295f)) * 0.3f;
             if (!(fabsf(la) < 1.0f) && sp > 5.0f) {
                 float sg = bank < 0.0f ? -1.0f : 1.0f;
-                b_apply_force_center(W, mk((-(W.v.y / sp)) * la * sg, (W.v.x / sp) * la * sg));
+                { float is = 1.0f / sp; b_apply_force_center(W, mk((-(W.v.y * is)) * la * sg, (W.v.x * is) * la * sg)); }
             }
         }
         // steering :568-584
         if (fabsf(delta) > 0.01f && sp > 0.1f) {
-            float dav = sp * tanf(delta) / NCG_CAR_WHEELBASE;
+            float dav = sp * tanf(delta) * (1.0f / NCG_CAR_WHEELBASE);
             b_apply_torque(W, (dav - W.w) * NCG_CAR_MASS * 0.8f);
         }
     }
@@ -953,7 +953,7 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
                 if (fl & NCG_F_CROSSED) {
                     uint32_t lap_steps = step_pre - f2u(R[NCG_R_LAP_START]);
                     if (lap_steps >= NCG_MIN_LAP_STEPS && !(R[NCG_R_ODO] < T.min_lap)) {
-                        float lt = (float)lap_steps / 60.0f;
+                        float lt = (float)lap_steps * (1.0f / 60.0f);
                         R[NCG_R_LAST_LAP] = lt;
                         if (!(fl & NCG_F_HAS_BEST) || lt < R[NCG_R_BEST_LAP]) { R[NCG_R_BEST_LAP] = lt; fl |= NCG_F_HAS_BEST; }
                         fl |= NCG_F_HAS_LAST;
@@ -1070,7 +1070,7 @@ NCG_HD float ray_box_fraction(const float* w, V2 P1, V2 P2, float maxFraction) {
     float lower = 0.0f, upper = maxFraction; bool hit = false, miss = false;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float q = num[i] / den[i];
+        const float q = fdiv_fast(num[i], den[i]);
         const bool zero = den[i] == 0.0f;
         const bool enter = den[i] < 0.0f && num[i] < lower * den[i];
         const bool leave = den[i] > 0.0f && num[i] < upper * den[i];
@@ -1091,7 +1091,7 @@ NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, un
     const float ks[16] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f,
                           -0.70710678118654752f, -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f,
                           0.92387953251128674f, 1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
-    float ca = cosf(angle), sa = sinf(angle);
+    float sa, ca; sincosf(angle, &sa, &ca);
     float dx = ca * kc[i] - sa * ks[i], dy = sa * kc[i] + ca * ks[i];
     V2 P1 = mk(px, py), P2 = mk(px + dx * 250.0f, py + dy * 250.0f);
     float best = 1.0f;
@@ -1105,7 +1105,7 @@ NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, un
         // Amanatides-Woo in units of ray fraction (t in [0,1] <-> 250 m)
         float ddx = P2.x - P1.x, ddy = P2.y - P1.y;
         int sx = ddx > 0.0f ? 1 : -1, sy = ddy > 0.0f ? 1 : -1;
-        float tdx = ddx != 0.0f ? T.cell / fabsf(ddx) : INFINITY, tdy = ddy != 0.0f ? T.cell / fabsf(ddy) : INFINITY;
+        float tdx = ddx != 0.0f ? fdiv_fast(T.cell, fabsf(ddx)) : INFINITY, tdy = ddy != 0.0f ? fdiv_fast(T.cell, fabsf(ddy)) : INFINITY;
         float fx = gx - (float)ix, fy = gy - (float)iy;
         float tmx = ddx != 0.0f ? (ddx > 0.0f ? (1.0f - fx) : fx) * tdx : INFINITY;
         float tmy = ddy != 0.0f ? (ddy > 0.0f ? (1.0f - fy) : fy) * tdy : INFINITY;
@@ -1134,7 +1134,7 @@ NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, un
     *tests += nt;
     return best < 1.0f ? best * 250.0f : 250.0f;
 }
-NCG_HD float sensor_obs(float dist) { float n = dist / 250.0f; return n < 0.0f ? 0.0f : (n > 1.0f ? 1.0f : n); }
+NCG_HD float sensor_obs(float dist) { float n = dist * 0.004f; return n < 0.0f ? 0.0f : (n > 1.0f ? 1.0f : n); }
 
 // ------------------------------------------------------------------ Philox4x32-10 (synthetic actions)
 NCG_HD void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {

@@ -33,6 +33,15 @@ NCG_HD float u2f(uint32_t u) {
 #endif
 }
 
+// approximate division (MUFU.RCP + FMUL, <= 2 ulp) for the sensor rays only: their tolerance is 1e-3 normalised
+NCG_HD float fdiv_fast(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+
 // ---- Box2D 2.3 settings (b2Settings.h) -------------------------------------------------------------
 #define NCG_B2_PI 3.14159265359f
 #define NCG_B2_EPS 1.1920928955078125e-7f

@@ -19,7 +19,7 @@ _SO = os.path.join(_PKG, "libncg_b200.so")
 _CSRC = os.path.join(_PKG, "csrc")
 _SOURCES = ("ncg_b200.cu", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -60,7 +60,7 @@ class Stats(ctypes.Structure):
 
 EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_upload_tracks", "ncg_reset", "ncg_step",
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
-           "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count")
+           "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned")
 
 _lib = None
 
@@ -90,6 +90,8 @@ def load_library():
     lib.ncg_set_state_host.argtypes = [vp, vp]
     lib.ncg_read_stats.argtypes = [vp, ctypes.POINTER(Stats), i32]
     lib.ncg_launch_count.argtypes = [vp]
+    lib.ncg_host_buffers.argtypes = [vp] + [ctypes.POINTER(vp)] * 6
+    lib.ncg_step_pinned.argtypes = [vp, i32, ctypes.POINTER(i32)]
     lib.ncg_launch_count.restype = ctypes.c_int64
     _lib = lib
     return lib
@@ -219,6 +221,27 @@ class Engine:
         fin = np.empty((N, 38), dtype=np.float32) if want_final else None
         _check(self._lib.ncg_step_host(self._h, _np_ptr(actions), _np_ptr(obs), _np_ptr(rew), _np_ptr(te), _np_ptr(tr), _np_ptr(fin)))
         return obs, rew, te, tr, fin
+
+    def pinned_views(self):
+        """numpy views of the library's page-locked staging buffers (ncg_host_buffers)."""
+        if getattr(self, "_views", None) is None:
+            N, E = self.num_cars, self.num_envs
+            ptrs = [ctypes.c_void_p() for _ in range(6)]
+            _check(self._lib.ncg_host_buffers(self._h, *[ctypes.byref(p) for p in ptrs]))
+
+            def view(ptr, ctype, n, shape):
+                return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(n,)).reshape(shape)
+            act = view(ptrs[0], ctypes.c_int32, N, (N,)) if self.discrete else view(ptrs[0], ctypes.c_float, 2 * N, (N, 2))
+            self._views = dict(actions=act, obs=view(ptrs[1], ctypes.c_float, N * 38, (N, 38)), reward=view(ptrs[2], ctypes.c_float, N, (N,)),
+                               terminated=view(ptrs[3], ctypes.c_uint8, E, (E,)), truncated=view(ptrs[4], ctypes.c_uint8, E, (E,)),
+                               final_obs=view(ptrs[5], ctypes.c_float, N * 38, (N, 38)))
+        return self._views
+
+    def step_pinned(self, want_final: bool = True) -> bool:
+        """Step with actions already written into pinned_views()['actions']; results are read in place."""
+        done = ctypes.c_int32(0)
+        _check(self._lib.ncg_step_pinned(self._h, int(want_final), ctypes.byref(done)))
+        return bool(done.value)
 
     def get_state_host(self) -> np.ndarray:
         out = np.empty((self.num_cars, L.RECORD_WORDS), dtype=np.float32)

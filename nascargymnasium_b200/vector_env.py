@@ -33,7 +33,9 @@ class NascarVectorEnv:
     metadata = {"render_modes": ["human"], "render_fps": 60, "autoreset_mode": "same_step"}
 
     def __init__(self, num_envs: int, track_file: Union[None, str, Sequence[str]] = None, num_cars: int = 1,
-                 discrete_action_space: bool = False, reset_on_lap: bool = False, device: int = 0, track_info: bool = False):
+                 discrete_action_space: bool = False, reset_on_lap: bool = False, device: int = 0, track_info: bool = False,
+                 copy: bool = True):
+        self.copy = copy            # False: step() returns views of the pinned staging buffers (valid until the next step)
         if num_cars < 1 or num_cars > K.MAX_CARS:
             raise ValueError(f"Number of cars must be between 1 and {K.MAX_CARS}")
         if track_file is None:
@@ -68,16 +70,22 @@ class NascarVectorEnv:
         return obs.reshape(self._obs_shape), {}
 
     def step(self, actions):
-        a = np.asarray(actions, dtype=np.int32 if self.discrete else np.float32)
-        obs, rew, te, tr, fin = self.engine.step_host(a, want_final=True)
-        te, tr = te.astype(bool), tr.astype(bool)
-        done = te | tr
-        rew = rew.reshape(self._rew_shape)
+        """actions: (E[,C],2) float32 in [-1,1] or (E[,C]) ints.  Host buffers in, host buffers out: the actions go through
+        the library's page-locked staging buffer, one packed D2H copy brings obs/reward/flags back."""
+        v = self.engine.pinned_views()
+        v["actions"][...] = np.asarray(actions).reshape(v["actions"].shape)
+        any_done = self.engine.step_pinned(want_final=True)
+        obs = v["obs"].reshape(self._obs_shape)
+        rew = v["reward"].reshape(self._rew_shape)
+        if self.copy:
+            obs, rew = obs.copy(), rew.copy()
+        te, tr = v["terminated"].astype(bool), v["truncated"].astype(bool)
         self._ep_len += 1
         self._ep_ret += rew
         info = {}
-        if done.any():
-            fin = fin.reshape(self._obs_shape)
+        if any_done:
+            done = te | tr
+            fin = v["final_obs"].reshape(self._obs_shape)
             fo = np.empty(self.num_envs, dtype=object)
             ep_r = np.zeros(self._rew_shape, dtype=np.float64)
             ep_l = np.zeros(self.num_envs, dtype=np.int64)
@@ -88,7 +96,7 @@ class NascarVectorEnv:
                     "episode": {"r": ep_r, "l": ep_l}, "_episode": done.copy()}
             self._ep_ret[done] = 0.0
             self._ep_len[done] = 0
-        return obs.reshape(self._obs_shape), rew, te, tr, info
+        return obs, rew, te, tr, info
 
     # ------------------------------------------------------------------ torch API (device-resident)
     def _bufs(self):

@@ -186,10 +186,16 @@ FLAG_MASK = sum(F[k] for k in ("NCG_F_AWAKE", "NCG_F_HAS_KEY", "NCG_F_DISABLED",
                                "NCG_F_BACK_ACTIVE", "NCG_F_CROSSED", "NCG_F_HAS_LAST", "NCG_F_HAS_BEST", "NCG_F_HAS_POS"))
 
 
-def compare_records(got: np.ndarray, want: np.ndarray, contact_fields: bool = True):
-    """Returns a list of (field, got, want) mismatches between an engine record and the oracle's."""
+def compare_records(got: np.ndarray, want: np.ndarray, contact_fields: bool = True, touching: bool = False):
+    """Returns a list of (field, got, want) mismatches between an engine record and the oracle's.
+
+    `touching`: the step solved contact constraints.  Box2D's 2-point block solver accepts effective-mass matrices with
+    condition numbers up to 1000 (b2ContactSolver: k_maxConditionNumber), which amplifies float32 rounding of its inputs
+    by that factor into the angular impulse, so on such steps the angular velocity is compared at 1e-3 rad/s absolute."""
     bad = []
     for name, (cnt, rtol, atol) in FLOAT_FIELDS.items():
+        if touching and name == "NCG_R_OMEGA":
+            atol = 1e-3
         a, b = got[R[name]:R[name] + cnt].astype(np.float64), want[R[name]:R[name] + cnt].astype(np.float64)
         if not np.all(np.abs(a - b) <= atol + rtol * np.abs(b)):
             bad.append((name, a.copy(), b.copy()))
@@ -348,8 +354,12 @@ def check_cases(got_records, got_obs, got_reward, got_te, got_tr, exp, label="")
     n = len(exp["reward"])
     bad, lines = 0, []
     for i in range(n):
-        b = compare_records(got_records[i], exp["records"][i])
-        dobs = float(np.abs(got_obs[i, :22] - exp["obs"][i, :22]).max())
+        touching = bool(exp["touching"][i] > 0)
+        b = compare_records(got_records[i], exp["records"][i], touching=touching)
+        d22 = np.abs(got_obs[i, :22] - exp["obs"][i, :22])
+        if touching:
+            d22[6] = max(0.0, d22[6] - 1e-4)          # obs[6] = omega / 10: see compare_records
+        dobs = float(d22.max())
         dsens = float(np.abs(got_obs[i, 22:] - exp["obs"][i, 22:]).max())
         drew = abs(float(got_reward[i]) - float(exp["reward"][i]))
         flags_ok = bool(got_te[i]) == bool(exp["terminated"][i]) and bool(got_tr[i]) == bool(exp["truncated"][i])

@@ -1,0 +1,169 @@
+"""GPU tests of the drop-in surfaces (CarEnv, NascarVectorEnv, rollout kernel, auto-reset) through the C ABI."""
+import numpy as np
+import pytest
+
+from nascargymnasium_b200 import layout as L
+from nascargymnasium_b200 import track as T
+from tests import parity_util as P
+
+pytestmark = pytest.mark.gpu
+R, F = L.R, L.F
+
+
+def test_car_env_mirror_matches_oracle_and_reference_info_keys():
+    from nascargymnasium_b200.car_env import CarEnv
+    from oracle import oracle as O
+    env = CarEnv(track_file="tracks/nascar.track")
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros(2, dtype=np.float32))
+    obs, info = env.reset(seed=3)
+    orc = O.OracleEnv(T.builtin_track_text("nascar"))
+    assert np.abs(obs - orc.reset()[0]).max() < 1e-6 and obs.shape == (38,) and obs.dtype == np.float32
+    for k in ("simulation_time", "num_cars", "followed_car_index", "termination_reason", "cars", "physics"):
+        assert k in info
+    for k in ("car_index", "disabled", "car_position", "car_speed_kmh", "car_speed_ms", "on_track", "performance", "lap_timing",
+              "cumulative_reward", "cumulative_impact_force"):
+        assert k in info["cars"][0]
+    assert set(info["cars"][0]["lap_timing"]) == {"current_lap_time", "last_lap_time", "best_lap_time", "lap_count", "is_timing",
+                                                  "has_crossed_startline", "total_distance_traveled", "formatted_current",
+                                                  "formatted_last", "formatted_best"}
+    with pytest.raises(AssertionError):
+        env.step(np.array([2.0, 0.0], dtype=np.float32))
+    rng = np.random.default_rng(0)
+    ret = 0.0
+    for t in range(300):
+        a = np.array([rng.uniform(0.3, 1), rng.uniform(-0.1, 0.1)], dtype=np.float32)
+        o, r, te, tr, info = env.step(a)
+        oo, ro, teo, tro = orc.step([a])
+        assert isinstance(te, bool) and isinstance(tr, bool) and o.shape == (38,)
+        assert np.abs(o - oo[0]).max() < 2e-3 and abs(r - ro[0]) < 1e-3 and (te, tr) == (teo, tro)
+        assert info["cars"][0]["on_track"] == orc.on_track()
+        ret += float(r)
+    assert info["simulation_time"] == pytest.approx(orc.sim_time, abs=1e-12)
+    assert info["cars"][0]["cumulative_reward"] == pytest.approx(ret, abs=1e-2)
+    # same-track reset goes through reset_car semantics and returns the start observation
+    obs2, _ = env.reset()
+    assert np.abs(obs2 - obs).max() < 1e-6
+    env.close()
+
+
+def test_stuck_rule_disables_at_step_600_with_plus_ten():
+    """zero action -> -0.05 per step, +10 and terminated at step 600 (all_cars_disabled)."""
+    from nascargymnasium_b200.car_env import CarEnv
+    env = CarEnv(track_file="tracks/daytona.track", discrete_action_space=True)
+    env.reset()
+    total = 0.0
+    for t in range(1, 601):
+        o, r, te, tr, info = env.step(0)
+        total += float(r)
+        if t < 600:
+            assert not te and r == pytest.approx(-0.05)
+    assert te and not tr and r == pytest.approx(10.0)
+    assert info["termination_reason"] == "all_cars_disabled" and env.disabled_cars == {0}
+    assert total == pytest.approx(10 - 599 * 0.05, abs=1e-3)
+    env.close()
+
+
+def test_multi_car_env_matches_oracle():
+    from nascargymnasium_b200.car_env import CarEnv
+    from oracle import oracle as O
+    C = 10
+    env = CarEnv(track_file="tracks/talladega.track", num_cars=C)
+    orc = O.OracleEnv(T.builtin_track_text("talladega"), num_cars=C)
+    obs, _ = env.reset()
+    assert obs.shape == (C, 38) and np.abs(obs - orc.reset()).max() < 1e-6
+    rng = np.random.default_rng(4)
+    for t in range(250):
+        a = np.stack([rng.uniform(0.2, 1.0, C), rng.uniform(-0.2, 0.6, C)], axis=1).astype(np.float32)
+        o, r, te, tr, info = env.step(a)
+        oo, ro, teo, tro = orc.step(a)
+        assert (te, tr) == (teo, tro), t
+        assert r.shape == (C,) and np.abs(r - ro).max() < 2e-3, t
+        assert np.abs(o - oo).max() < 5e-3, t
+        if te or tr:
+            env.reset(); orc.reset(fresh=False)
+    env.close()
+
+
+def test_vector_env_autoreset_and_final_observation():
+    from nascargymnasium_b200.vector_env import NascarVectorEnv
+    E = 64
+    venv = NascarVectorEnv(E, track_file="tracks/martinsville.track", discrete_action_space=True)
+    obs0, _ = venv.reset()
+    assert obs0.shape == (E, 38)
+    acts = np.zeros(E, dtype=np.int64)
+    acts[::2] = 1                                       # odd envs never move -> stuck-disabled at step 600
+    seen_done = False
+    for t in range(1, 602):
+        obs, rew, te, tr, info = venv.step(acts)
+        if t == 600:
+            assert te[1::2].all() and not te[::2].any()
+            assert info["_final_observation"].tolist() == te.tolist()
+            assert np.allclose(rew[1::2], 10.0)
+            # finished envs come back already reset: observation equals the start observation, final obs does not
+            assert np.abs(obs[1::2] - obs0[1::2]).max() < 1e-6
+            assert info["episode"]["l"][1] == 600 and info["episode"]["r"][1] == pytest.approx(10 - 599 * 0.05, abs=1e-3)
+            seen_done = True
+    assert seen_done
+    venv.close()
+
+
+def test_rollout_kernel_equals_single_steps_with_the_same_philox_actions():
+    import bench
+    import torch
+    from nascargymnasium_b200.engine import Engine
+    E, Tn = 256, 40
+    a = Engine(E, 1, tracks=["michigan"], auto_reset=True)
+    b = Engine(E, 1, tracks=["michigan"], auto_reset=True)
+    a.reset_host(); b.reset_host()
+    obs_roll = torch.empty((Tn, E, 38), dtype=torch.float32, device="cuda:0")
+    rew_roll = torch.empty((Tn, E), dtype=torch.float32, device="cuda:0")
+    a.rollout(Tn, seed=5, mode=0, obs_rollout=obs_roll.view(-1), reward_rollout=rew_roll.view(-1))
+    torch.cuda.synchronize()
+    cars = np.arange(E)
+    for t in range(Tn):
+        obs, rew, te, tr, _ = b.step_host(bench.synthetic_actions(5, cars, t))
+        assert np.abs(obs - obs_roll[t].cpu().numpy()).max() < 1e-6, t
+        assert np.abs(rew - rew_roll[t].cpu().numpy()).max() < 1e-6, t
+    assert np.array_equal(a.get_state_host(), b.get_state_host())
+    a.close(); b.close()
+
+
+def test_torch_device_path_keeps_observations_on_device():
+    import torch
+    from nascargymnasium_b200.vector_env import NascarVectorEnv
+    venv = NascarVectorEnv(512, track_file=None)        # all 8 tracks, sorted by track id
+    obs = venv.reset_torch()
+    assert obs.is_cuda and obs.shape == (512, 38)
+    act = torch.rand((512, 2), device="cuda:0") * 2 - 1
+    for _ in range(20):
+        obs, rew, te, tr, fin = venv.step_torch(act)
+    torch.cuda.synchronize()
+    assert obs.is_cuda and torch.isfinite(obs).all() and rew.shape == (512,)
+    st = venv.engine.read_stats()
+    assert st["car_steps"] == 512 * 20
+    recs = venv.engine.get_state_host()
+    assert sorted(set(recs.view(np.uint32)[:, R["NCG_R_TRACK"]].tolist())) == list(range(8))
+    venv.close()
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 shape (8192 envs x 10 cars on talladega): size-independent invariants after a driving rollout."""
+    import torch
+    from nascargymnasium_b200.engine import Engine
+    eng = Engine(8192, 10, tracks=["talladega"], auto_reset=True)
+    eng.reset_host()
+    last = torch.empty((81920, 38), dtype=torch.float32, device="cuda:0")
+    eng.rollout(120, seed=9, mode=1, obs_last=last.view(-1))
+    torch.cuda.synchronize()
+    o = last.cpu().numpy()
+    assert np.isfinite(o).all() and o.min() >= -1.0 and o.max() <= 1.0
+    assert (o[:, 4] >= 0).all() and (o[:, 22:] >= 0).all()
+    st = eng.read_stats()
+    assert st["car_steps"] == 81920 * 120 and st["overflow"] == 0
+    recs = eng.get_state_host()
+    u = recs.view(np.uint32)
+    steps = u[:, R["NCG_R_STEP"]].reshape(8192, 10)
+    assert (steps == steps[:, :1]).all()                  # cars of an env share the env clock
+    assert ((u[:, R["NCG_R_NCONTACT"]] & 255) <= L.MAX_CONTACTS).all()
+    eng.close()
