@@ -244,7 +244,7 @@ def run_ours(args):
                                f"actions ~ U[-1,1]^2 (Philox on device), 16-ray observations written every step, same-step auto-reset",
                    "envs_per_gpu": E, "cars_per_env": C, "track": track, "steps_per_launch": T,
                    "l2": "flushed (256 MiB memset) between timed launches; the working set itself is L2-resident by construction",
-                   "cars_per_warp": os.environ.get("NCG_CARS_PER_WARP", "auto")},
+                   "rays_per_lane": os.environ.get("NCG_RAYS_PER_LANE", "2")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated"},
         "gpu_launches": int(gpu_launches),

@@ -1,12 +1,16 @@
 // ncg_b200.cu -- kernels and the C ABI (include/ncg_b200.h) of the batched CarEnv stepping engine.
 //
-// Work decomposition (DESIGN.md "Kernels"): a warp owns G consecutive car records (G = 1, 2, 4 or 8).
-// The scalar phases of a car-step (dynamics, tyres, Box2D step, lap timer, reward) run one car per lane on
-// lanes < G; the sensor phase spreads the warp's G*16 rays over all 32 lanes.  A CTA owns whole envs, so the
-// env-level termination of a multi-car env is a shared-memory exchange behind one __syncthreads().
-// Records live in shared memory for the duration of a launch and move to/from HBM as coalesced 16-byte
-// accesses; in the multi-step rollout kernel the CTA's track table is staged into shared memory once with a
-// TMA bulk copy (cp.async.bulk + mbarrier) and stays resident across all T steps.
+// Work decomposition (DESIGN.md "Kernels"): a CTA owns up to 32 car slots (whole envs) and is warp-specialised.
+//   warp 0  ("physics warp")  one car per lane: action -> forces -> tyres -> b2World.Step -> lap timer -> disable
+//                             rules -> obs[0..21] -> reward -> env termination -> same-step auto-reset.
+//   warps 1..RW ("ray warps") the CTA's 32 x 16 sensor rays, RPL rays per lane, then the coalesced store of the
+//                             finished 38-float observation rows to HBM.
+// The two halves are a producer/consumer pair over a double-buffered pose + observation block in shared memory,
+// handed over with named barriers (bar.sync / bar.arrive), so in a multi-step rollout the physics of step t+1
+// overlaps the rays of step t.  Records stay in shared memory for the whole launch (row stride 129 words: lane l
+// reading word k of its own record hits bank (l+k) mod 32, conflict-free) and move to/from HBM as coalesced
+// 16-byte accesses; the CTA's track table is staged into shared memory once per launch with a TMA bulk copy
+// (cp.async.bulk + mbarrier).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string>
@@ -32,21 +36,27 @@ struct KParams {
     DevStats* stats;
 };
 
-#define OBS_PAD 40
+#define CPB 32                    /* car slots per CTA = lanes of the physics warp */
+#define REC_STRIDE 129            /* shared-memory row stride of a record (odd: conflict-free column access) */
+#define OBS_STRIDE 41             /* shared-memory row stride of an observation row */
+#define BAR_FULL 1                /* named barriers 1,2: buffer b filled by the physics warp */
+#define BAR_EMPTY 3               /* named barriers 3,4: buffer b drained by the ray warps */
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS).
-__device__ __forceinline__ void tma_stage(float* dst, const float* src, unsigned bytes, unsigned long long* mbar) {
-    if (threadIdx.x == 0) {
-        unsigned mb = smem_u32(mbar);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
-    }
-    __syncthreads();
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP + SYNCS).  Issue and wait are split
+// so the record load overlaps the copy.
+__device__ __forceinline__ void tma_issue(float* dst, const float* src, unsigned bytes, unsigned long long* mbar) {
+    unsigned mb = smem_u32(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+}
+__device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
     unsigned mb = smem_u32(mbar), ok = 0;
     while (!ok) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
@@ -60,160 +70,194 @@ __device__ __noinline__ void reset_in_place(float* R, const Track& T, float* obs
     observe_state(R, obs);
 }
 
-// Sensor phase: lane <-> (car of this warp, ray).  `only_done`: cast only for cars that were just reset.
-template <int G>
-__device__ __forceinline__ unsigned sensor_phase(const KParams& p, const float* s_rec, float* s_obs, const Track& Tw, bool warp_uniform,
-                                                 const float* staged, int warp, int lane, int n_cars, bool only_done, const uint32_t* s_done) {
-    unsigned tests = 0;
-#pragma unroll 1
-    for (int task = lane; task < G * 16; task += 32) {
-        const int sl = warp * G + (task >> 4);
-        if (sl < n_cars && (!only_done || s_done[sl])) {
-            const float* Rr = s_rec + sl * NCG_RECORD_WORDS;
-            float d;
-            if (warp_uniform) d = cast_ray(Tw, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests);
-            else {
-                const float* g = p.blob + p.track_off[f2u(Rr[NCG_R_TRACK])];
-                const Track T = track_view(staged ? staged : g, g);
-                d = cast_ray(T, Rr[NCG_R_X], Rr[NCG_R_Y], Rr[NCG_R_ANGLE], task & 15, &tests);
-            }
-            s_obs[sl * OBS_PAD + 22 + (task & 15)] = sensor_obs(d);
-        }
-    }
-    return tests;
+struct SmemLayout {
+    int rec, obs, obs2, pose, pose2, flag, xf, track, total;      // word offsets
+};
+__host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
+    SmemLayout L; int o = 0;
+    L.rec = o; o += CPB * REC_STRIDE;
+    L.obs = o; o += 2 * CPB * OBS_STRIDE;          // [2][CPB][OBS_STRIDE]: the step's observation rows
+    L.obs2 = o; o += 2 * CPB * OBS_STRIDE;         // [2][CPB][OBS_STRIDE]: reset observation rows of finished cars
+    o = (o + 3) & ~3;
+    L.pose = o; o += 2 * CPB * 4;                  // [2][CPB] float4 {x, y, angle, -}
+    L.pose2 = o; o += 2 * CPB * 4;
+    L.flag = o; o += 2 * CPB;                      // [2][CPB] u32: bit0 terminated, bit1 truncated
+    L.xf = o; o += CPB;
+    o = (o + 3) & ~3;
+    L.track = o; o += (int)stage_words;            // 16-byte aligned for the TMA copy
+    L.total = o;
+    return L;
 }
 
-template <int G>
-__global__ void __launch_bounds__(320) ncg_step_kernel(KParams p) {
+template <int RPL>
+__global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p) {
+    constexpr int RW = 16 / RPL;                    // ray warps
+    constexpr int NT = 32 * (1 + RW);
+    constexpr int LPC = 16 / RPL;                   // lanes per car in a ray warp
+    constexpr int CPW = 32 / LPC;                   // cars per ray warp
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long s_mbar;
+    const SmemLayout L = smem_layout(0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cpc = p.epb * p.C;                      // car slots per CTA
-    float* s_rec = smem;                              // [cpc][128]
-    float* s_obs = s_rec + cpc * NCG_RECORD_WORDS;    // [cpc][OBS_PAD]
-    uint32_t* s_xf = (uint32_t*)(s_obs + cpc * OBS_PAD);
-    float* s_rew = (float*)(s_xf + cpc);
-    uint32_t* s_done = (uint32_t*)(s_rew + cpc);      // per car slot: bit0 terminated, bit1 truncated
-    float* s_track = smem + ((cpc * (NCG_RECORD_WORDS + OBS_PAD + 3) + 3) & ~3);   // 16-byte aligned for the TMA copy
+    float* s_rec = smem + L.rec;
+    float* s_obs = smem + L.obs;
+    float* s_obs2 = smem + L.obs2;
+    float4* s_pose = reinterpret_cast<float4*>(smem + L.pose);
+    float4* s_pose2 = reinterpret_cast<float4*>(smem + L.pose2);
+    uint32_t* s_flag = reinterpret_cast<uint32_t*>(smem + L.flag);
+    uint32_t* s_xf = reinterpret_cast<uint32_t*>(smem + L.xf);
+    float* s_track = smem + L.track;
 
     const int env0 = blockIdx.x * p.epb;
     const int n_env = min(p.epb, p.E - env0);
     const int n_cars = n_env * p.C, car0 = env0 * p.C;
     const int N = p.E * p.C;
 
-    // ---- records HBM -> shared (coalesced float4)
-    {
-        const float4* src = reinterpret_cast<const float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
-        float4* dst = reinterpret_cast<float4*>(s_rec);
-        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    // ---- track table: staged by TMA when the whole CTA shares a track (rollout kernel), else read through L1/L2
+    // ---- track table: staged by TMA when the whole CTA shares a track, else read through L1/L2
     const float* staged = nullptr;
     if (p.stage) {
-        const float* g = p.blob + p.track_off[f2u(s_rec[NCG_R_TRACK])];
-        unsigned words = f2u(__ldg(g + TH_STAGE_WORDS));
-        tma_stage(s_track, g, words * 4u, &s_mbar);
+        if (threadIdx.x == 0) {
+            const uint32_t tid = f2u(p.records[(size_t)car0 * NCG_RECORD_WORDS + NCG_R_TRACK]);
+            const float* g = p.blob + p.track_off[tid];
+            tma_issue(s_track, g, f2u(__ldg(g + TH_STAGE_WORDS)) * 4u, &s_mbar);
+        }
         staged = s_track;
     }
+    // ---- records HBM -> shared (coalesced float4 reads, scalar shared stores into the padded rows)
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
+        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += NT) {
+            const float4 v = src[i];
+            float* d = s_rec + (i >> 5) * REC_STRIDE + (i & 31) * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+    __syncthreads();
+    if (p.stage) tma_wait(&s_mbar);
 
-    const int slot = warp * G + lane;                 // car slot for the scalar phases
-    const bool active = lane < G && slot < n_cars;
-    float* R = s_rec + (active ? slot : 0) * NCG_RECORD_WORDS;
-    Counters cnt = {0, 0, 0, 0, 0};
-    unsigned long long episodes = 0; double ret_sum = 0.0;
+    // the car slot this thread serves: its lane (physics warp) or the car its rays belong to (ray warps)
+    const int slot = warp == 0 ? lane : (warp - 1) * CPW + lane / LPC;
+    const bool active = slot < n_cars;
     // track views are fixed for the launch (auto-reset keeps an env on its track): build them once
-    const int wslot0 = min(warp * G, max(n_cars - 1, 0));
-    const uint32_t my_tid = f2u(s_rec[(active ? slot : wslot0) * NCG_RECORD_WORDS + NCG_R_TRACK]);
-    const bool warp_uniform = __all_sync(0xffffffffu, my_tid == f2u(s_rec[wslot0 * NCG_RECORD_WORDS + NCG_R_TRACK]));
+    const uint32_t my_tid = f2u(s_rec[(active ? slot : 0) * REC_STRIDE + NCG_R_TRACK]);
     const float* gblob = p.blob + p.track_off[my_tid];
     const Track T = track_view(staged ? staged : gblob, gblob);
+    const bool do_reset = p.auto_reset != 0;
+    unsigned long long ray_tests = 0;
 
-    for (int t = 0; t < p.T; ++t) {
-        float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
-        float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
-        // ---- A: scalar car phase
-        if (active) {
-            float thr, brk, st;
-            const int gc = car0 + slot;
-            if (p.actions) {
-                if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
-                else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
-            } else action_synthetic(p.seed, (uint32_t)gc, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
-            uint32_t xf;
-            s_rew[slot] = car_step(R, T, thr, brk, st, p.contacts != 0, s_obs + slot * OBS_PAD, &xf, &cnt);
-            s_xf[slot] = xf;
-            if (p.track_info) {
-                uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
-                if (on_track(T, R[NCG_R_X], R[NCG_R_Y])) fl |= NCG_F_ON_TRACK;
-                R[NCG_R_FLAGS] = u2f(fl);
+    if (warp == 0) {
+        // =============================================================== physics warp: one car per lane
+        float* R = s_rec + (active ? slot : 0) * REC_STRIDE;
+        Counters cnt = {0, 0, 0, 0, 0};
+        unsigned long long episodes = 0; double ret_sum = 0.0;
+        for (int t = 0; t < p.T; ++t) {
+            const int b = t & 1;
+            if (t >= 2) bar_sync(BAR_EMPTY + b, NT);            // the ray warps have drained buffer b (step t-2)
+            float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
+            float rew = 0.0f;
+            if (active) {
+                float thr, brk, st;
+                const int gc = car0 + slot;
+                if (p.actions) {
+                    if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
+                    else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
+                } else action_synthetic(p.seed, (uint32_t)gc, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
+                uint32_t xf;
+                rew = car_step(R, T, thr, brk, st, p.contacts != 0, s_obs + (b * CPB + slot) * OBS_STRIDE, &xf, &cnt);
+                s_xf[slot] = xf;
+                if (p.track_info) {
+                    uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
+                    if (on_track(T, R[NCG_R_X], R[NCG_R_Y])) fl |= NCG_F_ON_TRACK;
+                    R[NCG_R_FLAGS] = u2f(fl);
+                }
             }
-        }
-        __syncwarp();
-        // ---- B: sensor phase, the warp's G*16 rays over 32 lanes
-        cnt.ray_tests += sensor_phase<G>(p, s_rec, s_obs, T, warp_uniform, staged, warp, lane, n_cars, false, s_done);
-        if (p.C > 1) __syncthreads(); else __syncwarp();
-        // ---- C: env phase (every car of an env computes the same decision from the env's xf words)
-        bool done = false;
-        if (active) {
-            const int le = slot / p.C;
-            bool te, tr; int why;
-            env_decide(s_xf + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
-            float rew = s_rew[slot];
-            car_finish(R, rew);
-            rew_out[car0 + slot] = rew;
-            done = te || tr;
-            s_done[slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
-            if (slot % p.C == 0) {
-                const int ge = env0 + le;
-                if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
-                else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
-                if (done) ++episodes;
-            }
-            if (done) ret_sum += (double)R[NCG_R_CUM_REWARD];
-        }
-        __syncwarp();
-        // ---- D: observations shared -> HBM (coalesced), terminal observations of finished envs to final_obs
-        const bool do_reset = p.auto_reset != 0;
-        for (int i = lane; i < G * NCG_OBS_DIM; i += 32) {
-            int sl = warp * G + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
-            if (sl < n_cars) {
-                float v = s_obs[sl * OBS_PAD + k];
-                size_t o = (size_t)(car0 + sl) * NCG_OBS_DIM + k;
-                if (s_done[sl] && do_reset) { if (p.final_obs) p.final_obs[o] = v; }
-                else if (obs_out) obs_out[o] = v;
-            }
-        }
-        // ---- E: same-step auto-reset (CarPhysics.reset_car semantics) + reset observation
-        if (do_reset && __any_sync(0xffffffffu, active && done)) {
-            if (active && done) reset_in_place(R, T, s_obs + slot * OBS_PAD);
             __syncwarp();
-            cnt.ray_tests += sensor_phase<G>(p, s_rec, s_obs, T, warp_uniform, staged, warp, lane, n_cars, true, s_done);
-            __syncwarp();
-            for (int i = lane; i < G * NCG_OBS_DIM; i += 32) {
-                int sl = warp * G + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
-                if (sl < n_cars && s_done[sl] && obs_out) obs_out[(size_t)(car0 + sl) * NCG_OBS_DIM + k] = s_obs[sl * OBS_PAD + k];
+            // ---- env phase (every car of an env computes the same decision from the env's xf words)
+            if (active) {
+                const int le = slot / p.C;
+                bool te, tr; int why;
+                env_decide(s_xf + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
+                car_finish(R, rew);
+                if (rew_out) rew_out[car0 + slot] = rew;
+                const bool done = te || tr;
+                if (slot == le * p.C) {
+                    const int ge = env0 + le;
+                    if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
+                    else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
+                    if (done) ++episodes;
+                }
+                if (done) ret_sum += (double)R[NCG_R_CUM_REWARD];
+                s_pose[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
+                // ---- same-step auto-reset (CarPhysics.reset_car semantics) + reset observation words 0..21
+                if (done && do_reset) {
+                    reset_in_place(R, T, s_obs2 + (b * CPB + slot) * OBS_STRIDE);
+                    s_pose2[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
+                }
+                s_flag[b * CPB + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
             }
+            __syncwarp();
+            __threadfence_block();
+            bar_arrive(BAR_FULL + b, NT);
         }
-        if (p.C > 1) __syncthreads(); else __syncwarp();
+        // ---- counters
+        unsigned long long v[7] = {active ? (unsigned long long)p.T : 0ull, episodes, cnt.laps, 0ull, cnt.contact_steps, cnt.toi_events, cnt.overflow};
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            unsigned long long x = v[k];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0 && x) atomicAdd(((unsigned long long*)p.stats) + k, x);
+        }
+        for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_down_sync(0xffffffffu, ret_sum, o);
+        if (lane == 0 && ret_sum != 0.0) atomicAdd(&p.stats->return_sum, ret_sum);
+    } else {
+        // =============================================================== ray warps: RPL rays per lane
+        const int q = lane % LPC;
+        const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // a lane's rays are q0, q0+4, ... (90 deg apart)
+        const int wslot0 = (warp - 1) * CPW;                     // first car slot of this warp
+        unsigned tests = 0;
+        for (int t = 0; t < p.T; ++t) {
+            const int b = t & 1;
+            float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
+            bar_sync(BAR_FULL + b, NT);
+            if (active) {
+                const bool rs = do_reset && s_flag[b * CPB + slot] != 0u;
+                if (!rs || p.final_obs) {
+                    const float4 ps = s_pose[b * CPB + slot];
+                    cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
+                }
+                if (rs) {
+                    const float4 ps = s_pose2[b * CPB + slot];
+                    cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
+                }
+            }
+            __syncwarp();
+            // ---- observation rows of this warp's cars shared -> HBM (CPW x 38 consecutive floats)
+            for (int i = lane; i < CPW * NCG_OBS_DIM; i += 32) {
+                const int sl = wslot0 + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
+                if (sl < n_cars) {
+                    const size_t o = (size_t)(car0 + sl) * NCG_OBS_DIM + k;
+                    const int row = (b * CPB + sl) * OBS_STRIDE + k;
+                    if (do_reset && s_flag[b * CPB + sl] != 0u) {
+                        if (p.final_obs) p.final_obs[o] = s_obs[row];
+                        if (obs_out) obs_out[o] = s_obs2[row];
+                    } else if (obs_out) obs_out[o] = s_obs[row];
+                }
+            }
+            if (t + 2 < p.T) bar_arrive(BAR_EMPTY + b, NT);
+        }
+        ray_tests = tests;
+        for (int o = 16; o > 0; o >>= 1) ray_tests += __shfl_down_sync(0xffffffffu, ray_tests, o);
+        if (lane == 0 && ray_tests) atomicAdd(((unsigned long long*)p.stats) + 3, ray_tests);
     }
     // ---- records shared -> HBM
     __syncthreads();
     {
         float4* dst = reinterpret_cast<float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
-        const float4* src = reinterpret_cast<const float4*>(s_rec);
-        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += NT) {
+            const float* d = s_rec + (i >> 5) * REC_STRIDE + (i & 31) * 4;
+            dst[i] = make_float4(d[0], d[1], d[2], d[3]);
+        }
     }
-    // ---- counters
-    unsigned long long v[7] = {active ? (unsigned long long)p.T : 0ull, episodes, cnt.laps, cnt.ray_tests, cnt.contact_steps, cnt.toi_events, cnt.overflow};
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        unsigned long long x = v[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(((unsigned long long*)p.stats) + k, x);
-    }
-    for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_down_sync(0xffffffffu, ret_sum, o);
-    if (lane == 0 && ret_sum != 0.0) atomicAdd(&p.stats->return_sum, ret_sum);
 }
 
 // reset of masked envs + their initial observation; one warp per car (rays over lanes)
@@ -225,7 +269,7 @@ __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const fl
     const int env = car / C;
     if (mask && !mask[env]) return;
     float* R = records + (size_t)car * NCG_RECORD_WORDS;
-    __shared__ float s_obs[8][OBS_PAD];
+    __shared__ float s_obs[8][40];
     float* so = s_obs[threadIdx.x >> 5];
     uint32_t tid = track_id ? (uint32_t)track_id[env] : f2u(R[NCG_R_TRACK]);
     const float* g = blob + track_off[tid];
@@ -234,7 +278,7 @@ __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const fl
     __syncwarp();
     if (obs) {
         unsigned tests = 0;
-        if (lane < 16) so[22 + lane] = sensor_obs(cast_ray(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], lane, &tests));
+        if (lane < 16) cast_rays<1>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], lane, so + 22, &tests);
         __syncwarp();
         for (int k = lane; k < NCG_OBS_DIM; k += 32) obs[(size_t)car * NCG_OBS_DIM + k] = so[k];
     }
@@ -250,7 +294,7 @@ struct NcgHandle {
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0;
-    int cars_per_warp = 1;
+    int rays_per_lane = 2;
     long long launches = 0;
     // host-buffer path
     cudaStream_t stream = nullptr;
@@ -263,17 +307,16 @@ struct NcgHandle {
 namespace {
 
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
-    const int C = h->cfg.cars_per_env, G = h->cars_per_warp;
-    int epb = (8 * G) / C; if (epb < 1) epb = 1;
-    const int cpc = epb * C;
-    const int warps = (cpc + G - 1) / G;
+    const int C = h->cfg.cars_per_env, RPL = h->rays_per_lane;
+    const int epb = CPB / C;                                   // whole envs per CTA (C <= 10 < CPB)
     p.epb = epb;
-    size_t smem = (size_t)((cpc * (NCG_RECORD_WORDS + OBS_PAD + 3) + 3) & ~3) * 4;
-    if (p.stage) { unsigned mx = 0; for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx; smem += (size_t)mx * 4; }
+    unsigned mx = 0;
+    if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
+    const size_t smem = (size_t)smem_layout(mx).total * 4;
     const int grid = (h->cfg.num_envs + epb - 1) / epb;
-    void (*k)(KParams) = G == 1 ? ncg_step_kernel<1> : G == 2 ? ncg_step_kernel<2> : G == 4 ? ncg_step_kernel<4> : ncg_step_kernel<8>;
+    void (*k)(KParams) = RPL == 1 ? ncg_step_kernel<1> : RPL == 4 ? ncg_step_kernel<4> : ncg_step_kernel<2>;
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, warps * 32, smem, s>>>(p);
+    k<<<grid, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     return NCG_OK;
@@ -304,10 +347,10 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaSetDevice(cfg->device));
     NcgHandle* h = new NcgHandle();
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
-    const char* g = getenv("NCG_CARS_PER_WARP");
-    int G = g ? atoi(g) : 0;
-    if (G != 1 && G != 2 && G != 4 && G != 8) G = h->N >= 32768 ? 8 : (h->N >= 2048 ? 4 : (h->N >= 512 ? 2 : 1));   // measured: profiles/
-    h->cars_per_warp = G;
+    const char* g = getenv("NCG_RAYS_PER_LANE");
+    int rpl = g ? atoi(g) : 0;
+    if (rpl != 1 && rpl != 2 && rpl != 4) rpl = 2;                // measured: profiles/
+    h->rays_per_lane = rpl;
     size_t N = (size_t)h->N, E = (size_t)cfg->num_envs;
     CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));
     CUDA_TRY(cudaMemset(h->d_records, 0, N * NCG_RECORD_WORDS * 4));
@@ -359,6 +402,17 @@ static void note_tracks(NcgHandle* h, const uint8_t* mask, const int32_t* tid) {
     if (!tid) return;
     for (int e = 0; e < h->cfg.num_envs; ++e) if (!mask || mask[e]) h->h_env_track[e] = tid[e];
 }
+// a CTA stages one track table: that needs all of its envs on the same track
+static void update_grouping(NcgHandle* h) {
+    const int epb = CPB / h->cfg.cars_per_env;
+    bool ok = true;
+    for (int e = 0; e < h->cfg.num_envs && ok; ++e) if (h->h_env_track[e] != h->h_env_track[(e / epb) * epb]) ok = false;
+    h->tracks_grouped = ok;
+}
+static int want_stage(const NcgHandle* h) {
+    const char* ns = getenv("NCG_NO_STAGE");
+    return (h->tracks_grouped && !(ns && atoi(ns))) ? 1 : 0;
+}
 
 int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id, int32_t fresh, float* d_obs, void* stream) {
     if (!h) return fail(NCG_E_INVALID, "null handle");
@@ -383,6 +437,7 @@ int ncg_step(NcgHandle* h, const void* d_actions, float* d_obs, float* d_reward,
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams p = base_params(h);
     p.actions = d_actions; p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated; p.final_obs = d_final_obs;
+    p.stage = want_stage(h);
     return launch_step(h, p, (cudaStream_t)stream);
 }
 
@@ -396,8 +451,7 @@ int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float*
     p.obs_roll = d_obs_rollout; p.rew_roll = d_reward_rollout; p.done_roll = d_done_rollout; p.obs = d_obs_last; p.reward = nullptr;
     if (!d_reward_rollout) { p.reward = h->d_reward; }
     p.term = h->d_term; p.trunc = h->d_trunc;
-    const char* ns = getenv("NCG_NO_STAGE");
-    p.stage = (h->tracks_grouped && !(ns && atoi(ns))) ? 1 : 0;
+    p.stage = want_stage(h);
     h->step_base += (unsigned)steps;
     return launch_step(h, p, (cudaStream_t)stream);
 }
@@ -412,12 +466,7 @@ int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_tra
     int rc = ncg_reset(h, h_env_mask ? h->d_mask : nullptr, h_track_id ? h->d_tid : nullptr, fresh, h->d_obs, h->stream);
     if (rc) return rc;
     note_tracks(h, h_env_mask, h_track_id);
-    {   // the rollout kernel stages one track per CTA: that needs every CTA's envs on one track
-        const int C = h->cfg.cars_per_env, G = h->cars_per_warp; int epb = (8 * G) / C; if (epb < 1) epb = 1;
-        bool ok = true;
-        for (size_t e = 0; e < E && ok; ++e) if (h->h_env_track[e] != h->h_env_track[(e / epb) * epb]) ok = false;
-        h->tracks_grouped = ok;
-    }
+    update_grouping(h);
     if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, (size_t)h->N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return NCG_OK;
@@ -506,7 +555,7 @@ int ncg_set_state_host(NcgHandle* h, const float* h_records) {
         if ((int)t >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
         h->h_env_track[e] = (int)t;
     }
-    h->tracks_grouped = false;
+    update_grouping(h);
     h->was_reset = true;
     return NCG_OK;
 }

@@ -1052,39 +1052,45 @@ NCG_HD void car_finish(float* R, float reward) {
     R[NCG_R_FLAGS] = u2f(f2u(R[NCG_R_FLAGS]) | NCG_F_HAS_KEY);
 }
 
-// ------------------------------------------------------------------ one sensor ray (distance_sensor.py:71-117)
-// Returns the hit distance in metres (250 if nothing is hit).  Uniform-grid DDA over the wall boxes; each
-// candidate is tested with b2PolygonShape::RayCast's arithmetic, the minimum entry fraction wins.
-// b2PolygonShape::RayCast for a box, branch-free.  For the four box edges the generic dot(n_i, v_i - p1) and
-// dot(n_i, d) reduce exactly (x*0 = 0, x*1 = x, x*-1 = -x) to the expressions below, so every quotient is the
-// float32 value Box2D computes; the early exits of the reference loop are equivalent to testing at the end
-// because `lower` only grows and `upper` only shrinks.
-NCG_HD float ray_box_fraction(const float* w, V2 P1, V2 P2, float maxFraction) {
-    const float c = w[2], s = w[3], hx = w[4], hy = w[5];
-    const float ax = P1.x - w[0], ay = P1.y - w[1], bx = P2.x - w[0], by = P2.y - w[1];
-    const float p1x = c * ax + s * ay, p1y = -s * ax + c * ay;
-    const float p2x = c * bx + s * by, p2y = -s * bx + c * by;
-    const float dx = p2x - p1x, dy = p2y - p1y;
-    const float num[4] = {-((-hy) - p1y), hx - p1x, hy - p1y, -((-hx) - p1x)};
-    const float den[4] = {-dy, dx, dy, -dx};
-    float lower = 0.0f, upper = maxFraction; bool hit = false, miss = false;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float q = fdiv_fast(num[i], den[i]);
-        const bool zero = den[i] == 0.0f;
-        const bool enter = den[i] < 0.0f && num[i] < lower * den[i];
-        const bool leave = den[i] > 0.0f && num[i] < upper * den[i];
-        miss = miss || (zero && num[i] < 0.0f);
-        lower = enter ? q : lower; hit = hit || enter;
-        upper = (!enter && leave) ? q : upper;
-        miss = miss || upper < lower;
-    }
-    return (hit && !miss) ? lower : -1.0f;
+NCG_HD float sensor_obs_m(float dist) { float n = dist * 0.004f; return n < 0.0f ? 0.0f : (n > 1.0f ? 1.0f : n); }
+// ------------------------------------------------------------------ sensor rays (distance_sensor.py:71-117)
+// 16 rays per car from the body origin, direction = heading - i*22.5 deg, length 250 m, nearest wall-box entry.
+// The reference goes through b2World::RayCast -> b2PolygonShape::RayCast per fixture; here a uniform-grid DDA
+// (32 m cells, CSR lists in the staged track table) visits the boxes near the ray and each candidate gets a slab
+// test in the box frame: entry/exit distances along the unit direction, MUFU.RCP reciprocals and FFMA products.
+// That is the same intersection as Box2D's half-plane clipping (a hit needs an entry crossing at t > 0, so an
+// origin inside a box reports nothing for that box) evaluated to ~1e-6 relative instead of bit-for-bit: rays only
+// feed obs[22..37], whose stated tolerance is 1e-3 normalised (0.25 m); tests/hostcheck compares this traversal
+// with Box2D's own clipping arithmetic over all walls.
+NCG_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
 }
-NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, unsigned* tests) {
-    // direction = heading rotated by -i*22.5 deg.  The reference evaluates cos/sin(theta - i*pi/8) in float64
-    // (distance_sensor.py:95-103); rotating the float32 heading by a constant table keeps the axis-aligned rays
-    // of the start pose (theta = 0) exactly axis-aligned, as they are in float64, instead of 4e-8 rad off.
+// entry distance (metres) of the ray origin (px,py), unit direction (dx,dy) into wall row w, or -1
+NCG_HD float ray_box_slab(const float* w, float px, float py, float dx, float dy, float tmax) {
+    const float c = w[2], s = w[3];
+    const float ax = w[0] - px, ay = w[1] - py;
+    const float mx = fmaf(c, ax, s * ay), my = fmaf(c, ay, -(s * ax));      // box centre seen from the origin, box frame
+    // direction in the box frame; the 1e-30 keeps a ray parallel to a face off 0*inf = NaN when its origin lies
+    // exactly in the face's plane (every car starts at x = 0, where two wall boxes abut)
+    const float ex = fmaf(c, dx, fmaf(s, dy, 1e-30f)), ey = fmaf(c, dy, fmaf(-s, dx, 1e-30f));
+    const float ix = rcp_fast(ex), iy = rcp_fast(ey);
+    const float x0 = (mx - w[4]) * ix, x1 = (mx + w[4]) * ix, y0 = (my - w[5]) * iy, y1 = (my + w[5]) * iy;
+    const float tn = fmaxf(fminf(x0, x1), fminf(y0, y1)), tf = fminf(fmaxf(x0, x1), fmaxf(y0, y1));
+    return (tn > 0.0f && tn <= tf && tn < tmax) ? tn : -1.0f;
+}
+#define NCG_RAY_LEN 250.0f
+// One lane's RPL rays of one car: ray indices q0, q0+4, ... (successive rays are 90 deg apart, so a lane's total
+// work mixes along-track and across-track rays and the lanes of a warp finish together).  All RPL rays run in one
+// flattened loop -- every iteration is "leave the cell if its list is exhausted, then test one candidate" -- so
+// lanes never sit in different loop nests.  Normalised distances go to dst[q0 + 4*j].
+template <int RPL>
+NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
+    // cos/sin(-q0*22.5 deg): the reference evaluates cos/sin(theta - i*pi/8) in float64 (distance_sensor.py:95-103);
+    // rotating the float32 heading by a constant keeps the axis-aligned rays of the start pose exactly axis-aligned.
     const float kc[16] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.0f, -0.38268343236508977f,
                           -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f, -0.70710678118654752f,
                           -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
@@ -1092,49 +1098,64 @@ NCG_HD float cast_ray(const Track& T, float px, float py, float angle, int i, un
                           -0.70710678118654752f, -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f,
                           0.92387953251128674f, 1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
     float sa, ca; sincosf(angle, &sa, &ca);
-    float dx = ca * kc[i] - sa * ks[i], dy = sa * kc[i] + ca * ks[i];
-    V2 P1 = mk(px, py), P2 = mk(px + dx * 250.0f, py + dy * 250.0f);
-    float best = 1.0f;
+    float dx = ca * kc[q0] - sa * ks[q0], dy = sa * kc[q0] + ca * ks[q0];
     unsigned nt = 0;
-    // grid coordinates of the origin
-    float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
-    int ix = (int)floorf(gx), iy = (int)floorf(gy);
-    if (ix < 0 || iy < 0 || ix >= T.gnx || iy >= T.gny) {
-        for (int wi = 0; wi < T.n_walls; ++wi) { float fr = ray_box_fraction(T.walls + wi * WALL_STRIDE, P1, P2, best); ++nt; if (fr >= 0.0f) best = fr; }
-    } else {
-        // Amanatides-Woo in units of ray fraction (t in [0,1] <-> 250 m)
-        float ddx = P2.x - P1.x, ddy = P2.y - P1.y;
-        int sx = ddx > 0.0f ? 1 : -1, sy = ddy > 0.0f ? 1 : -1;
-        float tdx = ddx != 0.0f ? fdiv_fast(T.cell, fabsf(ddx)) : INFINITY, tdy = ddy != 0.0f ? fdiv_fast(T.cell, fabsf(ddy)) : INFINITY;
-        float fx = gx - (float)ix, fy = gy - (float)iy;
-        float tmx = ddx != 0.0f ? (ddx > 0.0f ? (1.0f - fx) : fx) * tdx : INFINITY;
-        float tmy = ddy != 0.0f ? (ddy > 0.0f ? (1.0f - fy) : fy) * tdy : INFINITY;
-        int last0 = -1, last1 = -1;
-        for (;;) {
-            int cell = iy * T.gnx + ix;
-            int b = T.cells[cell], e = T.cells[cell + 1];
-            for (int k = b; k < e; ++k) {
-                int wi = T.items[k];
-                if (wi == last0 || wi == last1) continue;
-                last1 = last0; last0 = wi;
-                const float* w = T.walls + wi * WALL_STRIDE;
-                // conservative reject: bounding circle (w[7] = radius + 1 cm) against the ray's line and extent
-                float cx = w[0] - px, cy = w[1] - py;
-                float along = cx * dx + cy * dy, perp = cx * dy - cy * dx;
-                if (fabsf(perp) > w[7] || along < -w[7] || along > best * 250.0f + w[7]) continue;
-                float fr = ray_box_fraction(w, P1, P2, best); ++nt;
-                if (fr >= 0.0f) best = fr;
+    const float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
+    const int ix0 = (int)floorf(gx), iy0 = (int)floorf(gy);
+    if (ix0 < 0 || iy0 < 0 || ix0 >= T.gnx || iy0 >= T.gny) {          // origin outside the grid: scan every wall
+        for (int j = 0; j < RPL; ++j) {
+            float best = NCG_RAY_LEN;
+            for (int wi = 0; wi < T.n_walls; ++wi) { float t = ray_box_slab(T.walls + wi * WALL_STRIDE, px, py, dx, dy, best); ++nt; if (t >= 0.0f) best = t; }
+            dst[q0 + 4 * j] = sensor_obs_m(best);
+            float t = dx; dx = dy; dy = -t;
+        }
+        *tests += nt;
+        return;
+    }
+    const float fx = gx - (float)ix0, fy = gy - (float)iy0;
+    // Amanatides-Woo in metres along the unit direction
+    float tdx = dx != 0.0f ? T.cell * rcp_fast(fabsf(dx)) : INFINITY, tdy = dy != 0.0f ? T.cell * rcp_fast(fabsf(dy)) : INFINITY;
+    float tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
+    float tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
+    int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
+    int ix = ix0, iy = iy0;
+    const int c0 = iy0 * T.gnx + ix0;
+    const int k0 = T.cells[c0], e0 = T.cells[c0 + 1];
+    int k = k0, e = e0, last0 = -1, last1 = -1, j = 0;
+    float best = NCG_RAY_LEN;
+    for (;;) {
+        if (k >= e) {                                                   // this cell's list is done: leave or finish
+            const float texit = fminf(tmx, tmy);
+            bool fin = best <= texit || texit >= NCG_RAY_LEN;
+            if (!fin) {
+                if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)T.gnx; }
+                else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)T.gny; }
+                if (!fin) { const int cell = iy * T.gnx + ix; k = T.cells[cell]; e = T.cells[cell + 1]; }
             }
-            float texit = fminf(tmx, tmy);
-            if (best <= texit || texit >= 1.0f) break;
-            if (tmx < tmy) { ix += sx; tmx += tdx; if (ix < 0 || ix >= T.gnx) break; }
-            else { iy += sy; tmy += tdy; if (iy < 0 || iy >= T.gny) break; }
+            if (fin) {
+                dst[q0 + 4 * j] = sensor_obs_m(best);
+                if (++j == RPL) break;
+                // next ray of this lane: the direction turns by -90 deg, (dx,dy) -> (dy,-dx), so the DDA strides swap
+                { float t = dx; dx = dy; dy = -t; }
+                { float t = tdx; tdx = tdy; tdy = t; }
+                { int t = sx; sx = sy; sy = -t; }
+                tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
+                tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
+                ix = ix0; iy = iy0; k = k0; e = e0; last0 = -1; last1 = -1; best = NCG_RAY_LEN;
+            }
+        }
+        if (k < e) {
+            const int wi = T.items[k]; ++k;
+            if (wi != last0 && wi != last1) {                           // walls span cells: skip the two most recent
+                last1 = last0; last0 = wi;
+                const float t = ray_box_slab(T.walls + wi * WALL_STRIDE, px, py, dx, dy, best); ++nt;
+                if (t >= 0.0f) best = t;
+            }
         }
     }
     *tests += nt;
-    return best < 1.0f ? best * 250.0f : 250.0f;
 }
-NCG_HD float sensor_obs(float dist) { float n = dist * 0.004f; return n < 0.0f ? 0.0f : (n > 1.0f ? 1.0f : n); }
+NCG_HD float sensor_obs(float dist) { return sensor_obs_m(dist); }
 
 // ------------------------------------------------------------------ Philox4x32-10 (synthetic actions)
 NCG_HD void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {

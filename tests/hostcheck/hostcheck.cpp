@@ -17,7 +17,7 @@ void hc_env_step(const float* blob, float* records, int C, const float* act3, in
         float* R = records + i * NCG_RECORD_WORDS;
         reward[i] = car_step(R, T, act3[i * 3], act3[i * 3 + 1], act3[i * 3 + 2], contacts != 0, obs + i * 38, &xf[i], &cnt);
         unsigned tests = 0;
-        for (int k = 0; k < 16; ++k) obs[i * 38 + 22 + k] = sensor_obs(cast_ray(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, &tests));
+        for (int k = 0; k < 16; ++k) cast_rays<1>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
         cnt.ray_tests += tests;
     }
     bool te, tr; int why;
@@ -35,25 +35,13 @@ void hc_env_reset(const float* blob, float* records, int C, int fresh, int track
         if (obs) {
             observe_state(R, obs + i * 38);
             unsigned tests = 0;
-            for (int k = 0; k < 16; ++k) obs[i * 38 + 22 + k] = sensor_obs(cast_ray(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, &tests));
+            for (int k = 0; k < 16; ++k) cast_rays<1>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
         }
     }
 }
 
-// brute-force sensor (all walls) for checking the grid traversal
-void hc_sensors_brute(const float* blob, float x, float y, float angle, float* out16) {
-    Track T = track_view(blob, blob);
-    for (int i = 0; i < 16; ++i) {
-        Track B = T; B.gnx = 0; B.gny = 0;   // an empty grid sends cast_ray down its all-walls path
-        unsigned tests = 0;
-        out16[i] = cast_ray(B, x, y, angle, i, &tests);
-    }
-}
-void hc_sensors_grid(const float* blob, float x, float y, float angle, float* out16, unsigned* tests) {
-    Track T = track_view(blob, blob);
-    for (int i = 0; i < 16; ++i) out16[i] = cast_ray(T, x, y, angle, i, tests);
-}
-// the generic b2PolygonShape::RayCast loop, kept here to prove the branch-free box version bit-identical
+// b2PolygonShape::RayCast for a box, Box2D's own half-plane clipping loop (b2PolygonShape.cpp), float32: the
+// arithmetic the reference's sensors go through.  Test-side reference for the product's slab test.
 static float ray_box_generic(const float* w, V2 P1, V2 P2, float maxFraction) {
     Rot q; q.c = w[2]; q.s = w[3]; V2 pos = mk(w[0], w[1]); Box b; b.hx = w[4]; b.hy = w[5];
     V2 p1 = mulT(q, P1 - pos), p2 = mulT(q, P2 - pos), d = p2 - p1;
@@ -70,14 +58,32 @@ static float ray_box_generic(const float* w, V2 P1, V2 P2, float maxFraction) {
     }
     return index >= 0 ? lower : -1.0f;
 }
-// returns the number of walls on which the two implementations disagree (bitwise) for one ray
-int hc_ray_box_mismatches(const float* blob, float x1, float y1, float x2, float y2, float maxFraction) {
-    Track T = track_view(blob, blob); int bad = 0;
-    for (int wi = 0; wi < T.n_walls; ++wi) {
-        float a = ray_box_fraction(T.walls + wi * WALL_STRIDE, mk(x1, y1), mk(x2, y2), maxFraction);
-        float b = ray_box_generic(T.walls + wi * WALL_STRIDE, mk(x1, y1), mk(x2, y2), maxFraction);
-        if (f2u(a) != f2u(b)) ++bad;
+// all-walls scan with Box2D's arithmetic (metres), the way DistanceSensor sets the ray up (distance_sensor.py:95-113)
+void hc_sensors_brute(const float* blob, float x, float y, float angle, float* out16) {
+    Track T = track_view(blob, blob);
+    for (int i = 0; i < 16; ++i) {
+        double a = (double)angle - (double)i * (3.14159265358979323846 / 8.0);
+        V2 P1 = mk(x, y), P2 = mk((float)((double)x + cos(a) * 250.0), (float)((double)y + sin(a) * 250.0));
+        float best = 1.0f;
+        for (int wi = 0; wi < T.n_walls; ++wi) { float fr = ray_box_generic(T.walls + wi * WALL_STRIDE, P1, P2, 1.0f); if (fr >= 0.0f && fr < best) best = fr; }
+        out16[i] = best * 250.0f;
     }
+}
+// the product's grid traversal + slab test; out16 in metres
+void hc_sensors_grid(const float* blob, float x, float y, float angle, float* out16, unsigned* tests) {
+    Track T = track_view(blob, blob);
+    float n[16];
+    for (int i = 0; i < 16; ++i) cast_rays<1>(T, x, y, angle, i, n, tests);
+    for (int i = 0; i < 16; ++i) out16[i] = n[i] * 250.0f;
+}
+// the 2- and 4-rays-per-lane variants the kernel uses must give the same 16 numbers as the 1-ray variant
+int hc_sensors_multi_mismatches(const float* blob, float x, float y, float angle) {
+    Track T = track_view(blob, blob);
+    float a[16], b[16], c[16]; unsigned tests = 0; int bad = 0;
+    for (int i = 0; i < 16; ++i) cast_rays<1>(T, x, y, angle, i, a, &tests);
+    for (int q = 0; q < 8; ++q) cast_rays<2>(T, x, y, angle, q < 4 ? q : q + 4, b, &tests);
+    for (int q = 0; q < 4; ++q) cast_rays<4>(T, x, y, angle, q, c, &tests);
+    for (int i = 0; i < 16; ++i) if (f2u(a[i]) != f2u(b[i]) || f2u(a[i]) != f2u(c[i])) ++bad;
     return bad;
 }
 int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }

@@ -256,6 +256,8 @@ def hostcheck():
         lib.hc_env_reset.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, fp]
         lib.hc_sensors_brute.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_float, fp]
         lib.hc_sensors_grid.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_float, fp, ctypes.POINTER(ctypes.c_uint)]
+        lib.hc_sensors_multi_mismatches.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_float]
+        lib.hc_sensors_multi_mismatches.restype = ctypes.c_int
         lib.hc_on_track.argtypes = [fp, ctypes.c_float, ctypes.c_float]
         lib.hc_synthetic_action.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int, fp]
         _HC = lib
