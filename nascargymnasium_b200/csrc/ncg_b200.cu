@@ -29,7 +29,7 @@ struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, conta
 
 struct KParams {
     float* records; const float* blob; const long long* track_off;
-    int E, C, epb, discrete, reset_on_lap, auto_reset, contacts, stage, track_info;
+    int E, C, epb, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
     int T; unsigned long long seed; int mode; unsigned step_base;
     float* obs_roll; float* rew_roll; uint8_t* done_roll;
@@ -39,8 +39,9 @@ struct KParams {
 #define CPB 32                    /* car slots per CTA = lanes of the physics warp */
 #define REC_STRIDE 129            /* shared-memory row stride of a record (odd: conflict-free column access) */
 #define OBS_STRIDE 41             /* shared-memory row stride of an observation row */
-#define BAR_FULL 1                /* named barriers 1,2: buffer b filled by the physics warp */
-#define BAR_EMPTY 3               /* named barriers 3,4: buffer b drained by the ray warps */
+#define BAR_POSE 1                /* named barriers 1,2: the new poses of buffer b are published (rays can start) */
+#define BAR_FULL 3                /* named barriers 3,4: buffer b complete (obs[0..21], flags, reset poses) */
+#define BAR_EMPTY 5               /* named barriers 5,6: buffer b drained by the ray warps */
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
             if (t >= 2) bar_sync(BAR_EMPTY + b, NT);            // the ray warps have drained buffer b (step t-2)
             float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
             float rew = 0.0f;
+            StepCtx ctx;
             if (active) {
                 float thr, brk, st;
                 const int gc = car0 + slot;
@@ -162,8 +164,16 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
                     if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
                     else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
                 } else action_synthetic(p.seed, (uint32_t)gc, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
-                uint32_t xf;
-                rew = car_step(R, T, thr, brk, st, p.contacts != 0, s_obs + (b * CPB + slot) * OBS_STRIDE, &xf, &cnt);
+                if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts != 0, &ctx, &cnt);
+                s_pose[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
+            }
+            // the pose exists: let the ray warps start while this warp does the rest of the step
+            __syncwarp();
+            __threadfence_block();
+            bar_arrive(BAR_POSE + b, NT);
+            if (active) {
+                uint32_t xf = 0;
+                if (!(p.debug_skip & 2)) rew = car_step_rules(R, T, &ctx, s_obs + (b * CPB + slot) * OBS_STRIDE, &xf, &cnt);
                 s_xf[slot] = xf;
                 if (p.track_info) {
                     uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
@@ -187,7 +197,6 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
                     if (done) ++episodes;
                 }
                 if (done) ret_sum += (double)R[NCG_R_CUM_REWARD];
-                s_pose[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
                 // ---- same-step auto-reset (CarPhysics.reset_car semantics) + reset observation words 0..21
                 if (done && do_reset) {
                     reset_in_place(R, T, s_obs2 + (b * CPB + slot) * OBS_STRIDE);
@@ -218,17 +227,15 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
         for (int t = 0; t < p.T; ++t) {
             const int b = t & 1;
             float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
+            bar_sync(BAR_POSE + b, NT);
+            if (active && !(p.debug_skip & 1)) {
+                const float4 ps = s_pose[b * CPB + slot];
+                cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
+            }
             bar_sync(BAR_FULL + b, NT);
-            if (active) {
-                const bool rs = do_reset && s_flag[b * CPB + slot] != 0u;
-                if (!rs || p.final_obs) {
-                    const float4 ps = s_pose[b * CPB + slot];
-                    cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
-                }
-                if (rs) {
-                    const float4 ps = s_pose2[b * CPB + slot];
-                    cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
-                }
+            if (active && do_reset && s_flag[b * CPB + slot] != 0u) {            // finished and reset: rays of the reset pose
+                const float4 ps = s_pose2[b * CPB + slot];
+                cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
             }
             __syncwarp();
             // ---- observation rows of this warp's cars shared -> HBM (CPW x 38 consecutive floats)
@@ -294,7 +301,7 @@ struct NcgHandle {
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0;
-    int rays_per_lane = 2;
+    int rays_per_lane = 2; int num_sms = 0;
     long long launches = 0;
     // host-buffer path
     cudaStream_t stream = nullptr;
@@ -306,9 +313,23 @@ struct NcgHandle {
 
 namespace {
 
+// Whole envs per CTA: at most CPB car slots, fewer when that spreads a small batch over all SMs (4096 single-car
+// envs: 28 per CTA = 147 CTAs on 148 SMs instead of 128 CTAs of 32).
+int envs_per_cta(const NcgHandle* h) {
+    const int C = h->cfg.cars_per_env, E = h->cfg.num_envs;
+    const int epb_max = CPB / C;                               // C <= 10 < CPB
+    const int min_ctas = (E + epb_max - 1) / epb_max;
+    const int sms = h->num_sms > 0 ? h->num_sms : 148;
+    const int target = ((min_ctas + sms - 1) / sms) * sms;     // whole waves of one CTA per SM
+    int epb = (E + target - 1) / target;
+    if (epb < 1) epb = 1;
+    if (epb > epb_max) epb = epb_max;
+    return epb;
+}
+
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
-    const int C = h->cfg.cars_per_env, RPL = h->rays_per_lane;
-    const int epb = CPB / C;                                   // whole envs per CTA (C <= 10 < CPB)
+    const int RPL = h->rays_per_lane;
+    const int epb = envs_per_cta(h);
     p.epb = epb;
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
@@ -327,6 +348,7 @@ KParams base_params(NcgHandle* h) {
     p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off;
     p.E = h->cfg.num_envs; p.C = h->cfg.cars_per_env; p.discrete = h->cfg.discrete; p.reset_on_lap = h->cfg.reset_on_lap;
     p.auto_reset = h->cfg.auto_reset; p.contacts = h->cfg.contacts; p.track_info = h->cfg.track_info; p.stats = h->d_stats; p.T = 1;
+    { const char* d = getenv("NCG_DEBUG_SKIP"); p.debug_skip = d ? atoi(d) : 0; }   // profiling only: 1 = no rays, 2 = no physics
     return p;
 }
 
@@ -346,6 +368,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     if (cfg->device < 0 || cfg->device >= ndev) return fail(NCG_E_INVALID, "no such CUDA device");
     CUDA_TRY(cudaSetDevice(cfg->device));
     NcgHandle* h = new NcgHandle();
+    CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
     const char* g = getenv("NCG_RAYS_PER_LANE");
     int rpl = g ? atoi(g) : 0;
@@ -404,7 +427,7 @@ static void note_tracks(NcgHandle* h, const uint8_t* mask, const int32_t* tid) {
 }
 // a CTA stages one track table: that needs all of its envs on the same track
 static void update_grouping(NcgHandle* h) {
-    const int epb = CPB / h->cfg.cars_per_env;
+    const int epb = envs_per_cta(h);
     bool ok = true;
     for (int e = 0; e < h->cfg.num_envs && ok; ++e) if (h->h_env_track[e] != h->h_env_track[(e / epb) * epb]) ok = false;
     h->tracks_grouped = ok;

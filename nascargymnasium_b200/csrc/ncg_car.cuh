@@ -18,13 +18,14 @@ namespace ncg {
 // Blob layout is produced by nascargymnasium_b200/track.py::build_track_table.
 struct Track {
     const float* hdr; const float* segs; const double* seg64; const float* walls; const float* aabb;
-    const uint16_t* cells; const uint16_t* items;
+    const uint16_t* cells; const uint16_t* items; const uint16_t* longw;
     int n_walls, n_segs, gnx, gny, has_bank;
     float gx0, gy0, inv_cell, cell, ltot, min_lap, slx0, sly0, sldx, sldy, sllen2, slhalfw, half_ltot;
 };
 enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEGS, TH_OFF_WALLS, TH_OFF_AABB, TH_OFF_CELLS,
        TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
-       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64 };
+       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64, TH_OFF_LONG, TH_NLONG };
+#define NCG_ITEM_LONG 0x8000   /* grid item = NCG_ITEM_LONG | long id for a wall listed in >= 3 cells, else the wall index */
 enum { SEG_STRIDE = 12, WALL_STRIDE = 8, SEG64_STRIDE = 5 };
 // `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
 NCG_HD Track track_view(const float* staged, const float* global) {
@@ -34,13 +35,15 @@ NCG_HD Track track_view(const float* staged, const float* global) {
     t.segs = staged + f2u(staged[TH_OFF_SEGS]); t.walls = staged + f2u(staged[TH_OFF_WALLS]);
     t.seg64 = (const double*)(staged + f2u(staged[TH_OFF_SEG64]));
     t.cells = (const uint16_t*)(staged + f2u(staged[TH_OFF_CELLS])); t.items = (const uint16_t*)(staged + f2u(staged[TH_OFF_ITEMS]));
-    t.aabb = global + f2u(staged[TH_OFF_AABB]);
+    t.longw = (const uint16_t*)(staged + f2u(staged[TH_OFF_LONG]));
+    t.aabb = staged + f2u(staged[TH_OFF_AABB]);
     t.gx0 = staged[TH_GX0]; t.gy0 = staged[TH_GY0]; t.inv_cell = staged[TH_INVCELL]; t.cell = staged[TH_CELL];
     t.ltot = staged[TH_LTOT]; t.min_lap = staged[TH_MINLAP]; t.slx0 = staged[TH_SLX0]; t.sly0 = staged[TH_SLY0];
     t.sldx = staged[TH_SLDX]; t.sldy = staged[TH_SLDY]; t.sllen2 = staged[TH_SLLEN2]; t.slhalfw = staged[TH_SLHALFW];
     t.half_ltot = staged[TH_HALF_LTOT];
     return t;
 }
+NCG_HD int item_wall(const Track& T, int it) { return (it & NCG_ITEM_LONG) ? (int)T.longw[it & 31] : it; }
 NCG_HD void wall_get(const Track& T, int i, Xf* xf, Box* b) {
     const float* w = T.walls + i * WALL_STRIDE;
     xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[4]; b->hy = w[5];
@@ -196,7 +199,7 @@ NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
         int cell = iy * T.gnx + ix;
         int b = T.cells[cell], e = T.cells[cell + 1];
         for (int k = b; k < e; ++k) {
-            int wi = T.items[k];
+            int wi = item_wall(T, T.items[k]);
             if (!aabb_overlap(W.b.fat, wall_fat(T, wi))) continue;
             bool have = false;
             for (int j = 0; j < W.nc; ++j) if (W.c[j].wall == wi) { have = true; break; }
@@ -533,7 +536,7 @@ NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
     ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
         int cell = iy * T.gnx + ix;
-        for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) if (aabb_overlap(fat, wall_fat(T, T.items[k]))) return true;
+        for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) if (aabb_overlap(fat, wall_fat(T, item_wall(T, T.items[k])))) return true;
     }
     return false;
 }
@@ -731,7 +734,7 @@ NCG_HDN bool on_track(const Track& T, float x, float y) {
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
         int cell = iy * T.gnx + ix;
         for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) {
-            int wi = T.items[k];
+            int wi = item_wall(T, T.items[k]);
             if (!aabb_overlap(q, wall_fat(T, wi))) continue;
             Xf xf; Box b; wall_get(T, wi, &xf, &b);
             V2 pl = mulT(xf.q, mk(x, y) - xf.p);
@@ -803,9 +806,13 @@ NCG_HD void observe_state(const float* R, float* obs) {
 
 // ------------------------------------------------------------------ the scalar car phase of one step
 // Runs CarPhysics.step and every per-car part of CarEnv._step_multi_car up to (not including) the env-level
-// termination.  Writes obs[0..21], returns the reward; *xflags gets NCG_X_* bits for the env phase.
-NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, float* obs,
-                       uint32_t* xflags, Counters* cnt) {
+// termination, in two halves so the kernel can hand the new pose to the ray warps as soon as it exists:
+//   car_step_dynamics  inputs -> forces -> tyres -> b2World.Step; the record holds the new pose when it returns
+//   car_step_rules     banking/progress, impact and stuck rules, lap timer, obs[0..21], reward; returns the reward,
+//                      *xflags gets NCG_X_* bits for the env phase.
+struct StepCtx { uint32_t fl, xf, laps_pre; bool dis_pre; float impulse; };
+NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, StepCtx* ctx,
+                               Counters* cnt) {
     uint32_t fl = f2u(R[NCG_R_FLAGS]);
     uint32_t xf = 0;
     const bool dis_pre = (fl & NCG_F_DISABLED) != 0;
@@ -923,8 +930,15 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
     body_step(W, R, T, NCG_DT, contacts, cnt);
     b_store(W, R, &fl);
     if (W.overflow) cnt->overflow++;
-    const float x = W.sweep.c.x, y = W.sweep.c.y;
-    const float speed = length(W.v);
+    ctx->fl = fl; ctx->xf = xf; ctx->laps_pre = laps_pre; ctx->dis_pre = dis_pre; ctx->impulse = W.impulse;
+}
+NCG_HD float car_step_rules(float* R, const Track& T, const StepCtx* ctx, float* obs, uint32_t* xflags, Counters* cnt) {
+    uint32_t fl = ctx->fl, xf = ctx->xf;
+    const uint32_t laps_pre = ctx->laps_pre;
+    const bool dis_pre = ctx->dis_pre;
+    struct { float impulse; } W; W.impulse = ctx->impulse;
+    const float x = R[NCG_R_X], y = R[NCG_R_Y];
+    const float speed = length(mk(R[NCG_R_VX], R[NCG_R_VY]));
     // banking refresh + progress (one segment scan serves both)
     float bank_new, progress;
     nearest_segment(T, x, y, &bank_new, &progress);
@@ -1015,6 +1029,12 @@ NCG_HDN float car_step(float* R, const Track& T, float thr_in, float brk_in, flo
     *xflags = xf;
     return reward;
 }
+NCG_HD float car_step(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, float* obs,
+                      uint32_t* xflags, Counters* cnt) {
+    StepCtx ctx;
+    car_step_dynamics(R, T, thr_in, brk_in, steer_in, contacts, &ctx, cnt);
+    return car_step_rules(R, T, &ctx, obs, xflags, cnt);
+}
 
 // ------------------------------------------------------------------ env phase (car_env.py:672-676, 1115-1158, 773-797)
 // xf[0..C) are the cars' NCG_X_* words of this step, step_after the env clock after its increment.
@@ -1071,14 +1091,16 @@ NCG_HD float rcp_fast(float x) {
 }
 // entry distance (metres) of the ray origin (px,py), unit direction (dx,dy) into wall row w, or -1
 NCG_HD float ray_box_slab(const float* w, float px, float py, float dx, float dy, float tmax) {
-    const float c = w[2], s = w[3];
-    const float ax = w[0] - px, ay = w[1] - py;
+    // one wall row = two 16-byte loads (rows are 32 bytes, 16-byte aligned in the blob and in shared memory)
+    const F4 wa = *reinterpret_cast<const F4*>(w), wb = *reinterpret_cast<const F4*>(w + 4);
+    const float c = wa.z, s = wa.w;
+    const float ax = wa.x - px, ay = wa.y - py;
     const float mx = fmaf(c, ax, s * ay), my = fmaf(c, ay, -(s * ax));      // box centre seen from the origin, box frame
     // direction in the box frame; the 1e-30 keeps a ray parallel to a face off 0*inf = NaN when its origin lies
     // exactly in the face's plane (every car starts at x = 0, where two wall boxes abut)
     const float ex = fmaf(c, dx, fmaf(s, dy, 1e-30f)), ey = fmaf(c, dy, fmaf(-s, dx, 1e-30f));
     const float ix = rcp_fast(ex), iy = rcp_fast(ey);
-    const float x0 = (mx - w[4]) * ix, x1 = (mx + w[4]) * ix, y0 = (my - w[5]) * iy, y1 = (my + w[5]) * iy;
+    const float x0 = (mx - wb.x) * ix, x1 = (mx + wb.x) * ix, y0 = (my - wb.y) * iy, y1 = (my + wb.y) * iy;
     const float tn = fmaxf(fminf(x0, x1), fminf(y0, y1)), tf = fminf(fmaxf(x0, x1), fmaxf(y0, y1));
     return (tn > 0.0f && tn <= tf && tn < tmax) ? tn : -1.0f;
 }
@@ -1122,6 +1144,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     const int c0 = iy0 * T.gnx + ix0;
     const int k0 = T.cells[c0], e0 = T.cells[c0 + 1];
     int k = k0, e = e0, last0 = -1, last1 = -1, j = 0;
+    uint32_t seen = 0u;                                                 // long walls this ray has tested
     float best = NCG_RAY_LEN;
     for (;;) {
         if (k >= e) {                                                   // this cell's list is done: leave or finish
@@ -1141,13 +1164,19 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
                 { int t = sx; sx = sy; sy = -t; }
                 tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
                 tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
-                ix = ix0; iy = iy0; k = k0; e = e0; last0 = -1; last1 = -1; best = NCG_RAY_LEN;
+                ix = ix0; iy = iy0; k = k0; e = e0; last0 = -1; last1 = -1; seen = 0u; best = NCG_RAY_LEN;
             }
         }
         if (k < e) {
-            const int wi = T.items[k]; ++k;
-            if (wi != last0 && wi != last1) {                           // walls span cells: skip the two most recent
-                last1 = last0; last0 = wi;
+            // walls span cells: a long wall (listed in many cells) is tested once per ray, remembered in a bit mask;
+            // a short one is skipped if it is one of the two most recently tested
+            const int it = T.items[k]; ++k;
+            const bool lg = (it & NCG_ITEM_LONG) != 0;
+            const uint32_t bit = 1u << (it & 31);
+            const bool fresh = lg ? (seen & bit) == 0u : (it != last0 && it != last1);
+            if (fresh) {
+                int wi = it;
+                if (lg) { seen |= bit; wi = (int)T.longw[it & 31]; } else { last1 = last0; last0 = it; }
                 const float t = ray_box_slab(T.walls + wi * WALL_STRIDE, px, py, dx, dy, best); ++nt;
                 if (t >= 0.0f) best = t;
             }

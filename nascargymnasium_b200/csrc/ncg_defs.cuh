@@ -17,6 +17,13 @@
 
 namespace ncg {
 
+// 16-byte vector load type: CUDA's float4 on the device build, a plain struct in the host test build
+#if defined(__CUDACC__)
+typedef float4 F4;
+#else
+struct F4 { float x, y, z, w; };
+#endif
+
 // bit casts between the float32 record words and u32 payloads
 NCG_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)
