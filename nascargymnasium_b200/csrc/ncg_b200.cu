@@ -71,6 +71,12 @@ __device__ __noinline__ void reset_in_place(float* R, const Track& T, float* obs
     observe_state(R, obs);
 }
 
+// rays of a freshly reset car (once per episode: out of line, generic loads)
+template <int RPL>
+__device__ __noinline__ void cast_rays_reset(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
+    cast_rays<RPL, false>(T, px, py, angle, q0, dst, tests);
+}
+
 struct SmemLayout {
     int rec, obs, obs2, pose, pose2, flag, xf, track, total;      // word offsets
 };
@@ -230,12 +236,14 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
             bar_sync(BAR_POSE + b, NT);
             if (active && !(p.debug_skip & 1)) {
                 const float4 ps = s_pose[b * CPB + slot];
-                cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
+                float* dst = s_obs + (b * CPB + slot) * OBS_STRIDE + 22;
+                if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, q0, dst, &tests);
+                else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, q0, dst, &tests);
             }
             bar_sync(BAR_FULL + b, NT);
             if (active && do_reset && s_flag[b * CPB + slot] != 0u) {            // finished and reset: rays of the reset pose
                 const float4 ps = s_pose2[b * CPB + slot];
-                cast_rays<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
+                cast_rays_reset<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
             }
             __syncwarp();
             // ---- observation rows of this warp's cars shared -> HBM (CPW x 38 consecutive floats)
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const fl
     __syncwarp();
     if (obs) {
         unsigned tests = 0;
-        if (lane < 16) cast_rays<1>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], lane, so + 22, &tests);
+        if (lane < 16) cast_rays<1, false>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], lane, so + 22, &tests);
         __syncwarp();
         for (int k = lane; k < NCG_OBS_DIM; k += 32) obs[(size_t)car * NCG_OBS_DIM + k] = so[k];
     }

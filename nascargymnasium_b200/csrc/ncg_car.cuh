@@ -18,14 +18,14 @@ namespace ncg {
 // Blob layout is produced by nascargymnasium_b200/track.py::build_track_table.
 struct Track {
     const float* hdr; const float* segs; const double* seg64; const float* walls; const float* aabb;
-    const uint16_t* cells; const uint16_t* items; const uint16_t* longw;
+    const uint32_t* cells; const uint16_t* items;     // per cell: first block | n_blocks << 16; items in blocks of 4 u16
     int n_walls, n_segs, gnx, gny, has_bank;
     float gx0, gy0, inv_cell, cell, ltot, min_lap, slx0, sly0, sldx, sldy, sllen2, slhalfw, half_ltot;
 };
 enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEGS, TH_OFF_WALLS, TH_OFF_AABB, TH_OFF_CELLS,
        TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
-       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64, TH_OFF_LONG, TH_NLONG };
-#define NCG_ITEM_LONG 0x8000   /* grid item = NCG_ITEM_LONG | long id for a wall listed in >= 3 cells, else the wall index */
+       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64 };
+#define NCG_ITEM_NONE 0xFFFF   /* padding entry of a grid item block */
 enum { SEG_STRIDE = 12, WALL_STRIDE = 8, SEG64_STRIDE = 5 };
 // `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
 NCG_HD Track track_view(const float* staged, const float* global) {
@@ -34,8 +34,7 @@ NCG_HD Track track_view(const float* staged, const float* global) {
     t.gnx = (int)f2u(staged[TH_GNX]); t.gny = (int)f2u(staged[TH_GNY]); t.has_bank = (int)f2u(staged[TH_HASBANK]);
     t.segs = staged + f2u(staged[TH_OFF_SEGS]); t.walls = staged + f2u(staged[TH_OFF_WALLS]);
     t.seg64 = (const double*)(staged + f2u(staged[TH_OFF_SEG64]));
-    t.cells = (const uint16_t*)(staged + f2u(staged[TH_OFF_CELLS])); t.items = (const uint16_t*)(staged + f2u(staged[TH_OFF_ITEMS]));
-    t.longw = (const uint16_t*)(staged + f2u(staged[TH_OFF_LONG]));
+    t.cells = (const uint32_t*)(staged + f2u(staged[TH_OFF_CELLS])); t.items = (const uint16_t*)(staged + f2u(staged[TH_OFF_ITEMS]));
     t.aabb = staged + f2u(staged[TH_OFF_AABB]);
     t.gx0 = staged[TH_GX0]; t.gy0 = staged[TH_GY0]; t.inv_cell = staged[TH_INVCELL]; t.cell = staged[TH_CELL];
     t.ltot = staged[TH_LTOT]; t.min_lap = staged[TH_MINLAP]; t.slx0 = staged[TH_SLX0]; t.sly0 = staged[TH_SLY0];
@@ -43,7 +42,9 @@ NCG_HD Track track_view(const float* staged, const float* global) {
     t.half_ltot = staged[TH_HALF_LTOT];
     return t;
 }
-NCG_HD int item_wall(const Track& T, int it) { return (it & NCG_ITEM_LONG) ? (int)T.longw[it & 31] : it; }
+// the k-th wall of a grid cell's list, or -1 past its end (lists are padded to blocks of 4 with NCG_ITEM_NONE)
+NCG_HD int cell_count_max(const Track& T, int cell) { return (int)(T.cells[cell] >> 16) * 4; }
+NCG_HD int cell_item(const Track& T, int cell, int k) { int w = T.items[(T.cells[cell] & 0xFFFFu) * 4u + (uint32_t)k]; return w == NCG_ITEM_NONE ? -1 : w; }
 NCG_HD void wall_get(const Track& T, int i, Xf* xf, Box* b) {
     const float* w = T.walls + i * WALL_STRIDE;
     xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[4]; b->hy = w[5];
@@ -197,9 +198,10 @@ NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
     int found[NCG_MAX_CONTACTS]; int nf = 0;
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
         int cell = iy * T.gnx + ix;
-        int b = T.cells[cell], e = T.cells[cell + 1];
-        for (int k = b; k < e; ++k) {
-            int wi = item_wall(T, T.items[k]);
+        const int nk = cell_count_max(T, cell);
+        for (int k = 0; k < nk; ++k) {
+            int wi = cell_item(T, cell, k);
+            if (wi < 0) break;
             if (!aabb_overlap(W.b.fat, wall_fat(T, wi))) continue;
             bool have = false;
             for (int j = 0; j < W.nc; ++j) if (W.c[j].wall == wi) { have = true; break; }
@@ -536,7 +538,8 @@ NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
     ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
         int cell = iy * T.gnx + ix;
-        for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) if (aabb_overlap(fat, wall_fat(T, item_wall(T, T.items[k])))) return true;
+        const int nk = cell_count_max(T, cell);
+        for (int k = 0; k < nk; ++k) { int wi = cell_item(T, cell, k); if (wi < 0) break; if (aabb_overlap(fat, wall_fat(T, wi))) return true; }
     }
     return false;
 }
@@ -733,8 +736,10 @@ NCG_HDN bool on_track(const Track& T, float x, float y) {
     ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
         int cell = iy * T.gnx + ix;
-        for (int k = T.cells[cell]; k < T.cells[cell + 1]; ++k) {
-            int wi = item_wall(T, T.items[k]);
+        const int nk = cell_count_max(T, cell);
+        for (int k = 0; k < nk; ++k) {
+            int wi = cell_item(T, cell, k);
+            if (wi < 0) break;
             if (!aabb_overlap(q, wall_fat(T, wi))) continue;
             Xf xf; Box b; wall_get(T, wi, &xf, &b);
             V2 pl = mulT(xf.q, mk(x, y) - xf.p);
@@ -1076,8 +1081,8 @@ NCG_HD float sensor_obs_m(float dist) { float n = dist * 0.004f; return n < 0.0f
 // ------------------------------------------------------------------ sensor rays (distance_sensor.py:71-117)
 // 16 rays per car from the body origin, direction = heading - i*22.5 deg, length 250 m, nearest wall-box entry.
 // The reference goes through b2World::RayCast -> b2PolygonShape::RayCast per fixture; here a uniform-grid DDA
-// (32 m cells, CSR lists in the staged track table) visits the boxes near the ray and each candidate gets a slab
-// test in the box frame: entry/exit distances along the unit direction, MUFU.RCP reciprocals and FFMA products.
+// (per-track cell size, lists in the staged track table) visits the boxes near the ray and each candidate gets a
+// slab test in the box frame: entry/exit distances along the unit direction, MUFU.RCP reciprocals and FFMA products.
 // That is the same intersection as Box2D's half-plane clipping (a hit needs an entry crossing at t > 0, so an
 // origin inside a box reports nothing for that box) evaluated to ~1e-6 relative instead of bit-for-bit: rays only
 // feed obs[22..37], whose stated tolerance is 1e-3 normalised (0.25 m); tests/hostcheck compares this traversal
@@ -1089,10 +1094,31 @@ NCG_HD float rcp_fast(float x) {
     return 1.0f / x;
 #endif
 }
-// entry distance (metres) of the ray origin (px,py), unit direction (dx,dy) into wall row w, or -1
-NCG_HD float ray_box_slab(const float* w, float px, float py, float dx, float dy, float tmax) {
-    // one wall row = two 16-byte loads (rows are 32 bytes, 16-byte aligned in the blob and in shared memory)
-    const F4 wa = *reinterpret_cast<const F4*>(w), wb = *reinterpret_cast<const F4*>(w + 4);
+// Loads of the ray loop.  SH = the track table is staged in shared memory: ld.shared (LDS) instead of the
+// generic-address loads the compiler would otherwise emit for a pointer it cannot trace to a __shared__ object.
+template <bool SH> NCG_HD F4 ld_f4(const float* p) {
+#if defined(__CUDA_ARCH__)
+    if (SH) {
+        F4 v; asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+        return v;
+    }
+#endif
+    return *reinterpret_cast<const F4*>(p);
+}
+template <bool SH> NCG_HD uint32_t ld_u32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    if (SH) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
+#endif
+    return *p;
+}
+template <bool SH> NCG_HD void ld_u32x2(const uint16_t* p, uint32_t* lo, uint32_t* hi) {
+#if defined(__CUDA_ARCH__)
+    if (SH) { asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(*lo), "=r"(*hi) : "r"((unsigned)__cvta_generic_to_shared(p))); return; }
+#endif
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p); *lo = q[0]; *hi = q[1];
+}
+// entry distance (metres) of the ray origin (px,py), unit direction (dx,dy) into the wall row (wa, wb), or +inf
+NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx, float dy) {
     const float c = wa.z, s = wa.w;
     const float ax = wa.x - px, ay = wa.y - py;
     const float mx = fmaf(c, ax, s * ay), my = fmaf(c, ay, -(s * ax));      // box centre seen from the origin, box frame
@@ -1102,14 +1128,15 @@ NCG_HD float ray_box_slab(const float* w, float px, float py, float dx, float dy
     const float ix = rcp_fast(ex), iy = rcp_fast(ey);
     const float x0 = (mx - wb.x) * ix, x1 = (mx + wb.x) * ix, y0 = (my - wb.y) * iy, y1 = (my + wb.y) * iy;
     const float tn = fmaxf(fminf(x0, x1), fminf(y0, y1)), tf = fminf(fmaxf(x0, x1), fmaxf(y0, y1));
-    return (tn > 0.0f && tn <= tf && tn < tmax) ? tn : -1.0f;
+    return (tn > 0.0f && tn <= tf) ? tn : INFINITY;
 }
 #define NCG_RAY_LEN 250.0f
 // One lane's RPL rays of one car: ray indices q0, q0+4, ... (successive rays are 90 deg apart, so a lane's total
-// work mixes along-track and across-track rays and the lanes of a warp finish together).  All RPL rays run in one
-// flattened loop -- every iteration is "leave the cell if its list is exhausted, then test one candidate" -- so
-// lanes never sit in different loop nests.  Normalised distances go to dst[q0 + 4*j].
-template <int RPL>
+// work mixes along-track and across-track rays).  All RPL rays run in one flattened loop -- every iteration is
+// "fetch the next cell if this one's list is exhausted, then test one block of four walls" -- so lanes never sit
+// in different loop nests, and the four slab tests of a block are independent instruction streams that overlap
+// their shared-memory and MUFU latencies.  Normalised distances go to dst[q0 + 4*j].
+template <int RPL, bool SH>
 NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
     // cos/sin(-q0*22.5 deg): the reference evaluates cos/sin(theta - i*pi/8) in float64 (distance_sensor.py:95-103);
     // rotating the float32 heading by a constant keeps the axis-aligned rays of the start pose exactly axis-aligned.
@@ -1127,7 +1154,10 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     if (ix0 < 0 || iy0 < 0 || ix0 >= T.gnx || iy0 >= T.gny) {          // origin outside the grid: scan every wall
         for (int j = 0; j < RPL; ++j) {
             float best = NCG_RAY_LEN;
-            for (int wi = 0; wi < T.n_walls; ++wi) { float t = ray_box_slab(T.walls + wi * WALL_STRIDE, px, py, dx, dy, best); ++nt; if (t >= 0.0f) best = t; }
+            for (int wi = 0; wi < T.n_walls; ++wi) {
+                const float* w = T.walls + wi * WALL_STRIDE;
+                best = fminf(best, ray_box_slab(ld_f4<SH>(w), ld_f4<SH>(w + 4), px, py, dx, dy)); ++nt;
+            }
             dst[q0 + 4 * j] = sensor_obs_m(best);
             float t = dx; dx = dy; dy = -t;
         }
@@ -1141,10 +1171,9 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     float tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
     int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
     int ix = ix0, iy = iy0;
-    const int c0 = iy0 * T.gnx + ix0;
-    const int k0 = T.cells[c0], e0 = T.cells[c0 + 1];
-    int k = k0, e = e0, last0 = -1, last1 = -1, j = 0;
-    uint32_t seen = 0u;                                                 // long walls this ray has tested
+    const uint32_t h0 = ld_u32<SH>(T.cells + iy0 * T.gnx + ix0);
+    const int k0 = (int)(h0 & 0xFFFFu), e0 = k0 + (int)(h0 >> 16);   // block range of the origin cell
+    int k = k0, e = e0, j = 0;
     float best = NCG_RAY_LEN;
     for (;;) {
         if (k >= e) {                                                   // this cell's list is done: leave or finish
@@ -1153,7 +1182,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
             if (!fin) {
                 if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)T.gnx; }
                 else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)T.gny; }
-                if (!fin) { const int cell = iy * T.gnx + ix; k = T.cells[cell]; e = T.cells[cell + 1]; }
+                if (!fin) { const uint32_t h = ld_u32<SH>(T.cells + iy * T.gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
             }
             if (fin) {
                 dst[q0 + 4 * j] = sensor_obs_m(best);
@@ -1164,22 +1193,22 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
                 { int t = sx; sx = sy; sy = -t; }
                 tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
                 tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
-                ix = ix0; iy = iy0; k = k0; e = e0; last0 = -1; last1 = -1; seen = 0u; best = NCG_RAY_LEN;
+                ix = ix0; iy = iy0; k = k0; e = e0; best = NCG_RAY_LEN;
             }
         }
-        if (k < e) {
-            // walls span cells: a long wall (listed in many cells) is tested once per ray, remembered in a bit mask;
-            // a short one is skipped if it is one of the two most recently tested
-            const int it = T.items[k]; ++k;
-            const bool lg = (it & NCG_ITEM_LONG) != 0;
-            const uint32_t bit = 1u << (it & 31);
-            const bool fresh = lg ? (seen & bit) == 0u : (it != last0 && it != last1);
-            if (fresh) {
-                int wi = it;
-                if (lg) { seen |= bit; wi = (int)T.longw[it & 31]; } else { last1 = last0; last0 = it; }
-                const float t = ray_box_slab(T.walls + wi * WALL_STRIDE, px, py, dx, dy, best); ++nt;
-                if (t >= 0.0f) best = t;
-            }
+        if (k < e) {                                                    // one block: four walls (padding repeats wall 0, masked)
+            uint32_t lo, hi; ld_u32x2<SH>(T.items + 4 * k, &lo, &hi); ++k;
+            const uint32_t i0 = lo & 0xFFFFu, i1 = lo >> 16, i2 = hi & 0xFFFFu, i3 = hi >> 16;
+            const float* w0 = T.walls + i0 * WALL_STRIDE;               // a block's first entry is always a wall
+            const float* w1 = T.walls + (i1 == NCG_ITEM_NONE ? i0 : i1) * WALL_STRIDE;
+            const float* w2 = T.walls + (i2 == NCG_ITEM_NONE ? i0 : i2) * WALL_STRIDE;
+            const float* w3 = T.walls + (i3 == NCG_ITEM_NONE ? i0 : i3) * WALL_STRIDE;
+            const F4 a0 = ld_f4<SH>(w0), b0 = ld_f4<SH>(w0 + 4), a1 = ld_f4<SH>(w1), b1 = ld_f4<SH>(w1 + 4);
+            const F4 a2 = ld_f4<SH>(w2), b2 = ld_f4<SH>(w2 + 4), a3 = ld_f4<SH>(w3), b3 = ld_f4<SH>(w3 + 4);
+            const float t0 = ray_box_slab(a0, b0, px, py, dx, dy), t1 = ray_box_slab(a1, b1, px, py, dx, dy);
+            const float t2 = ray_box_slab(a2, b2, px, py, dx, dy), t3 = ray_box_slab(a3, b3, px, py, dx, dy);
+            best = fminf(best, fminf(fminf(t0, t1), fminf(t2, t3)));
+            nt += 4u - (i1 == NCG_ITEM_NONE) - (i2 == NCG_ITEM_NONE) - (i3 == NCG_ITEM_NONE);
         }
     }
     *tests += nt;

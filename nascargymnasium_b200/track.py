@@ -304,10 +304,8 @@ H_GX0, H_GY0, H_INVCELL, H_CELL, H_LTOT, H_MINLAP, H_SLX0, H_SLY0, H_SLDX, H_SLD
     H_HALF_LTOT = range(12, 25)
 H_STAGE_WORDS = 25       # words [0, H_STAGE_WORDS) are what a CTA stages into shared memory (the whole table)
 H_OFF_SEG64 = 26         # float64 rows [sx,sy,ex,ey,cum_chord] per segment (tie-exact nearest-segment search)
-H_OFF_LONG = 27          # uint16[MAX_LONG] wall index of each "long" wall (one that is listed in >= 3 grid cells)
-H_NLONG = 28
-MAX_LONG = 32            # a ray remembers the long walls it has tested in a 32-bit mask
-ITEM_LONG = 0x8000       # grid item = ITEM_LONG | long id  for a long wall, else the wall index
+ITEM_BLOCK = 4           # grid item lists are padded to blocks of 4 (one 8-byte load, four slab tests in flight)
+ITEM_NONE = 0xFFFF       # padding entry
 SEG64_STRIDE = 5
 
 
@@ -435,20 +433,22 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     off_segs = HDR_WORDS
     off_seg64 = off_segs + MAX_SEGS * SEG_STRIDE               # even word offset => 8-byte aligned doubles
     off_walls = off_seg64 + pad4(MAX_SEGS * SEG64_STRIDE * 2)
+    # device layout of the grid: one u32 per cell = first block | n_blocks << 16, items in blocks of ITEM_BLOCK u16
+    blk_first = np.zeros(nx * ny, dtype=np.int64)
+    blk_count = np.zeros(nx * ny, dtype=np.int64)
+    padded: List[int] = []
+    for i, l in enumerate(lists):
+        nb = (len(l) + ITEM_BLOCK - 1) // ITEM_BLOCK
+        blk_first[i], blk_count[i] = len(padded) // ITEM_BLOCK, nb
+        padded.extend(l)
+        padded.extend([ITEM_NONE] * (nb * ITEM_BLOCK - len(l)))
+    if len(padded) // ITEM_BLOCK >= 65536:
+        raise ValueError("grid item list exceeds 16-bit block offsets; use a larger cell")
     off_cells = off_walls + pad4(n * WALL_STRIDE)
-    cells_words = pad4((len(cell_start) + 1) // 2)
+    cells_words = pad4(nx * ny)
     off_items = off_cells + cells_words
-    items_words = pad4((len(items) + 1) // 2)
-    # long walls (the boxes of the straights) are listed in every cell they cross; the ray traversal tests each of
-    # them once per ray, which needs an id small enough for a bit mask
-    ncell_of = np.zeros(n, dtype=np.int64)
-    for l in lists:
-        for w in l:
-            ncell_of[w] += 1
-    long_walls = [int(w) for w in np.argsort(-ncell_of, kind="stable") if ncell_of[w] >= 3][:MAX_LONG]
-    long_id = {w: i for i, w in enumerate(long_walls)}
-    off_long = off_items + items_words
-    off_aabb = off_long + MAX_LONG // 2         # wall fat AABBs (broad phase)
+    items_words = pad4((len(padded) + 1) // 2)
+    off_aabb = off_items + items_words          # wall fat AABBs (broad phase)
     total = off_aabb + pad4(n * 4)
     blob = np.zeros(total, dtype=np.float32)
     hi = blob.view(np.int32)
@@ -463,11 +463,9 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     hi[H_OFF_AABB] = off_aabb
     hi[H_OFF_CELLS] = off_cells
     hi[H_OFF_ITEMS] = off_items
-    hi[H_NITEMS] = len(items)
+    hi[H_NITEMS] = len(padded)
     hi[H_STAGE_WORDS] = total
     hi[H_OFF_SEG64] = off_seg64
-    hi[H_OFF_LONG] = off_long
-    hi[H_NLONG] = len(long_walls)
     blob[H_GX0] = x0
     blob[H_GY0] = y0
     blob[H_INVCELL] = 1.0 / cell
@@ -495,15 +493,10 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     wrows[:, 7] = np.sqrt(boxes[:, 4].astype(np.float64) ** 2 + boxes[:, 5].astype(np.float64) ** 2) + 0.01   # ray pre-cull circle
     blob[off_walls:off_walls + n * WALL_STRIDE] = wrows.reshape(-1)
     blob[off_aabb:off_aabb + n * 4] = fat.reshape(-1)
-    cs16 = np.zeros(cells_words * 2, dtype=np.uint16)
-    cs16[:len(cell_start)] = cell_start
-    blob.view(np.uint16)[off_cells * 2: off_cells * 2 + len(cs16)] = cs16
-    it16 = np.zeros(items_words * 2, dtype=np.uint16)
-    it16[:len(items)] = [ITEM_LONG | long_id[int(w)] if int(w) in long_id else int(w) for w in items]
+    blob.view(np.uint32)[off_cells: off_cells + nx * ny] = (blk_first | (blk_count << 16)).astype(np.uint32)
+    it16 = np.full(items_words * 2, ITEM_NONE, dtype=np.uint16)
+    it16[:len(padded)] = padded
     blob.view(np.uint16)[off_items * 2: off_items * 2 + len(it16)] = it16
-    lw16 = np.zeros(MAX_LONG, dtype=np.uint16)
-    lw16[:len(long_walls)] = long_walls
-    blob.view(np.uint16)[off_long * 2: off_long * 2 + MAX_LONG] = lw16
     return TrackTable(track, boxes, fat, segs, seg64, (x0, y0), (nx, ny), cell_start, items, blob)
 
 

@@ -17,7 +17,7 @@ void hc_env_step(const float* blob, float* records, int C, const float* act3, in
         float* R = records + i * NCG_RECORD_WORDS;
         reward[i] = car_step(R, T, act3[i * 3], act3[i * 3 + 1], act3[i * 3 + 2], contacts != 0, obs + i * 38, &xf[i], &cnt);
         unsigned tests = 0;
-        for (int k = 0; k < 16; ++k) cast_rays<1>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
+        for (int k = 0; k < 16; ++k) cast_rays<1, false>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
         cnt.ray_tests += tests;
     }
     bool te, tr; int why;
@@ -35,7 +35,7 @@ void hc_env_reset(const float* blob, float* records, int C, int fresh, int track
         if (obs) {
             observe_state(R, obs + i * 38);
             unsigned tests = 0;
-            for (int k = 0; k < 16; ++k) cast_rays<1>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
+            for (int k = 0; k < 16; ++k) cast_rays<1, false>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
         }
     }
 }
@@ -73,16 +73,16 @@ void hc_sensors_brute(const float* blob, float x, float y, float angle, float* o
 void hc_sensors_grid(const float* blob, float x, float y, float angle, float* out16, unsigned* tests) {
     Track T = track_view(blob, blob);
     float n[16];
-    for (int i = 0; i < 16; ++i) cast_rays<1>(T, x, y, angle, i, n, tests);
+    for (int i = 0; i < 16; ++i) cast_rays<1, false>(T, x, y, angle, i, n, tests);
     for (int i = 0; i < 16; ++i) out16[i] = n[i] * 250.0f;
 }
 // the 2- and 4-rays-per-lane variants the kernel uses must give the same 16 numbers as the 1-ray variant
 int hc_sensors_multi_mismatches(const float* blob, float x, float y, float angle) {
     Track T = track_view(blob, blob);
     float a[16], b[16], c[16]; unsigned tests = 0; int bad = 0;
-    for (int i = 0; i < 16; ++i) cast_rays<1>(T, x, y, angle, i, a, &tests);
-    for (int q = 0; q < 8; ++q) cast_rays<2>(T, x, y, angle, q < 4 ? q : q + 4, b, &tests);
-    for (int q = 0; q < 4; ++q) cast_rays<4>(T, x, y, angle, q, c, &tests);
+    for (int i = 0; i < 16; ++i) cast_rays<1, false>(T, x, y, angle, i, a, &tests);
+    for (int q = 0; q < 8; ++q) cast_rays<2, false>(T, x, y, angle, q < 4 ? q : q + 4, b, &tests);
+    for (int q = 0; q < 4; ++q) cast_rays<4, false>(T, x, y, angle, q, c, &tests);
     for (int i = 0; i < 16; ++i) if (f2u(a[i]) != f2u(b[i]) || f2u(a[i]) != f2u(c[i])) ++bad;
     return bad;
 }
