@@ -28,6 +28,7 @@
 #ifndef NCG_B200_H
 #define NCG_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -176,6 +177,18 @@ int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_tra
 int ncg_host_buffers(NcgHandle* h, void** actions, float** obs, float** reward, uint8_t** terminated, uint8_t** truncated,
                      float** final_obs);
 int ncg_step_pinned(NcgHandle* h, int32_t want_final, int32_t* any_done);
+
+/* Zero-staging variant: every buffer is page-locked, device-mapped host memory from ncg_host_alloc, and the kernel
+ * itself reads the actions and writes observations / rewards / flags across PCIe -- a step is one kernel launch and one
+ * stream synchronise.  Buffers are the caller's, so a binding can rotate result buffers and hand them out without
+ * copying.  For envs that finish in this step (auto_reset on): h_final_obs rows (float32[E*C*38], may be NULL) get the
+ * terminal observation, h_ep_return[car] (float32[E*C], may be NULL) the episode return CarEnv accumulates in
+ * cumulative_rewards (src/car_env.py:785-789) and h_ep_length[env] (int32[E], may be NULL) the episode's step count;
+ * rows of envs that did not finish are left untouched.  *any_done != 0 when at least one env finished. */
+int ncg_host_alloc(size_t bytes, void** out);
+int ncg_host_free(void* p);
+int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
+                    uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done);
 
 /* Raw records, NCG_RECORD_WORDS words per car, car-major; d_records float32[n_cars*128]. */
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream);

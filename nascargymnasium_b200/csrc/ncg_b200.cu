@@ -33,6 +33,7 @@ struct KParams {
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
     int T; unsigned long long seed; int mode; unsigned step_base;
     float* obs_roll; float* rew_roll; uint8_t* done_roll;
+    float* ep_return; int* ep_length; int* any_done;      // optional: episode return per car / length per env of finished envs
     DevStats* stats;
 };
 
@@ -202,7 +203,11 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
                     else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
                     if (done) ++episodes;
                 }
-                if (done) ret_sum += (double)R[NCG_R_CUM_REWARD];
+                if (done) {
+                    ret_sum += (double)R[NCG_R_CUM_REWARD];
+                    if (p.ep_return) p.ep_return[car0 + slot] = R[NCG_R_CUM_REWARD];
+                    if (slot == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
+                }
                 // ---- same-step auto-reset (CarPhysics.reset_car semantics) + reset observation words 0..21
                 if (done && do_reset) {
                     reset_in_place(R, T, s_obs2 + (b * CPB + slot) * OBS_STRIDE);
@@ -317,6 +322,7 @@ struct NcgHandle {
     uint8_t* d_mask = nullptr; int* d_tid = nullptr;
     void* p_actions = nullptr; float* p_obs = nullptr; float* p_final = nullptr; float* p_reward = nullptr; uint8_t* p_flags = nullptr;
     void* d_pack = nullptr; void* p_pack = nullptr; size_t pack_bytes = 0;
+    int* p_any_done = nullptr;                       // page-locked, device-mapped flag word of ncg_step_mapped
 };
 
 namespace {
@@ -395,6 +401,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaMalloc(&h->d_mask, E)); CUDA_TRY(cudaMalloc(&h->d_tid, E * 4));
     CUDA_TRY(cudaMallocHost(&h->p_actions, N * 8)); CUDA_TRY(cudaMallocHost(&h->p_pack, h->pack_bytes)); CUDA_TRY(cudaMallocHost(&h->p_final, N * NCG_OBS_DIM * 4));
     h->p_obs = (float*)h->p_pack; h->p_reward = h->p_obs + N * NCG_OBS_DIM; h->p_flags = (uint8_t*)(h->p_reward + N);
+    CUDA_TRY(cudaHostAlloc((void**)&h->p_any_done, 64, cudaHostAllocMapped | cudaHostAllocPortable));
     h->h_env_track.assign(E, 0);
     *out = h;
     return NCG_OK;
@@ -406,7 +413,7 @@ int ncg_destroy(NcgHandle* h) {
     cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
     cudaFree(h->d_mask); cudaFree(h->d_tid);
-    cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final);
+    cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return NCG_OK;
@@ -554,6 +561,35 @@ int ncg_step_pinned(NcgHandle* h, int32_t want_final, int32_t* any_done) {
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     return step_pinned(h, want_final != 0, any_done);
+}
+
+int ncg_host_alloc(size_t bytes, void** out) {
+    if (!out || !bytes) return fail(NCG_E_INVALID, "bad ncg_host_alloc arguments");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+    return NCG_OK;
+}
+int ncg_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return NCG_OK;
+}
+
+// One step with every buffer in page-locked, device-mapped host memory: the kernel reads the actions and writes
+// observations / rewards / flags over PCIe itself, so a step is one launch and one stream synchronise.
+int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                    float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
+    if (!h || !h_actions || !h_obs || !h_reward || !h_terminated || !h_truncated) return fail(NCG_E_INVALID, "null argument");
+    if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    KParams p = base_params(h);
+    p.actions = h_actions; p.obs = h_obs; p.reward = h_reward; p.term = h_terminated; p.trunc = h_truncated; p.final_obs = h_final_obs;
+    p.ep_return = h_ep_return; p.ep_length = h_ep_length; p.any_done = h->p_any_done;
+    p.stage = want_stage(h);
+    *h->p_any_done = 0;
+    int rc = launch_step(h, p, h->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (any_done) *any_done = *h->p_any_done;
+    return NCG_OK;
 }
 
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream) {

@@ -7,6 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
+import sys
 from typing import Optional, Sequence
 
 import numpy as np
@@ -60,7 +61,8 @@ class Stats(ctypes.Structure):
 
 EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_upload_tracks", "ncg_reset", "ncg_step",
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
-           "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned")
+           "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
+           "ncg_host_free", "ncg_step_mapped")
 
 _lib = None
 
@@ -93,6 +95,9 @@ def load_library():
     lib.ncg_host_buffers.argtypes = [vp] + [ctypes.POINTER(vp)] * 6
     lib.ncg_step_pinned.argtypes = [vp, i32, ctypes.POINTER(i32)]
     lib.ncg_launch_count.restype = ctypes.c_int64
+    lib.ncg_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.ncg_host_free.argtypes = [vp]
+    lib.ncg_step_mapped.argtypes = [vp] * 9 + [ctypes.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -110,6 +115,53 @@ def _check(rc: int):
 
 def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class _HostAllocation:
+    """Owner of one ncg_host_alloc allocation; freed when the last array over it dies."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load_library()
+        p = ctypes.c_void_p()
+        _check(self._lib.ncg_host_alloc(nbytes, ctypes.byref(p)))
+        self.ptr = p
+
+    def __del__(self):
+        try:
+            if self.ptr is not None and self.ptr.value:
+                self._lib.ncg_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+class HostBlock:
+    """A page-locked, device-mapped host allocation (ncg_host_alloc) carved into named numpy arrays.  The arrays are
+    what the kernel reads and writes directly; `busy()` tells whether the caller still holds views of any of them.  The
+    memory lives as long as the block or any view of its arrays."""
+
+    def __init__(self, fields):
+        sizes = [int(np.prod(shape)) * np.dtype(dt).itemsize for _, shape, dt in fields]
+        offs, total = [], 0
+        for sz in sizes:
+            offs.append(total)
+            total += (sz + 255) // 256 * 256
+        self._alloc = _HostAllocation(max(total, 256))
+        base = self._alloc.ptr.value
+        # numpy collapses .base chains to the first array over a foreign buffer, so every view a caller holds keeps a
+        # reference on the flat array made here: its reference count says whether the block may be overwritten
+        self._flat, self.arrays, self.ptrs = {}, {}, {}
+        for (name, shape, dt), off in zip(fields, offs):
+            n = int(np.prod(shape))
+            raw = (ctypes.c_char * (n * np.dtype(dt).itemsize)).from_address(base + off)
+            raw._owner = self._alloc                 # views -> flat -> raw -> allocation
+            self._flat[name] = np.frombuffer(raw, dtype=dt, count=n)
+            self.arrays[name] = self._flat[name].reshape(shape)
+            self.ptrs[name] = ctypes.c_void_p(base + off)
+        self._base_refs = {k: sys.getrefcount(a) for k, a in self._flat.items()}
+
+    def busy(self) -> bool:
+        return any(sys.getrefcount(a) > self._base_refs[k] for k, a in self._flat.items())
 
 
 class Engine:
@@ -241,6 +293,27 @@ class Engine:
         """Step with actions already written into pinned_views()['actions']; results are read in place."""
         done = ctypes.c_int32(0)
         _check(self._lib.ncg_step_pinned(self._h, int(want_final), ctypes.byref(done)))
+        return bool(done.value)
+
+    def result_block(self) -> "HostBlock":
+        """A fresh set of mapped host result buffers for step_mapped."""
+        N, E = self.num_cars, self.num_envs
+        return HostBlock([("obs", (N, 38), np.float32), ("reward", (N,), np.float32), ("terminated", (E,), np.uint8),
+                          ("truncated", (E,), np.uint8)])
+
+    def aux_block(self) -> "HostBlock":
+        """Mapped host buffers for the actions and the rarely read per-episode outputs of step_mapped."""
+        N, E = self.num_cars, self.num_envs
+        act = ("actions", (N,), np.int32) if self.discrete else ("actions", (N, 2), np.float32)
+        return HostBlock([act, ("final_obs", (N, 38), np.float32), ("ep_return", (N,), np.float32), ("ep_length", (E,), np.int32)])
+
+    def step_mapped(self, aux: "HostBlock", res: "HostBlock") -> bool:
+        """One step: actions from aux['actions'], results into `res` (written by the kernel across PCIe).  Returns
+        True when at least one env finished (then aux final_obs / ep_return / ep_length hold those envs' values)."""
+        done = ctypes.c_int32(0)
+        a, r = aux.ptrs, res.ptrs
+        _check(self._lib.ncg_step_mapped(self._h, a["actions"], r["obs"], r["reward"], r["terminated"], r["truncated"],
+                                         a["final_obs"], a["ep_return"], a["ep_length"], ctypes.byref(done)))
         return bool(done.value)
 
     def get_state_host(self) -> np.ndarray:

@@ -34,8 +34,8 @@ class NascarVectorEnv:
 
     def __init__(self, num_envs: int, track_file: Union[None, str, Sequence[str]] = None, num_cars: int = 1,
                  discrete_action_space: bool = False, reset_on_lap: bool = False, device: int = 0, track_info: bool = False,
-                 copy: bool = True):
-        self.copy = copy            # False: step() returns views of the pinned staging buffers (valid until the next step)
+                 max_result_blocks: int = 64):
+        self.max_result_blocks = int(max_result_blocks)   # result buffers kept alive for the caller before step() copies
         if num_cars < 1 or num_cars > K.MAX_CARS:
             raise ValueError(f"Number of cars must be between 1 and {K.MAX_CARS}")
         if track_file is None:
@@ -57,45 +57,65 @@ class NascarVectorEnv:
         self.track_id = (np.arange(num_envs, dtype=np.int64) * len(tracks) // num_envs).astype(np.int32)
         self._obs_shape = (num_envs, K.OBS_DIM) if num_cars == 1 else (num_envs, num_cars, K.OBS_DIM)
         self._rew_shape = (num_envs,) if num_cars == 1 else (num_envs, num_cars)
-        self._ep_len = np.zeros(num_envs, dtype=np.int64)
-        self._ep_ret = np.zeros(self._rew_shape, dtype=np.float64)
+        self._aux, self._ring, self._ring_pos, self._spill = None, [], 0, None
         self._torch_bufs = None
         self.closed = False
 
     # ------------------------------------------------------------------ numpy API
     def reset(self, seed=None, options=None):
         obs = self.engine.reset_host(track_id=self.track_id, fresh=True)
-        self._ep_len[:] = 0
-        self._ep_ret[...] = 0.0
         return obs.reshape(self._obs_shape), {}
 
+    def _next_result_block(self):
+        """Result buffers nobody holds views of any more: the next one of the ring, or a new one while the caller keeps
+        earlier results alive (so returned arrays are never overwritten -- copy semantics without the copy)."""
+        for _ in range(len(self._ring)):
+            self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+            blk = self._ring[self._ring_pos]
+            if not blk.busy():
+                return blk
+        if len(self._ring) >= self.max_result_blocks:
+            return None
+        blk = self.engine.result_block()
+        self._ring.insert(self._ring_pos + 1, blk)
+        self._ring_pos += 1
+        return blk
+
     def step(self, actions):
-        """actions: (E[,C],2) float32 in [-1,1] or (E[,C]) ints.  Host buffers in, host buffers out: the actions go through
-        the library's page-locked staging buffer, one packed D2H copy brings obs/reward/flags back."""
-        v = self.engine.pinned_views()
-        v["actions"][...] = np.asarray(actions).reshape(v["actions"].shape)
-        any_done = self.engine.step_pinned(want_final=True)
-        obs = v["obs"].reshape(self._obs_shape)
-        rew = v["reward"].reshape(self._rew_shape)
-        if self.copy:
-            obs, rew = obs.copy(), rew.copy()
-        te, tr = v["terminated"].astype(bool), v["truncated"].astype(bool)
-        self._ep_len += 1
-        self._ep_ret += rew
+        """actions: (E[,C],2) float32 in [-1,1] or (E[,C]) ints.  Host buffers in, host buffers out.  The actions are
+        written into a page-locked buffer the kernel reads directly; observations, rewards and flags are written by the
+        kernel straight into page-locked result buffers (ncg_step_mapped), which are handed out without a copy and not
+        reused while the caller still references them."""
+        if self._aux is None:
+            self._aux = self.engine.aux_block()
+            self._ring, self._ring_pos = [self.engine.result_block() for _ in range(2)], 0
+        aux = self._aux.arrays
+        aux["actions"][...] = np.asarray(actions).reshape(aux["actions"].shape)
+        blk = self._next_result_block()
+        spill = blk is None
+        if spill:                                   # the caller holds max_result_blocks results: fall back to copying
+            if self._spill is None:
+                self._spill = self.engine.result_block()
+            blk = self._spill
+        any_done = self.engine.step_mapped(self._aux, blk)
+        r = blk.arrays
+        obs, rew = r["obs"].reshape(self._obs_shape), r["reward"].reshape(self._rew_shape)
+        te, tr = r["terminated"].view(np.bool_), r["truncated"].view(np.bool_)
+        if spill:
+            obs, rew, te, tr = obs.copy(), rew.copy(), te.copy(), tr.copy()
         info = {}
         if any_done:
             done = te | tr
-            fin = v["final_obs"].reshape(self._obs_shape)
+            fin = aux["final_obs"].reshape(self._obs_shape)
             fo = np.empty(self.num_envs, dtype=object)
-            ep_r = np.zeros(self._rew_shape, dtype=np.float64)
-            ep_l = np.zeros(self.num_envs, dtype=np.int64)
             for e in np.nonzero(done)[0]:
                 fo[e] = fin[e].copy()
-            ep_r[done], ep_l[done] = self._ep_ret[done], self._ep_len[done]
+            ep_r = np.zeros(self._rew_shape, dtype=np.float64)
+            ep_l = np.zeros(self.num_envs, dtype=np.int64)
+            ep_r[done] = aux["ep_return"].reshape(self._rew_shape)[done]
+            ep_l[done] = aux["ep_length"][done]
             info = {"final_observation": fo, "_final_observation": done.copy(),
                     "episode": {"r": ep_r, "l": ep_l}, "_episode": done.copy()}
-            self._ep_ret[done] = 0.0
-            self._ep_len[done] = 0
         return obs, rew, te, tr, info
 
     # ------------------------------------------------------------------ torch API (device-resident)
@@ -131,6 +151,8 @@ class NascarVectorEnv:
 
     def close(self):
         if not self.closed:
+            # blocks the caller still references stay allocated until those arrays die (HostBlock.__del__ frees them)
+            self._ring, self._aux, self._spill = [], None, None
             self.engine.close()
             self.closed = True
 

@@ -167,3 +167,29 @@ def test_full_size_properties_config3():
     assert (steps == steps[:, :1]).all()                  # cars of an env share the env clock
     assert ((u[:, R["NCG_R_NCONTACT"]] & 255) <= L.MAX_CONTACTS).all()
     eng.close()
+
+
+def test_vector_env_results_are_handed_out_without_copy_and_never_overwritten_while_held():
+    """step() returns views of page-locked buffers the kernel wrote; a buffer is reused only after the caller drops them."""
+    from nascargymnasium_b200.vector_env import NascarVectorEnv
+    E = 96
+    venv = NascarVectorEnv(E, track_file="tracks/nascar.track")
+    ref = NascarVectorEnv(E, track_file="tracks/nascar.track")
+    venv.reset(); ref.reset()
+    rng = np.random.default_rng(2)
+    held = []
+    for t in range(7):
+        a = rng.uniform(-1, 1, (E, 2)).astype(np.float32)
+        o, r, te, tr, _ = venv.step(a)
+        o2, r2, te2, tr2, _ = ref.step(a)                # second env: its results are dropped every step (ring of 2)
+        assert np.array_equal(o, o2) and np.array_equal(r, r2) and te.dtype == np.bool_ and o.dtype == np.float32
+        held.append((o, o.copy(), r, r.copy(), te, te.copy()))
+        del o2, r2, te2, tr2
+    for o, oc, r, rc, te, tec in held:
+        assert np.array_equal(o, oc) and np.array_equal(r, rc) and np.array_equal(te, tec)
+    assert len(venv._ring) >= 7 and len(ref._ring) == 2
+    # the mapped path and the staged-copy path are the same kernel: same numbers
+    eng_obs, eng_rew, *_ = ref.engine.step_host(a)
+    o3, r3, *_ = venv.step(a)
+    assert np.array_equal(o3, eng_obs) and np.array_equal(r3, eng_rew)
+    venv.close(); ref.close()
