@@ -36,6 +36,19 @@ METRIC = "car-steps/sec (16-ray sensors) at 4096-65536 envs, 1/2/4/8 B200 vs hos
 UNIT = "car-steps/s"
 
 
+def profiled_traffic(steps_per_launch: int, n_cars: int):
+    """DRAM bytes per launch of the rollout kernel from the committed `ncu --set full` capture (profiles/), or None when
+    the capture was taken at another launch shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)
+        if int(t["steps_per_launch"]) == steps_per_launch and int(t["cars"]) == n_cars:
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -105,22 +118,52 @@ def cpu_throughput(track: str, steps_per_proc: int, procs: int, seed: int = 0, w
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every 5 ms; nvidia-smi as a fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons, self._stop, self._t = index, [], [], set(), threading.Event(), None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for bit, nm in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        s = [x.strip() for x in out.split(",")]
+        if s[0].replace(".", "").isdigit():
+            self.sm.append(float(s[0]))
+        if len(s) > 1 and s[1].replace(".", "").isdigit():
+            self.mx.append(float(s[1]))
+        for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
+                self.reasons.add(nm)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self._nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.005 if self._nvml else 0.05)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -132,16 +175,8 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for k, nm in enumerate(names):
-                if len(s) > 3 + k and s[3 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -162,8 +197,11 @@ def run_ours(args):
     E, C, track = args.envs, args.cars, args.track
     N = E * C
     K, Wm, T = args.steps, args.warmup, args.steps_per_launch
-    eng = Engine(E, C, tracks=[track], discrete=False, auto_reset=True, device=local)
-    eng.reset_host()
+    from nascargymnasium_b200 import track as TR
+    tracks = list(TR.BUILTIN_TRACK_NAMES) if track == "all" else [track]
+    track_id = (np.arange(E, dtype=np.int64) * len(tracks) // E).astype(np.int32)      # contiguous blocks of envs per track
+    eng = Engine(E, C, tracks=tracks, discrete=False, auto_reset=True, device=local)
+    eng.reset_host(track_id=track_id)
     obs_roll = torch.empty((T, N, 38), dtype=torch.float32, device=dev)
     rew_roll = torch.empty((T, N), dtype=torch.float32, device=dev)
     done_roll = torch.empty((T, E), dtype=torch.uint8, device=dev)
@@ -176,7 +214,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def launch(n):
-        eng.rollout(n, seed=args.seed, mode=0, obs_rollout=obs_roll[:n].reshape(-1) if n != T else obs_roll.reshape(-1),
+        eng.rollout(n, seed=args.seed, mode=args.mode, obs_rollout=obs_roll[:n].reshape(-1) if n != T else obs_roll.reshape(-1),
                     reward_rollout=rew_roll[:n].reshape(-1) if n != T else rew_roll.reshape(-1),
                     done_rollout=done_roll[:n].reshape(-1) if n != T else done_roll.reshape(-1))
 
@@ -211,7 +249,7 @@ def run_ours(args):
     value = world * N * K / (kern_ms_max / 1e3)
 
     # ---- e2e: host buffers through the CarEnv-facing API, H2D + D2H every step
-    venv = NascarVectorEnv(num_envs=E, track_file=f"tracks/{track}.track", num_cars=C, device=local)
+    venv = NascarVectorEnv(num_envs=E, track_file=None if track == "all" else f"tracks/{track}.track", num_cars=C, device=local)
     venv.reset()
     Ke = args.e2e_steps
     cars = np.arange(N, dtype=np.int64) + rank * N
@@ -241,14 +279,18 @@ def run_ours(args):
         "ms_per_step": kern_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{E} batched {'single-car' if C == 1 else str(C) + '-car'} envs on {track}.track per GPU, continuous "
-                               f"actions ~ U[-1,1]^2 (Philox on device), 16-ray observations written every step, same-step auto-reset",
+                               f"actions {'~ U[-1,1]^2' if args.mode == 0 else 'driving distribution tb~U[0.2,1], steer~U[-0.2,0.6]'} (Philox on "
+                               f"device), 16-ray observations written every step, same-step auto-reset",
                    "envs_per_gpu": E, "cars_per_env": C, "track": track, "steps_per_launch": T,
                    "l2": "flushed (256 MiB memset) between timed launches; the working set itself is L2-resident by construction",
                    "rays_per_lane": os.environ.get("NCG_RAYS_PER_LANE", "2")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated"},
+                "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated; actions are copied into "
+                       "page-locked memory the kernel reads across PCIe, results are written by the kernel into page-locked host "
+                       "buffers and returned without a further copy"},
         "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": profiled_traffic(T, N) if args.mode == 0 and track == "daytona" else None,
                      "peak_source": peak_src, "kernel": "ncg_step_kernel", "algorithmic_bytes_per_car_step": ALGO_BYTES_PER_CAR_STEP,
                      "car_steps_per_launch": N * (K / len(chunks)), "avg_launch_ms": per_launch_s * 1e3},
         "clocks": clk.summary(),
@@ -257,7 +299,7 @@ def run_ours(args):
     }
     if rank == 0 and world == 1:
         t0 = time.perf_counter()
-        v = cpu_throughput(track, args.cpu_steps, 1, seed=args.seed)
+        v = cpu_throughput(tracks[0], args.cpu_steps, 1, seed=args.seed)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"1 single-car env on {track}.track, {args.cpu_steps} steps after 600 warm-up, same Philox action "
                                           f"stream, oracle/ncg_oracle.cpp single thread ({time.perf_counter() - t0:.1f} s)"}
@@ -280,7 +322,7 @@ def run_reference(args):
     # each "step" is a bounded sample: every core advances one single-car env by cpu_steps/ K ... keep total ~20-40 s
     per_proc = max(200, min(args.cpu_steps, 40000))
     t0 = time.perf_counter()
-    v = cpu_throughput(args.track, per_proc, cores, seed=args.seed)
+    v = cpu_throughput("daytona" if args.track == "all" else args.track, per_proc, cores, seed=args.seed)
     dt = time.perf_counter() - t0
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -299,16 +341,18 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3000)
-    ap.add_argument("--warmup", type=int, default=600)
+    ap.add_argument("--steps", type=int, default=30000)
+    ap.add_argument("--warmup", type=int, default=3000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--cars", type=int, default=1)
-    ap.add_argument("--track", default="daytona")
+    ap.add_argument("--track", default="daytona", help="a built-in track name, or 'all' = the 8 .track files in equal blocks of envs")
     ap.add_argument("--steps-per-launch", type=int, default=100)
-    ap.add_argument("--e2e-steps", type=int, default=500)
+    ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--cpu-steps", type=int, default=40000)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--mode", type=int, default=0, help="synthetic action distribution: 0 = action_space.sample() (the metric), "
+                    "1 = 'driving' (tb~U[0.2,1], steer~U[-0.2,0.6]: laps, wall contacts, episodes)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

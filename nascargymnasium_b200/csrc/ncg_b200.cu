@@ -29,6 +29,7 @@ struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, conta
 
 struct KParams {
     float* records; const float* blob; const long long* track_off;
+    const int2* cta_tab;                                   // per CTA: {first env, number of envs}; all of one track
     int E, C, epb, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
     int T; unsigned long long seed; int mode; unsigned step_base;
@@ -116,8 +117,8 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
     uint32_t* s_xf = reinterpret_cast<uint32_t*>(smem + L.xf);
     float* s_track = smem + L.track;
 
-    const int env0 = blockIdx.x * p.epb;
-    const int n_env = min(p.epb, p.E - env0);
+    const int2 cta = p.cta_tab[blockIdx.x];
+    const int env0 = cta.x, n_env = cta.y;
     const int n_cars = n_env * p.C, car0 = env0 * p.C;
     const int N = p.E * p.C;
 
@@ -310,7 +311,8 @@ struct NcgHandle {
     NcgConfig cfg; int N;
     float* d_records = nullptr; float* d_blob = nullptr; long long* d_track_off = nullptr; int n_tracks = 0;
     std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
-    std::vector<int> h_env_track; bool tracks_grouped = false;
+    std::vector<int> h_env_track;
+    int2* d_cta_tab = nullptr; int n_ctas = 0; bool cta_dirty = true;
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0;
@@ -341,17 +343,39 @@ int envs_per_cta(const NcgHandle* h) {
     return epb;
 }
 
+// CTA table: consecutive envs are cut into CTAs of at most envs_per_cta, and never across a track boundary, so every CTA
+// stages exactly one track table.  Rebuilt (host side, one small upload) whenever the env -> track map changes.
+int build_cta_table(NcgHandle* h) {
+    const int E = h->cfg.num_envs, epb = envs_per_cta(h);
+    std::vector<int2> tab;
+    int e = 0;
+    while (e < E) {
+        int n = 1;
+        while (n < epb && e + n < E && h->h_env_track[e + n] == h->h_env_track[e]) ++n;
+        tab.push_back(make_int2(e, n));
+        e += n;
+    }
+    if ((int)tab.size() > h->n_ctas) {
+        cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_cta_tab, tab.size() * sizeof(int2)));
+    }
+    CUDA_TRY(cudaMemcpy(h->d_cta_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    h->n_ctas = (int)tab.size();
+    h->cta_dirty = false;
+    return NCG_OK;
+}
+
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     const int RPL = h->rays_per_lane;
-    const int epb = envs_per_cta(h);
-    p.epb = epb;
+    if (h->cta_dirty) { int rc = build_cta_table(h); if (rc) return rc; }
+    p.cta_tab = h->d_cta_tab;
+    { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
     const size_t smem = (size_t)smem_layout(mx).total * 4;
-    const int grid = (h->cfg.num_envs + epb - 1) / epb;
     void (*k)(KParams) = RPL == 1 ? ncg_step_kernel<1> : RPL == 4 ? ncg_step_kernel<4> : ncg_step_kernel<2>;
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 32 * (1 + 16 / RPL), smem, s>>>(p);
+    k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     return NCG_OK;
@@ -412,7 +436,7 @@ int ncg_destroy(NcgHandle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
-    cudaFree(h->d_mask); cudaFree(h->d_tid);
+    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab);
     cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -436,22 +460,6 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
     return NCG_OK;
 }
 
-static void note_tracks(NcgHandle* h, const uint8_t* mask, const int32_t* tid) {
-    if (!tid) return;
-    for (int e = 0; e < h->cfg.num_envs; ++e) if (!mask || mask[e]) h->h_env_track[e] = tid[e];
-}
-// a CTA stages one track table: that needs all of its envs on the same track
-static void update_grouping(NcgHandle* h) {
-    const int epb = envs_per_cta(h);
-    bool ok = true;
-    for (int e = 0; e < h->cfg.num_envs && ok; ++e) if (h->h_env_track[e] != h->h_env_track[(e / epb) * epb]) ok = false;
-    h->tracks_grouped = ok;
-}
-static int want_stage(const NcgHandle* h) {
-    const char* ns = getenv("NCG_NO_STAGE");
-    return (h->tracks_grouped && !(ns && atoi(ns))) ? 1 : 0;
-}
-
 int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id, int32_t fresh, float* d_obs, void* stream) {
     if (!h) return fail(NCG_E_INVALID, "null handle");
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called before ncg_reset");
@@ -464,7 +472,18 @@ int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     h->was_reset = true;
-    if (d_track_id) h->tracks_grouped = false;   // device-side ids: grouping unknown, the rollout kernel will not stage
+    if (d_track_id) {                            // device-side ids: bring them back once so the CTA table can follow
+        const int E = h->cfg.num_envs;
+        std::vector<int> ids(E); std::vector<uint8_t> mk(d_env_mask ? E : 0);
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        CUDA_TRY(cudaMemcpy(ids.data(), d_track_id, (size_t)E * 4, cudaMemcpyDeviceToHost));
+        if (d_env_mask) CUDA_TRY(cudaMemcpy(mk.data(), d_env_mask, E, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < E; ++e) if (!d_env_mask || mk[e]) {
+            if (ids[e] < 0 || ids[e] >= h->n_tracks) return fail(NCG_E_INVALID, "track id out of range");
+            h->h_env_track[e] = ids[e];
+        }
+        h->cta_dirty = true;
+    }
     return NCG_OK;
 }
 
@@ -475,7 +494,6 @@ int ncg_step(NcgHandle* h, const void* d_actions, float* d_obs, float* d_reward,
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams p = base_params(h);
     p.actions = d_actions; p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated; p.final_obs = d_final_obs;
-    p.stage = want_stage(h);
     return launch_step(h, p, (cudaStream_t)stream);
 }
 
@@ -489,7 +507,6 @@ int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float*
     p.obs_roll = d_obs_rollout; p.rew_roll = d_reward_rollout; p.done_roll = d_done_rollout; p.obs = d_obs_last; p.reward = nullptr;
     if (!d_reward_rollout) { p.reward = h->d_reward; }
     p.term = h->d_term; p.trunc = h->d_trunc;
-    p.stage = want_stage(h);
     h->step_base += (unsigned)steps;
     return launch_step(h, p, (cudaStream_t)stream);
 }
@@ -503,8 +520,6 @@ int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_tra
     if (h_track_id) CUDA_TRY(cudaMemcpyAsync(h->d_tid, h_track_id, E * 4, cudaMemcpyHostToDevice, h->stream));
     int rc = ncg_reset(h, h_env_mask ? h->d_mask : nullptr, h_track_id ? h->d_tid : nullptr, fresh, h->d_obs, h->stream);
     if (rc) return rc;
-    note_tracks(h, h_env_mask, h_track_id);
-    update_grouping(h);
     if (h_obs) CUDA_TRY(cudaMemcpyAsync(h_obs, h->d_obs, (size_t)h->N * NCG_OBS_DIM * 4, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return NCG_OK;
@@ -583,7 +598,6 @@ int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_
     KParams p = base_params(h);
     p.actions = h_actions; p.obs = h_obs; p.reward = h_reward; p.term = h_terminated; p.trunc = h_truncated; p.final_obs = h_final_obs;
     p.ep_return = h_ep_return; p.ep_length = h_ep_length; p.any_done = h->p_any_done;
-    p.stage = want_stage(h);
     *h->p_any_done = 0;
     int rc = launch_step(h, p, h->stream);
     if (rc) return rc;
@@ -622,7 +636,7 @@ int ncg_set_state_host(NcgHandle* h, const float* h_records) {
         if ((int)t >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
         h->h_env_track[e] = (int)t;
     }
-    update_grouping(h);
+    h->cta_dirty = true;
     h->was_reset = true;
     return NCG_OK;
 }
