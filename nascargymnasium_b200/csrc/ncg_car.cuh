@@ -25,7 +25,6 @@ struct Track {
 enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEGS, TH_OFF_WALLS, TH_OFF_AABB, TH_OFF_CELLS,
        TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
        TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64 };
-#define NCG_ITEM_NONE 0xFFFF   /* padding entry of a grid item block */
 enum { SEG_STRIDE = 12, WALL_STRIDE = 8, SEG64_STRIDE = 5 };
 // `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
 NCG_HD Track track_view(const float* staged, const float* global) {
@@ -42,9 +41,10 @@ NCG_HD Track track_view(const float* staged, const float* global) {
     t.half_ltot = staged[TH_HALF_LTOT];
     return t;
 }
-// the k-th wall of a grid cell's list, or -1 past its end (lists are padded to blocks of 4 with NCG_ITEM_NONE)
+// the k-th wall of a grid cell's list (lists are padded to blocks of 4 by repeating a block's first wall, so a wall
+// can appear twice: every consumer is insensitive to duplicates)
 NCG_HD int cell_count_max(const Track& T, int cell) { return (int)(T.cells[cell] >> 16) * 4; }
-NCG_HD int cell_item(const Track& T, int cell, int k) { int w = T.items[(T.cells[cell] & 0xFFFFu) * 4u + (uint32_t)k]; return w == NCG_ITEM_NONE ? -1 : w; }
+NCG_HD int cell_item(const Track& T, int cell, int k) { return (int)T.items[(T.cells[cell] & 0xFFFFu) * 4u + (uint32_t)k]; }
 NCG_HD void wall_get(const Track& T, int i, Xf* xf, Box* b) {
     const float* w = T.walls + i * WALL_STRIDE;
     xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[4]; b->hy = w[5];
@@ -201,7 +201,6 @@ NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
         const int nk = cell_count_max(T, cell);
         for (int k = 0; k < nk; ++k) {
             int wi = cell_item(T, cell, k);
-            if (wi < 0) break;
             if (!aabb_overlap(W.b.fat, wall_fat(T, wi))) continue;
             bool have = false;
             for (int j = 0; j < W.nc; ++j) if (W.c[j].wall == wi) { have = true; break; }
@@ -539,7 +538,7 @@ NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
         int cell = iy * T.gnx + ix;
         const int nk = cell_count_max(T, cell);
-        for (int k = 0; k < nk; ++k) { int wi = cell_item(T, cell, k); if (wi < 0) break; if (aabb_overlap(fat, wall_fat(T, wi))) return true; }
+        for (int k = 0; k < nk; ++k) { int wi = cell_item(T, cell, k); if (aabb_overlap(fat, wall_fat(T, wi))) return true; }
     }
     return false;
 }
@@ -739,7 +738,6 @@ NCG_HDN bool on_track(const Track& T, float x, float y) {
         const int nk = cell_count_max(T, cell);
         for (int k = 0; k < nk; ++k) {
             int wi = cell_item(T, cell, k);
-            if (wi < 0) break;
             if (!aabb_overlap(q, wall_fat(T, wi))) continue;
             Xf xf; Box b; wall_get(T, wi, &xf, &b);
             V2 pl = mulT(xf.q, mk(x, y) - xf.p);
@@ -1089,34 +1087,43 @@ NCG_HD float sensor_obs_m(float dist) { float n = dist * 0.004f; return n < 0.0f
 // with Box2D's own clipping arithmetic over all walls.
 NCG_HD float rcp_fast(float x) {
 #if defined(__CUDA_ARCH__)
-    return __fdividef(1.0f, x);
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;     // one MUFU.RCP (no range fix-up code)
 #else
     return 1.0f / x;
 #endif
 }
-// Loads of the ray loop.  SH = the track table is staged in shared memory: ld.shared (LDS) instead of the
-// generic-address loads the compiler would otherwise emit for a pointer it cannot trace to a __shared__ object.
-template <bool SH> NCG_HD F4 ld_f4(const float* p) {
+// Loads of the ray loop.  SH = the track table is staged in shared memory: the table pointers are turned into 32-bit
+// shared-window addresses once per call and the loop uses ld.shared (LDS) with integer address arithmetic, instead of
+// the generic-address loads the compiler emits for a pointer it cannot trace to a __shared__ object.
+template <bool SH> struct RayMem {
 #if defined(__CUDA_ARCH__)
-    if (SH) {
-        F4 v; asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
-        return v;
+    unsigned walls, cells, items; const Track* t;
+    __device__ __forceinline__ RayMem(const Track& T) : t(&T) {
+        if (SH) { walls = (unsigned)__cvta_generic_to_shared(T.walls); cells = (unsigned)__cvta_generic_to_shared(T.cells); items = (unsigned)__cvta_generic_to_shared(T.items); }
     }
+    __device__ __forceinline__ void wall(uint32_t wi, F4* a, F4* b) const {
+        if (SH) {
+            const unsigned ad = walls + wi * (WALL_STRIDE * 4u);
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w) : "r"(ad));
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "r"(ad));
+        } else { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); *b = *reinterpret_cast<const F4*>(w + 4); }
+    }
+    __device__ __forceinline__ uint32_t cell(int c) const {
+        if (SH) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(cells + 4u * (unsigned)c)); return v; }
+        return t->cells[c];
+    }
+    __device__ __forceinline__ void block(int k, uint32_t* lo, uint32_t* hi) const {
+        if (SH) { asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(*lo), "=r"(*hi) : "r"(items + 8u * (unsigned)k)); return; }
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(t->items + 4 * k); *lo = q[0]; *hi = q[1];
+    }
+#else
+    const Track* t;
+    RayMem(const Track& T) : t(&T) {}
+    void wall(uint32_t wi, F4* a, F4* b) const { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); *b = *reinterpret_cast<const F4*>(w + 4); }
+    uint32_t cell(int c) const { return t->cells[c]; }
+    void block(int k, uint32_t* lo, uint32_t* hi) const { const uint32_t* q = reinterpret_cast<const uint32_t*>(t->items + 4 * k); *lo = q[0]; *hi = q[1]; }
 #endif
-    return *reinterpret_cast<const F4*>(p);
-}
-template <bool SH> NCG_HD uint32_t ld_u32(const uint32_t* p) {
-#if defined(__CUDA_ARCH__)
-    if (SH) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p))); return v; }
-#endif
-    return *p;
-}
-template <bool SH> NCG_HD void ld_u32x2(const uint16_t* p, uint32_t* lo, uint32_t* hi) {
-#if defined(__CUDA_ARCH__)
-    if (SH) { asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(*lo), "=r"(*hi) : "r"((unsigned)__cvta_generic_to_shared(p))); return; }
-#endif
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p); *lo = q[0]; *hi = q[1];
-}
+};
 // entry distance (metres) of the ray origin (px,py), unit direction (dx,dy) into the wall row (wa, wb), or +inf
 NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx, float dy) {
     const float c = wa.z, s = wa.w;
@@ -1149,15 +1156,13 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     float sa, ca; sincosf(angle, &sa, &ca);
     float dx = ca * kc[q0] - sa * ks[q0], dy = sa * kc[q0] + ca * ks[q0];
     unsigned nt = 0;
+    const RayMem<SH> M(T);
     const float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
     const int ix0 = (int)floorf(gx), iy0 = (int)floorf(gy);
     if (ix0 < 0 || iy0 < 0 || ix0 >= T.gnx || iy0 >= T.gny) {          // origin outside the grid: scan every wall
         for (int j = 0; j < RPL; ++j) {
             float best = NCG_RAY_LEN;
-            for (int wi = 0; wi < T.n_walls; ++wi) {
-                const float* w = T.walls + wi * WALL_STRIDE;
-                best = fminf(best, ray_box_slab(ld_f4<SH>(w), ld_f4<SH>(w + 4), px, py, dx, dy)); ++nt;
-            }
+            for (int wi = 0; wi < T.n_walls; ++wi) { F4 a, b; M.wall((uint32_t)wi, &a, &b); best = fminf(best, ray_box_slab(a, b, px, py, dx, dy)); ++nt; }
             dst[q0 + 4 * j] = sensor_obs_m(best);
             float t = dx; dx = dy; dy = -t;
         }
@@ -1171,7 +1176,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     float tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
     int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
     int ix = ix0, iy = iy0;
-    const uint32_t h0 = ld_u32<SH>(T.cells + iy0 * T.gnx + ix0);
+    const uint32_t h0 = M.cell(iy0 * T.gnx + ix0);
     const int k0 = (int)(h0 & 0xFFFFu), e0 = k0 + (int)(h0 >> 16);   // block range of the origin cell
     int k = k0, e = e0, j = 0;
     float best = NCG_RAY_LEN;
@@ -1182,7 +1187,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
             if (!fin) {
                 if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)T.gnx; }
                 else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)T.gny; }
-                if (!fin) { const uint32_t h = ld_u32<SH>(T.cells + iy * T.gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
+                if (!fin) { const uint32_t h = M.cell(iy * T.gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
             }
             if (fin) {
                 dst[q0 + 4 * j] = sensor_obs_m(best);
@@ -1197,18 +1202,13 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
             }
         }
         if (k < e) {                                                    // one block: four walls (padding repeats wall 0, masked)
-            uint32_t lo, hi; ld_u32x2<SH>(T.items + 4 * k, &lo, &hi); ++k;
-            const uint32_t i0 = lo & 0xFFFFu, i1 = lo >> 16, i2 = hi & 0xFFFFu, i3 = hi >> 16;
-            const float* w0 = T.walls + i0 * WALL_STRIDE;               // a block's first entry is always a wall
-            const float* w1 = T.walls + (i1 == NCG_ITEM_NONE ? i0 : i1) * WALL_STRIDE;
-            const float* w2 = T.walls + (i2 == NCG_ITEM_NONE ? i0 : i2) * WALL_STRIDE;
-            const float* w3 = T.walls + (i3 == NCG_ITEM_NONE ? i0 : i3) * WALL_STRIDE;
-            const F4 a0 = ld_f4<SH>(w0), b0 = ld_f4<SH>(w0 + 4), a1 = ld_f4<SH>(w1), b1 = ld_f4<SH>(w1 + 4);
-            const F4 a2 = ld_f4<SH>(w2), b2 = ld_f4<SH>(w2 + 4), a3 = ld_f4<SH>(w3), b3 = ld_f4<SH>(w3 + 4);
+            uint32_t lo, hi; M.block(k, &lo, &hi); ++k;
+            F4 a0, b0, a1, b1, a2, b2, a3, b3;                           // a short block is padded by repeating its first wall
+            M.wall(lo & 0xFFFFu, &a0, &b0); M.wall(lo >> 16, &a1, &b1); M.wall(hi & 0xFFFFu, &a2, &b2); M.wall(hi >> 16, &a3, &b3);
             const float t0 = ray_box_slab(a0, b0, px, py, dx, dy), t1 = ray_box_slab(a1, b1, px, py, dx, dy);
             const float t2 = ray_box_slab(a2, b2, px, py, dx, dy), t3 = ray_box_slab(a3, b3, px, py, dx, dy);
             best = fminf(best, fminf(fminf(t0, t1), fminf(t2, t3)));
-            nt += 4u - (i1 == NCG_ITEM_NONE) - (i2 == NCG_ITEM_NONE) - (i3 == NCG_ITEM_NONE);
+            nt += 4u;
         }
     }
     *tests += nt;

@@ -305,7 +305,6 @@ H_GX0, H_GY0, H_INVCELL, H_CELL, H_LTOT, H_MINLAP, H_SLX0, H_SLY0, H_SLDX, H_SLD
 H_STAGE_WORDS = 25       # words [0, H_STAGE_WORDS) are what a CTA stages into shared memory (the whole table)
 H_OFF_SEG64 = 26         # float64 rows [sx,sy,ex,ey,cum_chord] per segment (tie-exact nearest-segment search)
 ITEM_BLOCK = 4           # grid item lists are padded to blocks of 4 (one 8-byte load, four slab tests in flight)
-ITEM_NONE = 0xFFFF       # padding entry
 SEG64_STRIDE = 5
 
 
@@ -441,7 +440,8 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
         nb = (len(l) + ITEM_BLOCK - 1) // ITEM_BLOCK
         blk_first[i], blk_count[i] = len(padded) // ITEM_BLOCK, nb
         padded.extend(l)
-        padded.extend([ITEM_NONE] * (nb * ITEM_BLOCK - len(l)))
+        if l:                                        # pad the last block by repeating its first wall (a harmless re-test)
+            padded.extend([l[(nb - 1) * ITEM_BLOCK]] * (nb * ITEM_BLOCK - len(l)))
     if len(padded) // ITEM_BLOCK >= 65536:
         raise ValueError("grid item list exceeds 16-bit block offsets; use a larger cell")
     off_cells = off_walls + pad4(n * WALL_STRIDE)
@@ -494,10 +494,101 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     blob[off_walls:off_walls + n * WALL_STRIDE] = wrows.reshape(-1)
     blob[off_aabb:off_aabb + n * 4] = fat.reshape(-1)
     blob.view(np.uint32)[off_cells: off_cells + nx * ny] = (blk_first | (blk_count << 16)).astype(np.uint32)
-    it16 = np.full(items_words * 2, ITEM_NONE, dtype=np.uint16)
+    it16 = np.zeros(items_words * 2, dtype=np.uint16)
     it16[:len(padded)] = padded
     blob.view(np.uint16)[off_items * 2: off_items * 2 + len(it16)] = it16
     return TrackTable(track, boxes, fat, segs, seg64, (x0, y0), (nx, ny), cell_start, items, blob)
+
+
+# ----------------------------------------------------------------------------
+# Grid cell size: picked per track from a cost model of the ray loop
+# ----------------------------------------------------------------------------
+CELL_CANDIDATES = (8.0, 12.0, 16.0, 24.0, 32.0, 48.0)
+MAX_TABLE_BYTES = 64 * 1024          # a CTA stages the whole table next to ~43 KB of its own state
+COST_PER_CELL, COST_PER_BLOCK = 25.0, 210.0     # instructions per DDA cell step / per block of four slab tests (ncu)
+
+
+def _sample_rays(tab: TrackTable, n_poses: int = 120, seed: int = 0):
+    """Ray origins near the racing surface with random headings, 16 rays each, and their true hit distances."""
+    rng = np.random.default_rng(seed)
+    P = []
+    for _ in range(n_poses):
+        s = tab.seg64[rng.integers(0, len(tab.seg64))]
+        u = rng.uniform()
+        x = s[0] + u * (s[2] - s[0]) + rng.uniform(-4, 4)
+        y = s[1] + u * (s[3] - s[1]) + rng.uniform(-4, 4)
+        a = rng.uniform(-math.pi, math.pi)
+        for k in range(K.NUM_SENSORS):
+            P.append((x, y, math.cos(a - k * math.pi / 8), math.sin(a - k * math.pi / 8)))
+    px, py, dx, dy = np.array(P).T
+    b = tab.boxes.astype(np.float64)
+    c, s_ = b[:, 2][None, :], b[:, 3][None, :]
+    ax, ay = b[:, 0][None, :] - px[:, None], b[:, 1][None, :] - py[:, None]
+    mx, my = c * ax + s_ * ay, c * ay - s_ * ax
+    ex, ey = c * dx[:, None] + s_ * dy[:, None] + 1e-30, c * dy[:, None] - s_ * dx[:, None] + 1e-30
+    x0, x1, y0, y1 = (mx - b[:, 4]) / ex, (mx + b[:, 4]) / ex, (my - b[:, 5]) / ey, (my + b[:, 5]) / ey
+    tn = np.maximum(np.minimum(x0, x1), np.minimum(y0, y1))
+    tf = np.minimum(np.maximum(x0, x1), np.maximum(y0, y1))
+    hit = np.minimum(np.where((tn > 0) & (tn <= tf), tn, np.inf).min(axis=1), K.SENSOR_MAX_DISTANCE)
+    return px, py, dx, dy, hit
+
+
+def ray_loop_cost(tab: TrackTable, cell: float, rays) -> float:
+    """Mean modelled instruction count per ray of csrc/ncg_car.cuh::cast_rays on this table (same traversal rule)."""
+    px, py, dx, dy, hit = rays
+    x0, y0 = tab.grid_origin
+    nx, ny = tab.grid_dims
+    nblk = (np.diff(tab.cell_start.astype(np.int64)) + ITEM_BLOCK - 1) // ITEM_BLOCK
+    total = 0.0
+    for i in range(len(px)):
+        gx, gy = (px[i] - x0) / cell, (py[i] - y0) / cell
+        ix, iy = int(math.floor(gx)), int(math.floor(gy))
+        if not (0 <= ix < nx and 0 <= iy < ny):
+            continue
+        fx, fy = gx - ix, gy - iy
+        tdx = cell / abs(dx[i]) if dx[i] != 0 else math.inf
+        tdy = cell / abs(dy[i]) if dy[i] != 0 else math.inf
+        tmx = ((1 - fx) if dx[i] > 0 else fx) * tdx if dx[i] != 0 else math.inf
+        tmy = ((1 - fy) if dy[i] > 0 else fy) * tdy if dy[i] != 0 else math.inf
+        sx, sy = (1 if dx[i] > 0 else -1), (1 if dy[i] > 0 else -1)
+        while True:
+            total += COST_PER_CELL + COST_PER_BLOCK * nblk[iy * nx + ix]
+            texit = min(tmx, tmy)
+            if hit[i] <= texit or texit >= K.SENSOR_MAX_DISTANCE:
+                break
+            if tmx < tmy:
+                ix += sx
+                tmx += tdx
+            else:
+                iy += sy
+                tmy += tdy
+            if not (0 <= ix < nx and 0 <= iy < ny):
+                break
+    return total / len(px)
+
+
+def build_best_track_table(track: Track) -> TrackTable:
+    """build_track_table at the candidate cell size with the lowest modelled ray cost that fits the staging budget
+    (large ovals end up at 32 m, the half-mile tracks with their ~1 m chords at 8-12 m)."""
+    forced = os.environ.get("NCG_GRID_CELL")
+    if forced:
+        return build_track_table(track, cell=float(forced))
+    best, rays = None, None
+    for cell in CELL_CANDIDATES:
+        try:
+            tab = build_track_table(track, cell=cell)
+        except ValueError:
+            continue
+        if tab.blob.nbytes > MAX_TABLE_BYTES:
+            continue
+        if rays is None:
+            rays = _sample_rays(tab)
+        cost = ray_loop_cost(tab, cell, rays)
+        if best is None or cost < best[0]:
+            best = (cost, tab)
+    if best is None:
+        return build_track_table(track)
+    return best[1]
 
 
 _TABLE_CACHE: Dict[str, TrackTable] = {}
@@ -506,5 +597,5 @@ _TABLE_CACHE: Dict[str, TrackTable] = {}
 def get_track_table(path_or_name: str) -> TrackTable:
     key = os.path.abspath(path_or_name) if os.path.exists(path_or_name) else track_name_of(path_or_name)
     if key not in _TABLE_CACHE:
-        _TABLE_CACHE[key] = build_track_table(load_track(path_or_name))
+        _TABLE_CACHE[key] = build_best_track_table(load_track(path_or_name))
     return _TABLE_CACHE[key]

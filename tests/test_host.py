@@ -80,16 +80,33 @@ def test_track_parser_errors():
 
 
 def test_grid_lists_every_wall_in_every_cell_it_touches():
-    tab = T.get_track_table("martinsville")
-    nx, ny = tab.grid_dims
-    x0, y0 = tab.grid_origin
-    cs = T._wall_corners(tab.boxes)
-    for w in range(0, tab.n_walls, 37):
-        for cx, cy in cs[w]:
-            ix, iy = int((cx - x0) // T.GRID_CELL), int((cy - y0) // T.GRID_CELL)
-            c = iy * nx + ix
-            assert w in tab.cell_items[tab.cell_start[c]:tab.cell_start[c + 1]]
-    assert len(tab.blob) % 4 == 0 and tab.blob.view(np.int32)[T.H_STAGE_WORDS] % 4 == 0
+    for name in ("martinsville", "daytona"):
+        tab = T.get_track_table(name)
+        cell = float(tab.blob[T.H_CELL])
+        nx, ny = tab.grid_dims
+        x0, y0 = tab.grid_origin
+        cs = T._wall_corners(tab.boxes)
+        hdr = tab.blob.view(np.uint32)
+        cells = hdr[hdr[T.H_OFF_CELLS]: hdr[T.H_OFF_CELLS] + nx * ny]
+        items = tab.blob.view(np.uint16)[2 * hdr[T.H_OFF_ITEMS]:]
+        for w in range(0, tab.n_walls, 37):
+            for cx, cy in cs[w]:
+                ix, iy = int((cx - x0) // cell), int((cy - y0) // cell)
+                c = iy * nx + ix
+                assert w in tab.cell_items[tab.cell_start[c]:tab.cell_start[c + 1]]
+                # device layout: u32 per cell = first block | n_blocks << 16, blocks of four u16 wall indices
+                first, nblk = int(cells[c] & 0xFFFF), int(cells[c] >> 16)
+                dev = items[4 * first: 4 * (first + nblk)]
+                assert w in dev and set(dev.tolist()) == set(tab.cell_items[tab.cell_start[c]:tab.cell_start[c + 1]].tolist())
+        assert len(tab.blob) % 4 == 0 and tab.blob.view(np.int32)[T.H_STAGE_WORDS] % 4 == 0
+        assert tab.blob.nbytes <= T.MAX_TABLE_BYTES
+
+
+def test_cell_size_is_chosen_per_track():
+    """Half-mile tracks (1 m chords) get a finer grid than the superspeedways; the choice is deterministic."""
+    assert float(T.get_track_table("martinsville").blob[T.H_CELL]) < float(T.get_track_table("daytona").blob[T.H_CELL])
+    a = T.build_best_track_table(T.load_track("nascar2"))
+    assert np.array_equal(a.blob, T.get_track_table("nascar2").blob)
 
 
 def test_step_count_thresholds_are_the_float64_clock():
