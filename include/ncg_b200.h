@@ -198,6 +198,12 @@ int ncg_set_state_host(NcgHandle* h, const float* h_records);
 
 int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset);
 
+/* The launch plan of ncg_step / ncg_rollout, exposed for inspection and tests (pure host code, no CUDA call): envs are
+ * cut into CTAs of whole envs, at most 32 car slots each, never across a change of track id, and small batches are
+ * spread over num_sms SMs.  Writes up to `capacity` entries and returns the number of CTAs. */
+int32_t ncg_plan_ctas(const int32_t* h_env_track, int32_t num_envs, int32_t cars_per_env, int32_t num_sms,
+                      int32_t* h_first_env, int32_t* h_num_envs, int32_t capacity);
+
 /* Number of kernels this library has launched on the handle (for bench.py's gpu_launches). */
 int64_t ncg_launch_count(NcgHandle* h);
 

@@ -30,7 +30,7 @@ struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, conta
 struct KParams {
     float* records; const float* blob; const long long* track_off;
     const int2* cta_tab;                                   // per CTA: {first env, number of envs}; all of one track
-    int E, C, epb, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip;
+    int E, C, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
     int T; unsigned long long seed; int mode; unsigned step_base;
     float* obs_roll; float* rew_roll; uint8_t* done_roll;
@@ -331,30 +331,33 @@ namespace {
 
 // Whole envs per CTA: at most CPB car slots, fewer when that spreads a small batch over all SMs (4096 single-car
 // envs: 28 per CTA = 147 CTAs on 148 SMs instead of 128 CTAs of 32).
-int envs_per_cta(const NcgHandle* h) {
-    const int C = h->cfg.cars_per_env, E = h->cfg.num_envs;
+int envs_per_cta(int E, int C, int sms) {
     const int epb_max = CPB / C;                               // C <= 10 < CPB
     const int min_ctas = (E + epb_max - 1) / epb_max;
-    const int sms = h->num_sms > 0 ? h->num_sms : 148;
+    if (sms <= 0) sms = 148;
     const int target = ((min_ctas + sms - 1) / sms) * sms;     // whole waves of one CTA per SM
     int epb = (E + target - 1) / target;
     if (epb < 1) epb = 1;
     if (epb > epb_max) epb = epb_max;
     return epb;
 }
-
 // CTA table: consecutive envs are cut into CTAs of at most envs_per_cta, and never across a track boundary, so every CTA
-// stages exactly one track table.  Rebuilt (host side, one small upload) whenever the env -> track map changes.
-int build_cta_table(NcgHandle* h) {
-    const int E = h->cfg.num_envs, epb = envs_per_cta(h);
-    std::vector<int2> tab;
+// stages exactly one track table.
+void plan_ctas(const int* env_track, int E, int C, int sms, std::vector<int2>& tab) {
+    const int epb = envs_per_cta(E, C, sms);
+    tab.clear();
     int e = 0;
     while (e < E) {
         int n = 1;
-        while (n < epb && e + n < E && h->h_env_track[e + n] == h->h_env_track[e]) ++n;
+        while (n < epb && e + n < E && env_track[e + n] == env_track[e]) ++n;
         tab.push_back(make_int2(e, n));
         e += n;
     }
+}
+// Rebuilt (host side, one small upload) whenever the env -> track map changes.
+int build_cta_table(NcgHandle* h) {
+    std::vector<int2> tab;
+    plan_ctas(h->h_env_track.data(), h->cfg.num_envs, h->cfg.cars_per_env, h->num_sms, tab);
     if ((int)tab.size() > h->n_ctas) {
         cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr;
         CUDA_TRY(cudaMalloc(&h->d_cta_tab, tab.size() * sizeof(int2)));
@@ -576,6 +579,15 @@ int ncg_step_pinned(NcgHandle* h, int32_t want_final, int32_t* any_done) {
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     return step_pinned(h, want_final != 0, any_done);
+}
+
+int32_t ncg_plan_ctas(const int32_t* h_env_track, int32_t num_envs, int32_t cars_per_env, int32_t num_sms, int32_t* h_first_env,
+                      int32_t* h_num_envs, int32_t capacity) {
+    if (!h_env_track || num_envs < 1 || cars_per_env < 1 || cars_per_env > NCG_MAX_CARS) return fail(NCG_E_INVALID, "bad ncg_plan_ctas arguments");
+    std::vector<int2> tab;
+    plan_ctas(h_env_track, num_envs, cars_per_env, num_sms, tab);
+    for (int i = 0; i < (int)tab.size() && i < capacity; ++i) { if (h_first_env) h_first_env[i] = tab[i].x; if (h_num_envs) h_num_envs[i] = tab[i].y; }
+    return (int32_t)tab.size();
 }
 
 int ncg_host_alloc(size_t bytes, void** out) {

@@ -62,7 +62,7 @@ class Stats(ctypes.Structure):
 EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_upload_tracks", "ncg_reset", "ncg_step",
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
-           "ncg_host_free", "ncg_step_mapped")
+           "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas")
 
 _lib = None
 
@@ -98,6 +98,8 @@ def load_library():
     lib.ncg_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
     lib.ncg_host_free.argtypes = [vp]
     lib.ncg_step_mapped.argtypes = [vp] * 9 + [ctypes.POINTER(i32)]
+    lib.ncg_plan_ctas.argtypes = [vp, i32, i32, i32, vp, vp, i32]
+    lib.ncg_plan_ctas.restype = i32
     _lib = lib
     return lib
 
@@ -115,6 +117,18 @@ def _check(rc: int):
 
 def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def plan_ctas(env_track: np.ndarray, cars_per_env: int, num_sms: int = 148):
+    """(first_env, num_envs) per CTA of the step kernel's launch plan for this env -> track map (ncg_plan_ctas)."""
+    lib = load_library()
+    tid = np.ascontiguousarray(env_track, dtype=np.int32)
+    first = np.zeros(len(tid), dtype=np.int32)
+    count = np.zeros(len(tid), dtype=np.int32)
+    n = lib.ncg_plan_ctas(_np_ptr(tid), len(tid), int(cars_per_env), int(num_sms), _np_ptr(first), _np_ptr(count), len(tid))
+    if n < 0:
+        _check(n)
+    return first[:n].copy(), count[:n].copy()
 
 
 class _HostAllocation:

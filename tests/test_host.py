@@ -180,3 +180,27 @@ def test_car_env_argument_errors_match_reference():
         CarEnv(track_file="tracks/nascar.track", num_cars=2, car_names=["a"])
     with pytest.raises(FileNotFoundError):
         CarEnv(track_file="tracks/nope.track")
+
+
+def test_launch_plan_keeps_ctas_on_one_track_and_fills_the_sms():
+    """ncg_plan_ctas (pure host code of the C ABI): whole envs per CTA, <= 32 car slots, never across a track boundary."""
+    from nascargymnasium_b200 import engine
+    # BASELINE config 2: 4096 single-car envs -> 147 CTAs of <= 28 on 148 SMs (not 128 CTAs of 32)
+    first, count = engine.plan_ctas(np.zeros(4096, np.int32), 1, 148)
+    assert len(first) == 147 and count.max() == 28 and count.sum() == 4096 and first[0] == 0
+    assert np.array_equal(first[1:], np.cumsum(count)[:-1])
+    # config 3: 10-car envs -> 3 envs (30 car slots) per CTA
+    first, count = engine.plan_ctas(np.zeros(8192, np.int32), 10, 148)
+    assert count.max() == 3 and count.sum() == 8192
+    # config 4 per GPU: 8192 envs over 8 tracks in blocks -> no CTA straddles a block boundary
+    tid = (np.arange(8192) * 8 // 8192).astype(np.int32)
+    first, count = engine.plan_ctas(tid, 1, 148)
+    assert count.sum() == 8192 and count.max() <= 32
+    for f, c in zip(first, count):
+        assert len(set(tid[f:f + c].tolist())) == 1
+    # worst case (track id alternating per env) degrades to one env per CTA but stays correct
+    first, count = engine.plan_ctas((np.arange(64) % 2).astype(np.int32), 1, 148)
+    assert len(first) == 64 and (count == 1).all()
+    # a single env is one CTA
+    first, count = engine.plan_ctas(np.zeros(1, np.int32), 10, 148)
+    assert first.tolist() == [0] and count.tolist() == [1]
