@@ -283,7 +283,7 @@ def run_ours(args):
                                f"device), 16-ray observations written every step, same-step auto-reset",
                    "envs_per_gpu": E, "cars_per_env": C, "track": track, "steps_per_launch": T,
                    "l2": "flushed (256 MiB memset) between timed launches; the working set itself is L2-resident by construction",
-                   "rays_per_lane": os.environ.get("NCG_RAYS_PER_LANE", "2")},
+                   "rays_per_lane": os.environ.get("NCG_RAYS_PER_LANE", "auto")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated; actions are copied into "
                        "page-locked memory the kernel reads across PCIe, results are written by the kernel into page-locked host "

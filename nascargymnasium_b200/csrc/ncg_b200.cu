@@ -68,14 +68,14 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
 }
 
 // same-track reset of one record + observation words 0..21 (kept out of line: it runs once per episode)
-__device__ __noinline__ void reset_in_place(float* R, const Track& T, float* obs) {
+__device__ __noinline__ void reset_in_place(float* R, const Track T, float* obs) {
     reset_record(R, T, false, f2u(R[NCG_R_TRACK]));
     observe_state(R, obs);
 }
 
 // rays of a freshly reset car (once per episode: out of line, generic loads)
 template <int RPL>
-__device__ __noinline__ void cast_rays_reset(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
+__device__ __noinline__ void cast_rays_reset(const Track T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
     cast_rays<RPL, false>(T, px, py, angle, q0, dst, tests);
 }
 
@@ -98,8 +98,11 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
     return L;
 }
 
-template <int RPL>
-__global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p) {
+// MINB = CTAs per SM the register allocation must allow: 1 lets the physics warp keep its whole working set (track
+// view, body, tyres) in registers -- right when the batch is at most one CTA per SM; 2 trades a few spills for
+// twice the resident warps when there are waves of CTAs.
+template <int RPL, int MINB>
+__global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
     constexpr int RW = 16 / RPL;                    // ray warps
     constexpr int NT = 32 * (1 + RW);
     constexpr int LPC = 16 / RPL;                   // lanes per car in a ray warp
@@ -249,7 +252,9 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL)) ncg_step_kernel(KParams p
             bar_sync(BAR_FULL + b, NT);
             if (active && do_reset && s_flag[b * CPB + slot] != 0u) {            // finished and reset: rays of the reset pose
                 const float4 ps = s_pose2[b * CPB + slot];
-                cast_rays_reset<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &tests);
+                unsigned t2 = 0;
+                cast_rays_reset<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &t2);
+                tests += t2;
             }
             __syncwarp();
             // ---- observation rows of this warp's cars shared -> HBM (CPW x 38 consecutive floats)
@@ -316,7 +321,7 @@ struct NcgHandle {
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0;
-    int rays_per_lane = 2; int num_sms = 0;
+    int rays_per_lane = 0; int num_sms = 0;
     long long launches = 0;
     // host-buffer path
     cudaStream_t stream = nullptr;
@@ -369,14 +374,20 @@ int build_cta_table(NcgHandle* h) {
 }
 
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
-    const int RPL = h->rays_per_lane;
     if (h->cta_dirty) { int rc = build_cta_table(h); if (rc) return rc; }
+    const int sms = h->num_sms > 0 ? h->num_sms : 148;
+    // rays per lane: 2 (8 ray warps per CTA) while the batch is latency-bound, 4 (4 ray warps, better lane balance and
+    // fewer instructions per car-step) once there are waves of CTAs; measured in profiles/
+    const int RPL = h->rays_per_lane ? h->rays_per_lane : (h->n_ctas > 2 * sms ? 4 : 2);
     p.cta_tab = h->d_cta_tab;
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
     const size_t smem = (size_t)smem_layout(mx).total * 4;
-    void (*k)(KParams) = RPL == 1 ? ncg_step_kernel<1> : RPL == 4 ? ncg_step_kernel<4> : ncg_step_kernel<2>;
+    int minb = h->n_ctas <= sms ? 1 : 2;
+    { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && (atoi(mb) == 1 || atoi(mb) == 2)) minb = atoi(mb); }
+    void (*k)(KParams) = minb == 1 ? (RPL == 1 ? ncg_step_kernel<1, 1> : RPL == 4 ? ncg_step_kernel<4, 1> : ncg_step_kernel<2, 1>)
+                                   : (RPL == 1 ? ncg_step_kernel<1, 2> : RPL == 4 ? ncg_step_kernel<4, 2> : ncg_step_kernel<2, 2>);
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
@@ -413,7 +424,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
     const char* g = getenv("NCG_RAYS_PER_LANE");
     int rpl = g ? atoi(g) : 0;
-    if (rpl != 1 && rpl != 2 && rpl != 4) rpl = 2;                // measured: profiles/
+    if (rpl != 1 && rpl != 2 && rpl != 4) rpl = 0;                // 0 = chosen per launch from the batch size
     h->rays_per_lane = rpl;
     size_t N = (size_t)h->N, E = (size_t)cfg->num_envs;
     CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));

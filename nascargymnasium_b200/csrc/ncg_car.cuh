@@ -545,7 +545,9 @@ NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
 // The general b2World::Step for a car with (or about to get) contacts.  `resume`: the fast path has already done
 // Collide (nothing to do) and Solve for a car whose contact list was empty, and found that the moved proxy now
 // overlaps a wall; continue from FindNewContacts.
-NCG_HDN void step_with_contacts(Body& B, float* R, const Track& T, float dt, bool resume, Counters* cnt) {
+// (Track by value and the caller passes copies of its Body / Counters: nothing of the inlined fast path has its
+// address taken, so the fast path keeps all of it in registers.)
+NCG_HDN void step_with_contacts(Body& B, float* R, const Track T, float dt, bool resume, Counters* cnt) {
     World W; W.b = B;
     w_load_contacts(W, R);
     float dtRatio = B.inv_dt0 * dt;
@@ -570,7 +572,7 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
     if (!slow && contacts && B.newFixture) {           // first Step of a fresh world: pairs of the initial proxy
         if (any_wall_overlap(T, B.fat)) slow = true; else { B.newFixture = false; B.proxyMoved = false; }
     }
-    if (slow) step_with_contacts(B, R, T, dt, false, cnt);
+    if (slow) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, false, &c2); B = b2; *cnt = c2; }
     else {
         if (B.awake) {                                 // b2Island::Solve of a lone body
             B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
@@ -581,7 +583,7 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
             b_sync_fixtures(B);
         }
         if (contacts && B.proxyMoved) {                // FindNewContacts
-            if (any_wall_overlap(T, B.fat)) step_with_contacts(B, R, T, dt, true, cnt);
+            if (any_wall_overlap(T, B.fat)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, true, &c2); B = b2; *cnt = c2; }
             else B.proxyMoved = false;
         }
     }
@@ -675,7 +677,7 @@ NCG_HD void friction_forces(float* ff, const float* R, float driving, float thro
 // SURVEY App. F) have two chords that coincide to ~1e-14 m near the start line, and the reference's answer there
 // hangs on float64 digits -- so a float32 scan picks the winner only when it is clear-cut, and otherwise the
 // search is redone in float64 with the reference's exact expressions.
-NCG_HDN void nearest_segment64(const Track& T, float xf, float yf, float* banking, float* progress) {
+NCG_HDN void nearest_segment64(const Track T, float xf, float yf, float* banking, float* progress) {
     const double x = (double)xf, y = (double)yf;
     double best = INFINITY; int bi = 0; double bcx = 0.0, bcy = 0.0;
     for (int i = 0; i < T.n_segs; ++i) {
@@ -708,7 +710,7 @@ NCG_HD void nearest_segment(const Track& T, float x, float y, float* banking, fl
     }
     // float32 projection error is ~1e-4 m at these coordinates: demand a clear margin in distance, else go to float64
     float db = sqrtf(best), ds = sqrtf(second);
-    if (ds - db < 2e-3f + 1e-4f * ds) { nearest_segment64(T, x, y, banking, progress); return; }
+    if (ds - db < 2e-3f + 1e-4f * ds) { float b64, p64; nearest_segment64(T, x, y, &b64, &p64); *banking = b64; *progress = p64; return; }
     const float* s = T.segs + bi * SEG_STRIDE;
     *banking = s[9];
     float px = bcx - s[0], py = bcy - s[1];
@@ -727,7 +729,7 @@ NCG_HD bool on_startline(const Track& T, float x, float y) {
     return d <= T.slhalfw;
 }
 // car_physics.py:470-524 (AABB query of +-0.5 m, TestPoint, corner distance)
-NCG_HDN bool on_track(const Track& T, float x, float y) {
+NCG_HDN bool on_track(const Track T, float x, float y) {
     const float radius = 0.5f;
     AABB q; q.lx = x - radius; q.ly = y - radius; q.ux = x + radius; q.uy = y + radius;
     int ix0 = (int)floorf((q.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((q.ux - T.gx0) * T.inv_cell);
@@ -1157,9 +1159,10 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     float dx = ca * kc[q0] - sa * ks[q0], dy = sa * kc[q0] + ca * ks[q0];
     unsigned nt = 0;
     const RayMem<SH> M(T);
+    const int gnx = T.gnx, gny = T.gny;
     const float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
     const int ix0 = (int)floorf(gx), iy0 = (int)floorf(gy);
-    if (ix0 < 0 || iy0 < 0 || ix0 >= T.gnx || iy0 >= T.gny) {          // origin outside the grid: scan every wall
+    if (ix0 < 0 || iy0 < 0 || ix0 >= gnx || iy0 >= gny) {              // origin outside the grid: scan every wall
         for (int j = 0; j < RPL; ++j) {
             float best = NCG_RAY_LEN;
             for (int wi = 0; wi < T.n_walls; ++wi) { F4 a, b; M.wall((uint32_t)wi, &a, &b); best = fminf(best, ray_box_slab(a, b, px, py, dx, dy)); ++nt; }
@@ -1176,7 +1179,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     float tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
     int sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
     int ix = ix0, iy = iy0;
-    const uint32_t h0 = M.cell(iy0 * T.gnx + ix0);
+    const uint32_t h0 = M.cell(iy0 * gnx + ix0);
     const int k0 = (int)(h0 & 0xFFFFu), e0 = k0 + (int)(h0 >> 16);   // block range of the origin cell
     int k = k0, e = e0, j = 0;
     float best = NCG_RAY_LEN;
@@ -1185,9 +1188,9 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
             const float texit = fminf(tmx, tmy);
             bool fin = best <= texit || texit >= NCG_RAY_LEN;
             if (!fin) {
-                if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)T.gnx; }
-                else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)T.gny; }
-                if (!fin) { const uint32_t h = M.cell(iy * T.gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
+                if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)gnx; }
+                else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)gny; }
+                if (!fin) { const uint32_t h = M.cell(iy * gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
             }
             if (fin) {
                 dst[q0 + 4 * j] = sensor_obs_m(best);
