@@ -503,9 +503,8 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
 # ----------------------------------------------------------------------------
 # Grid cell size: picked per track from a cost model of the ray loop
 # ----------------------------------------------------------------------------
-CELL_CANDIDATES = (8.0, 12.0, 16.0, 24.0, 32.0, 48.0)
+CELL_CANDIDATES = (12.0, 16.0, 24.0, 32.0, 48.0, 64.0)
 MAX_TABLE_BYTES = 64 * 1024          # a CTA stages the whole table next to ~43 KB of its own state
-COST_PER_CELL, COST_PER_BLOCK = 25.0, 210.0     # instructions per DDA cell step / per block of four slab tests (ncu)
 
 
 def _sample_rays(tab: TrackTable, n_poses: int = 120, seed: int = 0):
@@ -534,12 +533,15 @@ def _sample_rays(tab: TrackTable, n_poses: int = 120, seed: int = 0):
 
 
 def ray_loop_cost(tab: TrackTable, cell: float, rays) -> float:
-    """Mean modelled instruction count per ray of csrc/ncg_car.cuh::cast_rays on this table (same traversal rule)."""
+    """Modelled cost of csrc/ncg_car.cuh::cast_rays on this table: iterations of its flattened loop (one per block of four
+    walls, at least one per visited cell; same traversal rule as the device code) for the busiest lane of a car, averaged
+    over the sampled cars.  A warp advances at the pace of its busiest lane, so the long rays are what matter; a lane
+    owns rays q and q+4 (the kernel's 2-rays-per-lane mapping)."""
     px, py, dx, dy, hit = rays
     x0, y0 = tab.grid_origin
     nx, ny = tab.grid_dims
     nblk = (np.diff(tab.cell_start.astype(np.int64)) + ITEM_BLOCK - 1) // ITEM_BLOCK
-    total = 0.0
+    iters = np.zeros(len(px))
     for i in range(len(px)):
         gx, gy = (px[i] - x0) / cell, (py[i] - y0) / cell
         ix, iy = int(math.floor(gx)), int(math.floor(gy))
@@ -551,8 +553,9 @@ def ray_loop_cost(tab: TrackTable, cell: float, rays) -> float:
         tmx = ((1 - fx) if dx[i] > 0 else fx) * tdx if dx[i] != 0 else math.inf
         tmy = ((1 - fy) if dy[i] > 0 else fy) * tdy if dy[i] != 0 else math.inf
         sx, sy = (1 if dx[i] > 0 else -1), (1 if dy[i] > 0 else -1)
+        n = 0
         while True:
-            total += COST_PER_CELL + COST_PER_BLOCK * nblk[iy * nx + ix]
+            n += max(1, int(nblk[iy * nx + ix]))
             texit = min(tmx, tmy)
             if hit[i] <= texit or texit >= K.SENSOR_MAX_DISTANCE:
                 break
@@ -564,12 +567,16 @@ def ray_loop_cost(tab: TrackTable, cell: float, rays) -> float:
                 tmy += tdy
             if not (0 <= ix < nx and 0 <= iy < ny):
                 break
-    return total / len(px)
+        iters[i] = n
+    it = iters.reshape(-1, K.NUM_SENSORS)
+    lanes = [q if q < 4 else q + 4 for q in range(8)]
+    per_lane = it[:, lanes] + it[:, [q + 4 for q in lanes]]
+    return float(per_lane.max(axis=1).mean())
 
 
 def build_best_track_table(track: Track) -> TrackTable:
     """build_track_table at the candidate cell size with the lowest modelled ray cost that fits the staging budget
-    (large ovals end up at 32 m, the half-mile tracks with their ~1 m chords at 8-12 m)."""
+    (the superspeedways end up at 48 m, the half-mile tracks with their ~1 m chords at 16-24 m)."""
     forced = os.environ.get("NCG_GRID_CELL")
     if forced:
         return build_track_table(track, cell=float(forced))

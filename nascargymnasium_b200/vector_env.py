@@ -108,8 +108,10 @@ class NascarVectorEnv:
             done = te | tr
             fin = aux["final_obs"].reshape(self._obs_shape)
             fo = np.empty(self.num_envs, dtype=object)
-            for e in np.nonzero(done)[0]:
-                fo[e] = fin[e].copy()
+            idx = np.nonzero(done)[0]
+            rows = fin[idx]                               # one gather-copy out of the mapped buffer; rows are views of it
+            for j, e in enumerate(idx):
+                fo[e] = rows[j]
             ep_r = np.zeros(self._rew_shape, dtype=np.float64)
             ep_l = np.zeros(self.num_envs, dtype=np.int64)
             ep_r[done] = aux["ep_return"].reshape(self._rew_shape)[done]
