@@ -193,3 +193,59 @@ def test_vector_env_results_are_handed_out_without_copy_and_never_overwritten_wh
     o3, r3, *_ = venv.step(a)
     assert np.array_equal(o3, eng_obs) and np.array_equal(r3, eng_rew)
     venv.close(); ref.close()
+
+
+def test_rollout_is_deterministic_across_launch_shapes_on_the_track_mix():
+    """The physics-warp / ray-warp hand-off is double-buffered across steps: one 600-step launch, launches of 7+250+343
+    steps and five single steps + 595 must give bit-identical records and observations (config 4 track mix)."""
+    import torch
+    from nascargymnasium_b200.engine import Engine
+    E, Tn = 2048, 600
+    tid = (np.arange(E) * len(T.BUILTIN_TRACK_NAMES) // E).astype(np.int32)
+    outs = []
+    for chunks in ([600], [7, 250, 343], [1] * 5 + [595]):
+        eng = Engine(E, 1, tracks=list(T.BUILTIN_TRACK_NAMES), auto_reset=True)
+        eng.reset_host(track_id=tid)
+        obs = torch.zeros((Tn, E, 38), dtype=torch.float32, device="cuda:0")
+        rew = torch.zeros((Tn, E), dtype=torch.float32, device="cuda:0")
+        t0 = 0
+        for n in chunks:
+            eng.rollout(n, seed=11, mode=1, obs_rollout=obs[t0:t0 + n].reshape(-1), reward_rollout=rew[t0:t0 + n].reshape(-1))
+            t0 += n
+        torch.cuda.synchronize()
+        outs.append((eng.get_state_host(), obs.cpu().numpy(), rew.cpu().numpy(), eng.read_stats()))
+        eng.close()
+    ref = outs[0]
+    assert ref[3]["contact_steps"] > 100 and ref[3]["episodes"] > 0           # the driving distribution hits walls and resets
+    for o in outs[1:]:
+        assert np.array_equal(o[0].view(np.uint32), ref[0].view(np.uint32))
+        assert np.array_equal(o[1].view(np.uint32), ref[1].view(np.uint32)) and np.array_equal(o[2].view(np.uint32), ref[2].view(np.uint32))
+        assert o[3]["car_steps"] == E * Tn == ref[3]["car_steps"]
+
+
+def test_teacher_forced_steps_on_all_tracks_in_one_engine():
+    """One engine holding all 8 tracks in blocks of envs (the CTA table keeps every CTA on one track): every block is
+    teacher-forced from oracle states of its own track and must match the oracle like the single-track engines do."""
+    from nascargymnasium_b200.engine import Engine
+    per = 60
+    names = list(T.BUILTIN_TRACK_NAMES)
+    cases = [P.collect_cases(nm, per, kind="drive", seed=20 + i) for i, nm in enumerate(names)]
+    n_each = min(len(c[0]) for c in cases)
+    E = n_each * len(names)
+    eng = Engine(E, 1, tracks=names, auto_reset=False)
+    tid = np.repeat(np.arange(len(names), dtype=np.int32), n_each)
+    eng.reset_host(track_id=tid)
+    recs = np.concatenate([c[0][:n_each] for c in cases])
+    recs.view(np.uint32)[:, R["NCG_R_TRACK"]] = tid
+    eng.set_state_host(recs)
+    raws = np.concatenate([np.array(c[2][:n_each], dtype=np.float32) for c in cases])
+    obs, rew, te, tr, _ = eng.step_host(raws)
+    got = eng.get_state_host()
+    for i, nm in enumerate(names):
+        sl = slice(i * n_each, (i + 1) * n_each)
+        exp = {k: v[:n_each] for k, v in cases[i][3].items()}
+        g = got[sl].copy()
+        g.view(np.uint32)[:, R["NCG_R_TRACK"]] = exp["records"].view(np.uint32)[:, R["NCG_R_TRACK"]]     # single-track oracle: id 0
+        bad, report = P.check_cases(g, obs[sl], rew[sl], te[sl], tr[sl], exp, label=nm)
+        assert bad == 0, report
+    eng.close()
