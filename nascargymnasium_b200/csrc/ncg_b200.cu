@@ -30,6 +30,7 @@ struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, conta
 struct KParams {
     float* records; const float* blob; const long long* track_off;
     const int2* cta_tab;                                   // per CTA: {first env, number of envs}; all of one track
+    const float* reset_obs;                                // [n_tracks][NCG_OBS_DIM]: the observation every reset_car yields on a track
     int E, C, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
     int T; unsigned long long seed; int mode; unsigned step_base;
@@ -67,29 +68,22 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
     }
 }
 
-// same-track reset of one record + observation words 0..21 (kept out of line: it runs once per episode)
-__device__ __noinline__ void reset_in_place(float* R, const Track T, float* obs) {
+// same-track reset of one record (kept out of line: it runs once per episode).  The observation after a reset_car is
+// the same for every car of a track -- start pose, zero velocity, fresh tyres, the 16 rays of the start pose -- so it is
+// computed once per track (ncg_reset_obs_kernel) instead of once per reset.
+__device__ __noinline__ void reset_in_place(float* R, const Track T) {
     reset_record(R, T, false, f2u(R[NCG_R_TRACK]));
-    observe_state(R, obs);
-}
-
-// rays of a freshly reset car (once per episode: out of line, generic loads)
-template <int RPL>
-__device__ __noinline__ void cast_rays_reset(const Track T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
-    cast_rays<RPL, false>(T, px, py, angle, q0, dst, tests);
 }
 
 struct SmemLayout {
-    int rec, obs, obs2, pose, pose2, flag, xf, track, total;      // word offsets
+    int rec, obs, pose, flag, xf, track, total;      // word offsets
 };
 __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
     SmemLayout L; int o = 0;
     L.rec = o; o += CPB * REC_STRIDE;
     L.obs = o; o += 2 * CPB * OBS_STRIDE;          // [2][CPB][OBS_STRIDE]: the step's observation rows
-    L.obs2 = o; o += 2 * CPB * OBS_STRIDE;         // [2][CPB][OBS_STRIDE]: reset observation rows of finished cars
     o = (o + 3) & ~3;
     L.pose = o; o += 2 * CPB * 4;                  // [2][CPB] float4 {x, y, angle, -}
-    L.pose2 = o; o += 2 * CPB * 4;
     L.flag = o; o += 2 * CPB;                      // [2][CPB] u32: bit0 terminated, bit1 truncated
     L.xf = o; o += CPB;
     o = (o + 3) & ~3;
@@ -113,9 +107,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* s_rec = smem + L.rec;
     float* s_obs = smem + L.obs;
-    float* s_obs2 = smem + L.obs2;
     float4* s_pose = reinterpret_cast<float4*>(smem + L.pose);
-    float4* s_pose2 = reinterpret_cast<float4*>(smem + L.pose2);
     uint32_t* s_flag = reinterpret_cast<uint32_t*>(smem + L.flag);
     uint32_t* s_xf = reinterpret_cast<uint32_t*>(smem + L.xf);
     float* s_track = smem + L.track;
@@ -212,11 +204,8 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
                     if (p.ep_return) p.ep_return[car0 + slot] = R[NCG_R_CUM_REWARD];
                     if (slot == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
                 }
-                // ---- same-step auto-reset (CarPhysics.reset_car semantics) + reset observation words 0..21
-                if (done && do_reset) {
-                    reset_in_place(R, T, s_obs2 + (b * CPB + slot) * OBS_STRIDE);
-                    s_pose2[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
-                }
+                // ---- same-step auto-reset (CarPhysics.reset_car semantics)
+                if (done && do_reset) reset_in_place(R, T);
                 s_flag[b * CPB + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
             }
             __syncwarp();
@@ -238,6 +227,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
         const int q = lane % LPC;
         const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // a lane's rays are q0, q0+4, ... (90 deg apart)
         const int wslot0 = (warp - 1) * CPW;                     // first car slot of this warp
+        const float* reset_row = p.reset_obs + (size_t)my_tid * NCG_OBS_DIM;
         unsigned tests = 0;
         for (int t = 0; t < p.T; ++t) {
             const int b = t & 1;
@@ -250,12 +240,6 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
                 else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, q0, dst, &tests);
             }
             bar_sync(BAR_FULL + b, NT);
-            if (active && do_reset && s_flag[b * CPB + slot] != 0u) {            // finished and reset: rays of the reset pose
-                const float4 ps = s_pose2[b * CPB + slot];
-                unsigned t2 = 0;
-                cast_rays_reset<RPL>(T, ps.x, ps.y, ps.z, q0, s_obs2 + (b * CPB + slot) * OBS_STRIDE + 22, &t2);
-                tests += t2;
-            }
             __syncwarp();
             // ---- observation rows of this warp's cars shared -> HBM (CPW x 38 consecutive floats)
             for (int i = lane; i < CPW * NCG_OBS_DIM; i += 32) {
@@ -265,7 +249,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
                     const int row = (b * CPB + sl) * OBS_STRIDE + k;
                     if (do_reset && s_flag[b * CPB + sl] != 0u) {
                         if (p.final_obs) p.final_obs[o] = s_obs[row];
-                        if (obs_out) obs_out[o] = s_obs2[row];
+                        if (obs_out) obs_out[o] = __ldg(reset_row + k);          // finished and reset: the track's reset observation
                     } else if (obs_out) obs_out[o] = s_obs[row];
                 }
             }
@@ -284,6 +268,21 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             dst[i] = make_float4(d[0], d[1], d[2], d[3]);
         }
     }
+}
+
+// the observation of the reset state of each track; one warp per track
+__global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, const long long* track_off, float* reset_obs) {
+    __shared__ float s_rec[NCG_RECORD_WORDS];
+    __shared__ float s_o[40];
+    const int lane = threadIdx.x, tid = blockIdx.x;
+    const float* g = blob + track_off[tid];
+    Track T = track_view(g, g);
+    if (lane == 0) { reset_record(s_rec, T, true, (uint32_t)tid); observe_state(s_rec, s_o); }
+    __syncwarp();
+    unsigned tests = 0;
+    if (lane < 16) cast_rays<1, false>(T, s_rec[NCG_R_X], s_rec[NCG_R_Y], s_rec[NCG_R_ANGLE], lane, s_o + 22, &tests);
+    __syncwarp();
+    for (int k = lane; k < NCG_OBS_DIM; k += 32) reset_obs[(size_t)tid * NCG_OBS_DIM + k] = s_o[k];
 }
 
 // reset of masked envs + their initial observation; one warp per car (rays over lanes)
@@ -315,6 +314,7 @@ __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const fl
 struct NcgHandle {
     NcgConfig cfg; int N;
     float* d_records = nullptr; float* d_blob = nullptr; long long* d_track_off = nullptr; int n_tracks = 0;
+    float* d_reset_obs = nullptr;
     std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
     std::vector<int> h_env_track;
     int2* d_cta_tab = nullptr; int n_ctas = 0; bool cta_dirty = true;
@@ -384,10 +384,14 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
     const size_t smem = (size_t)smem_layout(mx).total * 4;
-    int minb = h->n_ctas <= sms ? 1 : 2;
-    { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && (atoi(mb) == 1 || atoi(mb) == 2)) minb = atoi(mb); }
+    // resident CTAs per SM the register allocation allows: as many as the batch has use for, up to what shared memory
+    // (~69 KB per CTA) admits; the 4-rays-per-lane shape (160 threads) fits three
+    int minb = h->n_ctas <= sms ? 1 : (h->n_ctas <= 2 * sms || RPL != 4 ? 2 : 3);
+    { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && atoi(mb) >= 1 && atoi(mb) <= 3) minb = atoi(mb); }
+    if (minb == 3 && RPL != 4) minb = 2;
     void (*k)(KParams) = minb == 1 ? (RPL == 1 ? ncg_step_kernel<1, 1> : RPL == 4 ? ncg_step_kernel<4, 1> : ncg_step_kernel<2, 1>)
-                                   : (RPL == 1 ? ncg_step_kernel<1, 2> : RPL == 4 ? ncg_step_kernel<4, 2> : ncg_step_kernel<2, 2>);
+                       : minb == 2 ? (RPL == 1 ? ncg_step_kernel<1, 2> : RPL == 4 ? ncg_step_kernel<4, 2> : ncg_step_kernel<2, 2>)
+                                   : ncg_step_kernel<4, 3>;
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
@@ -397,7 +401,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
 
 KParams base_params(NcgHandle* h) {
     KParams p; memset(&p, 0, sizeof(p));
-    p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off;
+    p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off; p.reset_obs = h->d_reset_obs;
     p.E = h->cfg.num_envs; p.C = h->cfg.cars_per_env; p.discrete = h->cfg.discrete; p.reset_on_lap = h->cfg.reset_on_lap;
     p.auto_reset = h->cfg.auto_reset; p.contacts = h->cfg.contacts; p.track_info = h->cfg.track_info; p.stats = h->d_stats; p.T = 1;
     { const char* d = getenv("NCG_DEBUG_SKIP"); p.debug_skip = d ? atoi(d) : 0; }   // profiling only: 1 = no rays, 2 = no physics
@@ -448,7 +452,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
 int ncg_destroy(NcgHandle* h) {
     if (!h) return NCG_OK;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats);
+    cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
     cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab);
     cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
@@ -461,7 +465,7 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
     if (!h || !h_blob || !h_offsets || n_tracks < 1) return fail(NCG_E_INVALID, "bad track upload");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     for (int i = 0; i <= n_tracks; ++i) if (h_offsets[i] % 4) return fail(NCG_E_INVALID, "track offsets must be multiples of 4 words");
-    cudaFree(h->d_blob); cudaFree(h->d_track_off); h->d_blob = nullptr; h->d_track_off = nullptr;
+    cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_reset_obs); h->d_blob = nullptr; h->d_track_off = nullptr; h->d_reset_obs = nullptr;
     size_t words = (size_t)h_offsets[n_tracks];
     CUDA_TRY(cudaMalloc(&h->d_blob, words * 4));
     CUDA_TRY(cudaMemcpy(h->d_blob, h_blob, words * 4, cudaMemcpyHostToDevice));
@@ -471,6 +475,11 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
     h->h_stage_words.clear();
     for (int i = 0; i < n_tracks; ++i) { uint32_t w; memcpy(&w, h_blob + h_offsets[i] + TH_STAGE_WORDS, 4); h->h_stage_words.push_back(w); }
     h->n_tracks = n_tracks;
+    CUDA_TRY(cudaMalloc(&h->d_reset_obs, (size_t)n_tracks * NCG_OBS_DIM * 4));
+    ncg_reset_obs_kernel<<<n_tracks, 32>>>(h->d_blob, h->d_track_off, h->d_reset_obs);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    ++h->launches;
     return NCG_OK;
 }
 
