@@ -76,7 +76,7 @@ __device__ __noinline__ void reset_in_place(float* R, const Track T) {
 }
 
 struct SmemLayout {
-    int rec, obs, pose, flag, xf, track, total;      // word offsets
+    int rec, obs, pose, flag, xf, act, otab, track, total;      // word offsets
 };
 __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
     SmemLayout L; int o = 0;
@@ -86,6 +86,9 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
     L.pose = o; o += 2 * CPB * 4;                  // [2][CPB] float4 {x, y, angle, -}
     L.flag = o; o += 2 * CPB;                      // [2][CPB] u32: bit0 terminated, bit1 truncated
     L.xf = o; o += CPB;
+    o = (o + 3) & ~3;
+    L.act = o; o += 2 * CPB * 4;                   // [2][CPB] float4 {throttle, brake, steer, -}: synthetic actions, made two steps ahead
+    L.otab = o; o += 2 * 40;                       // observation scale[38] (padded to 40) and lower clip bound[38]
     o = (o + 3) & ~3;
     L.track = o; o += (int)stage_words;            // 16-byte aligned for the TMA copy
     L.total = o;
@@ -110,6 +113,8 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
     float4* s_pose = reinterpret_cast<float4*>(smem + L.pose);
     uint32_t* s_flag = reinterpret_cast<uint32_t*>(smem + L.flag);
     uint32_t* s_xf = reinterpret_cast<uint32_t*>(smem + L.xf);
+    float4* s_act = reinterpret_cast<float4*>(smem + L.act);
+    float* s_otab = smem + L.otab;
     float* s_track = smem + L.track;
 
     const int2 cta = p.cta_tab[blockIdx.x];
@@ -134,6 +139,15 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             const float4 v = src[i];
             float* d = s_rec + (i >> 5) * REC_STRIDE + (i & 31) * 4;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    }
+    if (threadIdx.x < NCG_OBS_DIM) { s_otab[threadIdx.x] = obs_scale(threadIdx.x); s_otab[40 + threadIdx.x] = obs_lo(threadIdx.x); }
+    const bool synth = p.actions == nullptr;
+    if (synth && warp == 1 && lane < n_cars) {               // ray warp 0 makes the synthetic actions, two steps ahead of the physics warp
+        for (int t = 0; t < 2 && t < p.T; ++t) {
+            float thr, brk, st;
+            action_synthetic(p.seed, (uint32_t)(car0 + lane), p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
+            s_act[t * CPB + lane] = make_float4(thr, brk, st, 0.0f);
         }
     }
     __syncthreads();
@@ -163,10 +177,10 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             if (active) {
                 float thr, brk, st;
                 const int gc = car0 + slot;
-                if (p.actions) {
+                if (!synth) {
                     if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
                     else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
-                } else action_synthetic(p.seed, (uint32_t)gc, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
+                } else { const float4 a = s_act[b * CPB + slot]; thr = a.x; brk = a.y; st = a.z; }
                 if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts != 0, &ctx, &cnt);
                 s_pose[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
             }
@@ -176,7 +190,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             bar_arrive(BAR_POSE + b, NT);
             if (active) {
                 uint32_t xf = 0;
-                if (!(p.debug_skip & 2)) rew = car_step_rules(R, T, &ctx, s_obs + (b * CPB + slot) * OBS_STRIDE, &xf, &cnt);
+                if (!(p.debug_skip & 2)) rew = car_step_rules<true>(R, T, &ctx, s_obs + (b * CPB + slot) * OBS_STRIDE, &xf, &cnt);
                 s_xf[slot] = xf;
                 if (p.track_info) {
                     uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
@@ -228,6 +242,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
         const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // a lane's rays are q0, q0+4, ... (90 deg apart)
         const int wslot0 = (warp - 1) * CPW;                     // first car slot of this warp
         const float* reset_row = p.reset_obs + (size_t)my_tid * NCG_OBS_DIM;
+        float kcq, ksq; ray_rotation(q0, &kcq, &ksq);
         unsigned tests = 0;
         for (int t = 0; t < p.T; ++t) {
             const int b = t & 1;
@@ -236,8 +251,13 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             if (active && !(p.debug_skip & 1)) {
                 const float4 ps = s_pose[b * CPB + slot];
                 float* dst = s_obs + (b * CPB + slot) * OBS_STRIDE + 22;
-                if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, q0, dst, &tests);
-                else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, q0, dst, &tests);
+                if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, q0, kcq, ksq, dst, &tests);
+                else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, q0, kcq, ksq, dst, &tests);
+            }
+            if (synth && warp == 1 && lane < n_cars && t + 2 < p.T) {     // actions of step t+2 (this buffer's next use)
+                float thr, brk, st;
+                action_synthetic(p.seed, (uint32_t)(car0 + lane), p.step_base + (unsigned)(t + 2), p.mode, p.discrete != 0, &thr, &brk, &st);
+                s_act[b * CPB + lane] = make_float4(thr, brk, st, 0.0f);
             }
             bar_sync(BAR_FULL + b, NT);
             __syncwarp();
@@ -246,14 +266,16 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
                 const int sl = wslot0 + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
                 if (sl < n_cars) {
                     const size_t o = (size_t)(car0 + sl) * NCG_OBS_DIM + k;
-                    const int row = (b * CPB + sl) * OBS_STRIDE + k;
+                    // words 0..21 arrive raw from the physics warp and are scaled and clipped here; the ray words
+                    // are already in [0,1] (scale 1, lower bound 0 leave them unchanged)
+                    const float v = obs_word(s_obs[(b * CPB + sl) * OBS_STRIDE + k], s_otab[k], s_otab[40 + k]);
                     if (do_reset && s_flag[b * CPB + sl] != 0u) {
-                        if (p.final_obs) p.final_obs[o] = s_obs[row];
+                        if (p.final_obs) p.final_obs[o] = v;
                         if (obs_out) obs_out[o] = __ldg(reset_row + k);          // finished and reset: the track's reset observation
-                    } else if (obs_out) obs_out[o] = s_obs[row];
+                    } else if (obs_out) obs_out[o] = v;
                 }
             }
-            if (t + 2 < p.T) bar_arrive(BAR_EMPTY + b, NT);
+            if (t + 2 < p.T) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NT); }
         }
         ray_tests = tests;
         for (int o = 16; o > 0; o >>= 1) ray_tests += __shfl_down_sync(0xffffffffu, ray_tests, o);

@@ -101,6 +101,13 @@ NCG_HD void b_set_transform(Body& B, V2 p, float angle) {
     B.sweep.c = mul(B.xf, mk(0.0f, 0.0f)); B.sweep.a = angle; B.sweep.c0 = B.sweep.c; B.sweep.a0 = angle;
     b_move_proxy(B, box_aabb(car_box(), B.xf), mk(0.0f, 0.0f));
 }
+// b2Body::SynchronizeFixtures with the start-of-step transform xf1 given (it equals rot(a0), c0 when no TOI advance
+// has touched the sweep, which saves a sincosf on the contact-free path)
+NCG_HD void b_sync_fixtures_from(Body& B, const Xf& xf1) {
+    AABB a1 = box_aabb(car_box(), xf1), a2 = box_aabb(car_box(), B.xf);
+    AABB c; c.lx = fminb(a1.lx, a2.lx); c.ly = fminb(a1.ly, a2.ly); c.ux = fmaxb(a1.ux, a2.ux); c.uy = fmaxb(a1.uy, a2.uy);
+    b_move_proxy(B, c, B.xf.p - xf1.p);
+}
 NCG_HD void b_sync_fixtures(Body& B) {
     Xf xf1; xf1.q = rot(B.sweep.a0); xf1.p = B.sweep.c0 - mul(xf1.q, mk(0.0f, 0.0f));
     AABB a1 = box_aabb(car_box(), xf1), a2 = box_aabb(car_box(), B.xf);
@@ -575,12 +582,13 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
     if (slow) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, false, &c2); B = b2; *cnt = c2; }
     else {
         if (B.awake) {                                 // b2Island::Solve of a lone body
+            const Xf xf0 = B.xf;                       // == (rot(a0), c0): b_load synchronised it from the sweep
             B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
             b_integrate_velocity(B, dt);
             integrate_position(B.sweep.c, B.sweep.a, B.v, B.w, dt);
             b_sync_transform(B);
             b_sleep(B, dt, true);
-            b_sync_fixtures(B);
+            b_sync_fixtures_from(B, xf0);
         }
         if (contacts && B.proxyMoved) {                // FindNewContacts
             if (any_wall_overlap(T, B.fat)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, true, &c2); B = b2; *cnt = c2; }
@@ -786,18 +794,23 @@ NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id
 
 // ------------------------------------------------------------------ observation words 0..21 (car_env.py:891-946)
 NCG_HD float clip1(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
-NCG_HD void observe_state(const float* R, float* obs) {
+// Observation word k (< 22) = clip(raw_k * scale_k, lo_k, 1).  observe_raw gathers the 22 raw values on the physics
+// warp; the scaling and clipping can then be done by whoever stores the row (the ray warps, spread over lanes).
+#define NCG_OBS_STATE_DIM 22
+NCG_HD float obs_scale(int k) {
+    const float t[NCG_OBS_STATE_DIM] = {1e-4f, 1e-4f, 1.0f / 111.1f, 1.0f / 111.1f, 1.0f / 111.1f, 1.0f / 3.14159265358979f, 0.1f,
+                                        1.0f / 29430.0f, 1.0f / 29430.0f, 1.0f / 29430.0f, 1.0f / 29430.0f, 0.005f, 0.005f, 0.005f, 0.005f,
+                                        0.01f, 0.01f, 0.01f, 0.01f, 1.0f / 50000.0f, 1.0f / 3.14159265358979f, 1.0f / 250000.0f};
+    return k < NCG_OBS_STATE_DIM ? t[k] : 1.0f;
+}
+NCG_HD float obs_lo(int k) { return (k <= 3 || k == 5 || k == 6 || k == 20) ? -1.0f : 0.0f; }
+NCG_HD float obs_word(float raw, float scale, float lo) { return clip1(raw * scale, lo, 1.0f); }
+NCG_HD void observe_raw(const float* R, float* raw) {
     float vx = R[NCG_R_VX], vy = R[NCG_R_VY];
-    obs[0] = clip1(R[NCG_R_X] * 1e-4f, -1.0f, 1.0f); obs[1] = clip1(R[NCG_R_Y] * 1e-4f, -1.0f, 1.0f);
-    obs[2] = clip1(vx * (1.0f / 111.1f), -1.0f, 1.0f); obs[3] = clip1(vy * (1.0f / 111.1f), -1.0f, 1.0f);
-    obs[4] = clip1(sqrtf(vx * vx + vy * vy) * (1.0f / 111.1f), 0.0f, 1.0f);
-    obs[5] = clip1(R[NCG_R_ANGLE] * (1.0f / 3.14159265358979f), -1.0f, 1.0f); obs[6] = clip1(R[NCG_R_OMEGA] * 0.1f, -1.0f, 1.0f);
+    raw[0] = R[NCG_R_X]; raw[1] = R[NCG_R_Y]; raw[2] = vx; raw[3] = vy; raw[4] = sqrtf(vx * vx + vy * vy);
+    raw[5] = R[NCG_R_ANGLE]; raw[6] = R[NCG_R_OMEGA];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        obs[7 + k] = clip1(R[NCG_R_TYRE_LOAD + k] * (1.0f / 29430.0f), 0.0f, 1.0f);
-        obs[11 + k] = clip1(R[NCG_R_TYRE_TEMP + k] * 0.005f, 0.0f, 1.0f);
-        obs[15 + k] = clip1(R[NCG_R_TYRE_WEAR + k] * 0.01f, 0.0f, 1.0f);
-    }
+    for (int k = 0; k < 4; ++k) { raw[7 + k] = R[NCG_R_TYRE_LOAD + k]; raw[11 + k] = R[NCG_R_TYRE_TEMP + k]; raw[15 + k] = R[NCG_R_TYRE_WEAR + k]; }
     float ci = R[NCG_R_IMPULSE], ca = 0.0f;
     if (ci < 100.0f) ci = 0.0f;
     else if (((f2u(R[NCG_R_NCONTACT]) >> 8) & 255u) > 0) {
@@ -805,8 +818,12 @@ NCG_HD void observe_state(const float* R, float* obs) {
         while (ca > 3.14159265358979f) ca -= 6.28318530717959f;
         while (ca < -3.14159265358979f) ca += 6.28318530717959f;
     }
-    obs[19] = clip1(ci * (1.0f / 50000.0f), 0.0f, 1.0f); obs[20] = clip1(ca * (1.0f / 3.14159265358979f), -1.0f, 1.0f);
-    obs[21] = clip1(R[NCG_R_CUM_IMPACT] * (1.0f / 250000.0f), 0.0f, 1.0f);
+    raw[19] = ci; raw[20] = ca; raw[21] = R[NCG_R_CUM_IMPACT];
+}
+NCG_HD void observe_state(const float* R, float* obs) {
+    float raw[NCG_OBS_STATE_DIM]; observe_raw(R, raw);
+#pragma unroll
+    for (int k = 0; k < NCG_OBS_STATE_DIM; ++k) obs[k] = obs_word(raw[k], obs_scale(k), obs_lo(k));
 }
 
 // ------------------------------------------------------------------ the scalar car phase of one step
@@ -937,6 +954,8 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
     if (W.overflow) cnt->overflow++;
     ctx->fl = fl; ctx->xf = xf; ctx->laps_pre = laps_pre; ctx->dis_pre = dis_pre; ctx->impulse = W.impulse;
 }
+// RAW: obs[0..21] receives observe_raw's values (the caller normalises them when it stores the row)
+template <bool RAW>
 NCG_HD float car_step_rules(float* R, const Track& T, const StepCtx* ctx, float* obs, uint32_t* xflags, Counters* cnt) {
     uint32_t fl = ctx->fl, xf = ctx->xf;
     const uint32_t laps_pre = ctx->laps_pre;
@@ -998,7 +1017,7 @@ NCG_HD float car_step_rules(float* R, const Track& T, const StepCtx* ctx, float*
     }
     R[NCG_R_STUCK_STEPS] = u2f(stuck);
     // ---- observation words 0..21 (before the end-of-step impulse reset)
-    observe_state(R, obs);
+    if (RAW) observe_raw(R, obs); else observe_state(R, obs);
     // ---- reward (car_env.py:980-1113)
     float reward = 0.0f;
     if (!(disabled && !jd)) {
@@ -1038,7 +1057,7 @@ NCG_HD float car_step(float* R, const Track& T, float thr_in, float brk_in, floa
                       uint32_t* xflags, Counters* cnt) {
     StepCtx ctx;
     car_step_dynamics(R, T, thr_in, brk_in, steer_in, contacts, &ctx, cnt);
-    return car_step_rules(R, T, &ctx, obs, xflags, cnt);
+    return car_step_rules<false>(R, T, &ctx, obs, xflags, cnt);
 }
 
 // ------------------------------------------------------------------ env phase (car_env.py:672-676, 1115-1158, 773-797)
@@ -1145,18 +1164,21 @@ NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx
 // "fetch the next cell if this one's list is exhausted, then test one block of four walls" -- so lanes never sit
 // in different loop nests, and the four slab tests of a block are independent instruction streams that overlap
 // their shared-memory and MUFU latencies.  Normalised distances go to dst[q0 + 4*j].
-template <int RPL, bool SH>
-NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
-    // cos/sin(-q0*22.5 deg): the reference evaluates cos/sin(theta - i*pi/8) in float64 (distance_sensor.py:95-103);
-    // rotating the float32 heading by a constant keeps the axis-aligned rays of the start pose exactly axis-aligned.
+// cos/sin(-q*22.5 deg): the reference evaluates cos/sin(theta - i*pi/8) in float64 (distance_sensor.py:95-103);
+// rotating the float32 heading by a constant keeps the axis-aligned rays of the start pose exactly axis-aligned.
+NCG_HD void ray_rotation(int q, float* kcq, float* ksq) {
     const float kc[16] = {1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.0f, -0.38268343236508977f,
                           -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f, -0.70710678118654752f,
                           -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
     const float ks[16] = {0.0f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.0f, -0.92387953251128674f,
                           -0.70710678118654752f, -0.38268343236508977f, 0.0f, 0.38268343236508977f, 0.70710678118654752f,
                           0.92387953251128674f, 1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
+    *kcq = kc[q]; *ksq = ks[q];
+}
+template <int RPL, bool SH>
+NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float kcq, float ksq, float* dst, unsigned* tests) {
     float sa, ca; sincosf(angle, &sa, &ca);
-    float dx = ca * kc[q0] - sa * ks[q0], dy = sa * kc[q0] + ca * ks[q0];
+    float dx = ca * kcq - sa * ksq, dy = sa * kcq + ca * ksq;
     unsigned nt = 0;
     const RayMem<SH> M(T);
     const int gnx = T.gnx, gny = T.gny;
@@ -1215,6 +1237,12 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
         }
     }
     *tests += nt;
+}
+// convenience form: looks the ray's rotation constants up (the kernel hoists that out of its step loop)
+template <int RPL, bool SH>
+NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
+    float kcq, ksq; ray_rotation(q0, &kcq, &ksq);
+    cast_rays<RPL, SH>(T, px, py, angle, q0, kcq, ksq, dst, tests);
 }
 NCG_HD float sensor_obs(float dist) { return sensor_obs_m(dist); }
 
