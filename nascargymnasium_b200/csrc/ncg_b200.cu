@@ -243,6 +243,14 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
         const int wslot0 = (warp - 1) * CPW;                     // first car slot of this warp
         const float* reset_row = p.reset_obs + (size_t)my_tid * NCG_OBS_DIM;
         float kcq, ksq; ray_rotation(q0, &kcq, &ksq);
+        // which (car of this warp, word pair) this lane stores in each pass of the row write-out: fixed for the launch
+        constexpr int NIT = (CPW * (NCG_OBS_DIM / 2) + 31) / 32;
+        uint32_t pair_sk[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int m = lane + 32 * it;
+            pair_sk[it] = m < CPW * (NCG_OBS_DIM / 2) ? (uint32_t)(((m / (NCG_OBS_DIM / 2)) << 8) | ((m % (NCG_OBS_DIM / 2)) * 2)) : 0xFFFFFFFFu;
+        }
         unsigned tests = 0;
         for (int t = 0; t < p.T; ++t) {
             const int b = t & 1;
@@ -261,18 +269,23 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             }
             bar_sync(BAR_FULL + b, NT);
             __syncwarp();
-            // ---- observation rows of this warp's cars shared -> HBM (CPW x 38 consecutive floats)
-            for (int i = lane; i < CPW * NCG_OBS_DIM; i += 32) {
-                const int sl = wslot0 + i / NCG_OBS_DIM, k = i % NCG_OBS_DIM;
-                if (sl < n_cars) {
-                    const size_t o = (size_t)(car0 + sl) * NCG_OBS_DIM + k;
-                    // words 0..21 arrive raw from the physics warp and are scaled and clipped here; the ray words
-                    // are already in [0,1] (scale 1, lower bound 0 leave them unchanged)
-                    const float v = obs_word(s_obs[(b * CPB + sl) * OBS_STRIDE + k], s_otab[k], s_otab[40 + k]);
+            // ---- observation rows of this warp's cars shared -> HBM: CPW x 38 consecutive floats, written as float2
+            // (a row is 19 float2, so a pair never straddles two cars and every store is 8-byte aligned).  Words 0..21
+            // arrive raw from the physics warp and are scaled and clipped here; the ray words are already in [0,1]
+            // (scale 1, lower bound 0 leave them unchanged).
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int sl = wslot0 + (int)(pair_sk[it] >> 8), k = (int)(pair_sk[it] & 255u);
+                if (pair_sk[it] != 0xFFFFFFFFu && sl < n_cars) {
+                    const float* row = s_obs + (b * CPB + sl) * OBS_STRIDE + k;
+                    float2 v;
+                    v.x = obs_word(row[0], s_otab[k], s_otab[40 + k]);
+                    v.y = obs_word(row[1], s_otab[k + 1], s_otab[41 + k]);
+                    const size_t o = ((size_t)(car0 + sl) * NCG_OBS_DIM + k) >> 1;
                     if (do_reset && s_flag[b * CPB + sl] != 0u) {
-                        if (p.final_obs) p.final_obs[o] = v;
-                        if (obs_out) obs_out[o] = __ldg(reset_row + k);          // finished and reset: the track's reset observation
-                    } else if (obs_out) obs_out[o] = v;
+                        if (p.final_obs) reinterpret_cast<float2*>(p.final_obs)[o] = v;
+                        if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = __ldg(reinterpret_cast<const float2*>(reset_row + k));   // the track's reset observation
+                    } else if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = v;
                 }
             }
             if (t + 2 < p.T) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NT); }
