@@ -297,6 +297,28 @@ def run_ours(args):
         "counters": {k: int(v) if k != "return_sum" else float(v) for k, v in stats.items()},
         "wall_s_timed_region": t_wall,
     }
+    if rank == 0 and world == 1 and args.sweep:
+        # the same kernel at larger batches (informational: the metric is quoted at 4096-65536 envs); short runs
+        line["batch_sweep"] = []
+        eng.close()
+        for Es, trk in ((8192, track), (16384, track), (65536, track), (65536, "all")):
+            names = list(TR.BUILTIN_TRACK_NAMES) if trk == "all" else [trk]
+            e2 = Engine(Es, C, tracks=names, discrete=False, auto_reset=True, device=local)
+            e2.reset_host(track_id=(np.arange(Es, dtype=np.int64) * len(names) // Es).astype(np.int32))
+            o2 = torch.empty((50, Es * C, 38), dtype=torch.float32, device=dev)
+            for _ in range(6):
+                e2.rollout(50, seed=args.seed, mode=args.mode, obs_rollout=o2.reshape(-1))
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(10):
+                e2.rollout(50, seed=args.seed, mode=args.mode, obs_rollout=o2.reshape(-1))
+            b.record()
+            torch.cuda.synchronize()
+            line["batch_sweep"].append({"envs": Es, "track": trk, "value": Es * C * 500 / (a.elapsed_time(b) / 1e3), "unit": UNIT,
+                                        "steps": 500, "note": "rollout kernel, 50 steps per launch, no L2 flush"})
+            e2.close()
+            del o2
     if rank == 0 and world == 1:
         t0 = time.perf_counter()
         v = cpu_throughput(tracks[0], args.cpu_steps, 1, seed=args.seed)
@@ -351,6 +373,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--cpu-steps", type=int, default=40000)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--sweep", type=int, default=1, help="1: also time the rollout kernel at 8192/16384/65536 envs (N=1 only)")
     ap.add_argument("--mode", type=int, default=0, help="synthetic action distribution: 0 = action_space.sample() (the metric), "
                     "1 = 'driving' (tb~U[0.2,1], steer~U[-0.2,0.6]: laps, wall contacts, episodes)")
     args = ap.parse_args()

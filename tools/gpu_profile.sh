@@ -9,7 +9,7 @@ nproc >> $out/${tag}_gpu.txt
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err || { tail -5 $out/${tag}_bench.err; exit 1; }
 python bench.py --impl reference > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
-SHORT="--steps 300 --warmup 300 --e2e-steps 20 --cpu-steps 200"
+SHORT="--steps 300 --warmup 300 --e2e-steps 20 --cpu-steps 200 --sweep 0"
 python bench.py $SHORT > $out/${tag}_plain_short.json 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/${tag}_launches.csv \
     python bench.py $SHORT > $out/${tag}_ncu_list.log 2>&1

@@ -4,7 +4,7 @@ tag=$1; shift
 out=gpurun_out; mkdir -p $out
 for spec in "$@"; do
   name=${spec%%:*}; rest=${spec#*:}; envs=${rest%%:*}; args=${rest#*:}; [ "$args" = "$rest" ] && args=""
-  env $(echo $envs | tr ',' ' ') timeout 300 python bench.py --steps 2000 --warmup 600 --e2e-steps 200 --cpu-steps 200 $args > $out/${tag}_$name.json 2> $out/${tag}_$name.err
+  env $(echo $envs | tr ',' ' ') timeout 300 python bench.py --steps 2000 --warmup 600 --e2e-steps 200 --cpu-steps 200 --sweep 0 $args > $out/${tag}_$name.json 2> $out/${tag}_$name.err
   python - <<PY
 import json
 try:
