@@ -249,3 +249,18 @@ def test_teacher_forced_steps_on_all_tracks_in_one_engine():
         bad, report = P.check_cases(g, obs[sl], rew[sl], te[sl], tr[sl], exp, label=nm)
         assert bad == 0, report
     eng.close()
+
+
+def test_ppo_example_runs_on_device_end_to_end():
+    """examples/ppo_rollout.py (the learn/ppo.py loop shape over NascarVectorEnv.step_torch): two small iterations."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "ppo_rollout.py"), "--envs", "256", "--n-steps", "32", "--iters", "2",
+                          "--track", "martinsville", "--discrete", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2 and lines[-1]["obs_device"].startswith("cuda")
+    assert all(np.isfinite(l["policy_loss"]) and np.isfinite(l["value_loss"]) and l["rollout_env_steps_per_s"] > 0 for l in lines)
