@@ -264,3 +264,41 @@ def test_ppo_example_runs_on_device_end_to_end():
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 2 and lines[-1]["obs_device"].startswith("cuda")
     assert all(np.isfinite(l["policy_loss"]) and np.isfinite(l["value_loss"]) and l["rollout_env_steps_per_s"] > 0 for l in lines)
+
+
+def test_engine_bounce_and_tunnelling_known_answers():
+    """The analytic checks of tests/test_oracle_physics_kat.py on the CUDA engine: restitution 0.25 on a head-on hit,
+    the summed impulse in obs[19], and TOI sub-stepping keeping a 110 m/s car out of a 1 m wall."""
+    import math
+    from nascargymnasium_b200.engine import Engine
+    from oracle import oracle as O
+    from tests import test_oracle_physics_kat as KAT
+    speeds = [5.0, 20.0, 110.0]
+    recs = []
+    for v0 in speeds:
+        env = O.OracleEnv(T.builtin_track_text("daytona"))
+        env.reset()
+        KAT._place(env, 50.0, 0.0, math.pi / 2, 0.0, v0)
+        recs.append(P.oracle_to_record(env.get_state()))
+    eng = Engine(len(speeds), 1, tracks=["daytona"], auto_reset=False)
+    eng.reset_host()
+    eng.set_state_host(np.array(recs, dtype=np.float32))
+    zero = np.zeros((len(speeds), 2), dtype=np.float32)
+    vy_prev = np.array(speeds)
+    bounced = [None] * len(speeds)
+    worst = np.full(len(speeds), -1e9)
+    for _ in range(120):
+        obs, rew, te, tr, _ = eng.step_host(zero)
+        st = eng.get_state_host()
+        y, vy = st[:, R["NCG_R_Y"]], st[:, R["NCG_R_VY"]]
+        worst = np.maximum(worst, y + KAT.HALF_LEN - KAT.WALL_FACE_Y)
+        for i in range(len(speeds)):
+            if bounced[i] is None and vy[i] < 0:
+                bounced[i] = (vy_prev[i], -vy[i], obs[i, 19] * 50000.0)
+        vy_prev = vy.copy()
+    eng.close()
+    assert all(b is not None for b in bounced)
+    assert (worst < 0.05).all(), worst                                   # never past the wall face, even at 110 m/s
+    for v_in, v_out, imp in bounced[:2]:
+        assert v_out == pytest.approx(0.25 * v_in, rel=0.03)
+        assert imp == pytest.approx(min(1500.0 * 1.25 * v_in, 50000.0), rel=0.03)
