@@ -411,9 +411,12 @@ int build_cta_table(NcgHandle* h) {
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     if (h->cta_dirty) { int rc = build_cta_table(h); if (rc) return rc; }
     const int sms = h->num_sms > 0 ? h->num_sms : 148;
-    // rays per lane: 2 (8 ray warps per CTA) while the batch is latency-bound, 4 (4 ray warps, better lane balance and
-    // fewer instructions per car-step) once there are waves of CTAs; measured in profiles/
-    const int RPL = h->rays_per_lane ? h->rays_per_lane : (h->n_ctas > 2 * sms ? 4 : 2);
+    // rays per lane: 2 (8 ray warps per CTA) while the batch is at most one CTA per SM and latency-bound, 4 (4 ray warps,
+    // better lane balance and fewer instructions per car-step) beyond that; measured in profiles/.  Two things that were
+    // measured and are worse: cutting the batch into smaller CTAs so that they fill whole waves of resident slots evenly
+    // (a CTA's step time is set by the physics warp's dependent chain, so fewer cars per CTA only lowers the work per
+    // chain), and a fourth resident CTA per SM (28 car slots, wall AABBs left in L2, 96 registers with spills).
+    const int RPL = h->rays_per_lane ? h->rays_per_lane : (h->n_ctas > sms ? 4 : 2);
     p.cta_tab = h->d_cta_tab;
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
