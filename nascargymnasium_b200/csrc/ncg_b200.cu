@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
         const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // a lane's rays are q0, q0+4, ... (90 deg apart)
         const int wslot0 = (warp - 1) * CPW;                     // first car slot of this warp
         const float* reset_row = p.reset_obs + (size_t)my_tid * NCG_OBS_DIM;
-        float kcq, ksq; ray_rotation(q0, &kcq, &ksq);
+        const RaySet<RPL> rs = ray_set<RPL>(q0);
         // which (car of this warp, word pair) this lane stores in each pass of the row write-out: fixed for the launch
         constexpr int NIT = (CPW * (NCG_OBS_DIM / 2) + 31) / 32;
         uint32_t pair_sk[NIT];
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             if (active && !(p.debug_skip & 1)) {
                 const float4 ps = s_pose[b * CPB + slot];
                 float* dst = s_obs + (b * CPB + slot) * OBS_STRIDE + 22;
-                if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, q0, kcq, ksq, dst, &tests);
-                else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, q0, kcq, ksq, dst, &tests);
+                if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
+                else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
             }
             if (synth && warp == 1 && lane < n_cars && t + 2 < p.T) {     // actions of step t+2 (this buffer's next use)
                 float thr, brk, st;

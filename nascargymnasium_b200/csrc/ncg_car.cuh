@@ -1159,8 +1159,8 @@ NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx
     return (tn > 0.0f && tn <= tf) ? tn : INFINITY;
 }
 #define NCG_RAY_LEN 250.0f
-// One lane's RPL rays of one car: ray indices q0, q0+4, ... (successive rays are 90 deg apart, so a lane's total
-// work mixes along-track and across-track rays).  All RPL rays run in one flattened loop -- every iteration is
+// One lane's RPL rays of one car (see RaySet: a lane's total work mixes along-track and across-track rays).  All RPL
+// rays run in one flattened loop -- every iteration is
 // "fetch the next cell if this one's list is exhausted, then test one block of four walls" -- so lanes never sit
 // in different loop nests, and the four slab tests of a block are independent instruction streams that overlap
 // their shared-memory and MUFU latencies.  Normalised distances go to dst[q0 + 4*j].
@@ -1175,21 +1175,36 @@ NCG_HD void ray_rotation(int q, float* kcq, float* ksq) {
                           0.92387953251128674f, 1.0f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f};
     *kcq = kc[q]; *ksq = ks[q];
 }
+// The rays one lane casts: RPL ray indices and their rotation constants (fixed per lane, so the kernel builds this once
+// per launch).  RPL = 2: rays q and q+4; RPL = 4: rays q, q+4 and the pair opposite to the *other* diagonal,
+// ((q+2)&3)+8 and +12 -- a car's two longest rays are the ones along the track, 180 deg apart (r and r+8), and this
+// keeps them in different lanes.
+template <int RPL> struct RaySet { int idx[RPL]; float kc[RPL], ks[RPL]; };
+template <int RPL> NCG_HD RaySet<RPL> ray_set(int q) {
+    RaySet<RPL> rs;
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+        rs.idx[j] = RPL == 4 ? (j < 2 ? q + 4 * j : ((q + 2) & 3) + 4 * j) : q + 4 * j;
+        ray_rotation(rs.idx[j], &rs.kc[j], &rs.ks[j]);
+    }
+    return rs;
+}
 template <int RPL, bool SH>
-NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float kcq, float ksq, float* dst, unsigned* tests) {
+NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const RaySet<RPL>& rs, float* dst, unsigned* tests) {
     float sa, ca; sincosf(angle, &sa, &ca);
-    float dx = ca * kcq - sa * ksq, dy = sa * kcq + ca * ksq;
+    float dx = ca * rs.kc[0] - sa * rs.ks[0], dy = sa * rs.kc[0] + ca * rs.ks[0];
     unsigned nt = 0;
     const RayMem<SH> M(T);
     const int gnx = T.gnx, gny = T.gny;
     const float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
     const int ix0 = (int)floorf(gx), iy0 = (int)floorf(gy);
     if (ix0 < 0 || iy0 < 0 || ix0 >= gnx || iy0 >= gny) {              // origin outside the grid: scan every wall
+#pragma unroll
         for (int j = 0; j < RPL; ++j) {
+            dx = ca * rs.kc[j] - sa * rs.ks[j]; dy = sa * rs.kc[j] + ca * rs.ks[j];
             float best = NCG_RAY_LEN;
             for (int wi = 0; wi < T.n_walls; ++wi) { F4 a, b; M.wall((uint32_t)wi, &a, &b); best = fminf(best, ray_box_slab(a, b, px, py, dx, dy)); ++nt; }
-            dst[q0 + 4 * j] = sensor_obs_m(best);
-            float t = dx; dx = dy; dy = -t;
+            dst[rs.idx[j]] = sensor_obs_m(best);
         }
         *tests += nt;
         return;
@@ -1215,12 +1230,17 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
                 if (!fin) { const uint32_t h = M.cell(iy * gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
             }
             if (fin) {
-                dst[q0 + 4 * j] = sensor_obs_m(best);
+                // j is a run-time value here: pick this ray's slot and the next ray's constants with selects, not by
+                // indexing the (register-resident) arrays
+                int slot = rs.idx[0]; float kcn = 0.0f, ksn = 0.0f;
+#pragma unroll
+                for (int m = 1; m < RPL; ++m) { if (j == m) slot = rs.idx[m]; if (j + 1 == m) { kcn = rs.kc[m]; ksn = rs.ks[m]; } }
+                dst[slot] = sensor_obs_m(best);
                 if (++j == RPL) break;
-                // next ray of this lane: the direction turns by -90 deg, (dx,dy) -> (dy,-dx), so the DDA strides swap
-                { float t = dx; dx = dy; dy = -t; }
-                { float t = tdx; tdx = tdy; tdy = t; }
-                { int t = sx; sx = sy; sy = -t; }
+                // next ray of this lane, same origin cell
+                dx = ca * kcn - sa * ksn; dy = sa * kcn + ca * ksn;
+                tdx = dx != 0.0f ? T.cell * rcp_fast(fabsf(dx)) : INFINITY; tdy = dy != 0.0f ? T.cell * rcp_fast(fabsf(dy)) : INFINITY;
+                sx = dx > 0.0f ? 1 : -1; sy = dy > 0.0f ? 1 : -1;
                 tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
                 tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
                 ix = ix0; iy = iy0; k = k0; e = e0; best = NCG_RAY_LEN;
@@ -1238,11 +1258,11 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
     }
     *tests += nt;
 }
-// convenience form: looks the ray's rotation constants up (the kernel hoists that out of its step loop)
+// convenience form: builds the lane's ray set (the kernel hoists that out of its step loop)
 template <int RPL, bool SH>
 NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, float* dst, unsigned* tests) {
-    float kcq, ksq; ray_rotation(q0, &kcq, &ksq);
-    cast_rays<RPL, SH>(T, px, py, angle, q0, kcq, ksq, dst, tests);
+    const RaySet<RPL> rs = ray_set<RPL>(q0);
+    cast_rays<RPL, SH>(T, px, py, angle, rs, dst, tests);
 }
 NCG_HD float sensor_obs(float dist) { return sensor_obs_m(dist); }
 
