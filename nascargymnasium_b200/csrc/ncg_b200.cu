@@ -383,8 +383,19 @@ int envs_per_cta(int E, int C, int sms) {
 }
 // CTA table: consecutive envs are cut into CTAs of at most envs_per_cta, and never across a track boundary, so every CTA
 // stages exactly one track table.
+static int count_ctas(const int* env_track, int E, int epb) {
+    int n = 0, e = 0;
+    while (e < E) { int k = 1; while (k < epb && e + k < E && env_track[e + k] == env_track[e]) ++k; ++n; e += k; }
+    return n;
+}
 void plan_ctas(const int* env_track, int E, int C, int sms, std::vector<int2>& tab) {
-    const int epb = envs_per_cta(E, C, sms);
+    int epb = envs_per_cta(E, C, sms);
+    // track boundaries add CTAs (a CTA never spans two tracks); grow the CTAs a little if that spills the plan into one
+    // more wave of SMs than the batch needs (4096 envs over 8 tracks: 29 per CTA = 144 CTAs, not 28 = 152 on 148 SMs)
+    const int epb_max = CPB / C;
+    if (sms <= 0) sms = 148;
+    const int waves = (count_ctas(env_track, E, epb_max) + sms - 1) / sms;
+    while (epb < epb_max && count_ctas(env_track, E, epb) > waves * sms) ++epb;
     tab.clear();
     int e = 0;
     while (e < E) {

@@ -204,3 +204,12 @@ def test_launch_plan_keeps_ctas_on_one_track_and_fills_the_sms():
     # a single env is one CTA
     first, count = engine.plan_ctas(np.zeros(1, np.int32), 10, 148)
     assert first.tolist() == [0] and count.tolist() == [1]
+
+
+def test_launch_plan_does_not_spill_into_an_extra_wave_on_the_track_mix():
+    from nascargymnasium_b200 import engine
+    tid = (np.arange(4096) * 8 // 4096).astype(np.int32)         # BASELINE config 4 mix at 4096 envs: 8 blocks of 512
+    first, count = engine.plan_ctas(tid, 1, 148)
+    assert len(first) <= 148 and count.sum() == 4096 and count.max() <= 32
+    for f, c in zip(first, count):
+        assert len(set(tid[f:f + c].tolist())) == 1
