@@ -29,6 +29,42 @@ def _batched_space(space, n):
     return S.MultiDiscrete(np.broadcast_to(space.nvec, (n,) + space.nvec.shape).copy())
 
 
+class StepInfo(dict):
+    """`info` of a step in which at least one env finished.  The terminal observations arrive from the engine as a compact
+    (n_done, [C,] 38) array plus the indices of the finished envs; the Gymnasium-0.29 object array ``final_observation``
+    (and the Gymnasium-1.x dense ``final_obs``) are built from them only when somebody asks, because with thousands of
+    envs and short episodes building one Python object per finished env every step costs more than the step itself."""
+
+    def __init__(self, done: np.ndarray, index: np.ndarray, rows: np.ndarray, obs_shape, episode: dict):
+        super().__init__(_final_observation=done, _final_obs=done, _episode=done, episode=episode,
+                         final_obs_index=index, final_obs_rows=rows)
+        self._obs_shape = obs_shape
+
+    def __missing__(self, key):
+        if key == "final_observation":
+            fo = np.empty(self._obs_shape[0], dtype=object)
+            rows = self["final_obs_rows"]
+            for j, e in enumerate(self["final_obs_index"]):
+                fo[e] = rows[j]
+            self[key] = fo
+            return fo
+        if key == "final_obs":
+            dense = np.zeros(self._obs_shape, dtype=np.float32)
+            dense[self["final_obs_index"]] = self["final_obs_rows"]
+            self[key] = dense
+            return dense
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key in ("final_observation", "final_obs") or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
 class NascarVectorEnv:
     metadata = {"render_modes": ["human"], "render_fps": 60, "autoreset_mode": "same_step"}
 
@@ -106,18 +142,13 @@ class NascarVectorEnv:
         info = {}
         if any_done:
             done = te | tr
-            fin = aux["final_obs"].reshape(self._obs_shape)
-            fo = np.empty(self.num_envs, dtype=object)
-            idx = np.nonzero(done)[0]
-            rows = fin[idx]                               # one gather-copy out of the mapped buffer; rows are views of it
-            for j, e in enumerate(idx):
-                fo[e] = rows[j]
+            idx = np.flatnonzero(done)
+            rows = aux["final_obs"].reshape(self._obs_shape)[idx]          # one gather-copy out of the mapped buffer
             ep_r = np.zeros(self._rew_shape, dtype=np.float64)
             ep_l = np.zeros(self.num_envs, dtype=np.int64)
-            ep_r[done] = aux["ep_return"].reshape(self._rew_shape)[done]
-            ep_l[done] = aux["ep_length"][done]
-            info = {"final_observation": fo, "_final_observation": done.copy(),
-                    "episode": {"r": ep_r, "l": ep_l}, "_episode": done.copy()}
+            ep_r[idx] = aux["ep_return"].reshape(self._rew_shape)[idx]
+            ep_l[idx] = aux["ep_length"][idx]
+            info = StepInfo(done.copy(), idx, rows, self._obs_shape, {"r": ep_r, "l": ep_l})
         return obs, rew, te, tr, info
 
     # ------------------------------------------------------------------ torch API (device-resident)
@@ -182,8 +213,8 @@ def make_sb3_vec_env(num_envs: int, track_file=None, discrete_action_space: bool
             done = te | tr
             infos = [{} for _ in range(num_envs)]
             if info:
-                for e in np.nonzero(done)[0]:
-                    infos[e] = {"terminal_observation": info["final_observation"][e], "TimeLimit.truncated": bool(tr[e] and not te[e]),
+                for j, e in enumerate(info["final_obs_index"]):
+                    infos[e] = {"terminal_observation": info["final_obs_rows"][j], "TimeLimit.truncated": bool(tr[e] and not te[e]),
                                 "episode": {"r": float(info["episode"]["r"][e]), "l": int(info["episode"]["l"][e])}}
             return obs, rew, done, infos
 

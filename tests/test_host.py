@@ -213,3 +213,18 @@ def test_launch_plan_does_not_spill_into_an_extra_wave_on_the_track_mix():
     assert len(first) <= 148 and count.sum() == 4096 and count.max() <= 32
     for f, c in zip(first, count):
         assert len(set(tid[f:f + c].tolist())) == 1
+
+
+def test_step_info_builds_final_observation_lazily():
+    from nascargymnasium_b200.vector_env import StepInfo
+    done = np.array([False, True, False, True])
+    rows = np.arange(2 * 38, dtype=np.float32).reshape(2, 38)
+    info = StepInfo(done, np.flatnonzero(done), rows, (4, 38), {"r": np.zeros(4), "l": np.zeros(4, int)})
+    assert "final_observation" in info and "final_obs" in info and not dict.__contains__(info, "final_observation")
+    fo = info["final_observation"]                       # Gymnasium 0.29 form: object array, None for running envs
+    assert fo.dtype == object and fo[0] is None and np.array_equal(fo[3], rows[1]) and dict.__contains__(info, "final_observation")
+    dense = info["final_obs"]                            # Gymnasium 1.x form
+    assert dense.shape == (4, 38) and np.array_equal(dense[1], rows[0]) and not dense[0].any()
+    assert info["_final_observation"].tolist() == done.tolist() and info.get("missing") is None
+    with pytest.raises(KeyError):
+        info["missing"]
