@@ -19,9 +19,9 @@
  *
  * Conventions: every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch tensor
  * storage), contiguous, on the handle's device; h_* are HOST pointers.  All work is enqueued on the
- * `stream` argument (a cudaStream_t passed as void*); nothing synchronises implicitly except
- * ncg_step_host / ncg_reset_host, which copy through pinned staging buffers and return when the
- * results are in the host buffers.  Every call returns 0 on success or a negative NCG_E_* code;
+ * `stream` argument (a cudaStream_t passed as void*); nothing synchronises implicitly except the
+ * host-buffer calls (ncg_step_host / ncg_step_pinned / ncg_step_mapped / ncg_reset_host), which return
+ * when the results are in the host buffers.  Every call returns 0 on success or a negative NCG_E_* code;
  * ncg_last_error() returns the message for the calling thread.  A handle is not re-entrant.
  * There is no CPU fallback: ncg_create fails if no CUDA device is usable.
  */
@@ -52,8 +52,8 @@ enum {
 };
 
 /* Per-car state record: NCG_RECORD_WORDS 32-bit words, car-major (record[car][word]).  Words are
- * float32 unless marked u32.  A warp owns one record and moves it with one 512-byte coalesced
- * access.  Field list follows SURVEY.md App. C. */
+ * float32 unless marked u32.  A CTA moves its (at most 32) records between HBM and shared memory as
+ * coalesced 16-byte accesses and keeps them there for the whole launch.  Field list follows SURVEY.md App. C. */
 enum NcgRecordField {
     NCG_R_X = 0, NCG_R_Y, NCG_R_ANGLE, NCG_R_VX, NCG_R_VY, NCG_R_OMEGA,   /* b2Body sweep.c, sweep.a, velocity */
     NCG_R_SLEEP,              /* b2Body::m_sleepTime */
