@@ -19,12 +19,13 @@ namespace ncg {
 struct Track {
     const float* hdr; const float* segs; const double* seg64; const float* walls; const float* aabb;
     const uint32_t* cells; const uint16_t* items;     // per cell: first block | n_blocks << 16; items in blocks of 4 u16
+    const uint16_t* segmask;                          // per cell: segments whose chord can be nearest to a point of the cell
     int n_walls, n_segs, gnx, gny, has_bank;
     float gx0, gy0, inv_cell, cell, ltot, min_lap, slx0, sly0, sldx, sldy, sllen2, slhalfw, half_ltot;
 };
 enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEGS, TH_OFF_WALLS, TH_OFF_AABB, TH_OFF_CELLS,
        TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
-       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64 };
+       TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64, TH_OFF_SEGMASK };
 enum { SEG_STRIDE = 12, WALL_STRIDE = 8, SEG64_STRIDE = 5 };
 // `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
 NCG_HD Track track_view(const float* staged, const float* global) {
@@ -34,6 +35,7 @@ NCG_HD Track track_view(const float* staged, const float* global) {
     t.segs = staged + f2u(staged[TH_OFF_SEGS]); t.walls = staged + f2u(staged[TH_OFF_WALLS]);
     t.seg64 = (const double*)(staged + f2u(staged[TH_OFF_SEG64]));
     t.cells = (const uint32_t*)(staged + f2u(staged[TH_OFF_CELLS])); t.items = (const uint16_t*)(staged + f2u(staged[TH_OFF_ITEMS]));
+    t.segmask = (const uint16_t*)(staged + f2u(staged[TH_OFF_SEGMASK]));
     t.aabb = staged + f2u(staged[TH_OFF_AABB]);
     t.gx0 = staged[TH_GX0]; t.gy0 = staged[TH_GY0]; t.inv_cell = staged[TH_INVCELL]; t.cell = staged[TH_CELL];
     t.ltot = staged[TH_LTOT]; t.min_lap = staged[TH_MINLAP]; t.slx0 = staged[TH_SLX0]; t.sly0 = staged[TH_SLY0];
@@ -707,7 +709,15 @@ NCG_HDN void nearest_segment64(const Track T, float xf, float yf, float* banking
 }
 NCG_HD void nearest_segment(const Track& T, float x, float y, float* banking, float* progress) {
     float best = INFINITY, second = INFINITY; int bi = 0; float bcx = 0.0f, bcy = 0.0f;
-    for (int i = 0; i < T.n_segs; ++i) {
+    // candidate chords of this grid cell (all of them outside the grid): a superset of every chord that can be the
+    // minimum or fall inside the float64 tie band below, visited in ascending index like the reference's loop
+    uint32_t cand = (1u << T.n_segs) - 1u;
+    {
+        const int ix = (int)floorf((x - T.gx0) * T.inv_cell), iy = (int)floorf((y - T.gy0) * T.inv_cell);
+        if (ix >= 0 && iy >= 0 && ix < T.gnx && iy < T.gny) cand = T.segmask[iy * T.gnx + ix];
+    }
+    while (cand) {
+        const int i = ctz32(cand); cand &= cand - 1u;
         const float* s = T.segs + i * SEG_STRIDE;
         float sx = s[0], sy = s[1], dx = s[4], dy = s[5], l2 = s[6], cx, cy;
         if (l2 < 1e-6f) { cx = sx; cy = sy; }

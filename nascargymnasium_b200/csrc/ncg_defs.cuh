@@ -40,6 +40,15 @@ NCG_HD float u2f(uint32_t u) {
 #endif
 }
 
+// index of the lowest set bit (v != 0)
+NCG_HD int ctz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
 // approximate division (MUFU.RCP + FMUL, <= 2 ulp) for the sensor rays only: their tolerance is 1e-3 normalised
 NCG_HD float fdiv_fast(float a, float b) {
 #if defined(__CUDA_ARCH__)

@@ -304,6 +304,7 @@ H_GX0, H_GY0, H_INVCELL, H_CELL, H_LTOT, H_MINLAP, H_SLX0, H_SLY0, H_SLDX, H_SLD
     H_HALF_LTOT = range(12, 25)
 H_STAGE_WORDS = 25       # words [0, H_STAGE_WORDS) are what a CTA stages into shared memory (the whole table)
 H_OFF_SEG64 = 26         # float64 rows [sx,sy,ex,ey,cum_chord] per segment (tie-exact nearest-segment search)
+H_OFF_SEGMASK = 27       # uint16 per grid cell: which segments can be the chord-nearest one for a point of that cell
 ITEM_BLOCK = 4           # grid item lists are padded to blocks of 4 (one 8-byte load, four slab tests in flight)
 SEG64_STRIDE = 5
 
@@ -448,7 +449,30 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     cells_words = pad4(nx * ny)
     off_items = off_cells + cells_words
     items_words = pad4((len(padded) + 1) // 2)
-    off_aabb = off_items + items_words          # wall fat AABBs (broad phase)
+    # per cell: the segments whose chord can be nearest to some point of the cell (a conservative superset: distance from
+    # the cell centre within two half-diagonals + 0.5 m of the smallest), so the per-step nearest-segment search tests
+    # 1-3 chords instead of all of them and still finds the same first strict minimum and the same runner-up band
+    segmask = np.zeros(nx * ny, dtype=np.uint16)
+    hd = cell * math.sqrt(2.0) / 2.0
+    for iy in range(ny):
+        for ix in range(nx):
+            pcx, pcy = x0 + (ix + 0.5) * cell, y0 + (iy + 0.5) * cell
+            ds = []
+            for sg in segs_src:
+                sx, sy = sg.start
+                dx, dy = sg.end[0] - sx, sg.end[1] - sy
+                l2 = dx * dx + dy * dy
+                t = 0.0 if l2 < 1e-6 else max(0.0, min(1.0, ((pcx - sx) * dx + (pcy - sy) * dy) / l2))
+                ds.append(math.hypot(pcx - (sx + t * dx), pcy - (sy + t * dy)))
+            lim = min(ds) + 2.0 * hd + 0.5
+            m = 0
+            for i, d in enumerate(ds):
+                if d <= lim:
+                    m |= 1 << i
+            segmask[iy * nx + ix] = m
+    off_segmask = off_items + items_words
+    segmask_words = pad4((nx * ny + 1) // 2)
+    off_aabb = off_segmask + segmask_words      # wall fat AABBs (broad phase)
     total = off_aabb + pad4(n * 4)
     blob = np.zeros(total, dtype=np.float32)
     hi = blob.view(np.int32)
@@ -466,6 +490,7 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     hi[H_NITEMS] = len(padded)
     hi[H_STAGE_WORDS] = total
     hi[H_OFF_SEG64] = off_seg64
+    hi[H_OFF_SEGMASK] = off_segmask
     blob[H_GX0] = x0
     blob[H_GY0] = y0
     blob[H_INVCELL] = 1.0 / cell
@@ -497,6 +522,7 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     it16 = np.zeros(items_words * 2, dtype=np.uint16)
     it16[:len(padded)] = padded
     blob.view(np.uint16)[off_items * 2: off_items * 2 + len(it16)] = it16
+    blob.view(np.uint16)[off_segmask * 2: off_segmask * 2 + nx * ny] = segmask
     return TrackTable(track, boxes, fat, segs, seg64, (x0, y0), (nx, ny), cell_start, items, blob)
 
 

@@ -86,6 +86,13 @@ int hc_sensors_multi_mismatches(const float* blob, float x, float y, float angle
     for (int i = 0; i < 16; ++i) if (f2u(a[i]) != f2u(b[i]) || f2u(a[i]) != f2u(c[i])) ++bad;
     return bad;
 }
+// chord-nearest segment with the per-cell candidate mask (masked = 1) or over all segments (masked = 0: a view with an
+// empty grid sends nearest_segment down its all-segments path)
+void hc_nearest_segment(const float* blob, float x, float y, int masked, float* out2) {
+    Track T = track_view(blob, blob);
+    if (!masked) { T.gnx = 0; T.gny = 0; }
+    nearest_segment(T, x, y, out2, out2 + 1);
+}
 int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }
 void hc_synthetic_action(unsigned long long seed, unsigned car, unsigned step, int mode, int discrete, float* out3) {
     action_synthetic(seed, car, step, mode, discrete != 0, out3, out3 + 1, out3 + 2);

@@ -258,6 +258,7 @@ def hostcheck():
         lib.hc_sensors_grid.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_float, fp, ctypes.POINTER(ctypes.c_uint)]
         lib.hc_sensors_multi_mismatches.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_float]
         lib.hc_sensors_multi_mismatches.restype = ctypes.c_int
+        lib.hc_nearest_segment.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_int, fp]
         lib.hc_on_track.argtypes = [fp, ctypes.c_float, ctypes.c_float]
         lib.hc_synthetic_action.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int, fp]
         _HC = lib

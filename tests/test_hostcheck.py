@@ -105,3 +105,29 @@ def test_philox_stream_is_the_one_bench_uses_for_the_cpu_baseline():
             a3 = P.philox_actions_np(7, c, step)
             tb = a3[0] - a3[1]
             assert tb == pytest.approx(want[c, 0], abs=1e-7) and a3[2] == pytest.approx(want[c, 1], abs=1e-7)
+
+
+def test_nearest_segment_candidate_mask_is_exact():
+    """The per-cell candidate mask must never change the answer of the chord-nearest search (banking, progress), on the
+    racing surface, in the infield and outside the walls, including the points that fall back to float64."""
+    hc = P.hostcheck()
+    rng = np.random.default_rng(3)
+    for name in T.BUILTIN_TRACK_NAMES:
+        tab = T.get_track_table(name)
+        blob = np.ascontiguousarray(tab.blob)
+        cell = float(blob[T.H_CELL])
+        x0, y0 = tab.grid_origin
+        nx, ny = tab.grid_dims
+        pts = []
+        for _ in range(600):                                   # near the centre line
+            s = tab.seg64[rng.integers(0, len(tab.seg64))]
+            u = rng.uniform()
+            pts.append((s[0] + u * (s[2] - s[0]) + rng.uniform(-8, 8), s[1] + u * (s[3] - s[1]) + rng.uniform(-8, 8)))
+        for _ in range(600):                                   # anywhere in (and a little outside) the grid
+            pts.append((rng.uniform(x0 - 20, x0 + nx * cell + 20), rng.uniform(y0 - 20, y0 + ny * cell + 20)))
+        pts += [(0.0, 0.0), (0.0, 1e-6), (1e-3, -1e-6), (-0.5, 0.0)]      # the start-line overlap region
+        a, b = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        for x, y in pts:
+            hc.hc_nearest_segment(P._fp(blob), x, y, 1, P._fp(a))
+            hc.hc_nearest_segment(P._fp(blob), x, y, 0, P._fp(b))
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, x, y, a, b)
