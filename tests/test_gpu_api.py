@@ -324,3 +324,41 @@ def test_soak_driving_rollout_stays_finite_on_every_track():
     assert np.isfinite(o).all() and o.min() >= -1.0 and o.max() <= 1.0
     assert np.isfinite(recs[:, [R["NCG_R_X"], R["NCG_R_Y"], R["NCG_R_ANGLE"], R["NCG_R_VX"], R["NCG_R_VY"], R["NCG_R_OMEGA"]]]).all()
     eng.close()
+
+
+def test_sb3_vec_env_adapter_against_a_stub_of_the_sb3_base_class(monkeypatch):
+    """stable_baselines3 is not in the image; a minimal stand-in for its VecEnv base class lets the adapter's own logic
+    (step_async/step_wait, terminal_observation, TimeLimit.truncated, episode stats) run on the GPU engine."""
+    import sys
+    import types
+
+    class VecEnv:                                            # the part of SB3's base class the adapter relies on
+        def __init__(self, num_envs, observation_space, action_space):
+            self.num_envs, self.observation_space, self.action_space = num_envs, observation_space, action_space
+
+        def _get_indices(self, indices):
+            return range(self.num_envs) if indices is None else ([indices] if isinstance(indices, int) else indices)
+
+        def step(self, actions):
+            self.step_async(actions)
+            return self.step_wait()
+
+    names = ["stable_baselines3", "stable_baselines3.common", "stable_baselines3.common.vec_env",
+             "stable_baselines3.common.vec_env.base_vec_env"]
+    mods = {n: types.ModuleType(n) for n in names}
+    mods[names[-1]].VecEnv = VecEnv
+    for n, m in mods.items():
+        monkeypatch.setitem(sys.modules, n, m)
+    from nascargymnasium_b200.vector_env import make_sb3_vec_env
+    env = make_sb3_vec_env(32, "tracks/martinsville.track", discrete_action_space=True)
+    obs = env.reset()
+    assert obs.shape == (32, 38) and env.num_envs == 32
+    acts = np.zeros(32, dtype=np.int64)
+    acts[::2] = 1
+    for t in range(1, 601):
+        obs, rew, done, infos = env.step(acts)
+    assert done[1::2].all() and not done[::2].any()          # the idle cars are stuck-disabled at step 600
+    assert infos[1]["terminal_observation"].shape == (38,) and infos[1]["episode"]["l"] == 600
+    assert infos[1]["TimeLimit.truncated"] is False and infos[0] == {}
+    assert env.env_is_wrapped(None) == [False] * 32 and len(env.get_attr("num_envs")) == 32
+    env.close()
