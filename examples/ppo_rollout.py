@@ -177,8 +177,9 @@ def main():
                 loss.backward()
                 if world > 1:
                     for p_ in net.parameters():
-                        dist.all_reduce(p_.grad, op=dist.ReduceOp.SUM)
-                        p_.grad /= world
+                        if p_.grad is not None:              # (log_std has no gradient with a categorical head)
+                            dist.all_reduce(p_.grad, op=dist.ReduceOp.SUM)
+                            p_.grad /= world
                 nn.utils.clip_grad_norm_(net.parameters(), 0.5)
                 opt.step()
         torch.cuda.synchronize()
@@ -188,7 +189,7 @@ def main():
                               "rollout_env_steps_per_s": world * E * T / t_roll, "rollout_s": t_roll, "update_s": t_upd,
                               "mean_step_reward": float(b_rew.mean()), "episodes_done": float(done_count),
                               "mean_episode_return": float(done_returns / done_count.clamp(min=1)),
-                              "policy_loss": float(loss_p), "value_loss": float(loss_v), "obs_device": str(obs.device)}), flush=True)
+                              "policy_loss": float(loss_p.detach()), "value_loss": float(loss_v.detach()), "obs_device": str(obs.device)}), flush=True)
     venv.close()
     if world > 1:
         dist.destroy_process_group()
