@@ -27,8 +27,10 @@ enum { TH_NWALLS = 0, TH_NSEGS, TH_GNX, TH_GNY, TH_HASBANK, TH_WORDS, TH_OFF_SEG
        TH_OFF_ITEMS, TH_NITEMS, TH_GX0, TH_GY0, TH_INVCELL, TH_CELL, TH_LTOT, TH_MINLAP, TH_SLX0, TH_SLY0, TH_SLDX,
        TH_SLDY, TH_SLLEN2, TH_SLHALFW, TH_HALF_LTOT, TH_STAGE_WORDS, TH_OFF_SEG64, TH_OFF_SEGMASK };
 enum { SEG_STRIDE = 12, WALL_STRIDE = 8, SEG64_STRIDE = 5 };
-// `staged` points at the staged prefix (shared memory or the same global blob); `global` is the full blob.
+// `staged` points at the table the view should read (the copy in shared memory, or the blob in global memory); the whole
+// table is staged, so `global` (the blob it was copied from) is only kept for callers that want to re-point a member.
 NCG_HD Track track_view(const float* staged, const float* global) {
+    (void)global;
     Track t; t.hdr = staged;
     t.n_walls = (int)f2u(staged[TH_NWALLS]); t.n_segs = (int)f2u(staged[TH_NSEGS]);
     t.gnx = (int)f2u(staged[TH_GNX]); t.gny = (int)f2u(staged[TH_GNY]); t.has_bank = (int)f2u(staged[TH_HASBANK]);
