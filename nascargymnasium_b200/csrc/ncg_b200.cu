@@ -438,8 +438,8 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     int minb = h->n_ctas <= sms ? 1 : (h->n_ctas <= 2 * sms || RPL != 4 ? 2 : 3);
     { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && atoi(mb) >= 1 && atoi(mb) <= 3) minb = atoi(mb); }
     if (minb == 3 && RPL != 4) minb = 2;
-    void (*k)(KParams) = minb == 1 ? (RPL == 1 ? ncg_step_kernel<1, 1> : RPL == 4 ? ncg_step_kernel<4, 1> : ncg_step_kernel<2, 1>)
-                       : minb == 2 ? (RPL == 1 ? ncg_step_kernel<1, 2> : RPL == 4 ? ncg_step_kernel<4, 2> : ncg_step_kernel<2, 2>)
+    void (*k)(KParams) = minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1> : ncg_step_kernel<2, 1>)
+                       : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2> : ncg_step_kernel<2, 2>)
                                    : ncg_step_kernel<4, 3>;
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
@@ -477,7 +477,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
     const char* g = getenv("NCG_RAYS_PER_LANE");
     int rpl = g ? atoi(g) : 0;
-    if (rpl != 1 && rpl != 2 && rpl != 4) rpl = 0;                // 0 = chosen per launch from the batch size
+    if (rpl != 2 && rpl != 4) rpl = 0;                            // 0 = chosen per launch from the batch size
     h->rays_per_lane = rpl;
     size_t N = (size_t)h->N, E = (size_t)cfg->num_envs;
     CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));
