@@ -9,11 +9,11 @@ nproc >> $out/${tag}_gpu.txt
 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log
 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err || { tail -5 $out/${tag}_bench.err; exit 1; }
 python bench.py --impl reference > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err
-SHORT="--steps 300 --warmup 300 --e2e-steps 20 --cpu-steps 200 --sweep 0"
+SHORT="--steps 1000 --warmup 1000 --e2e-steps 20 --cpu-steps 200 --sweep 0"    # 3 warm-up launches + 1 timed launch of 1000 steps, then 25 single steps
 python bench.py $SHORT > $out/${tag}_plain_short.json 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $out/${tag}_launches.csv \
     python bench.py $SHORT > $out/${tag}_ncu_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:ncg_step_kernel --launch-skip 4 --launch-count 1 \
+ncu --set full --clock-control none --import-source on -k regex:ncg_step_kernel --launch-skip 3 --launch-count 1 \
     -o $out/${tag}_full -f python bench.py $SHORT > $out/${tag}_ncu_full.log 2>&1
 # the single-step (T=1) kernel of the e2e path: launches 8.. are NascarVectorEnv.step
 ncu --set full --clock-control none --import-source on -k regex:ncg_step_kernel --launch-skip 14 --launch-count 1 \

@@ -15,7 +15,7 @@ def raw(rep):
     return rows[0], rows[1], rows[2]
 
 out = []
-for name, rep, what in (("rollout kernel (T = 100 steps per launch, steady state)", f"{G}/{tag}_full.ncu-rep", "full"),
+for name, rep, what in (("rollout kernel (T = 1000 steps per launch, steady state)", f"{G}/{tag}_full.ncu-rep", "full"),
                         ("single-step kernel (T = 1, results written to mapped host memory: the e2e path)", f"{G}/{tag}_full_t1.ncu-rep", "full_t1")):
     if not os.path.exists(rep):
         continue
@@ -44,11 +44,11 @@ roll = [float(r[-1]) for r in rows if "ncg_step_kernel" in r[4] and float(r[-1])
 single = [float(r[-1]) for r in rows if "ncg_step_kernel" in r[4] and float(r[-1]) <= 3e5]
 hdr = f"""# ncu evidence, round {rnd[1:]} (capture set gpurun_out/{tag}_*, B200, clocks unlocked: --clock-control none)
 
-Command profiled: `python bench.py --steps 300 --warmup 300 --e2e-steps 20 --cpu-steps 200` (same code path as the default
+Command profiled: `python bench.py --steps 1000 --warmup 1000 --e2e-steps 20 --cpu-steps 200 --sweep 0` (same code path as the default
 bench line, shorter).  Launch list: `{rnd}_launches.csv` ({len(rows)} launches; ncu serialises launches and runs them cold).
 Share of GPU time in the list: ncg_* kernels {100 * ours / tot:.1f} % (the rest is torch's 256 MiB L2-flush memset between timed
-launches, outside the CUDA-event pairs).  Rollout launches (100 steps): {len(roll)} x {sum(roll) / max(len(roll), 1) / 1e3:.0f} us
-= {sum(roll) / max(len(roll), 1) / 100 / 1e3:.2f} us per step; single-step launches of the e2e path: {len(single)} x
+launches, outside the CUDA-event pairs).  Rollout launches (1000 steps): {len(roll)} x {sum(roll) / max(len(roll), 1) / 1e3:.0f} us
+= {sum(roll) / max(len(roll), 1) / 1000 / 1e3:.2f} us per step; single-step launches of the e2e path: {len(single)} x
 {sum(single) / max(len(single), 1) / 1e3:.1f} us (these write 647 KB per launch into mapped host memory).
 
 """
