@@ -356,7 +356,7 @@ struct NcgHandle {
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0;
-    int rays_per_lane = 0; int num_sms = 0;
+    int rays_per_lane = 0; int num_sms = 0; int max_smem = 0;
     long long launches = 0;
     // host-buffer path
     cudaStream_t stream = nullptr;
@@ -432,7 +432,11 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
-    const size_t smem = (size_t)smem_layout(mx).total * 4;
+    size_t smem = (size_t)smem_layout(mx).total * 4;
+    if (p.stage && h->max_smem > 0 && smem > (size_t)h->max_smem) {      // a user track too large to stage: read it through L1/L2
+        p.stage = 0;
+        smem = (size_t)smem_layout(0).total * 4;
+    }
     // resident CTAs per SM the register allocation allows: as many as the batch has use for, up to what shared memory
     // (~69 KB per CTA) admits; the 4-rays-per-lane shape (160 threads) fits three
     int minb = h->n_ctas <= sms ? 1 : (h->n_ctas <= 2 * sms || RPL != 4 ? 2 : 3);
@@ -474,6 +478,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaSetDevice(cfg->device));
     NcgHandle* h = new NcgHandle();
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
     const char* g = getenv("NCG_RAYS_PER_LANE");
     int rpl = g ? atoi(g) : 0;
