@@ -362,3 +362,22 @@ def test_sb3_vec_env_adapter_against_a_stub_of_the_sb3_base_class(monkeypatch):
     assert infos[1]["TimeLimit.truncated"] is False and infos[0] == {}
     assert env.env_is_wrapped(None) == [False] * 32 and len(env.get_attr("num_envs")) == 32
     env.close()
+
+
+def test_unstaged_track_table_gives_identical_results(monkeypatch):
+    """The fallback for track tables too large to stage (table read through L1/L2 instead of shared memory) must be the
+    same computation: bit-identical records and observations after a driving rollout."""
+    import torch
+    from nascargymnasium_b200.engine import Engine
+    outs = []
+    for no_stage in ("0", "1"):
+        monkeypatch.setenv("NCG_NO_STAGE", no_stage)
+        eng = Engine(300, 1, tracks=["trioval", "martinsville"], auto_reset=True)
+        eng.reset_host(track_id=(np.arange(300) * 2 // 300).astype(np.int32))
+        obs = torch.zeros((150, 300, 38), dtype=torch.float32, device="cuda:0")
+        eng.rollout(150, seed=4, mode=1, obs_rollout=obs.view(-1))
+        torch.cuda.synchronize()
+        outs.append((eng.get_state_host(), obs.cpu().numpy()))
+        eng.close()
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
