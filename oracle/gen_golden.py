@@ -174,3 +174,4 @@ if __name__ == "__main__":
     run("martinsville_laps", "martinsville", 4200, "controller", reset_on_lap=True, seed=5)
     run("nascar2_reverse", "nascar2", 2600, "reverse", seed=6)
     run("trioval_3cars_laplimit", "trioval", 3700, "controller", num_cars=3, reset_on_lap=True, seed=7)
+    run("nascar_banked_controller", "nascar_banked", 2400, "controller", seed=8)      # the one track with banking (car.py:509-566)
