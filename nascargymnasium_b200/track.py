@@ -530,7 +530,12 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
 # Grid cell size: picked per track from a cost model of the ray loop
 # ----------------------------------------------------------------------------
 CELL_CANDIDATES = (12.0, 16.0, 24.0, 32.0, 48.0, 64.0)
-MAX_TABLE_BYTES = 64 * 1024          # a CTA stages the whole table next to ~43 KB of its own state
+MAX_TABLE_BYTES = 64 * 1024          # a CTA stages the whole table next to ~32 KB of its own state
+# Three CTAs are resident per SM when a CTA's shared memory is at most 228 KB / 3 - 1 KB reserved - ~1 KB static, i.e. when
+# the table is at most ~44.8 KB next to the 30.9 KB of csrc/ncg_b200.cu::smem_layout.  A batch that mixes tracks sizes
+# every CTA for the largest table, so one track over this line costs all of them the third resident CTA.
+THREE_CTA_TABLE_BYTES = 44800
+THREE_CTA_COST_SLACK = 1.10          # a table that fits may cost this much more in the ray loop than the best one
 
 
 def _sample_rays(tab: TrackTable, n_poses: int = 120, seed: int = 0):
@@ -606,7 +611,7 @@ def build_best_track_table(track: Track) -> TrackTable:
     forced = os.environ.get("NCG_GRID_CELL")
     if forced:
         return build_track_table(track, cell=float(forced))
-    best, rays = None, None
+    best, small, rays = None, None, None
     for cell in CELL_CANDIDATES:
         try:
             tab = build_track_table(track, cell=cell)
@@ -619,8 +624,12 @@ def build_best_track_table(track: Track) -> TrackTable:
         cost = ray_loop_cost(tab, cell, rays)
         if best is None or cost < best[0]:
             best = (cost, tab)
+        if tab.blob.nbytes <= THREE_CTA_TABLE_BYTES and (small is None or cost < small[0]):
+            small = (cost, tab)
     if best is None:
         return build_track_table(track)
+    if small is not None and small[0] <= THREE_CTA_COST_SLACK * best[0]:
+        return small[1]
     return best[1]
 
 

@@ -84,6 +84,19 @@ int hc_sensors_multi_mismatches(const float* blob, float x, float y, float angle
     for (int q = 0; q < 8; ++q) cast_rays<2, false>(T, x, y, angle, q < 4 ? q : q + 4, b, &tests);
     for (int q = 0; q < 4; ++q) cast_rays<4, false>(T, x, y, angle, q, c, &tests);
     for (int i = 0; i < 16; ++i) if (f2u(a[i]) != f2u(b[i]) || f2u(a[i]) != f2u(c[i])) ++bad;
+    // the queued form (three cars so the job -> (class, car) split is exercised; the middle one is the pose under test)
+    float cars[3 * 8], rot[32], obs[3 * 41]; int ctr = 0;
+    for (int i = 0; i < 16; ++i) ray_rotation(i, &rot[2 * i], &rot[2 * i + 1]);
+    for (int cidx = 0; cidx < 3; ++cidx) {
+        const RayCar rc = ray_car(T, x + 3.0f * (float)(cidx - 1), y - 2.0f * (float)(cidx - 1), angle + 0.4f * (float)(cidx - 1));
+        float* d = cars + cidx * 8;
+        d[0] = rc.px; d[1] = rc.py; d[2] = rc.ca; d[3] = rc.sa; d[4] = rc.fx; d[5] = rc.fy; d[6] = u2f((uint32_t)rc.cell0); d[7] = u2f(rc.h0);
+    }
+    for (int i = 0; i < 3 * 41; ++i) obs[i] = -1.0f;
+    cast_rays_queue<false>(T, cars, 3, (65536u + 2u) / 3u, -1, &ctr, obs + 22, 41, rot, &tests);
+    for (int i = 0; i < 16; ++i) if (f2u(a[i]) != f2u(obs[41 + 22 + i])) ++bad;
+    for (int cidx = 0; cidx < 3; ++cidx) for (int i = 0; i < 16; ++i) if (!(obs[cidx * 41 + 22 + i] >= 0.0f)) ++bad;      // every job ran
+    if (ctr != 49) ++bad;                                  // 48 jobs claimed, one claim past the end
     return bad;
 }
 // chord-nearest segment with the per-cell candidate mask (masked = 1) or over all segments (masked = 0: a view with an
