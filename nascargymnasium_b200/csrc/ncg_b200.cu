@@ -29,7 +29,8 @@ struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, conta
 
 struct KParams {
     float* records; const float* blob; const long long* track_off;
-    const int2* cta_tab;                                   // per CTA: {first env, number of envs}; all of one track
+    const int2* cta_tab;                                   // per group: {first env, number of envs}; all of one track, <= 32 cars
+    const int2* pair_tab;                                  // two-physics-warp shape: per CTA the two groups it serves {g0, g1 or -1}
     const float* reset_obs;                                // [n_tracks][NCG_OBS_DIM]: the observation every reset_car yields on a track
     int E, C, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip, queue;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
@@ -78,19 +79,20 @@ __device__ __noinline__ void reset_in_place(float* R, const Track T) {
 struct SmemLayout {
     int rec, obs, pose, flag, xf, act, otab, ray, rot, ctr, track, total;      // word offsets
 };
-__host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
+// cpb = car slots of the CTA: 32 per physics warp
+__host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb) {
     SmemLayout L; int o = 0;
-    L.rec = o; o += CPB * REC_STRIDE;
-    L.obs = o; o += 2 * CPB * OBS_STRIDE;          // [2][CPB][OBS_STRIDE]: the step's observation rows
+    L.rec = o; o += cpb * REC_STRIDE;
+    L.obs = o; o += 2 * cpb * OBS_STRIDE;          // [2][cpb][OBS_STRIDE]: the step's observation rows
     o = (o + 3) & ~3;
-    L.pose = o; o += 2 * CPB * 4;                  // [2][CPB] float4 {x, y, angle, -}
-    L.flag = o; o += 2 * CPB;                      // [2][CPB] u32: bit0 terminated, bit1 truncated
-    L.xf = o; o += CPB;
+    L.pose = o; o += 2 * cpb * 4;                  // [2][cpb] float4 {x, y, angle, -}
+    L.flag = o; o += 2 * cpb;                      // [2][cpb] u32: bit0 terminated, bit1 truncated
+    L.xf = o; o += cpb;
     o = (o + 3) & ~3;
-    L.act = o; o += 2 * CPB * 4;                   // [2][CPB] float4 {throttle, brake, steer, -}: synthetic actions, made two steps ahead
+    L.act = o; o += 2 * cpb * 4;                   // [2][cpb] float4 {throttle, brake, steer, -}: synthetic actions, made two steps ahead
     L.otab = o; o += 2 * 40;                       // observation scale[38] (padded to 40) and lower clip bound[38]
     o = (o + 3) & ~3;
-    L.ray = o; o += CPB * 8;                       // [CPB] RayCar: what a ray job needs to know about its car (ray queue)
+    L.ray = o; o += cpb * 8;                       // [cpb] RayCar: what a ray job needs to know about its car (ray queue)
     L.rot = o; o += 32;                            // the 16 ray rotations (cos, sin)
     L.ctr = o; o += 4;                             // [2] next unclaimed ray job
     L.track = o; o += (int)stage_words;            // 16-byte aligned for the TMA copy
@@ -101,15 +103,20 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words) {
 // MINB = CTAs per SM the register allocation must allow: 1 lets the physics warp keep its whole working set (track
 // view, body, tyres) in registers -- right when the batch is at most one CTA per SM; 2 trades a few spills for
 // twice the resident warps when there are waves of CTAs.
-template <int RPL, int MINB>
-__global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
-    constexpr int RW = 16 / RPL;                    // ray warps
-    constexpr int NT = 32 * (1 + RW);
-    constexpr int LPC = 16 / RPL;                   // lanes per car in a ray warp
-    constexpr int CPW = 32 / LPC;                   // cars per ray warp
+// PW = physics warps per CTA.  1: the CTA is one group of the CTA table (<= 32 car slots) with 16/RPL ray warps.
+// 2: the CTA serves a pair of groups of one track -- two physics warps, 64 car slots, six ray warps that drain one ray
+// queue, one staged track table -- which puts four physics warps on an SM (2 CTAs x 256 threads x 128 registers) where
+// PW = 1 fits three (shared memory: three tables): at large batches a step is bound by the physics warps' dependent chains.
+template <int RPL, int MINB, int PW>
+__global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
+    constexpr int RW = PW == 2 ? 6 : 16 / RPL;      // ray warps
+    constexpr int NT = 32 * (PW + RW);
+    constexpr int SLOTS = 32 * PW;                  // car slots: physics warp w owns slots 32w .. 32w+31
+    constexpr int LPC = 16 / RPL;                   // fixed ray mapping (PW == 1): lanes per car in a ray warp
+    constexpr int CPW = 32 / LPC;                   //                              cars per ray warp
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long s_mbar;
-    const SmemLayout L = smem_layout(0);
+    const SmemLayout L = smem_layout(0, SLOTS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* s_rec = smem + L.rec;
     float* s_obs = smem + L.obs;
@@ -123,55 +130,62 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
     int* s_ctr = reinterpret_cast<int*>(smem + L.ctr);
     float* s_track = smem + L.track;
 
-    const int2 cta = p.cta_tab[blockIdx.x];
-    const int env0 = cta.x, n_env = cta.y;
-    const int n_cars = n_env * p.C, car0 = env0 * p.C;
+    // the groups of envs this CTA serves: n0 cars from global car cb0 in slots 0.., n1 cars from cb1 in slots 32..
+    int2 g0, g1 = make_int2(0, 0);
+    if (PW == 1) g0 = p.cta_tab[blockIdx.x];
+    else { const int2 pr = p.pair_tab[blockIdx.x]; g0 = p.cta_tab[pr.x]; if (pr.y >= 0) g1 = p.cta_tab[pr.y]; }
+    const int n0 = g0.y * p.C, n1 = g1.y * p.C, n_all = n0 + n1;
+    const int cb0 = g0.x * p.C, cb1 = g1.x * p.C;
     const int N = p.E * p.C;
+#define SLOT_OF(ci) ((ci) < n0 ? (ci) : 32 + (ci) - n0)           /* dense car index of the CTA -> slot */
+#define GCAR_OF(ci) ((ci) < n0 ? cb0 + (ci) : cb1 + (ci) - n0)     /*                          -> global car */
 
     // ---- track table: staged by TMA when the whole CTA shares a track, else read through L1/L2
     const float* staged = nullptr;
     if (p.stage) {
         if (threadIdx.x == 0) {
-            const uint32_t tid = f2u(p.records[(size_t)car0 * NCG_RECORD_WORDS + NCG_R_TRACK]);
+            const uint32_t tid = f2u(p.records[(size_t)cb0 * NCG_RECORD_WORDS + NCG_R_TRACK]);
             const float* g = p.blob + p.track_off[tid];
             tma_issue(s_track, g, f2u(__ldg(g + TH_STAGE_WORDS)) * 4u, &s_mbar);
         }
         staged = s_track;
     }
     // ---- records HBM -> shared (coalesced float4 reads, scalar shared stores into the padded rows)
-    {
-        const float4* src = reinterpret_cast<const float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
-        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += NT) {
-            const float4 v = src[i];
-            float* d = s_rec + (i >> 5) * REC_STRIDE + (i & 31) * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
+    for (int i = threadIdx.x; i < n_all * (NCG_RECORD_WORDS / 4); i += NT) {
+        const int ci = i >> 5;
+        const float4 v = reinterpret_cast<const float4*>(p.records + (size_t)GCAR_OF(ci) * NCG_RECORD_WORDS)[i & 31];
+        float* d = s_rec + SLOT_OF(ci) * REC_STRIDE + (i & 31) * 4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
     if (threadIdx.x < NCG_OBS_DIM) { s_otab[threadIdx.x] = obs_scale(threadIdx.x); s_otab[40 + threadIdx.x] = obs_lo(threadIdx.x); }
     if (threadIdx.x < 16) ray_rotation((int)threadIdx.x, &s_rot[2 * threadIdx.x], &s_rot[2 * threadIdx.x + 1]);
     const bool synth = p.actions == nullptr;
-    if (synth && warp == 1 && lane < n_cars) {               // ray warp 0 makes the synthetic actions, two steps ahead of the physics warp
+    // the first PW ray warps make the synthetic actions (one per physics warp), two steps ahead of the physics warps
+    const bool act_maker = synth && warp >= PW && warp < 2 * PW && lane < (warp == PW ? n0 : n1);
+    const int act_slot = (warp - PW) * 32 + lane, act_car = (warp == PW ? cb0 : cb1) + lane;
+    if (act_maker) {
         for (int t = 0; t < 2 && t < p.T; ++t) {
             float thr, brk, st;
-            action_synthetic(p.seed, (uint32_t)(car0 + lane), p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
-            s_act[t * CPB + lane] = make_float4(thr, brk, st, 0.0f);
+            action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
+            s_act[t * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
         }
     }
     __syncthreads();
     if (p.stage) tma_wait(&s_mbar);
 
-    // the car slot this thread serves: its lane (physics warp) or the car its rays belong to (ray warps)
-    const int slot = warp == 0 ? lane : (warp - 1) * CPW + lane / LPC;
-    const bool active = slot < n_cars;
+    // the car slot this thread serves: its lane (physics warps) or, with the fixed ray mapping, the car its rays belong to
+    const int slot = warp < PW ? warp * 32 + lane : (warp - 1) * CPW + lane / LPC;
+    const bool active = warp < PW ? lane < (warp == 0 ? n0 : n1) : (PW == 1 && slot < n0);
     // track views are fixed for the launch (auto-reset keeps an env on its track): build them once
-    const uint32_t my_tid = f2u(s_rec[(active ? slot : 0) * REC_STRIDE + NCG_R_TRACK]);
+    const uint32_t my_tid = f2u(s_rec[NCG_R_TRACK]);              // slot 0: a CTA serves one track
     const float* gblob = p.blob + p.track_off[my_tid];
     const Track T = track_view(staged ? staged : gblob, gblob);
     const bool do_reset = p.auto_reset != 0;
     unsigned long long ray_tests = 0;
 
-    if (warp == 0) {
-        // =============================================================== physics warp: one car per lane
+    if (warp < PW) {
+        // =============================================================== physics warps: one car per lane
+        const int car0 = warp == 0 ? cb0 : cb1, env0 = warp == 0 ? g0.x : g1.x;
         float* R = s_rec + (active ? slot : 0) * REC_STRIDE;
         Counters cnt = {0, 0, 0, 0, 0};
         unsigned long long episodes = 0; double ret_sum = 0.0;
@@ -183,22 +197,22 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             StepCtx ctx;
             if (active) {
                 float thr, brk, st;
-                const int gc = car0 + slot;
+                const int gc = car0 + lane;
                 if (!synth) {
                     if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
                     else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
-                } else { const float4 a = s_act[b * CPB + slot]; thr = a.x; brk = a.y; st = a.z; }
+                } else { const float4 a = s_act[b * SLOTS + slot]; thr = a.x; brk = a.y; st = a.z; }
                 if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts != 0, &ctx, &cnt);
-                s_pose[b * CPB + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
+                s_pose[b * SLOTS + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
             }
-            if (lane == 0) s_ctr[b] = 32 * RW;                  // ray queue: every ray lane starts on job = its index
+            if (threadIdx.x == 0) s_ctr[b] = 32 * RW;           // ray queue: every ray lane starts on job = its index
             // the pose exists: let the ray warps start while this warp does the rest of the step
             __syncwarp();
             __threadfence_block();
             bar_arrive(BAR_POSE + b, NT);
             if (active) {
                 uint32_t xf = 0;
-                if (!(p.debug_skip & 2)) rew = car_step_rules<true>(R, T, &ctx, s_obs + (b * CPB + slot) * OBS_STRIDE, &xf, &cnt);
+                if (!(p.debug_skip & 2)) rew = car_step_rules<true>(R, T, &ctx, s_obs + (b * SLOTS + slot) * OBS_STRIDE, &xf, &cnt);
                 s_xf[slot] = xf;
                 if (p.track_info) {
                     uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
@@ -209,13 +223,13 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
             __syncwarp();
             // ---- env phase (every car of an env computes the same decision from the env's xf words)
             if (active) {
-                const int le = slot / p.C;
+                const int le = lane / p.C;
                 bool te, tr; int why;
-                env_decide(s_xf + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
+                env_decide(s_xf + warp * 32 + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
                 car_finish(R, rew);
-                if (rew_out) rew_out[car0 + slot] = rew;
+                if (rew_out) rew_out[car0 + lane] = rew;
                 const bool done = te || tr;
-                if (slot == le * p.C) {
+                if (lane == le * p.C) {
                     const int ge = env0 + le;
                     if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
                     else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
@@ -223,12 +237,12 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
                 }
                 if (done) {
                     ret_sum += (double)R[NCG_R_CUM_REWARD];
-                    if (p.ep_return) p.ep_return[car0 + slot] = R[NCG_R_CUM_REWARD];
-                    if (slot == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
+                    if (p.ep_return) p.ep_return[car0 + lane] = R[NCG_R_CUM_REWARD];
+                    if (lane == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
                 }
                 // ---- same-step auto-reset (CarPhysics.reset_car semantics)
                 if (done && do_reset) reset_in_place(R, T);
-                s_flag[b * CPB + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
+                s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
             }
             __syncwarp();
             __threadfence_block();
@@ -245,68 +259,75 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
         for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_down_sync(0xffffffffu, ret_sum, o);
         if (lane == 0 && ret_sum != 0.0) atomicAdd(&p.stats->return_sum, ret_sum);
     } else {
-        // =============================================================== ray warps: RPL rays per lane
+        // =============================================================== ray warps
+        const int rt = (warp - PW) * 32 + lane;                  // index among the CTA's ray lanes
         const int q = lane % LPC;
-        const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // a lane's rays are q0, q0+4, ... (90 deg apart)
-        const int wslot0 = (warp - 1) * CPW;                     // first car slot of this warp
+        const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // fixed mapping: a lane's rays are q0, q0+4, ... (90 deg apart)
+        const int wslot0 = (warp - 1) * CPW;                     //                first car slot of this warp
         const float* reset_row = p.reset_obs + (size_t)my_tid * NCG_OBS_DIM;
         const RaySet<RPL> rs = ray_set<RPL>(q0);
-        // which (car of this warp, word pair) this lane stores in each pass of the row write-out: fixed for the launch
-        constexpr int NIT = (CPW * (NCG_OBS_DIM / 2) + 31) / 32;
+        // which (car, word pair) this lane stores in each pass of the row write-out: fixed for the launch.  PW == 1: a warp
+        // writes the rows of its own CPW cars; PW == 2: the dense cars of the CTA are dealt over all ray lanes.
+        constexpr int NIT = PW == 2 ? (SLOTS * (NCG_OBS_DIM / 2) + 32 * RW - 1) / (32 * RW) : (CPW * (NCG_OBS_DIM / 2) + 31) / 32;
         uint32_t pair_sk[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            const int m = lane + 32 * it;
-            pair_sk[it] = m < CPW * (NCG_OBS_DIM / 2) ? (uint32_t)(((m / (NCG_OBS_DIM / 2)) << 8) | ((m % (NCG_OBS_DIM / 2)) * 2)) : 0xFFFFFFFFu;
+            if (PW == 2) {
+                const int m = rt + 32 * RW * it;
+                pair_sk[it] = m < n_all * (NCG_OBS_DIM / 2) ? (uint32_t)(((m / (NCG_OBS_DIM / 2)) << 8) | ((m % (NCG_OBS_DIM / 2)) * 2)) : 0xFFFFFFFFu;
+            } else {
+                const int m = lane + 32 * it;
+                pair_sk[it] = m < CPW * (NCG_OBS_DIM / 2) ? (uint32_t)(((m / (NCG_OBS_DIM / 2)) << 8) | ((m % (NCG_OBS_DIM / 2)) * 2)) : 0xFFFFFFFFu;
+            }
         }
         unsigned tests = 0;
-        const unsigned magic = (65536u + (unsigned)n_cars - 1u) / (unsigned)n_cars;
+        const unsigned magic = (131072u + (unsigned)n_all - 1u) / (unsigned)n_all;
         for (int t = 0; t < p.T; ++t) {
             const int b = t & 1;
             float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
             bar_sync(BAR_POSE + b, NT);
-            if (p.queue && !(p.debug_skip & 1)) {
+            if ((PW == 2 || p.queue) && !(p.debug_skip & 1)) {
                 // every ray warp derives the cars' ray origins itself (same values to the same words: no barrier between
                 // the ray warps; nobody still reads last step's, every ray warp has passed that step's FULL barrier), then
-                // all ray lanes of the CTA drain one queue of 16 x n_cars rays
-                float* rc = s_ray;
-                if (lane < n_cars) {
-                    const float4 ps = s_pose[b * CPB + lane];
+                // all ray lanes of the CTA drain one queue of 16 x n_all rays
+                for (int ci = lane; ci < n_all; ci += 32) {
+                    const float4 ps = s_pose[b * SLOTS + SLOT_OF(ci)];
                     const RayCar c = ray_car(T, ps.x, ps.y, ps.z);
-                    reinterpret_cast<float4*>(rc)[2 * lane] = make_float4(c.px, c.py, c.ca, c.sa);
-                    reinterpret_cast<float4*>(rc)[2 * lane + 1] = make_float4(c.fx, c.fy, u2f((uint32_t)c.cell0), u2f(c.h0));
+                    reinterpret_cast<float4*>(s_ray)[2 * ci] = make_float4(c.px, c.py, c.ca, c.sa);
+                    reinterpret_cast<float4*>(s_ray)[2 * ci + 1] = make_float4(c.fx, c.fy, u2f((uint32_t)c.cell0), u2f(c.h0));
                 }
                 __syncwarp();
-                float* o22 = s_obs + b * CPB * OBS_STRIDE + 22;
-                if (staged) cast_rays_queue<true>(T, rc, n_cars, magic, (warp - 1) * 32 + lane, s_ctr + b, o22, OBS_STRIDE, s_rot, &tests);
-                else cast_rays_queue<false>(T, rc, n_cars, magic, (warp - 1) * 32 + lane, s_ctr + b, o22, OBS_STRIDE, s_rot, &tests);
-            } else if (active && !(p.debug_skip & 1)) {
-                const float4 ps = s_pose[b * CPB + slot];
-                float* dst = s_obs + (b * CPB + slot) * OBS_STRIDE + 22;
+                float* o22 = s_obs + b * SLOTS * OBS_STRIDE + 22;
+                if (staged) cast_rays_queue<true>(T, s_ray, n_all, magic, n0, 32 - n0, rt, s_ctr + b, o22, OBS_STRIDE, s_rot, &tests);
+                else cast_rays_queue<false>(T, s_ray, n_all, magic, n0, 32 - n0, rt, s_ctr + b, o22, OBS_STRIDE, s_rot, &tests);
+            } else if (PW == 1 && active && !(p.debug_skip & 1)) {
+                const float4 ps = s_pose[b * SLOTS + slot];
+                float* dst = s_obs + (b * SLOTS + slot) * OBS_STRIDE + 22;
                 if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
                 else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
             }
-            if (synth && warp == 1 && lane < n_cars && t + 2 < p.T) {     // actions of step t+2 (this buffer's next use)
+            if (act_maker && t + 2 < p.T) {                      // actions of step t+2 (this buffer's next use)
                 float thr, brk, st;
-                action_synthetic(p.seed, (uint32_t)(car0 + lane), p.step_base + (unsigned)(t + 2), p.mode, p.discrete != 0, &thr, &brk, &st);
-                s_act[b * CPB + lane] = make_float4(thr, brk, st, 0.0f);
+                action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)(t + 2), p.mode, p.discrete != 0, &thr, &brk, &st);
+                s_act[b * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
             }
             bar_sync(BAR_FULL + b, NT);
             __syncwarp();
-            // ---- observation rows of this warp's cars shared -> HBM: CPW x 38 consecutive floats, written as float2
-            // (a row is 19 float2, so a pair never straddles two cars and every store is 8-byte aligned).  Words 0..21
-            // arrive raw from the physics warp and are scaled and clipped here; the ray words are already in [0,1]
-            // (scale 1, lower bound 0 leave them unchanged).
+            // ---- observation rows shared -> HBM: 38 consecutive floats per car, written as float2 (a row is 19 float2,
+            // so a pair never straddles two cars and every store is 8-byte aligned).  Words 0..21 arrive raw from the
+            // physics warp and are scaled and clipped here; the ray words are already in [0,1] (scale 1, lower bound 0
+            // leave them unchanged).
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                const int sl = wslot0 + (int)(pair_sk[it] >> 8), k = (int)(pair_sk[it] & 255u);
-                if (pair_sk[it] != 0xFFFFFFFFu && sl < n_cars) {
-                    const float* row = s_obs + (b * CPB + sl) * OBS_STRIDE + k;
+                const int ci = (PW == 2 ? 0 : wslot0) + (int)(pair_sk[it] >> 8), k = (int)(pair_sk[it] & 255u);
+                if (pair_sk[it] != 0xFFFFFFFFu && ci < n_all) {
+                    const int sl = SLOT_OF(ci);
+                    const float* row = s_obs + (b * SLOTS + sl) * OBS_STRIDE + k;
                     float2 v;
                     v.x = obs_word(row[0], s_otab[k], s_otab[40 + k]);
                     v.y = obs_word(row[1], s_otab[k + 1], s_otab[41 + k]);
-                    const size_t o = ((size_t)(car0 + sl) * NCG_OBS_DIM + k) >> 1;
-                    if (do_reset && s_flag[b * CPB + sl] != 0u) {
+                    const size_t o = ((size_t)GCAR_OF(ci) * NCG_OBS_DIM + k) >> 1;
+                    if (do_reset && s_flag[b * SLOTS + sl] != 0u) {
                         if (p.final_obs) reinterpret_cast<float2*>(p.final_obs)[o] = v;
                         if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = __ldg(reinterpret_cast<const float2*>(reset_row + k));   // the track's reset observation
                     } else if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = v;
@@ -320,13 +341,13 @@ __global__ void __launch_bounds__(32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KPa
     }
     // ---- records shared -> HBM
     __syncthreads();
-    {
-        float4* dst = reinterpret_cast<float4*>(p.records + (size_t)car0 * NCG_RECORD_WORDS);
-        for (int i = threadIdx.x; i < n_cars * (NCG_RECORD_WORDS / 4); i += NT) {
-            const float* d = s_rec + (i >> 5) * REC_STRIDE + (i & 31) * 4;
-            dst[i] = make_float4(d[0], d[1], d[2], d[3]);
-        }
+    for (int i = threadIdx.x; i < n_all * (NCG_RECORD_WORDS / 4); i += NT) {
+        const int ci = i >> 5;
+        const float* d = s_rec + SLOT_OF(ci) * REC_STRIDE + (i & 31) * 4;
+        reinterpret_cast<float4*>(p.records + (size_t)GCAR_OF(ci) * NCG_RECORD_WORDS)[i & 31] = make_float4(d[0], d[1], d[2], d[3]);
     }
+#undef SLOT_OF
+#undef GCAR_OF
 }
 
 // the observation of the reset state of each track; one warp per track
@@ -376,7 +397,8 @@ struct NcgHandle {
     float* d_reset_obs = nullptr;
     std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
     std::vector<int> h_env_track;
-    int2* d_cta_tab = nullptr; int n_ctas = 0; bool cta_dirty = true;
+    int2* d_cta_tab = nullptr; int n_ctas = 0; bool cta_dirty = true;      // groups of <= 32 car slots (one CTA each, or two per CTA)
+    int2* d_pair_tab = nullptr; int n_pairs = 0;                          // groups paired by track for the two-physics-warp shape
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0;
@@ -434,11 +456,24 @@ int build_cta_table(NcgHandle* h) {
     std::vector<int2> tab;
     plan_ctas(h->h_env_track.data(), h->cfg.num_envs, h->cfg.cars_per_env, h->num_sms, tab);
     if ((int)tab.size() > h->n_ctas) {
-        cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr;
+        cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); h->d_cta_tab = nullptr;
         CUDA_TRY(cudaMalloc(&h->d_cta_tab, tab.size() * sizeof(int2)));
     }
     CUDA_TRY(cudaMemcpy(h->d_cta_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     h->n_ctas = (int)tab.size();
+    // neighbouring groups of one track, two by two (a group without such a neighbour stays alone)
+    std::vector<int2> pairs;
+    for (size_t g = 0; g < tab.size();) {
+        const bool two = g + 1 < tab.size() && h->h_env_track[tab[g + 1].x] == h->h_env_track[tab[g].x];
+        pairs.push_back(make_int2((int)g, two ? (int)g + 1 : -1));
+        g += two ? 2 : 1;
+    }
+    if ((int)pairs.size() > h->n_pairs) {
+        cudaFree(h->d_pair_tab); h->d_pair_tab = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_pair_tab, pairs.size() * sizeof(int2)));
+    }
+    CUDA_TRY(cudaMemcpy(h->d_pair_tab, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    h->n_pairs = (int)pairs.size();
     h->cta_dirty = false;
     return NCG_OK;
 }
@@ -452,30 +487,42 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     // (a CTA's step time is set by the physics warp's dependent chain, so fewer cars per CTA only lowers the work per
     // chain), and a fourth resident CTA per SM (28 car slots, wall AABBs left in L2, 96 registers with spills).
     const int RPL = h->rays_per_lane ? h->rays_per_lane : (h->n_ctas > sms ? 4 : 2);
-    p.cta_tab = h->d_cta_tab;
+    // physics warps per CTA: one CTA per group (three resident per SM), or one per pair of groups (two resident per SM =
+    // four physics warps).  Measured per resident wave the pair shape is ~1.2x slower (12 ray warps per SM serve 128 cars
+    // instead of 96), so it is chosen when it saves enough waves: 16384 envs run as 256 CTAs in one wave instead of 512 in
+    // two (+23 %), 8192 ten-car envs in 5 waves instead of 7 (+30 %), the 65536-env track mix in 4 instead of 5 (+7 %).
+    int PW = 1;
+    if (h->n_ctas > 2 * sms) {
+        const int waves1 = (h->n_ctas + 3 * sms - 1) / (3 * sms), waves2 = (h->n_pairs + 2 * sms - 1) / (2 * sms);
+        if (12 * waves2 < 10 * waves1) PW = 2;
+    }
+    { const char* pw = getenv("NCG_PHYS_WARPS"); if (pw && (atoi(pw) == 1 || atoi(pw) == 2)) PW = atoi(pw); }
+    p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab;
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
-    size_t smem = (size_t)smem_layout(mx).total * 4;
+    size_t smem = (size_t)smem_layout(mx, 32 * PW).total * 4;
     if (p.stage && h->max_smem > 0 && smem > (size_t)h->max_smem) {      // a user track too large to stage: read it through L1/L2
         p.stage = 0;
-        smem = (size_t)smem_layout(0).total * 4;
+        smem = (size_t)smem_layout(0, 32 * PW).total * 4;
     }
-    // resident CTAs per SM the register allocation allows: as many as the batch has use for, up to what shared memory
-    // (~69 KB per CTA) admits; the 4-rays-per-lane shape (160 threads) fits three
     // rays handed out from a per-CTA queue (longest first) instead of a fixed lane -> rays map: pays once the SM is
     // issue-bound, i.e. with three resident CTAs per SM (measured on B200, daytona: +22 % at 65536 envs, +9 % at 16384,
     // -5 % at 8192 and -7 % at 4096, where a step is bound by latency and the queue's claims and job set-up only add to it)
     p.queue = h->n_ctas > 2 * sms ? 1 : 0;
     { const char* q = getenv("NCG_RAY_QUEUE"); if (q) p.queue = atoi(q) ? 1 : 0; }
+    // resident CTAs per SM the register allocation allows: as many as the batch has use for, up to what shared memory
+    // (~72 KB per CTA) admits; the 4-rays-per-lane shape (160 threads) fits three
     int minb = h->n_ctas <= sms ? 1 : (h->n_ctas <= 2 * sms || RPL != 4 ? 2 : 3);
     { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && atoi(mb) >= 1 && atoi(mb) <= 3) minb = atoi(mb); }
     if (minb == 3 && RPL != 4) minb = 2;
-    void (*k)(KParams) = minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1> : ncg_step_kernel<2, 1>)
-                       : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2> : ncg_step_kernel<2, 2>)
-                                   : ncg_step_kernel<4, 3>;
+    void (*k)(KParams) = PW == 2 ? ncg_step_kernel<4, 2, 2>
+                       : minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1, 1> : ncg_step_kernel<2, 1, 1>)
+                       : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2, 1> : ncg_step_kernel<2, 2, 1>)
+                                   : ncg_step_kernel<4, 3, 1>;
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
+    if (PW == 2) k<<<h->n_pairs, 256, smem, s>>>(p);
+    else k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     return NCG_OK;
@@ -537,7 +584,7 @@ int ncg_destroy(NcgHandle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
-    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab);
+    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab);
     cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

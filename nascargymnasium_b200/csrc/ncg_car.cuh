@@ -1166,8 +1166,11 @@ NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx
     // exactly in the face's plane (every car starts at x = 0, where two wall boxes abut)
     const float ex = fmaf(c, dx, fmaf(s, dy, 1e-30f)), ey = fmaf(c, dy, fmaf(-s, dx, 1e-30f));
     const float ix = rcp_fast(ex), iy = rcp_fast(ey);
-    // entry / exit along each box axis: (m -+ h) / e = m/e -+ |h/e| -- one product and two FFMAs per axis, no min/max pairs
-    const float hxi = fabsf(wb.x * ix), hyi = fabsf(wb.y * iy);
+    // entry / exit along each box axis: (m -+ h) / e = m/e -+ |h/e| -- one product and two FFMAs per axis, no min/max pairs.
+    // wb.w is the half-length plus 0.1 mm: with m = h exactly (origin in the plane of an end face, ray parallel to it)
+    // m/e - |h/e| is the rounding error of one product times 1e30, of either sign, and a ray in the plane of the joint
+    // between two collinear boxes could miss both; with the margin it enters both
+    const float hxi = fabsf(wb.w * ix), hyi = fabsf(wb.y * iy);
     const float tn = fmaxf(fmaf(mx, ix, -hxi), fmaf(my, iy, -hyi)), tf = fminf(fmaf(mx, ix, hxi), fmaf(my, iy, hyi));
     return (tn > 0.0f && tn <= tf) ? tn : INFINITY;
 }
@@ -1298,12 +1301,14 @@ NCG_HD RayCar ray_car(const Track& T, float px, float py, float angle) {
     return rc;
 }
 #define NCG_RAY_ORDER 0xC4B5D3A6E297F180ULL      // nibble r = the ray index of job class r: 0,8,1,15,7,9,2,14,6,10,3,13,5,11,4,12
-// cars: n_cars RayCar rows; job j = (class j / n_cars, car j % n_cars), `magic` = ceil(65536 / n_cars) turns the division
-// into a multiply (exact for j < 512); j0 = this lane's first job (>= 16 * n_cars: none, < 0: claim one); *ctr = the next
-// unclaimed job.  obs22 = word 22 of car 0's observation row, rows obs_stride apart.  rot = the 16 (cos, sin) ray rotations.
+// cars: n_cars RayCar rows; job j = (class j / n_cars, car j % n_cars), `magic` = ceil(2^17 / n_cars) turns the division
+// into a multiply (exact for j < 1024, n_cars <= 64); car c's observation row is row c, or c + gap for c >= gap_at (a
+// CTA with two physics warps keeps the second one's cars from slot 32); j0 = this lane's first job (>= 16 * n_cars:
+// none, < 0: claim one); *ctr = the next unclaimed job.  obs22 = word 22 of row 0, rows obs_stride apart.  rot = the 16
+// (cos, sin) ray rotations.
 template <bool SH>
-NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsigned magic, int j0, int* ctr, float* obs22, int obs_stride,
-                            const float* rot, unsigned* tests) {
+NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsigned magic, int gap_at, int gap, int j0, int* ctr,
+                            float* obs22, int obs_stride, const float* rot, unsigned* tests) {
     const RayMem<SH> M(T);
     const int gnx = T.gnx, gny = T.gny, total = 16 * n_cars;
     unsigned nt = 0;
@@ -1331,13 +1336,13 @@ NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsig
 #endif
                 }
                 if (j >= total) break;
-                const unsigned r = ((unsigned)j * magic) >> 16;
+                const unsigned r = ((unsigned)j * magic) >> 17;
                 const int car = j - (int)r * n_cars, ray = (int)((NCG_RAY_ORDER >> (4u * r)) & 15ull);
                 const F4 c0 = *reinterpret_cast<const F4*>(cars + car * 8), c1 = *reinterpret_cast<const F4*>(cars + car * 8 + 4);
                 const float kc = rot[2 * ray], ks = rot[2 * ray + 1];
                 px = c0.x; py = c0.y;
                 dx = c0.z * kc - c0.w * ks; dy = c0.w * kc + c0.z * ks;
-                out = obs22 + car * obs_stride + ray;
+                out = obs22 + (car + (car >= gap_at ? gap : 0)) * obs_stride + ray;
                 best = NCG_RAY_LEN;
                 const int cell0 = (int)f2u(c1.z);
                 if (cell0 < 0) {                                        // origin outside the grid: scan every wall

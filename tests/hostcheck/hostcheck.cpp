@@ -93,7 +93,7 @@ int hc_sensors_multi_mismatches(const float* blob, float x, float y, float angle
         d[0] = rc.px; d[1] = rc.py; d[2] = rc.ca; d[3] = rc.sa; d[4] = rc.fx; d[5] = rc.fy; d[6] = u2f((uint32_t)rc.cell0); d[7] = u2f(rc.h0);
     }
     for (int i = 0; i < 3 * 41; ++i) obs[i] = -1.0f;
-    cast_rays_queue<false>(T, cars, 3, (65536u + 2u) / 3u, -1, &ctr, obs + 22, 41, rot, &tests);
+    cast_rays_queue<false>(T, cars, 3, (131072u + 2u) / 3u, 3, 0, -1, &ctr, obs + 22, 41, rot, &tests);
     for (int i = 0; i < 16; ++i) if (f2u(a[i]) != f2u(obs[41 + 22 + i])) ++bad;
     for (int cidx = 0; cidx < 3; ++cidx) for (int i = 0; i < 16; ++i) if (!(obs[cidx * 41 + 22 + i] >= 0.0f)) ++bad;      // every job ran
     if (ctr != 49) ++bad;                                  // 48 jobs claimed, one claim past the end

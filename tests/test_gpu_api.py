@@ -384,19 +384,28 @@ def test_unstaged_track_table_gives_identical_results(monkeypatch):
 
 
 def test_ray_queue_and_fixed_ray_mapping_give_identical_results(monkeypatch):
-    """Large batches hand the rays of a CTA's cars out from a queue (longest first), small ones use a fixed lane -> rays
-    map; both run the same traversal, so records and observations must be bit-identical -- staged and unstaged, with a
-    partly filled last CTA, on two tracks."""
+    """Large batches hand the rays of a CTA's cars out from a queue (longest first) and put two physics warps in a CTA,
+    small ones use a fixed lane -> rays map and one physics warp; all run the same computation per car, so records and
+    observations must be bit-identical -- staged and unstaged, with partly filled and unpaired groups, on two tracks."""
+    import torch
+    from nascargymnasium_b200.engine import Engine
+    for E, C in ((333, 1), (700, 3)):
+        _queue_variants_agree(monkeypatch, E, C)
+
+
+def _queue_variants_agree(monkeypatch, E, C):
     import torch
     from nascargymnasium_b200.engine import Engine
     outs = []
-    for queue, no_stage, rpl in (("0", "0", "2"), ("1", "0", "2"), ("1", "0", "4"), ("1", "1", "4"), ("0", "0", "4")):
+    for queue, no_stage, rpl, pw in (("0", "0", "2", "1"), ("1", "0", "2", "1"), ("1", "0", "4", "1"), ("1", "1", "4", "1"), ("0", "0", "4", "1"),
+                                     ("1", "0", "4", "2"), ("1", "1", "4", "2")):
         monkeypatch.setenv("NCG_RAY_QUEUE", queue)
         monkeypatch.setenv("NCG_NO_STAGE", no_stage)
         monkeypatch.setenv("NCG_RAYS_PER_LANE", rpl)
-        eng = Engine(333, 1, tracks=["daytona", "nascar2"], auto_reset=True)
-        eng.reset_host(track_id=(np.arange(333) * 2 // 333).astype(np.int32))
-        obs = torch.zeros((200, 333, 38), dtype=torch.float32, device="cuda:0")
+        monkeypatch.setenv("NCG_PHYS_WARPS", pw)       # 2: a CTA serves two groups of envs (two physics warps, six ray warps)
+        eng = Engine(E, C, tracks=["daytona", "nascar2"], auto_reset=True)
+        eng.reset_host(track_id=(np.arange(E) * 2 // E).astype(np.int32))
+        obs = torch.zeros((200, E * C, 38), dtype=torch.float32, device="cuda:0")
         eng.rollout(200, seed=9, mode=1, obs_rollout=obs.view(-1))
         torch.cuda.synchronize()
         outs.append((eng.get_state_host(), obs.cpu().numpy(), eng.read_stats()))

@@ -68,6 +68,30 @@ def test_grid_ray_traversal_matches_box2d_clipping_over_all_walls():
         assert worst < 1e-3, (name, worst)
 
 
+def test_rays_in_the_plane_of_a_wall_joint_never_slip_between_the_boxes():
+    """Origins exactly in the plane of a box's end face with axis-aligned headings (every car starts on such a pose:
+    x = 0, heading 0): some rays then run parallel to the face, in its plane, where the slab arithmetic degenerates.  The
+    ray half-length carries a 0.1 mm margin so that two boxes abutting end to end are watertight; Box2D's own clipping
+    may let such a ray through (then it reports a farther wall), so the check is one-sided: never farther than Box2D's
+    arithmetic by more than 2 mm."""
+    hc = P.hostcheck()
+    for name in ("daytona", "martinsville", "nascar2"):
+        tab = T.get_track_table(name)
+        blob = np.ascontiguousarray(tab.blob)
+        b = tab.boxes.astype(np.float64)
+        for w in range(0, len(b), 3):
+            c, s = b[w, 2], b[w, 3]
+            ex, ey = b[w, 0] + c * b[w, 4], b[w, 1] + s * b[w, 4]
+            for off in (-6.0, 6.0):
+                x, y = float(np.float32(ex - s * off)), float(np.float32(ey + c * off))
+                for th in (0.0, np.pi / 2, np.pi, -np.pi / 2):
+                    a, g = np.zeros(16, np.float32), np.zeros(16, np.float32)
+                    n = ctypes.c_uint(0)
+                    hc.hc_sensors_brute(P._fp(blob), x, y, float(np.float32(th)), P._fp(a))
+                    hc.hc_sensors_grid(P._fp(blob), x, y, float(np.float32(th)), P._fp(g), ctypes.byref(n))
+                    assert float((g - a).max()) < 2e-3, (name, w, x, y, th, a, g)
+
+
 def test_multi_car_env_and_same_track_reset_match_oracle():
     """Free-running 3-car env with reset_on_lap, including reset_car semantics after termination."""
     rng = np.random.default_rng(9)
