@@ -1172,7 +1172,13 @@ NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx
     // between two collinear boxes could miss both; with the margin it enters both
     const float hxi = fabsf(wb.w * ix), hyi = fabsf(wb.y * iy);
     const float tn = fmaxf(fmaf(mx, ix, -hxi), fmaf(my, iy, -hyi)), tf = fminf(fmaf(mx, ix, hxi), fmaf(my, iy, hyi));
+#if defined(__CUDA_ARCH__)
+    float r;                                                  // (tn > 0 && tn <= tf) ? tn : +inf as two FSETP (the second takes the first as input) and one FSEL
+    asm("{ .reg .pred q, p; setp.le.f32 q, %1, %2; setp.gt.and.f32 p, %1, 0f00000000, q; selp.f32 %0, %1, 0f7F800000, p; }" : "=f"(r) : "f"(tn), "f"(tf));
+    return r;
+#else
     return (tn > 0.0f && tn <= tf) ? tn : INFINITY;
+#endif
 }
 #define NCG_RAY_LEN 250.0f
 // One lane's RPL rays of one car (see RaySet: a lane's total work mixes along-track and across-track rays).  All RPL
