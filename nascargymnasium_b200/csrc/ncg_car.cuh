@@ -51,7 +51,7 @@ NCG_HD int cell_count_max(const Track& T, int cell) { return (int)(T.cells[cell]
 NCG_HD int cell_item(const Track& T, int cell, int k) { return (int)T.items[(T.cells[cell] & 0xFFFFu) * 4u + (uint32_t)k]; }
 NCG_HD void wall_get(const Track& T, int i, Xf* xf, Box* b) {
     const float* w = T.walls + i * WALL_STRIDE;
-    xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[4]; b->hy = w[5];
+    xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[7]; b->hy = w[5];      // w[4] is the rays' half-length
 }
 NCG_HD float wall_angle(const Track& T, int i) { return T.walls[i * WALL_STRIDE + 6]; }
 NCG_HD AABB wall_fat(const Track& T, int i) { const float* a = T.aabb + i * 4; AABB r; r.lx = a[0]; r.ly = a[1]; r.ux = a[2]; r.uy = a[3]; return r; }
@@ -911,12 +911,26 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
             float lo = fmaxf(-12.0f, fminf(12.0f, ax * f.x + ay * f.y));
             float la = fmaxf(-12.0f, fminf(12.0f, ax * l.x + ay * l.y));
             int n = (int)f2u(R[NCG_R_ACC_N]);
-            if (n == 10) { for (int i = 0; i < 18; ++i) R[NCG_R_ACC + i] = R[NCG_R_ACC + i + 2]; n = 9; }
-            R[NCG_R_ACC + 2 * n] = lo; R[NCG_R_ACC + 2 * n + 1] = la; ++n;
-            R[NCG_R_ACC_N] = u2f((uint32_t)n);
-            float s0 = 0.0f, s1 = 0.0f;
-            for (int i = 0; i < n; ++i) { s0 += R[NCG_R_ACC + 2 * i]; s1 += R[NCG_R_ACC + 2 * i + 1]; }
-            along = s0 / (float)n; alat = s1 / (float)n;
+            if (n == 10) {
+                // full window (every step but an episode's first nine): drop the oldest pair, append the new one and sum,
+                // through registers -- one batch of loads, the same left-to-right float32 sums, one batch of stores
+                float a[20];
+#pragma unroll
+                for (int i = 0; i < 18; ++i) a[i] = R[NCG_R_ACC + i + 2];
+                a[18] = lo; a[19] = la;
+                float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 10; ++i) { s0 += a[2 * i]; s1 += a[2 * i + 1]; }
+#pragma unroll
+                for (int i = 0; i < 20; ++i) R[NCG_R_ACC + i] = a[i];
+                along = s0 / 10.0f; alat = s1 / 10.0f;
+            } else {
+                R[NCG_R_ACC + 2 * n] = lo; R[NCG_R_ACC + 2 * n + 1] = la; ++n;
+                R[NCG_R_ACC_N] = u2f((uint32_t)n);
+                float s0 = 0.0f, s1 = 0.0f;
+                for (int i = 0; i < n; ++i) { s0 += R[NCG_R_ACC + 2 * i]; s1 += R[NCG_R_ACC + 2 * i + 1]; }
+                along = s0 / (float)n; alat = s1 / (float)n;
+            }
             R[NCG_R_PREV_VX] = W.v.x; R[NCG_R_PREV_VY] = W.v.y;
         }
         // tyres :354-357
@@ -1138,8 +1152,8 @@ template <bool SH> struct RayMem {
         if (SH) {
             const unsigned ad = walls + wi * (WALL_STRIDE * 4u);
             asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w) : "r"(ad));
-            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "r"(ad));
-        } else { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); *b = *reinterpret_cast<const F4*>(w + 4); }
+            asm("ld.shared.v2.f32 {%0,%1}, [%2+16];" : "=f"(b->x), "=f"(b->y) : "r"(ad));      // the rays' half extents only
+        } else { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); b->x = w[4]; b->y = w[5]; }
     }
     __device__ __forceinline__ uint32_t cell(int c) const {
         if (SH) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(cells + 4u * (unsigned)c)); return v; }
@@ -1152,7 +1166,7 @@ template <bool SH> struct RayMem {
 #else
     const Track* t;
     RayMem(const Track& T) : t(&T) {}
-    void wall(uint32_t wi, F4* a, F4* b) const { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); *b = *reinterpret_cast<const F4*>(w + 4); }
+    void wall(uint32_t wi, F4* a, F4* b) const { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); b->x = w[4]; b->y = w[5]; }
     uint32_t cell(int c) const { return t->cells[c]; }
     void block(int k, uint32_t* lo, uint32_t* hi) const { const uint32_t* q = reinterpret_cast<const uint32_t*>(t->items + 4 * k); *lo = q[0]; *hi = q[1]; }
 #endif
@@ -1167,10 +1181,10 @@ NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx
     const float ex = fmaf(c, dx, fmaf(s, dy, 1e-30f)), ey = fmaf(c, dy, fmaf(-s, dx, 1e-30f));
     const float ix = rcp_fast(ex), iy = rcp_fast(ey);
     // entry / exit along each box axis: (m -+ h) / e = m/e -+ |h/e| -- one product and two FFMAs per axis, no min/max pairs.
-    // wb.w is the half-length plus 0.1 mm: with m = h exactly (origin in the plane of an end face, ray parallel to it)
+    // wb.x is the half-length plus 0.1 mm (the exact one, for contacts, is word 7 of the row): with m = h exactly (origin in the plane of an end face, ray parallel to it)
     // m/e - |h/e| is the rounding error of one product times 1e30, of either sign, and a ray in the plane of the joint
     // between two collinear boxes could miss both; with the margin it enters both
-    const float hxi = fabsf(wb.w * ix), hyi = fabsf(wb.y * iy);
+    const float hxi = fabsf(wb.x * ix), hyi = fabsf(wb.y * iy);
     const float tn = fmaxf(fmaf(mx, ix, -hxi), fmaf(my, iy, -hyi)), tf = fminf(fmaf(mx, ix, hxi), fmaf(my, iy, hyi));
 #if defined(__CUDA_ARCH__)
     float r;                                                  // (tn > 0 && tn <= tf) ? tn : +inf as two FSETP (the second takes the first as input) and one FSEL

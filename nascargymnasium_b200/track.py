@@ -291,7 +291,7 @@ def wall_boxes(track: Track) -> np.ndarray:
 # ----------------------------------------------------------------------------
 MAX_SEGS = 16
 SEG_STRIDE = 12          # floats per segment row
-WALL_STRIDE = 8          # floats per wall row  [px,py,c,s,hx,hy,angle,hx for rays]
+WALL_STRIDE = 8          # floats per wall row  [px,py,c,s,hx for rays,hy,angle,hx]
 HDR_WORDS = 32
 GRID_CELL = 32.0
 POLY_RADIUS = 0.01       # b2_polygonRadius
@@ -517,7 +517,8 @@ def build_track_table(track: Track, cell: float = GRID_CELL) -> TrackTable:
     wrows[:, :7] = boxes
     # the half-length the sensor rays use: 0.1 mm longer, so that collinear boxes abutting end to end (every straight) are
     # watertight for a ray that runs exactly in the plane of the joint (every car starts on one: x = 0, heading 0)
-    wrows[:, 7] = (boxes[:, 4].astype(np.float64) + 1e-4).astype(np.float32)
+    wrows[:, 7] = boxes[:, 4]
+    wrows[:, 4] = (boxes[:, 4].astype(np.float64) + 1e-4).astype(np.float32)
     blob[off_walls:off_walls + n * WALL_STRIDE] = wrows.reshape(-1)
     blob[off_aabb:off_aabb + n * 4] = fat.reshape(-1)
     blob.view(np.uint32)[off_cells: off_cells + nx * ny] = (blk_first | (blk_count << 16)).astype(np.uint32)

@@ -43,7 +43,7 @@ void hc_env_reset(const float* blob, float* records, int C, int fresh, int track
 // b2PolygonShape::RayCast for a box, Box2D's own half-plane clipping loop (b2PolygonShape.cpp), float32: the
 // arithmetic the reference's sensors go through.  Test-side reference for the product's slab test.
 static float ray_box_generic(const float* w, V2 P1, V2 P2, float maxFraction) {
-    Rot q; q.c = w[2]; q.s = w[3]; V2 pos = mk(w[0], w[1]); Box b; b.hx = w[4]; b.hy = w[5];
+    Rot q; q.c = w[2]; q.s = w[3]; V2 pos = mk(w[0], w[1]); Box b; b.hx = w[7]; b.hy = w[5];      // the exact half-length (w[4] is the rays' own, 0.1 mm longer)
     V2 p1 = mulT(q, P1 - pos), p2 = mulT(q, P2 - pos), d = p2 - p1;
     float lower = 0.0f, upper = maxFraction; int index = -1;
     for (int i = 0; i < 4; ++i) {
