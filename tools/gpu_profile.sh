@@ -18,4 +18,7 @@ ncu --set full --clock-control none --import-source on -k regex:ncg_step_kernel 
 # the single-step (T=1) kernel of the e2e path: launches 8.. are NascarVectorEnv.step
 ncu --set full --clock-control none --import-source on -k regex:ncg_step_kernel --launch-skip 14 --launch-count 1 \
     -o $out/${tag}_full_t1 -f python bench.py $SHORT > $out/${tag}_ncu_full_t1.log 2>&1
+# a large batch (65536 envs: ray queue, pairs of env groups per CTA), one steady-state launch of 100 steps
+ncu --set full --clock-control none --import-source on -k regex:ncg_step_kernel --launch-skip 4 --launch-count 1 \
+    -o $out/${tag}_full_big -f python bench.py --envs 65536 --steps-per-launch 100 --steps 300 --warmup 300 --e2e-steps 20 --cpu-steps 200 --sweep 0 > $out/${tag}_ncu_full_big.log 2>&1
 tail -3 $out/${tag}_pytest.log; cat $out/${tag}_bench.json; cat $out/${tag}_bench_ref.json

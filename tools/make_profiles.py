@@ -16,7 +16,8 @@ def raw(rep):
 
 out = []
 for name, rep, what in (("rollout kernel (T = 1000 steps per launch, steady state)", f"{G}/{tag}_full.ncu-rep", "full"),
-                        ("single-step kernel (T = 1, results written to mapped host memory: the e2e path)", f"{G}/{tag}_full_t1.ncu-rep", "full_t1")):
+                        ("single-step kernel (T = 1, results written to mapped host memory: the e2e path)", f"{G}/{tag}_full_t1.ncu-rep", "full_t1"),
+                        ("rollout kernel at 65536 envs (T = 100 steps per launch; ray queue, launch shape picked by launch_step)", f"{G}/{tag}_full_big.ncu-rep", "full_big")):
     if not os.path.exists(rep):
         continue
     open(f"/tmp/{what}_raw.csv", "w").write(run(f"ncu -i {rep} --page raw --csv 2>/dev/null"))
