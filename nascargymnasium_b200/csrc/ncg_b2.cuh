@@ -33,7 +33,28 @@ NCG_HD float fmaxb(float a, float b) { return a > b ? a : b; }
 NCG_HD float clampb(float a, float lo, float hi) { return fmaxb(lo, fminb(a, hi)); }
 
 struct Rot { float s, c; };
-NCG_HD Rot rot(float a) { Rot q; sincosf(a, &q.s, &q.c); return q; }
+// sin and cos of a heading.  The library sincosf carries its large-argument path (Payne-Hanek, ~100 instructions and a
+// local array) inline at every call site; the physics warp then jumps over it twice per step and lands on a cold
+// instruction-cache line each time.  Headings stay small (a car turns a few radians per lap), so: three-term Cody-Waite
+// reduction by pi/2 with FMAs (exact to ~1e-11 rad for |a| < 4.8e4), the Cephes single-precision minimax polynomials on
+// [-pi/4, pi/4] (~1 ulp), quadrant fix-up with selects; anything larger goes to the library out of line.  sin(0) = 0
+// and cos(0) = 1 exactly, which keeps the axis-aligned sensor rays of the start pose axis-aligned.
+NCG_HDN void sincos_large(float a, float* s, float* c) { sincosf(a, s, c); }
+NCG_HD void sincos_heading(float a, float* sp, float* cp) {
+    if (!(fabsf(a) < 48000.0f)) { sincos_large(a, sp, cp); return; }
+    const float q = rintf(a * 0.63661977236758138f);
+    float r = fmaf(q, -1.5707963705062866f, a);             // pi/2 = 1.5707963705062866 - 4.371138828673793e-8 - 1.7151245100058819e-15 - 1e-23
+    r = fmaf(q, 4.371138828673793e-8f, r);
+    r = fmaf(q, 1.7151245100058819e-15f, r);
+    const float z = r * r;
+    const float sn = fmaf(r * z, fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+    const float cs = fmaf(z * z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f), fmaf(z, -0.5f, 1.0f));
+    const int k = (int)q;
+    const float s1 = (k & 1) ? cs : sn, c1 = (k & 1) ? sn : cs;
+    *sp = (k & 2) ? -s1 : s1;
+    *cp = ((k + 1) & 2) ? -c1 : c1;
+}
+NCG_HD Rot rot(float a) { Rot q; sincos_heading(a, &q.s, &q.c); return q; }
 struct Xf { V2 p; Rot q; };
 NCG_HD V2 mul(Rot q, V2 v) { return mk(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
 NCG_HD V2 mulT(Rot q, V2 v) { return mk(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }

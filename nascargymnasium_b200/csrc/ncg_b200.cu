@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                     if (lane == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
                 }
                 // ---- same-step auto-reset (CarPhysics.reset_car semantics)
-                if (done && do_reset) reset_in_place(R, T);
+                if (__builtin_expect(done && do_reset, 0)) reset_in_place(R, T);
                 s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
             }
             __syncwarp();

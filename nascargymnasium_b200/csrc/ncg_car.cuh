@@ -583,7 +583,7 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
     if (!slow && contacts && B.newFixture) {           // first Step of a fresh world: pairs of the initial proxy
         if (any_wall_overlap(T, B.fat)) slow = true; else { B.newFixture = false; B.proxyMoved = false; }
     }
-    if (slow) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, false, &c2); B = b2; *cnt = c2; }
+    if (__builtin_expect(slow, 0)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, false, &c2); B = b2; *cnt = c2; }
     else {
         if (B.awake) {                                 // b2Island::Solve of a lone body
             const Xf xf0 = B.xf;                       // == (rot(a0), c0): b_load synchronised it from the sweep
@@ -1195,6 +1195,17 @@ NCG_HD float ray_box_slab(const F4 wa, const F4 wb, float px, float py, float dx
 #endif
 }
 #define NCG_RAY_LEN 250.0f
+// the unit direction of a sensor ray: the heading (ca, sa) rotated by the ray's constant (kc, ks), with the roundings
+// pinned (one rounded product, one FMA per component) so that every kernel shape and both ray schedulers get the same
+// bits whatever the compiler would otherwise contract
+NCG_HD void ray_dir(float ca, float sa, float kc, float ks, float* dx, float* dy) {
+#if defined(__CUDA_ARCH__)
+    *dx = fmaf(ca, kc, -__fmul_rn(sa, ks)); *dy = fmaf(sa, kc, __fmul_rn(ca, ks));
+#else
+    const volatile float p0 = sa * ks, p1 = ca * ks;
+    *dx = fmaf(ca, kc, -p0); *dy = fmaf(sa, kc, p1);
+#endif
+}
 // One lane's RPL rays of one car (see RaySet: a lane's total work mixes along-track and across-track rays).  All RPL
 // rays run in one flattened loop -- every iteration is
 // "fetch the next cell if this one's list is exhausted, then test one block of four walls" -- so lanes never sit
@@ -1227,8 +1238,8 @@ template <int RPL> NCG_HD RaySet<RPL> ray_set(int q) {
 }
 template <int RPL, bool SH>
 NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const RaySet<RPL>& rs, float* dst, unsigned* tests) {
-    float sa, ca; sincosf(angle, &sa, &ca);
-    float dx = ca * rs.kc[0] - sa * rs.ks[0], dy = sa * rs.kc[0] + ca * rs.ks[0];
+    float sa, ca; sincos_heading(angle, &sa, &ca);
+    float dx, dy; ray_dir(ca, sa, rs.kc[0], rs.ks[0], &dx, &dy);
     unsigned nt = 0;
     const RayMem<SH> M(T);
     const int gnx = T.gnx, gny = T.gny;
@@ -1237,7 +1248,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const Ray
     if (ix0 < 0 || iy0 < 0 || ix0 >= gnx || iy0 >= gny) {              // origin outside the grid: scan every wall
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
-            dx = ca * rs.kc[j] - sa * rs.ks[j]; dy = sa * rs.kc[j] + ca * rs.ks[j];
+            ray_dir(ca, sa, rs.kc[j], rs.ks[j], &dx, &dy);
             float best = NCG_RAY_LEN;
             for (int wi = 0; wi < T.n_walls; ++wi) { F4 a, b; M.wall((uint32_t)wi, &a, &b); best = fminf(best, ray_box_slab(a, b, px, py, dx, dy)); ++nt; }
             dst[rs.idx[j]] = sensor_obs_m(best);
@@ -1274,7 +1285,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const Ray
                 dst[slot] = sensor_obs_m(best);
                 if (++j == RPL) break;
                 // next ray of this lane, same origin cell
-                dx = ca * kcn - sa * ksn; dy = sa * kcn + ca * ksn;
+                ray_dir(ca, sa, kcn, ksn, &dx, &dy);
                 tdx = dx != 0.0f ? T.cell * rcp_fast(fabsf(dx)) : INFINITY; tdy = dy != 0.0f ? T.cell * rcp_fast(fabsf(dy)) : INFINITY;
                 sx = dx > 0.0f ? 1 : -1; sy = dy > 0.0f ? 1 : -1;
                 tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
@@ -1311,7 +1322,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, int q0, f
 // RayCar is what a job needs to know about its car.
 struct RayCar { float px, py, ca, sa, fx, fy; int cell0; uint32_t h0; };      // 8 words; cell0 = ix0 | iy0 << 16, or -1 outside the grid
 NCG_HD RayCar ray_car(const Track& T, float px, float py, float angle) {
-    RayCar rc; rc.px = px; rc.py = py; sincosf(angle, &rc.sa, &rc.ca);
+    RayCar rc; rc.px = px; rc.py = py; sincos_heading(angle, &rc.sa, &rc.ca);
     const float gx = (px - T.gx0) * T.inv_cell, gy = (py - T.gy0) * T.inv_cell;
     const int ix0 = (int)floorf(gx), iy0 = (int)floorf(gy);
     const bool in = ix0 >= 0 && iy0 >= 0 && ix0 < T.gnx && iy0 < T.gny;
@@ -1361,7 +1372,7 @@ NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsig
                 const F4 c0 = *reinterpret_cast<const F4*>(cars + car * 8), c1 = *reinterpret_cast<const F4*>(cars + car * 8 + 4);
                 const float kc = rot[2 * ray], ks = rot[2 * ray + 1];
                 px = c0.x; py = c0.y;
-                dx = c0.z * kc - c0.w * ks; dy = c0.w * kc + c0.z * ks;
+                ray_dir(c0.z, c0.w, kc, ks, &dx, &dy);
                 out = obs22 + (car + (car >= gap_at ? gap : 0)) * obs_stride + ray;
                 best = NCG_RAY_LEN;
                 const int cell0 = (int)f2u(c1.z);
