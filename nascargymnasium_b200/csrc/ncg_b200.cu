@@ -210,35 +210,39 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
             __syncwarp();
             __threadfence_block();
             bar_arrive(BAR_POSE + b, NT);
+            // single-car envs (C == 1, uniform) decide from the car's own result word: no exchange through shared memory,
+            // no division by C, and the multi-car loops of env_decide unroll away
+            const bool solo = p.C == 1;
+            uint32_t xf = 0;
             if (active) {
-                uint32_t xf = 0;
                 if (!(p.debug_skip & 2)) rew = car_step_rules<true>(R, T, &ctx, s_obs + (b * SLOTS + slot) * OBS_STRIDE, &xf, &cnt);
-                s_xf[slot] = xf;
+                if (!solo) s_xf[slot] = xf;
                 if (p.track_info) {
                     uint32_t fl = f2u(R[NCG_R_FLAGS]) & ~(uint32_t)NCG_F_ON_TRACK;
                     if (on_track(T, R[NCG_R_X], R[NCG_R_Y])) fl |= NCG_F_ON_TRACK;
                     R[NCG_R_FLAGS] = u2f(fl);
                 }
             }
-            __syncwarp();
+            if (!solo) __syncwarp();
             // ---- env phase (every car of an env computes the same decision from the env's xf words)
             if (active) {
-                const int le = lane / p.C;
+                const int le = solo ? lane : lane / p.C;
                 bool te, tr; int why;
-                env_decide(s_xf + warp * 32 + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
+                if (solo) env_decide(&xf, 1, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
+                else env_decide(s_xf + warp * 32 + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
                 car_finish(R, rew);
                 if (rew_out) rew_out[car0 + lane] = rew;
                 const bool done = te || tr;
-                if (lane == le * p.C) {
+                if (solo || lane == le * p.C) {
                     const int ge = env0 + le;
                     if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
                     else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
                     if (done) ++episodes;
                 }
-                if (done) {
+                if (__builtin_expect(done, 0)) {
                     ret_sum += (double)R[NCG_R_CUM_REWARD];
                     if (p.ep_return) p.ep_return[car0 + lane] = R[NCG_R_CUM_REWARD];
-                    if (lane == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
+                    if (solo || lane == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
                 }
                 // ---- same-step auto-reset (CarPhysics.reset_car semantics)
                 if (__builtin_expect(done && do_reset, 0)) reset_in_place(R, T);

@@ -130,9 +130,9 @@ NCG_HD void b_integrate_velocity(Body& B, float h) {
 // integrate positions with b2_maxTranslation / b2_maxRotation clamps, on (c, a, v, w)
 NCG_HD void integrate_position(V2& c, float& a, V2& v, float& w, float h) {
     V2 tr = h * v;
-    if (dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION) { float ratio = NCG_B2_MAX_TRANSLATION / length(tr); v = ratio * v; }
+    if (__builtin_expect(dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION, 0)) { float ratio = NCG_B2_MAX_TRANSLATION / length(tr); v = ratio * v; }
     float ro = h * w;
-    if (ro * ro > NCG_B2_MAX_ROTATION * NCG_B2_MAX_ROTATION) { float ratio = NCG_B2_MAX_ROTATION / fabsf(ro); w *= ratio; }
+    if (__builtin_expect(ro * ro > NCG_B2_MAX_ROTATION * NCG_B2_MAX_ROTATION, 0)) { float ratio = NCG_B2_MAX_ROTATION / fabsf(ro); w *= ratio; }
     c = c + h * v; a += h * w;
 }
 // sleep bookkeeping at the end of b2Island::Solve
@@ -583,8 +583,8 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
     if (!slow && contacts && B.newFixture) {           // first Step of a fresh world: pairs of the initial proxy
         if (any_wall_overlap(T, B.fat)) slow = true; else { B.newFixture = false; B.proxyMoved = false; }
     }
-    if (__builtin_expect(slow, 0)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, false, &c2); B = b2; *cnt = c2; }
-    else {
+    int solver = slow ? 1 : 0;                          // 1: the whole Step with contacts, 2: only FindNewContacts + TOI after the lone-body step
+    if (!slow) {
         if (B.awake) {                                 // b2Island::Solve of a lone body
             const Xf xf0 = B.xf;                       // == (rot(a0), c0): b_load synchronised it from the sweep
             B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
@@ -595,10 +595,11 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
             b_sync_fixtures_from(B, xf0);
         }
         if (contacts && B.proxyMoved) {                // FindNewContacts
-            if (any_wall_overlap(T, B.fat)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, true, &c2); B = b2; *cnt = c2; }
-            else B.proxyMoved = false;
+            if (any_wall_overlap(T, B.fat)) solver = 2; else B.proxyMoved = false;
         }
     }
+    // one cold block for both ways in (a copy of the body goes in and comes back: see step_with_contacts)
+    if (__builtin_expect(solver != 0, 0)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, solver == 2, &c2); B = b2; *cnt = c2; }
     B.inv_dt0 = inv_dt;
     B.force = mk(0.0f, 0.0f); B.torque = 0.0f;
 }
@@ -817,6 +818,14 @@ NCG_HD float obs_scale(int k) {
 }
 NCG_HD float obs_lo(int k) { return (k <= 3 || k == 5 || k == 6 || k == 20) ? -1.0f : 0.0f; }
 NCG_HD float obs_word(float raw, float scale, float lo) { return clip1(raw * scale, lo, 1.0f); }
+// direction of the last collision relative to the heading, wrapped to [-pi, pi]; out of line: it runs on the few steps
+// with a hard impact, and inline its atan2f is 120 instructions the physics warp has to jump over on every other step
+NCG_HDN float collision_angle(float ny, float nx, float heading) {
+    float ca = atan2f(ny, nx) - heading;
+    while (ca > 3.14159265358979f) ca -= 6.28318530717959f;
+    while (ca < -3.14159265358979f) ca += 6.28318530717959f;
+    return ca;
+}
 NCG_HD void observe_raw(const float* R, float* raw) {
     float vx = R[NCG_R_VX], vy = R[NCG_R_VY];
     raw[0] = R[NCG_R_X]; raw[1] = R[NCG_R_Y]; raw[2] = vx; raw[3] = vy; raw[4] = sqrtf(vx * vx + vy * vy);
@@ -825,11 +834,7 @@ NCG_HD void observe_raw(const float* R, float* raw) {
     for (int k = 0; k < 4; ++k) { raw[7 + k] = R[NCG_R_TYRE_LOAD + k]; raw[11 + k] = R[NCG_R_TYRE_TEMP + k]; raw[15 + k] = R[NCG_R_TYRE_WEAR + k]; }
     float ci = R[NCG_R_IMPULSE], ca = 0.0f;
     if (ci < 100.0f) ci = 0.0f;
-    else if (((f2u(R[NCG_R_NCONTACT]) >> 8) & 255u) > 0) {
-        ca = atan2f(R[NCG_R_ACTIVE + 2], R[NCG_R_ACTIVE + 1]) - R[NCG_R_ANGLE];
-        while (ca > 3.14159265358979f) ca -= 6.28318530717959f;
-        while (ca < -3.14159265358979f) ca += 6.28318530717959f;
-    }
+    else if (((f2u(R[NCG_R_NCONTACT]) >> 8) & 255u) > 0) ca = collision_angle(R[NCG_R_ACTIVE + 2], R[NCG_R_ACTIVE + 1], R[NCG_R_ANGLE]);
     raw[19] = ci; raw[20] = ca; raw[21] = R[NCG_R_CUM_IMPACT];
 }
 NCG_HD void observe_state(const float* R, float* obs) {
@@ -844,6 +849,14 @@ NCG_HD void observe_state(const float* R, float* obs) {
 //   car_step_dynamics  inputs -> forces -> tyres -> b2World.Step; the record holds the new pose when it returns
 //   car_step_rules     banking/progress, impact and stuck rules, lap timer, obs[0..21], reward; returns the reward,
 //                      *xflags gets NCG_X_* bits for the env phase.
+// the acceleration window while it is still filling (an episode's first nine steps); out of line, see collision_angle
+NCG_HDN void acc_window_filling(float* R, int n, float lo, float la, float* along, float* alat) {
+    R[NCG_R_ACC + 2 * n] = lo; R[NCG_R_ACC + 2 * n + 1] = la; ++n;
+    R[NCG_R_ACC_N] = u2f((uint32_t)n);
+    float s0 = 0.0f, s1 = 0.0f;
+    for (int i = 0; i < n; ++i) { s0 += R[NCG_R_ACC + 2 * i]; s1 += R[NCG_R_ACC + 2 * i + 1]; }
+    *along = s0 / (float)n; *alat = s1 / (float)n;
+}
 struct StepCtx { uint32_t fl, xf, laps_pre; bool dis_pre; float impulse; };
 NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, StepCtx* ctx,
                                Counters* cnt) {
@@ -924,13 +937,7 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
 #pragma unroll
                 for (int i = 0; i < 20; ++i) R[NCG_R_ACC + i] = a[i];
                 along = s0 / 10.0f; alat = s1 / 10.0f;
-            } else {
-                R[NCG_R_ACC + 2 * n] = lo; R[NCG_R_ACC + 2 * n + 1] = la; ++n;
-                R[NCG_R_ACC_N] = u2f((uint32_t)n);
-                float s0 = 0.0f, s1 = 0.0f;
-                for (int i = 0; i < n; ++i) { s0 += R[NCG_R_ACC + 2 * i]; s1 += R[NCG_R_ACC + 2 * i + 1]; }
-                along = s0 / (float)n; alat = s1 / (float)n;
-            }
+            } else acc_window_filling(R, n, lo, la, &along, &alat);
             R[NCG_R_PREV_VX] = W.v.x; R[NCG_R_PREV_VY] = W.v.y;
         }
         // tyres :354-357
@@ -962,7 +969,8 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
         // banking :509-566
         float bank = R[NCG_R_BANK];
         if (!(fabsf(bank) < 0.1f) && !(sp < 1.0f)) {
-            float la = NCG_CAR_MASS * 9.81f * sinf(fabsf(bank * 0.017453292519943295f)) * 0.3f;
+            float sb, cb; sincos_heading(fabsf(bank * 0.017453292519943295f), &sb, &cb);     // (the library sinf would put its large-argument path inline here)
+            float la = NCG_CAR_MASS * 9.81f * sb * 0.3f;
             if (!(fabsf(la) < 1.0f) && sp > 5.0f) {
                 float sg = bank < 0.0f ? -1.0f : 1.0f;
                 { float is = 1.0f / sp; b_apply_force_center(W, mk((-(W.v.y * is)) * la * sg, (W.v.x * is) * la * sg)); }
@@ -970,7 +978,8 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
         }
         // steering :568-584
         if (fabsf(delta) > 0.01f && sp > 0.1f) {
-            float dav = sp * tanf(delta) * (1.0f / NCG_CAR_WHEELBASE);
+            float sd, cd; sincos_heading(delta, &sd, &cd);                 // |delta| <= pi/4; tan = s / c without the library's inline slow path
+            float dav = sp * (sd / cd) * (1.0f / NCG_CAR_WHEELBASE);
             b_apply_torque(W, (dav - W.w) * NCG_CAR_MASS * 0.8f);
         }
     }
