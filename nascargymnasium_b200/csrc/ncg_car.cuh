@@ -127,10 +127,11 @@ NCG_HD void b_integrate_velocity(Body& B, float h) {
     B.v = B.v + h * (1.0f * mk(0.0f, 0.0f) + NCG_INV_MASS * B.force);
     B.w += h * NCG_INV_I * B.torque;
 }
+NCG_HDN float max_translation_ratio(V2 tr) { return NCG_B2_MAX_TRANSLATION / length(tr); }      // out of line: see collision_angle
 // integrate positions with b2_maxTranslation / b2_maxRotation clamps, on (c, a, v, w)
 NCG_HD void integrate_position(V2& c, float& a, V2& v, float& w, float h) {
     V2 tr = h * v;
-    if (__builtin_expect(dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION, 0)) { float ratio = NCG_B2_MAX_TRANSLATION / length(tr); v = ratio * v; }
+    if (__builtin_expect(dot(tr, tr) > NCG_B2_MAX_TRANSLATION * NCG_B2_MAX_TRANSLATION, 0)) v = max_translation_ratio(tr) * v;     // > 2 m per step: never at racing speeds
     float ro = h * w;
     if (__builtin_expect(ro * ro > NCG_B2_MAX_ROTATION * NCG_B2_MAX_ROTATION, 0)) { float ratio = NCG_B2_MAX_ROTATION / fabsf(ro); w *= ratio; }
     c = c + h * v; a += h * w;
@@ -857,6 +858,11 @@ NCG_HDN void acc_window_filling(float* R, int n, float lo, float la, float* alon
     for (int i = 0; i < n; ++i) { s0 += R[NCG_R_ACC + 2 * i]; s1 += R[NCG_R_ACC + 2 * i + 1]; }
     *along = s0 / (float)n; *alat = s1 / (float)n;
 }
+// lateral force of a banked segment (car.py:509-566): m g sin(|banking|) * 0.3
+NCG_HDN float banking_force(float bank) {
+    float sb, cb; sincos_heading(fabsf(bank * 0.017453292519943295f), &sb, &cb);
+    return NCG_CAR_MASS * 9.81f * sb * 0.3f;
+}
 struct StepCtx { uint32_t fl, xf, laps_pre; bool dis_pre; float impulse; };
 NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, StepCtx* ctx,
                                Counters* cnt) {
@@ -969,8 +975,7 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
         // banking :509-566
         float bank = R[NCG_R_BANK];
         if (!(fabsf(bank) < 0.1f) && !(sp < 1.0f)) {
-            float sb, cb; sincos_heading(fabsf(bank * 0.017453292519943295f), &sb, &cb);     // (the library sinf would put its large-argument path inline here)
-            float la = NCG_CAR_MASS * 9.81f * sb * 0.3f;
+            const float la = banking_force(bank);      // (out of line: flat tracks never get here)
             if (!(fabsf(la) < 1.0f) && sp > 5.0f) {
                 float sg = bank < 0.0f ? -1.0f : 1.0f;
                 { float is = 1.0f / sp; b_apply_force_center(W, mk((-(W.v.y * is)) * la * sg, (W.v.x * is) * la * sg)); }
