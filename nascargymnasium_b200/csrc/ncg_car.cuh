@@ -543,14 +543,25 @@ NCG_HD void w_store_contacts(World& W, float* R) {
     for (int i = 0; i < W.na; ++i) { R[NCG_R_ACTIVE + 3 * i] = u2f((uint32_t)W.awall[i]); R[NCG_R_ACTIVE + 3 * i + 1] = W.anx[i]; R[NCG_R_ACTIVE + 3 * i + 2] = W.any[i]; }
 }
 // does any wall's fat AABB overlap the car's?  (what b2BroadPhase::UpdatePairs would turn into new contacts)
+// One block of four walls per iteration (the grid lists are blocks of four, a short one padded by repeating a wall):
+// the four AABB rows are independent loads and the four tests are branch-free, so a check is a few load latencies
+// instead of one dependent load chain per wall -- some lane of the physics warp runs this on almost every step.
+NCG_HD bool aabb_apart(const AABB& a, const F4 b) {      // the two early-outs of b2TestOverlap, b = {lx, ly, ux, uy}
+    return (b.x - a.ux > 0.0f) | (b.y - a.uy > 0.0f) | (a.lx - b.z > 0.0f) | (a.ly - b.w > 0.0f);
+}
 NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
     int ix0 = (int)floorf((fat.lx - T.gx0) * T.inv_cell), ix1 = (int)floorf((fat.ux - T.gx0) * T.inv_cell);
     int iy0 = (int)floorf((fat.ly - T.gy0) * T.inv_cell), iy1 = (int)floorf((fat.uy - T.gy0) * T.inv_cell);
     ix0 = ix0 < 0 ? 0 : ix0; iy0 = iy0 < 0 ? 0 : iy0; ix1 = ix1 >= T.gnx ? T.gnx - 1 : ix1; iy1 = iy1 >= T.gny ? T.gny - 1 : iy1;
     for (int iy = iy0; iy <= iy1; ++iy) for (int ix = ix0; ix <= ix1; ++ix) {
-        int cell = iy * T.gnx + ix;
-        const int nk = cell_count_max(T, cell);
-        for (int k = 0; k < nk; ++k) { int wi = cell_item(T, cell, k); if (aabb_overlap(fat, wall_fat(T, wi))) return true; }
+        const uint32_t h = T.cells[iy * T.gnx + ix];
+        for (uint32_t k = h & 0xFFFFu, e = k + (h >> 16); k < e; ++k) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(T.items + 4u * k);
+            const uint32_t lo = q[0], hi = q[1];
+            const F4 a0 = *reinterpret_cast<const F4*>(T.aabb + 4u * (lo & 0xFFFFu)), a1 = *reinterpret_cast<const F4*>(T.aabb + 4u * (lo >> 16));
+            const F4 a2 = *reinterpret_cast<const F4*>(T.aabb + 4u * (hi & 0xFFFFu)), a3 = *reinterpret_cast<const F4*>(T.aabb + 4u * (hi >> 16));
+            if (!(aabb_apart(fat, a0) & aabb_apart(fat, a1) & aabb_apart(fat, a2) & aabb_apart(fat, a3))) return true;
+        }
     }
     return false;
 }
