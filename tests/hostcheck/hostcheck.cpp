@@ -106,6 +106,7 @@ void hc_nearest_segment(const float* blob, float x, float y, int masked, float* 
     if (!masked) { T.gnx = 0; T.gny = 0; }
     nearest_segment(T, x, y, out2, out2 + 1);
 }
+void hc_sincos_heading(float a, float* out2) { sincos_heading(a, out2, out2 + 1); }
 int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }
 void hc_synthetic_action(unsigned long long seed, unsigned car, unsigned step, int mode, int discrete, float* out3) {
     action_synthetic(seed, car, step, mode, discrete != 0, out3, out3 + 1, out3 + 2);

@@ -92,6 +92,24 @@ def test_rays_in_the_plane_of_a_wall_joint_never_slip_between_the_boxes():
                     assert float((g - a).max()) < 2e-3, (name, w, x, y, th, a, g)
 
 
+def test_heading_sincos_is_accurate_and_exact_at_zero():
+    """csrc/ncg_b2.cuh::sincos_heading (Cody-Waite reduction + minimax polynomials, library fallback for huge angles)
+    against float64 sin/cos: <= 2 ulp of 1 over the headings a car can reach and beyond, exact at 0 (the start pose's
+    axis-aligned rays rely on it), and still right past the fallback threshold."""
+    hc = P.hostcheck()
+    hc.hc_sincos_heading.argtypes = [ctypes.c_float, ctypes.POINTER(ctypes.c_float)]
+    rng = np.random.default_rng(3)
+    out = np.zeros(2, np.float32)
+    hc.hc_sincos_heading(0.0, P._fp(out))
+    assert out[0] == 0.0 and out[1] == 1.0
+    worst = 0.0
+    for a in np.concatenate([rng.uniform(-8, 8, 4000), rng.uniform(-4.7e4, 4.7e4, 4000), rng.uniform(-1e6, 1e6, 200),
+                             np.arange(-40, 41) * (np.pi / 4)]).astype(np.float32):
+        hc.hc_sincos_heading(float(a), P._fp(out))
+        worst = max(worst, abs(float(out[0]) - np.sin(np.float64(a))), abs(float(out[1]) - np.cos(np.float64(a))))
+    assert worst < 2.5e-7, worst
+
+
 def test_multi_car_env_and_same_track_reset_match_oracle():
     """Free-running 3-car env with reset_on_lap, including reset_car semantics after termination."""
     rng = np.random.default_rng(9)
