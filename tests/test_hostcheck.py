@@ -66,6 +66,9 @@ def test_grid_ray_traversal_matches_box2d_clipping_over_all_walls():
             assert n.value < 16 * 80
             assert hc.hc_sensors_multi_mismatches(P._fp(blob), x, y, th) == 0
         assert worst < 1e-3, (name, worst)
+        # origins outside the grid (every ray scans all walls): the fixed map and the queue must still agree
+        for x, y in ((1.0e4, -3.0e3), (float(tab.grid_origin[0]) - 1.0, float(tab.grid_origin[1]) - 1.0)):
+            assert hc.hc_sensors_multi_mismatches(P._fp(blob), x, y, 0.3) == 0
 
 
 def test_rays_in_the_plane_of_a_wall_joint_never_slip_between_the_boxes():
