@@ -43,9 +43,8 @@ struct KParams {
 #define CPB 32                    /* car slots per CTA = lanes of the physics warp */
 #define REC_STRIDE 129            /* shared-memory row stride of a record (odd: conflict-free column access) */
 #define OBS_STRIDE 41             /* shared-memory row stride of an observation row */
-#define BAR_POSE 1                /* named barriers 1,2: the new poses of buffer b are published (rays can start) */
-#define BAR_FULL 3                /* named barriers 3,4: buffer b complete (obs[0..21], flags, reset poses) */
-#define BAR_EMPTY 5               /* named barriers 5,6: buffer b drained by the ray warps */
+/* named barriers, NB step buffers: 1..NB the new poses of buffer b are published (rays can start); NB+1..2NB buffer b
+   complete (obs[0..21], flags, reset poses); 2NB+1..3NB buffer b drained by the ray warps */
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -80,16 +79,16 @@ struct SmemLayout {
     int rec, obs, pose, flag, xf, act, otab, ray, rot, ctr, track, total;      // word offsets
 };
 // cpb = car slots of the CTA: 32 per physics warp
-__host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb) {
+__host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb, int nb) {
     SmemLayout L; int o = 0;
     L.rec = o; o += cpb * REC_STRIDE;
-    L.obs = o; o += 2 * cpb * OBS_STRIDE;          // [2][cpb][OBS_STRIDE]: the step's observation rows
+    L.obs = o; o += nb * cpb * OBS_STRIDE;         // [nb][cpb][OBS_STRIDE]: the step's observation rows
     o = (o + 3) & ~3;
-    L.pose = o; o += 2 * cpb * 4;                  // [2][cpb] float4 {x, y, angle, -}
-    L.flag = o; o += 2 * cpb;                      // [2][cpb] u32: bit0 terminated, bit1 truncated
+    L.pose = o; o += nb * cpb * 4;                 // [nb][cpb] float4 {x, y, angle, -}
+    L.flag = o; o += nb * cpb;                     // [nb][cpb] u32: bit0 terminated, bit1 truncated
     L.xf = o; o += cpb;
     o = (o + 3) & ~3;
-    L.act = o; o += 2 * cpb * 4;                   // [2][cpb] float4 {throttle, brake, steer, -}: synthetic actions, made two steps ahead
+    L.act = o; o += nb * cpb * 4;                  // [nb][cpb] float4 {throttle, brake, steer, -}: synthetic actions, made nb steps ahead
     L.otab = o; o += 2 * 40;                       // observation scale[38] (padded to 40) and lower clip bound[38]
     o = (o + 3) & ~3;
     L.ray = o; o += cpb * 8;                       // [cpb] RayCar: what a ray job needs to know about its car (ray queue)
@@ -116,7 +115,11 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     constexpr int CPW = 32 / LPC;                   //                              cars per ray warp
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long s_mbar;
-    const SmemLayout L = smem_layout(0, SLOTS);
+    // step buffers between the physics and the ray warps: three when a CTA has an SM to itself (the physics warp then
+    // never waits for a drained buffer; shared memory is not the limit there), two otherwise
+    constexpr int NB = MINB == 1 ? 3 : 2;
+    constexpr int BAR_POSE = 1, BAR_FULL = 1 + NB, BAR_EMPTY = 1 + 2 * NB;
+    const SmemLayout L = smem_layout(0, SLOTS, NB);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* s_rec = smem + L.rec;
     float* s_obs = smem + L.obs;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     const bool act_maker = synth && warp >= PW && warp < 2 * PW && lane < (warp == PW ? n0 : n1);
     const int act_slot = (warp - PW) * 32 + lane, act_car = (warp == PW ? cb0 : cb1) + lane;
     if (act_maker) {
-        for (int t = 0; t < 2 && t < p.T; ++t) {
+        for (int t = 0; t < NB && t < p.T; ++t) {
             float thr, brk, st;
             action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
             s_act[t * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
@@ -189,9 +192,8 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
         float* R = s_rec + (active ? slot : 0) * REC_STRIDE;
         Counters cnt = {0, 0, 0, 0, 0};
         unsigned long long episodes = 0; double ret_sum = 0.0;
-        for (int t = 0; t < p.T; ++t) {
-            const int b = t & 1;
-            if (t >= 2) bar_sync(BAR_EMPTY + b, NT);            // the ray warps have drained buffer b (step t-2)
+        for (int t = 0, b = 0; t < p.T; ++t, b = b + 1 == NB ? 0 : b + 1) {
+            if (t >= NB) bar_sync(BAR_EMPTY + b, NT);           // the ray warps have drained buffer b (step t-NB)
             float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
             float rew = 0.0f;
             StepCtx ctx;
@@ -286,8 +288,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
         }
         unsigned tests = 0;
         const unsigned magic = (131072u + (unsigned)n_all - 1u) / (unsigned)n_all;
-        for (int t = 0; t < p.T; ++t) {
-            const int b = t & 1;
+        for (int t = 0, b = 0; t < p.T; ++t, b = b + 1 == NB ? 0 : b + 1) {
             float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
             bar_sync(BAR_POSE + b, NT);
             if ((PW == 2 || p.queue) && !(p.debug_skip & 1)) {
@@ -310,9 +311,9 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                 if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
                 else cast_rays<RPL, false>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
             }
-            if (act_maker && t + 2 < p.T) {                      // actions of step t+2 (this buffer's next use)
+            if (act_maker && t + NB < p.T) {                     // actions of step t+NB (this buffer's next use)
                 float thr, brk, st;
-                action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)(t + 2), p.mode, p.discrete != 0, &thr, &brk, &st);
+                action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)(t + NB), p.mode, p.discrete != 0, &thr, &brk, &st);
                 s_act[b * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
             }
             bar_sync(BAR_FULL + b, NT);
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                     } else if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = v;
                 }
             }
-            if (t + 2 < p.T) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NT); }
+            if (t + NB < p.T) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NT); }
         }
         ray_tests = tests;
         for (int o = 16; o > 0; o >>= 1) ray_tests += __shfl_down_sync(0xffffffffu, ray_tests, o);
@@ -505,11 +506,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
-    size_t smem = (size_t)smem_layout(mx, 32 * PW).total * 4;
-    if (p.stage && h->max_smem > 0 && smem > (size_t)h->max_smem) {      // a user track too large to stage: read it through L1/L2
-        p.stage = 0;
-        smem = (size_t)smem_layout(0, 32 * PW).total * 4;
-    }
+    size_t smem = 0;        // (set below, once the shape is known: the number of step buffers depends on it)
     // rays handed out from a per-CTA queue (longest first) instead of a fixed lane -> rays map: pays once the SM is
     // issue-bound, i.e. with three resident CTAs per SM (measured on B200, daytona: +22 % at 65536 envs, +9 % at 16384,
     // -5 % at 8192 and -7 % at 4096, where a step is bound by latency and the queue's claims and job set-up only add to it)
@@ -520,6 +517,13 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     int minb = h->n_ctas <= sms ? 1 : (h->n_ctas <= 2 * sms || RPL != 4 ? 2 : 3);
     { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && atoi(mb) >= 1 && atoi(mb) <= 3) minb = atoi(mb); }
     if (minb == 3 && RPL != 4) minb = 2;
+    if (PW == 2) minb = 2;
+    const int nb = minb == 1 ? 3 : 2;                 // step buffers: NB of the kernel
+    smem = (size_t)smem_layout(mx, 32 * PW, nb).total * 4;
+    if (p.stage && h->max_smem > 0 && smem > (size_t)h->max_smem) {      // a user track too large to stage: read it through L1/L2
+        p.stage = 0;
+        smem = (size_t)smem_layout(0, 32 * PW, nb).total * 4;
+    }
     void (*k)(KParams) = PW == 2 ? ncg_step_kernel<4, 2, 2>
                        : minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1, 1> : ncg_step_kernel<2, 1, 1>)
                        : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2, 1> : ncg_step_kernel<2, 2, 1>)
