@@ -1291,6 +1291,11 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const Ray
     const uint32_t h0 = M.cell(iy0 * gnx + ix0);
     const int k0 = (int)(h0 & 0xFFFFu), e0 = k0 + (int)(h0 >> 16);   // block range of the origin cell
     int k = k0, e = e0, j = 0;
+    // the wall indices of block k are fetched one block ahead (while the previous block's walls are loaded and tested),
+    // which takes one shared-memory latency out of every iteration's dependent chain: small batches are bound by that
+    // chain, not by issue slots.  (At the end of a cell's list the fetch reads the next list's first block: unused.)
+    uint32_t blo, bhi; M.block(k0, &blo, &bhi);
+    const uint32_t blo0 = blo, bhi0 = bhi;
     float best = NCG_RAY_LEN;
     for (;;) {
         if (k >= e) {                                                   // this cell's list is done: leave or finish
@@ -1299,7 +1304,7 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const Ray
             if (!fin) {
                 if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)gnx; }
                 else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)gny; }
-                if (!fin) { const uint32_t h = M.cell(iy * gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
+                if (!fin) { const uint32_t h = M.cell(iy * gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); M.block(k, &blo, &bhi); }
             }
             if (fin) {
                 // j is a run-time value here: pick this ray's slot and the next ray's constants with selects, not by
@@ -1315,11 +1320,11 @@ NCG_HD void cast_rays(const Track& T, float px, float py, float angle, const Ray
                 sx = dx > 0.0f ? 1 : -1; sy = dy > 0.0f ? 1 : -1;
                 tmx = dx != 0.0f ? (dx > 0.0f ? 1.0f - fx : fx) * tdx : INFINITY;
                 tmy = dy != 0.0f ? (dy > 0.0f ? 1.0f - fy : fy) * tdy : INFINITY;
-                ix = ix0; iy = iy0; k = k0; e = e0; best = NCG_RAY_LEN;
+                ix = ix0; iy = iy0; k = k0; e = e0; best = NCG_RAY_LEN; blo = blo0; bhi = bhi0;
             }
         }
         if (k < e) {                                                    // one block: four walls (padding repeats wall 0, masked)
-            uint32_t lo, hi; M.block(k, &lo, &hi); ++k;
+            const uint32_t lo = blo, hi = bhi; ++k; M.block(k, &blo, &bhi);
             F4 a0, b0, a1, b1, a2, b2, a3, b3;                           // a short block is padded by repeating its first wall
             M.wall(lo & 0xFFFFu, &a0, &b0); M.wall(lo >> 16, &a1, &b1); M.wall(hi & 0xFFFFu, &a2, &b2); M.wall(hi >> 16, &a3, &b3);
             const float t0 = ray_box_slab(a0, b0, px, py, dx, dy), t1 = ray_box_slab(a1, b1, px, py, dx, dy);
