@@ -1377,6 +1377,7 @@ NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsig
     float px = 0.0f, py = 0.0f, dx = 1.0f, dy = 0.0f, tdx = INFINITY, tdy = INFINITY, tmx = INFINITY, tmy = INFINITY, best = NCG_RAY_LEN;
     int sx = 1, sy = 1, ix = 0, iy = 0, k = 0, e = 0;
     float* out = nullptr;
+    uint32_t blo = 0u, bhi = 0u;                    // the wall indices of block k, fetched one block ahead (see cast_rays)
     for (;;) {
         if (k >= e) {                                                   // this cell's list is done: leave or finish
             const float texit = fminf(tmx, tmy);
@@ -1384,7 +1385,7 @@ NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsig
             if (!fin) {
                 if (tmx < tmy) { ix += sx; tmx += tdx; fin = (unsigned)ix >= (unsigned)gnx; }
                 else { iy += sy; tmy += tdy; fin = (unsigned)iy >= (unsigned)gny; }
-                if (!fin) { const uint32_t h = M.cell(iy * gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); }
+                if (!fin) { const uint32_t h = M.cell(iy * gnx + ix); k = (int)(h & 0xFFFFu); e = k + (int)(h >> 16); M.block(k, &blo, &bhi); }
             }
             if (fin) {
                 if (out) *out = sensor_obs_m(best);
@@ -1418,10 +1419,11 @@ NCG_HD void cast_rays_queue(const Track& T, const float* cars, int n_cars, unsig
                 ix = cell0 & 0xFFFF; iy = cell0 >> 16;
                 const uint32_t h0 = f2u(c1.w);
                 k = (int)(h0 & 0xFFFFu); e = k + (int)(h0 >> 16);
+                M.block(k, &blo, &bhi);
             }
         }
         if (k < e) {                                                    // one block: four walls (padding repeats wall 0, masked)
-            uint32_t lo, hi; M.block(k, &lo, &hi); ++k;
+            const uint32_t lo = blo, hi = bhi; ++k; M.block(k, &blo, &bhi);
             F4 a0, b0, a1, b1, a2, b2, a3, b3;
             M.wall(lo & 0xFFFFu, &a0, &b0); M.wall(lo >> 16, &a1, &b1); M.wall(hi & 0xFFFFu, &a2, &b2); M.wall(hi >> 16, &a3, &b3);
             const float t0 = ray_box_slab(a0, b0, px, py, dx, dy), t1 = ray_box_slab(a1, b1, px, py, dx, dy);
