@@ -36,19 +36,6 @@ METRIC = "car-steps/sec (16-ray sensors) at 4096-65536 envs, 1/2/4/8 B200 vs hos
 UNIT = "car-steps/s"
 
 
-def profiled_traffic(steps_per_launch: int, n_cars: int):
-    """DRAM bytes per launch of the rollout kernel from the committed `ncu --set full` capture (profiles/), or None when
-    the capture was taken at another launch shape."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            t = json.load(f)
-        if int(t["steps_per_launch"]) == steps_per_launch and int(t["cars"]) == n_cars:
-            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
-    except Exception:
-        pass
-    return None
-
-
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -82,8 +69,33 @@ def synthetic_actions(seed: int, cars: np.ndarray, step: int) -> np.ndarray:
     return np.stack([np.float32(2.0) * u0 - np.float32(1.0), np.float32(2.0) * u1 - np.float32(1.0)], axis=1).astype(np.float32)
 
 
-# ----------------------------------------------------------------------------- CPU arm (oracle = port of the reference)
-def _cpu_worker(args):
+# ----------------------------------------------------------------------------- CPU arm
+# Tiers.  1: the real reference CarEnv over box2d-py + gymnasium (when they import);
+# 2: the reference's unmodified src/car_env.py over the stand-in Box2D/gymnasium/pygame modules of oracle/refshim
+# (every line of the reference's Python runs; the rigid-body step underneath is oracle/b2lite.h, not real Box2D);
+# 3: the C++ oracle port alone.  The reference tree is looked for in $NCG_REFERENCE, /root/reference (build container)
+# and baseline/_ref (git-ignored install that travels to the GPU box; __graft_entry__.build() makes it).
+def reference_root():
+    for p in (os.environ.get("NCG_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.isfile(os.path.join(p, "src", "car_env.py")):
+            return p
+    return None
+
+
+def available_tiers():
+    tiers = [3]
+    if reference_root():
+        tiers.insert(0, 2)
+        try:
+            import Box2D  # noqa: F401
+            import gymnasium  # noqa: F401
+            tiers.insert(0, 1)
+        except Exception:
+            pass
+    return tiers
+
+
+def _port_worker(args):
     track, car_base, n_steps, seed, warm = args
     from oracle import oracle as O
     from nascargymnasium_b200 import track as T
@@ -103,17 +115,65 @@ def _cpu_worker(args):
     return n_steps, time.perf_counter() - t0
 
 
-def cpu_throughput(track: str, steps_per_proc: int, procs: int, seed: int = 0, warm: int = 600):
-    """car-steps/s of the oracle with `procs` independent single-car envs, one per process."""
-    jobs = [(track, i, steps_per_proc, seed, warm) for i in range(procs)]
-    if procs == 1:
-        res = [_cpu_worker(jobs[0])]
+def _reference_worker(args):
+    """The reference's own CarEnv.step loop (src/car_env.py:678), stdout silenced (it prints on reset / disable events)."""
+    import contextlib
+    import io
+    track, car_base, n_steps, seed, warm, tier, ref = args
+    if tier == 2:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    sys.path.insert(0, ref)
+    cars = np.array([car_base], dtype=np.int64)
+    acts = [synthetic_actions(seed, cars, s)[0] for s in range(warm + n_steps)]
+    with contextlib.redirect_stdout(io.StringIO()):
+        from src.car_env import CarEnv
+        env = CarEnv(render_mode=None, track_file=os.path.join(ref, "tracks", f"{track}.track"), num_cars=1)
+        env.reset()
+        for s in range(warm):
+            _, _, te, tr, _ = env.step(acts[s])
+            if te or tr:
+                env.reset()
+        t0 = time.perf_counter()
+        for s in range(warm, warm + n_steps):
+            _, _, te, tr, _ = env.step(acts[s])
+            if te or tr:
+                env.reset()
+        dt = time.perf_counter() - t0
+    return n_steps, dt
+
+
+def cpu_throughput(track: str, steps_per_proc: int, procs: int, seed: int = 0, warm: int = 600, tier: int = 3):
+    """car-steps/s of `procs` independent single-car envs, one per process (fork), on the given tier."""
+    if tier == 3:
+        fn, jobs = _port_worker, [(track, i, steps_per_proc, seed, warm) for i in range(procs)]
     else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_cpu_worker, jobs)
+        fn, jobs = _reference_worker, [(track, i, steps_per_proc, seed, warm, tier, reference_root()) for i in range(procs)]
+    with mp.get_context("fork").Pool(procs) as pool:      # a pool even for one process: the reference's imports stay out of this one
+        res = pool.map(fn, jobs)
     total = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
     return total / slowest
+
+
+TIER_NOTE = {1: "the reference CarEnv (unmodified src/car_env.py) over real box2d-py + gymnasium",
+             2: "the reference CarEnv (unmodified src/car_env.py and everything it imports from src/) over the stand-in "
+                "Box2D/gymnasium/pygame modules of oracle/refshim: the reference's Python runs as is, the rigid-body step "
+                "underneath is oracle/b2lite.h, not real box2d-py (not installable offline)",
+             3: "oracle/ncg_oracle.cpp, the C++ restatement of the path (port)"}
+TIER_STEPS = {1: 4000, 2: 4000, 3: 40000}       # per process: ~8 s of the reference's Python, ~3-6 s of the port
+
+
+def cpu_tiers(track: str, procs: int, seed: int, scale: float = 1.0):
+    """Every tier that can run here, timed with `procs` processes.  Returns {tier: {...}} and the preferred (lowest) tier."""
+    out = {}
+    for tier in available_tiers():
+        n, warm = max(200, int(TIER_STEPS[tier] * scale)), (600 if tier == 3 else 300)
+        t0 = time.perf_counter()
+        v = cpu_throughput(track, n, procs, seed=seed, warm=warm, tier=tier)
+        out[tier] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port" if tier == 3 else "reference", "tier": tier,
+                     "sample": f"{procs} process(es) x 1 single-car env on {track}.track x {n} steps after {warm} warm-up, same Philox "
+                               f"action stream as the GPU arm ({time.perf_counter() - t0:.1f} s wall): {TIER_NOTE[tier]}"}
+    return out, min(out)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -180,184 +240,241 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    from nascargymnasium_b200.engine import Engine
-    from nascargymnasium_b200.vector_env import NascarVectorEnv
+def traffic_per_car_step():
+    """DRAM bytes per car-step of the rollout kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)
+        return (float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])) / (float(t["steps_per_launch"]) * float(t["cars"])), t.get("capture")
+    except Exception:
+        return None, None
 
-    E, C, track = args.envs, args.cars, args.track
-    N = E * C
-    K, Wm = args.steps, args.warmup
-    # steps per launch: long rollouts amortise the cold start of a launch (after the L2 flush the kernel's own code and the
-    # track tables come from HBM: ~0.16 ms per launch, measured); capped so the rollout buffer stays below 2 GB
-    T = max(1, min(args.steps_per_launch, K, int(2e9 // (N * 38 * 4))))
-    from nascargymnasium_b200 import track as TR
-    tracks = list(TR.BUILTIN_TRACK_NAMES) if track == "all" else [track]
-    track_id = (np.arange(E, dtype=np.int64) * len(tracks) // E).astype(np.int32)      # contiguous blocks of envs per track
-    eng = Engine(E, C, tracks=tracks, discrete=False, auto_reset=True, device=local)
-    eng.reset_host(track_id=track_id)
-    obs_roll = torch.empty((T, N, 38), dtype=torch.float32, device=dev)
-    rew_roll = torch.empty((T, N), dtype=torch.float32, device=dev)
-    done_roll = torch.empty((T, E), dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)    # > 126 MB L2
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+class Bench:
+    """One process per GPU.  A workload = (total envs over all ranks, cars per env, track(s), action distribution); rank r
+    owns the env slice distributed.shard_range gives it and draws the Philox streams of its own global car indices, so N
+    ranks simulate N disjoint slices of one job."""
 
-    def launch(n):
-        eng.rollout(n, seed=args.seed, mode=args.mode, obs_rollout=obs_roll[:n].reshape(-1) if n != T else obs_roll.reshape(-1),
-                    reward_rollout=rew_roll[:n].reshape(-1) if n != T else rew_roll.reshape(-1),
-                    done_rollout=done_roll[:n].reshape(-1) if n != T else done_roll.reshape(-1))
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device(f"cuda:{self.local}")
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)    # > 126 MB L2
+        self.roll_bytes = int(2e9)
+        self.roll = torch.empty(self.roll_bytes // 4, dtype=torch.float32, device=self.dev)  # every step's observations
+        self.launches = 0
 
-    # warm-up: W steps (at least 3 launches)
-    done = 0
-    for _ in range(max(3, (Wm + T - 1) // T)):
-        launch(T)
-        done += T
-    barrier()
-    eng.read_stats(reset=True)
-    launches0 = eng.launch_count
-    chunks = [T] * (K // T) + ([K % T] if K % T else [])
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in chunks]
-    with ClockSampler(local) as clk:
-        barrier()
-        t_wall0 = time.perf_counter()
-        for (e0, e1), n in zip(ev, chunks):
-            flush.zero_()                         # L2 flush between timed launches (not inside the event pair)
-            e0.record()
-            launch(n)
-            e1.record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
-    kern_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    gpu_launches = eng.launch_count - launches0
-    stats = eng.read_stats(reset=True)
-    assert stats["car_steps"] == N * K, (stats, N, K)
-    t = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    kern_ms_max = float(t.item())
-    value = world * N * K / (kern_ms_max / 1e3)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    # ---- e2e: host buffers through the CarEnv-facing API, H2D + D2H every step
-    venv = NascarVectorEnv(num_envs=E, track_file=None if track == "all" else f"tracks/{track}.track", num_cars=C, device=local)
-    venv.reset()
-    Ke = args.e2e_steps
-    cars = np.arange(N, dtype=np.int64) + rank * N
-    acts = [synthetic_actions(args.seed, cars, s).reshape(E, C, 2) if C > 1 else synthetic_actions(args.seed, cars, s) for s in range(Ke + 5)]
-    for s in range(5):
-        venv.step(acts[s])
-    barrier()
-    l0 = venv.engine.launch_count
-    t0 = time.perf_counter()
-    for s in range(5, Ke + 5):
-        o, r, te, tr, info = venv.step(acts[s])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    gpu_launches += venv.engine.launch_count - l0
-    te2 = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te2, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * Ke / float(te2.item())
-    h2d = N * 2 * 4
-    d2h = N * 38 * 4 + N * 4 + 2 * E
+    def max_ranks(self, x: float) -> float:
+        from nascargymnasium_b200 import distributed as D
+        return D.max_over_ranks(x, device=self.dev)
 
-    peak, peak_src = measured_peak()
-    per_launch_s = (kern_ms / 1e3) / len(chunks)
-    achieved = ALGO_BYTES_PER_CAR_STEP * N * (K / len(chunks)) / per_launch_s / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": kern_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{E} batched {'single-car' if C == 1 else str(C) + '-car'} envs on {track}.track per GPU, continuous "
-                               f"actions {'~ U[-1,1]^2' if args.mode == 0 else 'driving distribution tb~U[0.2,1], steer~U[-0.2,0.6]'} (Philox on "
-                               f"device), 16-ray observations written every step, same-step auto-reset",
-                   "envs_per_gpu": E, "cars_per_env": C, "track": track, "steps_per_launch": T,
-                   "l2": "flushed (256 MiB memset) between timed launches; the working set itself is L2-resident by construction",
-                   "rays_per_lane": os.environ.get("NCG_RAYS_PER_LANE", "auto")},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+    def sum_ranks(self, d: dict) -> dict:
+        from nascargymnasium_b200 import distributed as D
+        return D.reduce_stats(d, device=self.dev)
+
+    def make_engine(self, total_envs, cars, track):
+        """This rank's shard of a `total_envs`-env job."""
+        from nascargymnasium_b200.engine import Engine
+        from nascargymnasium_b200 import distributed as D
+        from nascargymnasium_b200 import track as TR
+        lo, hi = D.shard_range(total_envs, self.rank, self.world)
+        names = list(TR.BUILTIN_TRACK_NAMES) if track == "all" else [track]
+        eng = Engine(hi - lo, cars, tracks=names, discrete=False, auto_reset=True, device=self.local)
+        # config 4: env -> track = global env index mod 8 (SURVEY 8d), sorted inside the shard so a CTA serves one track
+        tid = D.shard_track_ids(total_envs, len(names), self.rank, self.world) if len(names) > 1 else np.zeros(hi - lo, dtype=np.int32)
+        eng.reset_host(track_id=tid)
+        eng.set_rollout_base(car_base=lo * cars)
+        return eng, lo, hi
+
+    def measure(self, total_envs, cars, track, mode, steps, warmup, steps_per_launch, min_timed_steps):
+        """Time the rollout kernel on one workload.  `steps` (K) are repeated R times so that the timed region holds at
+        least min_timed_steps steps, in launches of at most steps_per_launch steps with an L2 flush before each."""
+        torch, args = self.torch, self.args
+        eng, lo, hi = self.make_engine(total_envs, cars, track)
+        E = hi - lo
+        N = E * cars
+        R = max(1, -(-min_timed_steps // steps))
+        total = steps * R
+        T = max(1, min(steps_per_launch, total, self.roll_bytes // (N * 38 * 4)))
+        obs_roll = self.roll[:T * N * 38]
+        rew_roll = torch.empty((T, N), dtype=torch.float32, device=self.dev)
+        done_roll = torch.empty((T, E), dtype=torch.uint8, device=self.dev)
+
+        def launch(n):
+            eng.rollout(n, seed=args.seed, mode=mode, obs_rollout=obs_roll[:n * N * 38], reward_rollout=rew_roll[:n].reshape(-1),
+                        done_rollout=done_roll[:n].reshape(-1))
+
+        warm_steps = max(warmup, args.min_warmup)
+        warm_launches = max(3, -(-warm_steps // T))
+        for _ in range(warm_launches):
+            launch(T)
+        self.barrier()
+        eng.read_stats(reset=True)
+        l0 = eng.launch_count
+        chunks = [T] * (total // T) + ([total % T] if total % T else [])
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in chunks]
+        with ClockSampler(self.local) as clk:
+            self.barrier()
+            t_wall0 = time.perf_counter()
+            for (e0, e1), n in zip(ev, chunks):
+                self.flush.zero_()                    # L2 flush before every timed launch (outside the event pair)
+                e0.record()
+                launch(n)
+                e1.record()
+            self.barrier()
+            t_wall = time.perf_counter() - t_wall0
+        ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+        self.launches += eng.launch_count - l0
+        stats = eng.read_stats(reset=True)
+        assert stats["car_steps"] == N * total, (stats, N, total)
+        kern_ms = self.max_ranks(sum(ms))                                  # the slowest rank's device time
+        tot = self.sum_ranks({"cars": float(N), **{k: float(v) for k, v in stats.items()}})
+        per_step = [m / n for m, n in zip(ms, chunks)]
+        eng.close()
+        peak, peak_src = measured_peak()
+        car_steps_per_launch = N * total / len(chunks)
+        achieved = ALGO_BYTES_PER_CAR_STEP * car_steps_per_launch / (kern_ms / 1e3 / len(chunks)) / 1e9
+        tpc, cap = traffic_per_car_step()
+        return {
+            "value": tot["cars"] * total / (kern_ms / 1e3), "unit": UNIT, "ms_per_step": kern_ms / total,
+            "envs_total": total_envs, "envs_this_rank": E, "cars_per_env": cars, "track": track, "mode": mode,
+            "steps": steps, "repeats": R, "steps_timed": total, "steps_per_launch": T, "warmup_steps": warm_launches * T,
+            "launches": len(chunks), "kernel_ms_total": kern_ms,
+            "ms_per_step_per_launch": {"min": min(per_step), "mean": sum(per_step) / len(per_step), "max": max(per_step)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": tpc * car_steps_per_launch if tpc is not None else None,
+                         "traffic_source": f"{cap or 'profiles/roofline_traffic.json'}: DRAM read+write bytes per car-step of the "
+                                           "rollout kernel from the committed ncu --set full capture, scaled to this launch's car-steps",
+                         "peak_source": peak_src, "kernel": "ncg_step_kernel", "algorithmic_bytes_per_car_step": ALGO_BYTES_PER_CAR_STEP,
+                         "car_steps_per_launch": car_steps_per_launch, "avg_launch_ms": kern_ms / len(chunks),
+                         "time": "max over ranks of the summed CUDA-event launch durations"},
+            "clocks": clk.summary(),
+            "counters": {k: (float(v) if k == "return_sum" else int(v)) for k, v in tot.items() if k != "cars"},
+            "wall_s_timed_region": t_wall,
+        }
+
+    def measure_e2e(self, envs_per_gpu, cars, track, steps):
+        """The same metric through the reference-facing host API: numpy actions in, numpy results out, every step."""
+        from nascargymnasium_b200.vector_env import NascarVectorEnv
+        E, C = envs_per_gpu, cars
+        N = E * C
+        venv = NascarVectorEnv(num_envs=E, track_file=None if track == "all" else f"tracks/{track}.track", num_cars=C, device=self.local)
+        venv.reset()
+        carsx = np.arange(N, dtype=np.int64) + self.rank * N
+        acts = [synthetic_actions(self.args.seed, carsx, s).reshape(E, C, 2) if C > 1 else synthetic_actions(self.args.seed, carsx, s)
+                for s in range(steps + 5)]
+        for s in range(5):
+            venv.step(acts[s])
+        self.barrier()
+        l0 = venv.engine.launch_count
+        t0 = time.perf_counter()
+        for s in range(5, steps + 5):
+            venv.step(acts[s])
+        self.torch.cuda.synchronize()
+        dt = self.max_ranks(time.perf_counter() - t0)
+        self.launches += venv.engine.launch_count - l0
+        venv.close()
+        return {"value": self.world * N * steps / dt, "unit": UNIT, "h2d_bytes_per_step": N * 2 * 4,
+                "d2h_bytes_per_step": N * 38 * 4 + N * 4 + 2 * E, "steps": steps,
                 "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated; actions are copied into "
                        "page-locked memory the kernel reads across PCIe, results are written by the kernel into page-locked host "
-                       "buffers and returned without a further copy"},
-        "gpu_launches": int(gpu_launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": profiled_traffic(T, N) if args.mode == 0 and track == "daytona" else None,
-                     "peak_source": peak_src, "kernel": "ncg_step_kernel", "algorithmic_bytes_per_car_step": ALGO_BYTES_PER_CAR_STEP,
-                     "car_steps_per_launch": N * (K / len(chunks)), "avg_launch_ms": per_launch_s * 1e3},
-        "clocks": clk.summary(),
-        "counters": {k: int(v) if k != "return_sum" else float(v) for k, v in stats.items()},
-        "wall_s_timed_region": t_wall,
+                       "buffers and returned without a further copy"}
+
+
+def workload_text(envs, cars, track, mode, per_gpu=True):
+    return (f"{envs} batched {'single-car' if cars == 1 else str(cars) + '-car'} envs on "
+            f"{'the 8 .track files (env index mod 8)' if track == 'all' else track + '.track'}{' per GPU' if per_gpu else ' in total'}, continuous actions "
+            f"{'~ U[-1,1]^2' if mode == 0 else 'driving distribution tb~U[0.2,1], steer~U[-0.2,0.6]'} (Philox on device), "
+            "16-ray observations written every step, same-step auto-reset")
+
+
+def run_ours(args):
+    b = Bench(args)
+    world, rank = b.world, b.rank
+    E, C, track = args.envs, args.cars, args.track
+    K, Wm = args.steps, args.warmup
+    # headline workload: BASELINE.json configs[1] per GPU (weak scaling: `envs` per rank)
+    m = b.measure(E * world, C, track, args.mode, K, Wm, args.steps_per_launch, args.min_timed_steps)
+    e2e = b.measure_e2e(E, C, track, args.e2e_steps)
+    line = {
+        "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(E, C, track, args.mode), "envs_per_gpu": E, "cars_per_env": C, "track": track,
+                   "repeats": m["repeats"], "steps_timed": m["steps_timed"], "steps_per_launch": m["steps_per_launch"],
+                   "warmup_steps_run": m["warmup_steps"],
+                   "timing": f"the {K} steps are repeated {m['repeats']} times back to back ({m['steps_timed']} timed steps in "
+                             f"{m['launches']} launches of the rollout kernel, CUDA events around each launch, max over ranks); ms_per_step "
+                             "is the mean over all timed steps; warm-up is at least min_warmup steps so the timed region is the "
+                             "steady state of the policy",
+                   "ms_per_step_per_launch": m["ms_per_step_per_launch"],
+                   "l2": "flushed (256 MiB memset) before every timed launch; every step's observations stream to a rollout buffer "
+                         "larger than L2; the persistent state itself is L2/shared-memory resident by construction",
+                   "sharding": "rank r owns envs shard_range(total, r, world) and the Philox streams of its own global car indices",
+                   "rays_per_lane": os.environ.get("NCG_RAYS_PER_LANE", "auto")},
+        "e2e": e2e, "roofline": m["roofline"], "clocks": m["clocks"], "counters": m["counters"],
+        "wall_s_timed_region": m["wall_s_timed_region"],
     }
-    if rank == 0 and world == 1 and args.sweep:
-        # the same kernel at larger batches (informational: the metric is quoted at 4096-65536 envs); short runs
-        line["batch_sweep"] = []
-        eng.close()
-        for Es, trk in ((8192, track), (16384, track), (65536, track), (65536, "all")):
-            names = list(TR.BUILTIN_TRACK_NAMES) if trk == "all" else [trk]
-            e2 = Engine(Es, C, tracks=names, discrete=False, auto_reset=True, device=local)
-            e2.reset_host(track_id=(np.arange(Es, dtype=np.int64) * len(names) // Es).astype(np.int32))
-            o2 = torch.empty((50, Es * C, 38), dtype=torch.float32, device=dev)
-            for _ in range(6):
-                e2.rollout(50, seed=args.seed, mode=args.mode, obs_rollout=o2.reshape(-1))
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(10):
-                e2.rollout(50, seed=args.seed, mode=args.mode, obs_rollout=o2.reshape(-1))
-            b.record()
-            torch.cuda.synchronize()
-            line["batch_sweep"].append({"envs": Es, "track": trk, "value": Es * C * 500 / (a.elapsed_time(b) / 1e3), "unit": UNIT,
-                                        "steps": 500, "note": "rollout kernel, 50 steps per launch, no L2 flush"})
-            e2.close()
-            del o2
+    if args.extras:
+        # the other BASELINE.json configurations and the contact-heavy action distribution, each measured the same way
+        # with its own clocks sample.  configs 3 and 4 are fixed-size jobs split over the ranks (strong scaling).
+        ex = {}
+        ex["driving"] = dict(b.measure(E * world, C, track, 1, 1000, 3000, args.steps_per_launch, 3000), scaling="weak",
+                             workload=workload_text(E, C, track, 1))
+        ex["config3"] = dict(b.measure(8192, 10, "talladega", 0, 200, 600, args.steps_per_launch, 1000), scaling="strong",
+                             workload=workload_text(8192, 10, "talladega", 0, per_gpu=False) + "; car-car contact off (the reference has none)")
+        ex["config4"] = dict(b.measure(65536, 1, "all", 0, 200, 600, args.steps_per_launch, 3000), scaling="strong",
+                             workload=workload_text(65536, 1, "all", 0, per_gpu=False))
+        if world == 1 and args.sweep:
+            for Es in (8192, 16384, 65536):
+                ex[f"daytona_{Es}"] = dict(b.measure(Es, 1, "daytona", 0, 200, 600, args.steps_per_launch, 3000), scaling="weak",
+                                           workload=workload_text(Es, 1, "daytona", 0))
+        line["workloads"] = ex
+    line["gpu_launches"] = int(b.launches)
     if rank == 0 and world == 1:
-        t0 = time.perf_counter()
-        v = cpu_throughput(tracks[0], args.cpu_steps, 1, seed=args.seed)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"1 single-car env on {track}.track, {args.cpu_steps} steps after 600 warm-up, same Philox action "
-                                          f"stream, oracle/ncg_oracle.cpp single thread ({time.perf_counter() - t0:.1f} s)"}
+        tiers, best = cpu_tiers("daytona" if track == "all" else track, 1, args.seed)
+        line["cpu_baseline"] = dict(tiers[best], tiers={str(k): v for k, v in tiers.items()})
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        b.dist.barrier()
+        b.dist.destroy_process_group()
 
 
 def run_reference(args):
-    """The reference's CPU implementation of the path: real box2d-py/gymnasium are not installable offline, so this
-    arm times the oracle port (oracle/ncg_oracle.cpp) with one process per host core."""
+    """The reference's CPU implementation of the path on every host core: the best tier that runs here (see the CPU arm
+    above), one single-car env per process.  Rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
     K, Wm = args.steps, args.warmup
-    # each "step" is a bounded sample: every core advances one single-car env by cpu_steps/ K ... keep total ~20-40 s
-    per_proc = max(200, min(args.cpu_steps, 40000))
-    t0 = time.perf_counter()
-    v = cpu_throughput("daytona" if args.track == "all" else args.track, per_proc, cores, seed=args.seed)
-    dt = time.perf_counter() - t0
+    track = "daytona" if args.track == "all" else args.track
+    tiers, best = cpu_tiers(track, cores, args.seed)
+    v = tiers[best]["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": 1e3 * args.envs * args.cars / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64/f32", "data": "synthetic",
-        "config": {"workload": f"{args.envs} batched single-car envs on {args.track}.track per GPU, continuous actions ~ U[-1,1]^2",
-                   "envs_per_gpu": args.envs, "cars_per_env": args.cars, "track": args.track},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} processes x 1 single-car env x {per_proc} steps after 600 warm-up ({dt:.1f} s wall); "
-                                   "box2d-py/gymnasium absent offline, so the oracle port stands in for the reference CarEnv"},
+        "config": {"workload": workload_text(args.envs, args.cars, args.track, args.mode), "envs_per_gpu": args.envs,
+                   "cars_per_env": args.cars, "track": args.track,
+                   "sample": "each step is timed on a bounded sample: one single-car env per host core, see cpu_baseline.sample"},
+        "cpu_baseline": dict(tiers[best], tiers={str(k): t for k, t in tiers.items()}),
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -369,13 +486,15 @@ def main():
     ap.add_argument("--steps", type=int, default=30000)
     ap.add_argument("--warmup", type=int, default=3000)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=4096)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU of the headline workload")
     ap.add_argument("--cars", type=int, default=1)
-    ap.add_argument("--track", default="daytona", help="a built-in track name, or 'all' = the 8 .track files in equal blocks of envs")
+    ap.add_argument("--track", default="daytona", help="a built-in track name, or 'all' = the 8 .track files (env index mod 8)")
     ap.add_argument("--steps-per-launch", type=int, default=1000)
+    ap.add_argument("--min-timed-steps", type=int, default=20000, help="--steps is repeated until the timed region holds this many steps")
+    ap.add_argument("--min-warmup", type=int, default=3000, help="warm-up steps run at least (steady state of the random policy)")
     ap.add_argument("--e2e-steps", type=int, default=2000)
-    ap.add_argument("--cpu-steps", type=int, default=40000)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--extras", type=int, default=1, help="1: also measure the driving distribution and BASELINE configs 3 and 4")
     ap.add_argument("--sweep", type=int, default=1, help="1: also time the rollout kernel at 8192/16384/65536 envs (N=1 only)")
     ap.add_argument("--mode", type=int, default=0, help="synthetic action distribution: 0 = action_space.sample() (the metric), "
                     "1 = 'driving' (tb~U[0.2,1], steer~U[-0.2,0.6]: laps, wall contacts, episodes)")

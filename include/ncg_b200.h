@@ -142,7 +142,8 @@ int ncg_destroy(NcgHandle* h);
 int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offsets, int32_t n_tracks);
 
 /* Reset envs whose d_env_mask byte is non-zero (NULL = all).  d_track_id (int32[E], NULL = keep) selects
- * each reset env's track.  fresh=1 is a brand-new Box2D world (first reset / track change); fresh=0 is
+ * each reset env's track (the ids are copied back and range-checked before anything is launched: one synchronisation
+ * of `stream`; an id outside [0, n_tracks) fails with NCG_E_INVALID and changes nothing).  fresh=1 is a brand-new Box2D world (first reset / track change); fresh=0 is
  * CarPhysics.reset_car on the existing world.  Writes the initial observations of reset envs to d_obs
  * (float32[E*C*38], may be NULL). */
 int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id, int32_t fresh, float* d_obs,
@@ -190,7 +191,9 @@ int ncg_host_free(void* p);
 int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
                     uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done);
 
-/* Raw records, NCG_RECORD_WORDS words per car, car-major; d_records float32[n_cars*128]. */
+/* Raw records, NCG_RECORD_WORDS words per car, car-major; d_records float32[n_cars*128].  ncg_set_state* read the
+ * env -> track map out of the records (word NCG_R_TRACK of each env's first car), reject ids that were not uploaded
+ * (nothing is written then) and re-plan the launch; the device variant synchronises `stream` once to do so. */
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream);
 int ncg_set_state(NcgHandle* h, const float* d_records, void* stream);
 int ncg_get_state_host(NcgHandle* h, float* h_records);
@@ -203,6 +206,19 @@ int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset);
  * spread over num_sms SMs.  Writes up to `capacity` entries and returns the number of CTAs. */
 int32_t ncg_plan_ctas(const int32_t* h_env_track, int32_t num_envs, int32_t cars_per_env, int32_t num_sms,
                       int32_t* h_first_env, int32_t* h_num_envs, int32_t capacity);
+
+/* Offsets of ncg_rollout's synthetic action stream: the Philox counter of local car c at launch step t is
+ * (car_base + c, step_base + t).  R ranks that own disjoint env slices (rank r: car_base = r * E * C) draw the streams
+ * of one R*E-env job; a rank's slice is then bit-identical to the same envs inside a single larger engine.
+ * step_base otherwise counts the steps rolled out on the handle so far. */
+int ncg_set_rollout_base(NcgHandle* h, uint32_t car_base, uint32_t step_base);
+
+/* Monitor-style episode statistics on the device path (stable-baselines3 Monitor: /root/reference/learn/ppo.py:69):
+ * once set (pointers may be NULL to unset), every ncg_step writes, for envs that finish in that step,
+ * d_ep_return[car] = the episode return (CarEnv.cumulative_rewards, src/car_env.py:785-789) and d_ep_length[env] = the
+ * episode's step count, and sets *d_any_done = 1; rows of envs that did not finish are left untouched (the caller
+ * clears *d_any_done).  float32[E*C], int32[E], int32[1], device memory owned by the caller. */
+int ncg_set_episode_outputs(NcgHandle* h, float* d_ep_return, int32_t* d_ep_length, int32_t* d_any_done);
 
 /* Number of kernels this library has launched on the handle (for bench.py's gpu_launches). */
 int64_t ncg_launch_count(NcgHandle* h);

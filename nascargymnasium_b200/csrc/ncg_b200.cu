@@ -34,7 +34,7 @@ struct KParams {
     const float* reset_obs;                                // [n_tracks][NCG_OBS_DIM]: the observation every reset_car yields on a track
     int E, C, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip, queue;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
-    int T; unsigned long long seed; int mode; unsigned step_base;
+    int T; unsigned long long seed; int mode; unsigned step_base; unsigned car_base;
     float* obs_roll; float* rew_roll; uint8_t* done_roll;
     float* ep_return; int* ep_length; int* any_done;      // optional: episode return per car / length per env of finished envs
     DevStats* stats;
@@ -165,11 +165,11 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     const bool synth = p.actions == nullptr;
     // the first PW ray warps make the synthetic actions (one per physics warp), two steps ahead of the physics warps
     const bool act_maker = synth && warp >= PW && warp < 2 * PW && lane < (warp == PW ? n0 : n1);
-    const int act_slot = (warp - PW) * 32 + lane, act_car = (warp == PW ? cb0 : cb1) + lane;
+    const int act_slot = (warp - PW) * 32 + lane; const unsigned act_car = p.car_base + (unsigned)((warp == PW ? cb0 : cb1) + lane);
     if (act_maker) {
         for (int t = 0; t < NB && t < p.T; ++t) {
             float thr, brk, st;
-            action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
+            action_synthetic(p.seed, act_car, p.step_base + (unsigned)t, p.mode, p.discrete != 0, &thr, &brk, &st);
             s_act[t * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
         }
     }
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
             }
             if (act_maker && t + NB < p.T) {                     // actions of step t+NB (this buffer's next use)
                 float thr, brk, st;
-                action_synthetic(p.seed, (uint32_t)act_car, p.step_base + (unsigned)(t + NB), p.mode, p.discrete != 0, &thr, &brk, &st);
+                action_synthetic(p.seed, act_car, p.step_base + (unsigned)(t + NB), p.mode, p.discrete != 0, &thr, &brk, &st);
                 s_act[b * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
             }
             bar_sync(BAR_FULL + b, NT);
@@ -402,11 +402,12 @@ struct NcgHandle {
     float* d_reset_obs = nullptr;
     std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
     std::vector<int> h_env_track;
-    int2* d_cta_tab = nullptr; int n_ctas = 0; bool cta_dirty = true;      // groups of <= 32 car slots (one CTA each, or two per CTA)
-    int2* d_pair_tab = nullptr; int n_pairs = 0;                          // groups paired by track for the two-physics-warp shape
+    int2* d_cta_tab = nullptr; int n_ctas = 0; int cap_ctas = 0; bool cta_dirty = true;   // groups of <= 32 car slots (one CTA each, or two per CTA)
+    int2* d_pair_tab = nullptr; int n_pairs = 0; int cap_pairs = 0;       // groups paired by track for the two-physics-warp shape
     DevStats* d_stats = nullptr;
     bool was_reset = false;
-    unsigned step_base = 0;
+    unsigned step_base = 0, car_base = 0;              // Philox counter offsets of ncg_rollout (ncg_set_rollout_base)
+    float* d_ep_return = nullptr; int* d_ep_length = nullptr; int* d_ep_any = nullptr;   // ncg_set_episode_outputs
     int rays_per_lane = 0; int num_sms = 0; int max_smem = 0;
     long long launches = 0;
     // host-buffer path
@@ -460,9 +461,11 @@ void plan_ctas(const int* env_track, int E, int C, int sms, std::vector<int2>& t
 int build_cta_table(NcgHandle* h) {
     std::vector<int2> tab;
     plan_ctas(h->h_env_track.data(), h->cfg.num_envs, h->cfg.cars_per_env, h->num_sms, tab);
-    if ((int)tab.size() > h->n_ctas) {
-        cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); h->d_cta_tab = nullptr;
+    // (each table has its own capacity: the allocation only ever grows, and growing one never touches the other)
+    if ((int)tab.size() > h->cap_ctas) {
+        cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr; h->cap_ctas = 0;
         CUDA_TRY(cudaMalloc(&h->d_cta_tab, tab.size() * sizeof(int2)));
+        h->cap_ctas = (int)tab.size();
     }
     CUDA_TRY(cudaMemcpy(h->d_cta_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
     h->n_ctas = (int)tab.size();
@@ -473,9 +476,10 @@ int build_cta_table(NcgHandle* h) {
         pairs.push_back(make_int2((int)g, two ? (int)g + 1 : -1));
         g += two ? 2 : 1;
     }
-    if ((int)pairs.size() > h->n_pairs) {
-        cudaFree(h->d_pair_tab); h->d_pair_tab = nullptr;
+    if ((int)pairs.size() > h->cap_pairs) {
+        cudaFree(h->d_pair_tab); h->d_pair_tab = nullptr; h->cap_pairs = 0;
         CUDA_TRY(cudaMalloc(&h->d_pair_tab, pairs.size() * sizeof(int2)));
+        h->cap_pairs = (int)pairs.size();
     }
     CUDA_TRY(cudaMemcpy(h->d_pair_tab, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice));
     h->n_pairs = (int)pairs.size();
@@ -626,6 +630,17 @@ int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called before ncg_reset");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (!h->was_reset && (d_env_mask || !fresh)) return fail(NCG_E_STATE, "the first reset must be a full fresh reset");
+    const int E = h->cfg.num_envs;
+    std::vector<int> ids; std::vector<uint8_t> mk;
+    if (d_track_id) {
+        // device-side ids: brought back and range-checked BEFORE the kernel follows them into the track blob (one
+        // synchronisation of the caller's stream; the env -> track map on the host needs them anyway for the CTA table)
+        ids.resize(E); mk.resize(d_env_mask ? E : 0);
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        CUDA_TRY(cudaMemcpy(ids.data(), d_track_id, (size_t)E * 4, cudaMemcpyDeviceToHost));
+        if (d_env_mask) CUDA_TRY(cudaMemcpy(mk.data(), d_env_mask, E, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < E; ++e) if ((!d_env_mask || mk[e]) && (ids[e] < 0 || ids[e] >= h->n_tracks)) return fail(NCG_E_INVALID, "track id out of range");
+    }
     const int threads = 256, cars_per_block = threads / 32;
     const int grid = (h->N + cars_per_block - 1) / cars_per_block;
     ncg_reset_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(h->d_records, h->d_blob, h->d_track_off, h->cfg.num_envs, h->cfg.cars_per_env,
@@ -633,16 +648,8 @@ int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     h->was_reset = true;
-    if (d_track_id) {                            // device-side ids: bring them back once so the CTA table can follow
-        const int E = h->cfg.num_envs;
-        std::vector<int> ids(E); std::vector<uint8_t> mk(d_env_mask ? E : 0);
-        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-        CUDA_TRY(cudaMemcpy(ids.data(), d_track_id, (size_t)E * 4, cudaMemcpyDeviceToHost));
-        if (d_env_mask) CUDA_TRY(cudaMemcpy(mk.data(), d_env_mask, E, cudaMemcpyDeviceToHost));
-        for (int e = 0; e < E; ++e) if (!d_env_mask || mk[e]) {
-            if (ids[e] < 0 || ids[e] >= h->n_tracks) return fail(NCG_E_INVALID, "track id out of range");
-            h->h_env_track[e] = ids[e];
-        }
+    if (d_track_id) {                            // only now, with the launch accepted, does the host map follow
+        for (int e = 0; e < E; ++e) if (!d_env_mask || mk[e]) h->h_env_track[e] = ids[e];
         h->cta_dirty = true;
     }
     return NCG_OK;
@@ -655,6 +662,7 @@ int ncg_step(NcgHandle* h, const void* d_actions, float* d_obs, float* d_reward,
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams p = base_params(h);
     p.actions = d_actions; p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated; p.final_obs = d_final_obs;
+    p.ep_return = h->d_ep_return; p.ep_length = h->d_ep_length; p.any_done = h->d_ep_any;
     return launch_step(h, p, (cudaStream_t)stream);
 }
 
@@ -664,7 +672,7 @@ int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float*
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     KParams p = base_params(h);
-    p.T = steps; p.seed = seed; p.mode = mode; p.step_base = h->step_base; p.auto_reset = 1;
+    p.T = steps; p.seed = seed; p.mode = mode; p.step_base = h->step_base; p.car_base = h->car_base; p.auto_reset = 1;
     p.obs_roll = d_obs_rollout; p.rew_roll = d_reward_rollout; p.done_roll = d_done_rollout; p.obs = d_obs_last; p.reward = nullptr;
     if (!d_reward_rollout) { p.reward = h->d_reward; }
     p.term = h->d_term; p.trunc = h->d_trunc;
@@ -784,8 +792,21 @@ int ncg_get_state(NcgHandle* h, float* d_records, void* stream) {
 }
 int ncg_set_state(NcgHandle* h, const float* d_records, void* stream) {
     if (!h || !d_records) return fail(NCG_E_INVALID, "null argument");
+    if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called first");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    // the records carry the env -> track map (word NCG_R_TRACK of each env's first car): read it from the caller's copy,
+    // range-check it and let the CTA table follow, as ncg_set_state_host does -- a CTA stages ONE track table and would
+    // otherwise step foreign records against the wrong walls.  One synchronisation of the caller's stream.
+    const int E = h->cfg.num_envs;
+    std::vector<uint32_t> tid(E);
+    const size_t pitch = (size_t)h->cfg.cars_per_env * NCG_RECORD_WORDS * 4;
+    CUDA_TRY(cudaMemcpy2DAsync(tid.data(), 4, d_records + NCG_R_TRACK, pitch, 4, (size_t)E, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int e = 0; e < E; ++e) if ((int)tid[e] < 0 || (int)tid[e] >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
     CUDA_TRY(cudaMemcpyAsync(h->d_records, d_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    bool changed = false;
+    for (int e = 0; e < E; ++e) if (h->h_env_track[e] != (int)tid[e]) { h->h_env_track[e] = (int)tid[e]; changed = true; }
+    if (changed) h->cta_dirty = true;
     h->was_reset = true;
     return NCG_OK;
 }
@@ -800,10 +821,14 @@ int ncg_set_state_host(NcgHandle* h, const float* h_records) {
     if (!h || !h_records) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called first");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    for (int e = 0; e < h->cfg.num_envs; ++e) {
+        uint32_t t; memcpy(&t, h_records + (size_t)e * h->cfg.cars_per_env * NCG_RECORD_WORDS + NCG_R_TRACK, 4);
+        if ((int)t < 0 || (int)t >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(h->d_records, h_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyHostToDevice));
     for (int e = 0; e < h->cfg.num_envs; ++e) {
         uint32_t t; memcpy(&t, h_records + (size_t)e * h->cfg.cars_per_env * NCG_RECORD_WORDS + NCG_R_TRACK, 4);
-        if ((int)t >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
         h->h_env_track[e] = (int)t;
     }
     h->cta_dirty = true;
@@ -824,5 +849,17 @@ int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset) {
 }
 
 int64_t ncg_launch_count(NcgHandle* h) { return h ? h->launches : 0; }
+
+int ncg_set_rollout_base(NcgHandle* h, uint32_t car_base, uint32_t step_base) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    h->car_base = car_base; h->step_base = step_base;
+    return NCG_OK;
+}
+
+int ncg_set_episode_outputs(NcgHandle* h, float* d_ep_return, int32_t* d_ep_length, int32_t* d_any_done) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    h->d_ep_return = d_ep_return; h->d_ep_length = d_ep_length; h->d_ep_any = d_any_done;
+    return NCG_OK;
+}
 
 }  // extern "C"

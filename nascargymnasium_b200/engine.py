@@ -62,7 +62,7 @@ class Stats(ctypes.Structure):
 EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_upload_tracks", "ncg_reset", "ncg_step",
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
-           "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas")
+           "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs")
 
 _lib = None
 
@@ -100,6 +100,8 @@ def load_library():
     lib.ncg_step_mapped.argtypes = [vp] * 9 + [ctypes.POINTER(i32)]
     lib.ncg_plan_ctas.argtypes = [vp, i32, i32, i32, vp, vp, i32]
     lib.ncg_plan_ctas.restype = i32
+    lib.ncg_set_rollout_base.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32]
+    lib.ncg_set_episode_outputs.argtypes = [vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -253,10 +255,24 @@ class Engine:
         _check(self._lib.ncg_rollout(self._h, steps, seed, mode, self._ptr(obs_rollout), self._ptr(reward_rollout),
                                      self._ptr(done_rollout), self._ptr(obs_last), self._stream()))
 
+    def set_rollout_base(self, car_base: int = 0, step_base: int = 0):
+        """Philox counter offsets of rollout(): rank r of a sharded job passes car_base = r * num_cars."""
+        _check(self._lib.ncg_set_rollout_base(self._h, int(car_base) & 0xFFFFFFFF, int(step_base) & 0xFFFFFFFF))
+
+    def set_episode_outputs(self, ep_return=None, ep_length=None, any_done=None):
+        """Device tensors step() fills for envs that finish: ep_return float32[N], ep_length int32[E], any_done int32[1]."""
+        torch = self._torch()
+        self._dev(ep_return, torch.float32, self.num_cars, "ep_return")
+        self._dev(ep_length, torch.int32, self.num_envs, "ep_length")
+        self._dev(any_done, torch.int32, 1, "any_done")
+        self._ep_refs = (ep_return, ep_length, any_done)          # keep the storage alive while the engine points at it
+        _check(self._lib.ncg_set_episode_outputs(self._h, self._ptr(ep_return), self._ptr(ep_length), self._ptr(any_done)))
+
     def get_state(self, out=None):
         torch = self._torch()
         if out is None:
             out = torch.empty((self.num_cars, L.RECORD_WORDS), dtype=torch.float32, device=f"cuda:{self.device}")
+        self._dev(out, torch.float32, self.num_cars * L.RECORD_WORDS, "out")
         _check(self._lib.ncg_get_state(self._h, self._ptr(out), self._stream()))
         return out
 

@@ -70,7 +70,8 @@ class NascarVectorEnv:
 
     def __init__(self, num_envs: int, track_file: Union[None, str, Sequence[str]] = None, num_cars: int = 1,
                  discrete_action_space: bool = False, reset_on_lap: bool = False, device: int = 0, track_info: bool = False,
-                 max_result_blocks: int = 64):
+                 max_result_blocks: int = 64, validate_actions: bool = True):
+        self.validate_actions = bool(validate_actions)    # assert action_space.contains, like the reference's step()
         self.max_result_blocks = int(max_result_blocks)   # result buffers kept alive for the caller before step() copies
         if num_cars < 1 or num_cars > K.MAX_CARS:
             raise ValueError(f"Number of cars must be between 1 and {K.MAX_CARS}")
@@ -126,7 +127,14 @@ class NascarVectorEnv:
             self._aux = self.engine.aux_block()
             self._ring, self._ring_pos = [self.engine.result_block() for _ in range(2)], 0
         aux = self._aux.arrays
-        aux["actions"][...] = np.asarray(actions).reshape(aux["actions"].shape)
+        a = np.asarray(actions)
+        if self.validate_actions:
+            # CarEnv.step asserts action_space.contains(action) on every step (/root/reference/src/car_env.py:694)
+            if self.discrete:
+                assert a.dtype.kind in "iu" and a.size == aux["actions"].size and ((a >= 0) & (a < 5)).all(), "Invalid action"
+            else:
+                assert a.dtype == np.float32 and a.size == aux["actions"].size and (np.abs(a) <= 1.0).all(), "Invalid action"
+        aux["actions"][...] = a.reshape(aux["actions"].shape)
         blk = self._next_result_block()
         spill = blk is None
         if spill:                                   # the caller holds max_result_blocks results: fall back to copying
@@ -160,8 +168,24 @@ class NascarVectorEnv:
             self._torch_bufs = dict(obs=torch.empty((N, K.OBS_DIM), dtype=torch.float32, device=dev),
                                     final=torch.empty((N, K.OBS_DIM), dtype=torch.float32, device=dev),
                                     rew=torch.empty(N, dtype=torch.float32, device=dev),
-                                    te=torch.empty(E, dtype=torch.uint8, device=dev), tr=torch.empty(E, dtype=torch.uint8, device=dev))
+                                    te=torch.empty(E, dtype=torch.uint8, device=dev), tr=torch.empty(E, dtype=torch.uint8, device=dev),
+                                    ep_return=torch.zeros(N, dtype=torch.float32, device=dev), ep_length=torch.zeros(E, dtype=torch.int32, device=dev),
+                                    any_done=torch.zeros(1, dtype=torch.int32, device=dev))
+            b = self._torch_bufs
+            # Monitor-style episode statistics stay on the device too (learn/ppo.py:69 wraps every env in a Monitor)
+            self.engine.set_episode_outputs(b["ep_return"], b["ep_length"], b["any_done"])
         return self._torch_bufs
+
+    @property
+    def episode_returns(self):
+        """CUDA tensor (E[,C]): return of the episode an env finished most recently (valid where terminated | truncated
+        was set by a step_torch call; rows of running envs keep their previous value)."""
+        return self._bufs()["ep_return"].view(self._rew_shape)
+
+    @property
+    def episode_lengths(self):
+        """CUDA int32 tensor (E,): length in steps of the episode an env finished most recently."""
+        return self._bufs()["ep_length"]
 
     def reset_torch(self):
         import torch
