@@ -42,6 +42,7 @@ extern "C" {
 #define NCG_MAX_CONTACTS 12    /* broad-phase contacts kept per car (Box2D keeps an unbounded list) */
 #define NCG_MAX_TOUCHING 4     /* contacts with manifold points kept per car */
 #define NCG_MAX_ACTIVE 4       /* CarCollisionListener.active_collisions entries kept per car */
+#define NCG_VEL_HISTORY 600    /* Car.velocity_history: deque(maxlen=VELOCITY_HISTORY_SIZE), src/constants/environment.py:23 */
 
 enum {
     NCG_OK = 0,
@@ -114,7 +115,10 @@ typedef struct NcgConfig {
     int32_t reset_on_lap;    /* CarEnv(reset_on_lap=...) */
     int32_t auto_reset;      /* 1: envs that finish are reset inside the same step (VecEnv semantics) */
     int32_t contacts;        /* 1: car-wall contact solver + TOI enabled (default); 0: contact-free integrator */
-    int32_t track_info;      /* 1: also evaluate is_car_on_track() every step (NCG_F_ON_TRACK), for the info dict */
+    int32_t track_info;      /* 1: also keep what only the info dict needs: is_car_on_track() every step (NCG_F_ON_TRACK)
+                                and the 600-sample velocity history behind validate_performance (src/car.py:1060-1098) */
+    float start_x, start_y;  /* CarEnv(start_position=...) (src/car_env.py:114, 391, 398); (0, 0) = the GRID segment's start */
+    float start_angle;       /* CarEnv(start_angle=...), radians */
 } NcgConfig;
 
 typedef struct NcgHandle NcgHandle;
@@ -198,6 +202,11 @@ int ncg_get_state(NcgHandle* h, float* d_records, void* stream);
 int ncg_set_state(NcgHandle* h, const float* d_records, void* stream);
 int ncg_get_state_host(NcgHandle* h, float* h_records);
 int ncg_set_state_host(NcgHandle* h, const float* h_records);
+
+/* Car.velocity_history (src/car.py:173, 384-386, 1058): the velocity (vx, vy) update_physics saw on each of the last
+ * NCG_VEL_HISTORY steps of the running episode, a ring indexed by (episode step mod NCG_VEL_HISTORY);
+ * h_out float32[n_cars][NCG_VEL_HISTORY][2].  Kept only with NcgConfig.track_info = 1 (NCG_E_STATE otherwise). */
+int ncg_get_velocity_history_host(NcgHandle* h, float* h_out);
 
 int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset);
 

@@ -43,13 +43,14 @@ class CarEnv(_Base):
             self.car_names = list(car_names)
         if render_mode == "human":
             raise NotImplementedError("render_mode='human' (pygame window) is outside the accelerated path; use render_mode=None")
-        if start_position not in (None, (0.0, 0.0)) or start_angle != 0.0:
-            raise NotImplementedError("custom start_position/start_angle are not supported by the CUDA engine (grid start only)")
         self.render_mode = render_mode
         self.discrete_action_space = discrete_action_space
         self.num_cars = num_cars
         self.reset_on_lap = reset_on_lap
-        self.start_position, self.start_angle = (0.0, 0.0), 0.0
+        # car_env.py:114-115; (0, 0) is replaced by the GRID/STARTLINE segment's start (:236-241), which is the origin on
+        # every track the generator can produce (Track.add_segment starts at (0, 0))
+        self.start_position = tuple(float(v) for v in start_position) if start_position else (0.0, 0.0)
+        self.start_angle = float(start_angle)
         self.followed_car_index = 0
         self.action_space, self.observation_space = S.make_spaces(discrete_action_space, num_cars)
         self.track_file = track_file
@@ -93,7 +94,8 @@ class CarEnv(_Base):
     def _ensure_engine(self):
         if self._engine is None:
             self._engine = Engine(1, self.num_cars, tracks=self._tracks, discrete=self.discrete_action_space,
-                                  reset_on_lap=self.reset_on_lap, auto_reset=False, device=self._device, track_info=True)
+                                  reset_on_lap=self.reset_on_lap, auto_reset=False, device=self._device, track_info=True,
+                                  start_position=self.start_position, start_angle=self.start_angle)
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed: Optional[int] = None, options: Optional[Dict] = None):
@@ -158,7 +160,7 @@ class CarEnv(_Base):
         self.termination_reason = reason
 
     def _info(self, recs) -> Dict[str, Any]:
-        info = I.env_info(recs, self.termination_reason, self.followed_car_index)
+        info = I.env_info(recs, self.termination_reason, self.followed_car_index, hist=self._engine.velocity_history_host())
         n_bodies = 1 + self._engine.tables[self._track_index].n_walls
         for p in info["physics"]:
             p["bodies_in_world"] = n_bodies

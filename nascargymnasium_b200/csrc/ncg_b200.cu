@@ -36,6 +36,8 @@ struct KParams {
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
     int T; unsigned long long seed; int mode; unsigned step_base; unsigned car_base;
     float* obs_roll; float* rew_roll; uint8_t* done_roll;
+    StartPose start;                                       // CarEnv(start_position, start_angle)
+    float2* vel_hist;                                      // optional [N][NCG_VEL_HISTORY]: Car.velocity_history ring (info only)
     float* ep_return; int* ep_length; int* any_done;      // optional: episode return per car / length per env of finished envs
     DevStats* stats;
 };
@@ -71,8 +73,8 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
 // same-track reset of one record (kept out of line: it runs once per episode).  The observation after a reset_car is
 // the same for every car of a track -- start pose, zero velocity, fresh tyres, the 16 rays of the start pose -- so it is
 // computed once per track (ncg_reset_obs_kernel) instead of once per reset.
-__device__ __noinline__ void reset_in_place(float* R, const Track T) {
-    reset_record(R, T, false, f2u(R[NCG_R_TRACK]));
+__device__ __noinline__ void reset_in_place(float* R, const Track T, const StartPose sp) {
+    reset_record(R, T, false, f2u(R[NCG_R_TRACK]), sp);
 }
 
 struct SmemLayout {
@@ -204,6 +206,8 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                     if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
                     else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
                 } else { const float4 a = s_act[b * SLOTS + slot]; thr = a.x; brk = a.y; st = a.z; }
+                // Car.velocity_history (car.py:384-386): the speed update_physics saw, i.e. before b2World.Step (info only)
+                if (p.vel_hist) p.vel_hist[(size_t)gc * NCG_VEL_HISTORY + f2u(R[NCG_R_STEP]) % NCG_VEL_HISTORY] = make_float2(R[NCG_R_VX], R[NCG_R_VY]);
                 if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts != 0, &ctx, &cnt);
                 s_pose[b * SLOTS + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
             }
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                     if (solo || lane == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
                 }
                 // ---- same-step auto-reset (CarPhysics.reset_car semantics)
-                if (__builtin_expect(done && do_reset, 0)) reset_in_place(R, T);
+                if (__builtin_expect(done && do_reset, 0)) reset_in_place(R, T, p.start);
                 s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
             }
             __syncwarp();
@@ -356,13 +360,13 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
 }
 
 // the observation of the reset state of each track; one warp per track
-__global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, const long long* track_off, float* reset_obs) {
+__global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, const long long* track_off, float* reset_obs, const StartPose sp) {
     __shared__ float s_rec[NCG_RECORD_WORDS];
     __shared__ float s_o[40];
     const int lane = threadIdx.x, tid = blockIdx.x;
     const float* g = blob + track_off[tid];
     Track T = track_view(g, g);
-    if (lane == 0) { reset_record(s_rec, T, true, (uint32_t)tid); observe_state(s_rec, s_o); }
+    if (lane == 0) { reset_record(s_rec, T, true, (uint32_t)tid, sp); observe_state(s_rec, s_o); }
     __syncwarp();
     unsigned tests = 0;
     if (lane < 16) cast_rays<1, false>(T, s_rec[NCG_R_X], s_rec[NCG_R_Y], s_rec[NCG_R_ANGLE], lane, s_o + 22, &tests);
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, co
 
 // reset of masked envs + their initial observation; one warp per car (rays over lanes)
 __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const float* blob, const long long* track_off, int E, int C,
-                                                         const uint8_t* mask, const int* track_id, int fresh, float* obs) {
+                                                         const uint8_t* mask, const int* track_id, int fresh, float* obs, const StartPose sp) {
     const int lane = threadIdx.x & 31;
     const int car = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (car >= E * C) return;
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const fl
     uint32_t tid = track_id ? (uint32_t)track_id[env] : f2u(R[NCG_R_TRACK]);
     const float* g = blob + track_off[tid];
     Track T = track_view(g, g);
-    if (lane == 0) { reset_record(R, T, fresh != 0, tid); observe_state(R, so); }
+    if (lane == 0) { reset_record(R, T, fresh != 0, tid, sp); observe_state(R, so); }
     __syncwarp();
     if (obs) {
         unsigned tests = 0;
@@ -400,6 +404,7 @@ struct NcgHandle {
     NcgConfig cfg; int N;
     float* d_records = nullptr; float* d_blob = nullptr; long long* d_track_off = nullptr; int n_tracks = 0;
     float* d_reset_obs = nullptr;
+    float2* d_vel_hist = nullptr;                    // track_info only: the last NCG_VEL_HISTORY pre-step velocities of every car
     std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
     std::vector<int> h_env_track;
     int2* d_cta_tab = nullptr; int n_ctas = 0; int cap_ctas = 0; bool cta_dirty = true;   // groups of <= 32 car slots (one CTA each, or two per CTA)
@@ -420,6 +425,8 @@ struct NcgHandle {
 };
 
 namespace {
+
+StartPose start_pose(const NcgHandle* h) { StartPose sp; sp.x = h->cfg.start_x; sp.y = h->cfg.start_y; sp.a = h->cfg.start_angle; return sp; }
 
 // Whole envs per CTA: at most CPB car slots, fewer when that spreads a small batch over all SMs (4096 single-car
 // envs: 28 per CTA = 147 CTAs on 148 SMs instead of 128 CTAs of 32).
@@ -542,6 +549,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
 
 KParams base_params(NcgHandle* h) {
     KParams p; memset(&p, 0, sizeof(p));
+    p.start = start_pose(h); p.vel_hist = h->d_vel_hist;
     p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off; p.reset_obs = h->d_reset_obs;
     p.E = h->cfg.num_envs; p.C = h->cfg.cars_per_env; p.discrete = h->cfg.discrete; p.reset_on_lap = h->cfg.reset_on_lap;
     p.auto_reset = h->cfg.auto_reset; p.contacts = h->cfg.contacts; p.track_info = h->cfg.track_info; p.stats = h->d_stats; p.T = 1;
@@ -575,6 +583,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     size_t N = (size_t)h->N, E = (size_t)cfg->num_envs;
     CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));
     CUDA_TRY(cudaMemset(h->d_records, 0, N * NCG_RECORD_WORDS * 4));
+    if (cfg->track_info) CUDA_TRY(cudaMalloc(&h->d_vel_hist, N * NCG_VEL_HISTORY * sizeof(float2)));
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(DevStats)));
     CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(DevStats)));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -594,7 +603,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
 int ncg_destroy(NcgHandle* h) {
     if (!h) return NCG_OK;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
+    cudaFree(h->d_vel_hist); cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
     cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab);
     cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
@@ -618,7 +627,7 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
     for (int i = 0; i < n_tracks; ++i) { uint32_t w; memcpy(&w, h_blob + h_offsets[i] + TH_STAGE_WORDS, 4); h->h_stage_words.push_back(w); }
     h->n_tracks = n_tracks;
     CUDA_TRY(cudaMalloc(&h->d_reset_obs, (size_t)n_tracks * NCG_OBS_DIM * 4));
-    ncg_reset_obs_kernel<<<n_tracks, 32>>>(h->d_blob, h->d_track_off, h->d_reset_obs);
+    ncg_reset_obs_kernel<<<n_tracks, 32>>>(h->d_blob, h->d_track_off, h->d_reset_obs, start_pose(h));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     ++h->launches;
@@ -644,7 +653,7 @@ int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id
     const int threads = 256, cars_per_block = threads / 32;
     const int grid = (h->N + cars_per_block - 1) / cars_per_block;
     ncg_reset_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(h->d_records, h->d_blob, h->d_track_off, h->cfg.num_envs, h->cfg.cars_per_env,
-                                                                d_env_mask, d_track_id, fresh, d_obs);
+                                                                d_env_mask, d_track_id, fresh, d_obs, start_pose(h));
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     h->was_reset = true;
@@ -833,6 +842,15 @@ int ncg_set_state_host(NcgHandle* h, const float* h_records) {
     }
     h->cta_dirty = true;
     h->was_reset = true;
+    return NCG_OK;
+}
+
+int ncg_get_velocity_history_host(NcgHandle* h, float* h_out) {
+    if (!h || !h_out) return fail(NCG_E_INVALID, "null argument");
+    if (!h->d_vel_hist) return fail(NCG_E_STATE, "the velocity history is kept only with NcgConfig.track_info = 1");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h_out, h->d_vel_hist, (size_t)h->N * NCG_VEL_HISTORY * sizeof(float2), cudaMemcpyDeviceToHost));
     return NCG_OK;
 }
 

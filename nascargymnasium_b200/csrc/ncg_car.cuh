@@ -787,18 +787,21 @@ NCG_HDN bool on_track(const Track T, float x, float y) {
 
 // ------------------------------------------------------------------ reset (car_env.py:316-535)
 // fresh: new Box2D world (CarPhysics.__init__); otherwise CarPhysics.reset_car + Car.reset on the existing world.
-NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id) {
+// (sx, sy, sa): CarEnv(start_position=..., start_angle=...) (car_env.py:114-115, 391, 398); float32 as Box2D takes them
+struct StartPose { float x, y, a; };
+NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id, const StartPose sp) {
     uint32_t fl;
     if (fresh) {
         for (int i = 0; i < NCG_RECORD_WORDS; ++i) R[i] = 0.0f;
-        Xf xf; xf.p = mk(0.0f, 0.0f); xf.q = rot(0.0f);
+        Xf xf; xf.p = mk(sp.x, sp.y); xf.q = rot(sp.a);
+        R[NCG_R_X] = sp.x; R[NCG_R_Y] = sp.y; R[NCG_R_ANGLE] = sp.a;
         AABB a = box_aabb(car_box(), xf);
         R[NCG_R_FAT_LX] = a.lx - NCG_B2_AABB_EXT; R[NCG_R_FAT_LY] = a.ly - NCG_B2_AABB_EXT; R[NCG_R_FAT_UX] = a.ux + NCG_B2_AABB_EXT; R[NCG_R_FAT_UY] = a.uy + NCG_B2_AABB_EXT;
         fl = NCG_F_AWAKE | NCG_F_PROXY_MOVED | NCG_F_NEW_FIXTURE;
     } else {
         Body B; b_load(B, R);
-        V2 p = mk(0.0f, 0.0f);
-        b_set_transform(B, p, B.sweep.a); b_set_transform(B, p, 0.0f);
+        V2 p = mk(sp.x, sp.y);
+        b_set_transform(B, p, B.sweep.a); b_set_transform(B, p, sp.a);
         B.v = mk(0.0f, 0.0f); B.w = 0.0f;     // SetLinearVelocity(0)/SetAngularVelocity(0) do not wake
         B.impulse = 0.0f; B.hasKey = false;
         fl = f2u(R[NCG_R_FLAGS]) & (NCG_F_OVERFLOW);

@@ -47,7 +47,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 class _Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("num_envs", ctypes.c_int32), ("cars_per_env", ctypes.c_int32),
                 ("discrete", ctypes.c_int32), ("reset_on_lap", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
-                ("contacts", ctypes.c_int32), ("track_info", ctypes.c_int32)]
+                ("contacts", ctypes.c_int32), ("track_info", ctypes.c_int32),
+                ("start_x", ctypes.c_float), ("start_y", ctypes.c_float), ("start_angle", ctypes.c_float)]
 
 
 class Stats(ctypes.Structure):
@@ -62,7 +63,8 @@ class Stats(ctypes.Structure):
 EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_upload_tracks", "ncg_reset", "ncg_step",
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
-           "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs")
+           "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs",
+           "ncg_get_velocity_history_host")
 
 _lib = None
 
@@ -102,6 +104,7 @@ def load_library():
     lib.ncg_plan_ctas.restype = i32
     lib.ncg_set_rollout_base.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32]
     lib.ncg_set_episode_outputs.argtypes = [vp, vp, vp, vp]
+    lib.ncg_get_velocity_history_host.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -185,13 +188,15 @@ class Engine:
 
     def __init__(self, num_envs: int, cars_per_env: int = 1, tracks: Sequence[str] = ("nascar",), discrete: bool = False,
                  reset_on_lap: bool = False, auto_reset: bool = True, contacts: bool = True, device: int = 0,
-                 track_info: bool = False):
+                 track_info: bool = False, start_position=(0.0, 0.0), start_angle: float = 0.0):
         lib = load_library()
         self._lib = lib
         self.num_envs, self.cars_per_env = int(num_envs), int(cars_per_env)
         self.num_cars = self.num_envs * self.cars_per_env
         self.discrete, self.device = bool(discrete), int(device)
-        cfg = _Config(device, num_envs, cars_per_env, int(discrete), int(reset_on_lap), int(auto_reset), int(contacts), int(track_info))
+        cfg = _Config(device, num_envs, cars_per_env, int(discrete), int(reset_on_lap), int(auto_reset), int(contacts), int(track_info),
+                      float(start_position[0]), float(start_position[1]), float(start_angle))
+        self.track_info = bool(track_info)
         h = ctypes.c_void_p()
         _check(lib.ncg_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
@@ -356,6 +361,12 @@ class Engine:
         if records.size != self.num_cars * L.RECORD_WORDS:
             raise ValueError("records: wrong number of elements")
         _check(self._lib.ncg_set_state_host(self._h, _np_ptr(records)))
+
+    def velocity_history_host(self) -> np.ndarray:
+        """(N, 600, 2) ring of the pre-step velocities of the running episode (track_info engines only)."""
+        out = np.empty((self.num_cars, L.VEL_HISTORY, 2), dtype=np.float32)
+        _check(self._lib.ncg_get_velocity_history_host(self._h, _np_ptr(out)))
+        return out
 
     def read_stats(self, reset: bool = False) -> dict:
         s = Stats()

@@ -47,31 +47,53 @@ def lap_timing(rec: np.ndarray) -> dict:
     }
 
 
-def performance(rec: np.ndarray) -> dict:
-    """Car.validate_performance keys (car.py:1060-1098).  The 600-sample velocity history is not kept on the device;
-    ``current_max_speed`` is the episode maximum and the 0-100 km/h estimate is not available (0.0 => not valid)."""
-    return {"max_speed_ms": K.CAR_MAX_SPEED_MS, "target_100kmh_ms": K.CAR_TARGET_100KMH_MS, "target_acceleration_time": K.CAR_ACCELERATION_0_100_KMH,
-            "current_max_speed": float(rec[R["NCG_R_MAX_SPEED"]]), "estimated_0_100_time": 0.0, "performance_valid": False}
+def performance(rec: np.ndarray, hist: Optional[np.ndarray] = None) -> dict:
+    """Car.validate_performance (/root/reference/src/car.py:1060-1098) over Car.velocity_history: the (speed, dt) pairs of
+    the last 600 update_physics calls of the episode.  `hist` is the engine's (600, 2) velocity ring of this car
+    (Engine.velocity_history_host, kept with track_info=True); without it only the episode maximum is reported and the
+    result is never valid."""
+    out = {"max_speed_ms": K.CAR_MAX_SPEED_MS, "target_100kmh_ms": K.CAR_TARGET_100KMH_MS, "target_acceleration_time": K.CAR_ACCELERATION_0_100_KMH,
+           "current_max_speed": 0.0, "estimated_0_100_time": 0.0, "performance_valid": False}
+    if hist is None:
+        out["current_max_speed"] = float(rec[R["NCG_R_MAX_SPEED"]])
+        return out
+    step = _u(rec, R["NCG_R_STEP"])                    # update_physics calls since Car.reset cleared the deque
+    n = min(step, L.VEL_HISTORY)
+    if n > K.PERFORMANCE_VALIDATION_MIN_SAMPLES:
+        idx = np.arange(step - n, step) % L.VEL_HISTORY            # oldest sample of the window first
+        v = np.asarray(hist, dtype=np.float32)[idx]
+        speed = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]).astype(np.float64)   # b2Vec2.length: float32 arithmetic (car.py:928)
+        mx = float(speed.max())
+        out["current_max_speed"] = mx
+        hit = np.flatnonzero(speed >= K.CAR_TARGET_100KMH_MS)
+        if hit.size:
+            out["estimated_0_100_time"] = float(np.add.accumulate(np.full(int(hit[0]) + 1, 1.0 / 60.0))[-1])
+        t = out["estimated_0_100_time"]
+        out["performance_valid"] = bool(mx >= K.CAR_MAX_SPEED_MS * K.PERFORMANCE_SPEED_TOLERANCE and
+                                        (t <= K.CAR_ACCELERATION_0_100_KMH * K.PERFORMANCE_TIME_TOLERANCE if t > 0 else False))
+    return out
 
 
-def car_info(rec: np.ndarray, car_index: int) -> dict:
+def car_info(rec: np.ndarray, car_index: int, hist: Optional[np.ndarray] = None) -> dict:
     fl = _u(rec, R["NCG_R_FLAGS"])
     vx, vy = float(rec[R["NCG_R_VX"]]), float(rec[R["NCG_R_VY"]])
     speed = float(np.sqrt(np.float32(vx) * np.float32(vx) + np.float32(vy) * np.float32(vy)))
     return {
         "car_index": car_index, "disabled": bool(fl & F["NCG_F_DISABLED"]),
         "car_position": (float(rec[R["NCG_R_X"]]), float(rec[R["NCG_R_Y"]])), "car_speed_kmh": speed * 3.6, "car_speed_ms": speed,
-        "on_track": bool(fl & F["NCG_F_ON_TRACK"]), "performance": performance(rec), "lap_timing": lap_timing(rec),
+        "on_track": bool(fl & F["NCG_F_ON_TRACK"]), "performance": performance(rec, hist), "lap_timing": lap_timing(rec),
         "cumulative_reward": float(rec[R["NCG_R_CUM_REWARD"]]), "cumulative_impact_force": float(rec[R["NCG_R_CUM_IMPACT"]]),
     }
 
 
-def env_info(recs: np.ndarray, termination_reason: Optional[str] = None, followed_car_index: int = 0) -> dict:
-    """recs: (C,128) records of one env."""
+def env_info(recs: np.ndarray, termination_reason: Optional[str] = None, followed_car_index: int = 0,
+             hist: Optional[np.ndarray] = None) -> dict:
+    """recs: (C,128) records of one env; hist: (C,600,2) velocity rings of its cars, or None."""
     C = recs.shape[0]
     step = _u(recs[0], R["NCG_R_STEP"])
     t = sim_time(step)
-    physics = [{"physics_steps": step, "simulation_time": t, "average_fps": 60.0, "bodies_in_world": 0, **performance(recs[c])}
+    h = (lambda c: hist[c]) if hist is not None else (lambda c: None)
+    physics = [{"physics_steps": step, "simulation_time": t, "average_fps": 60.0, "bodies_in_world": 0, **performance(recs[c], h(c))}
                for c in range(C)]
     return {"simulation_time": t, "num_cars": C, "followed_car_index": followed_car_index, "termination_reason": termination_reason,
-            "cars": [car_info(recs[c], c) for c in range(C)], "physics": physics}
+            "cars": [car_info(recs[c], c, h(c)) for c in range(C)], "physics": physics}

@@ -45,3 +45,4 @@ OBS_DIM = DEFS["NCG_OBS_DIM"]
 MAX_CONTACTS = DEFS["NCG_MAX_CONTACTS"]
 MAX_TOUCHING = DEFS["NCG_MAX_TOUCHING"]
 MAX_ACTIVE = DEFS["NCG_MAX_ACTIVE"]
+VEL_HISTORY = DEFS["NCG_VEL_HISTORY"]

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """TEST INFRASTRUCTURE: generate tests/golden/* by running the REFERENCE's own code in the build container.
 
-    python oracle/gen_golden.py            # needs /root/reference (read-only); writes tests/golden/
+    python oracle/gen_golden.py                # needs /root/reference (read-only); writes tests/golden/
+    python oracle/gen_golden.py --real-box2d   # on a machine with `pip install box2d-py==2.3.8`: the same trajectories
+                                               # over REAL Box2D, written to tests/golden_real/ (pins the Box2D half)
 
 What runs: the reference's unmodified modules (src/car_env.py, car.py, car_physics.py, tyre*.py, lap_timer.py,
 track_generator.py, distance_sensor.py, constants/*) imported from /root/reference, over the stand-in modules in
@@ -22,8 +24,32 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 REF = os.environ.get("NCG_REFERENCE", "/root/reference")
 OUT = os.path.join(ROOT, "tests", "golden")
+REAL_BOX2D = "--real-box2d" in sys.argv
+if REAL_BOX2D:
+    OUT = os.path.join(ROOT, "tests", "golden_real")
 sys.path = [p for p in sys.path if os.path.abspath(p or ".") != HERE]      # "oracle" must resolve to the package
-sys.path.insert(0, os.path.join(HERE, "refshim"))
+
+
+def _stub_path():
+    """A directory holding only the stand-in modules that are needed: a module that imports for real is used for real
+    (and with --real-box2d the Box2D stand-in is never offered, so a missing box2d-py is an ImportError, not a silent
+    fall-back to the restatement)."""
+    import importlib.util
+    import tempfile
+    d = tempfile.mkdtemp(prefix="ncg_refshim_")
+    used = []
+    for mod in ("pygame", "gymnasium", "Box2D"):
+        if mod == "Box2D" and REAL_BOX2D:
+            continue
+        if mod != "Box2D" and importlib.util.find_spec(mod) is not None:
+            continue
+        os.symlink(os.path.join(HERE, "refshim", mod), os.path.join(d, mod))
+        used.append(mod)
+    print("stand-in modules:", used or "none", "| Box2D:", "REAL box2d-py" if REAL_BOX2D else "oracle/b2lite.h restatement")
+    return d
+
+
+sys.path.insert(0, _stub_path())
 sys.path.insert(0, REF)
 sys.path.insert(0, ROOT)
 
@@ -44,15 +70,15 @@ def controller(obs, state):
     return [tb, steer]
 
 
-def run(name, track, steps, policy, num_cars=1, discrete=False, reset_on_lap=False, seed=0):
+def run(name, track, steps, policy, num_cars=1, discrete=False, reset_on_lap=False, seed=0, start_position=None, start_angle=0.0):
     from src.car_env import CarEnv
     rng = np.random.default_rng(seed)
     with quiet():
         env = CarEnv(render_mode=None, track_file=os.path.join(REF, "tracks", f"{track}.track"), num_cars=num_cars,
-                     discrete_action_space=discrete, reset_on_lap=reset_on_lap)
+                     discrete_action_space=discrete, reset_on_lap=reset_on_lap, start_position=start_position, start_angle=start_angle)
         obs, info = env.reset()
     C = num_cars
-    A, O, R, TE, TR, RS, LAPS, DIS, ST, REASON, ONTRACK = [], [], [], [], [], [], [], [], [], [], []
+    A, O, R, TE, TR, RS, LAPS, DIS, ST, REASON, ONTRACK, PERF = [], [], [], [], [], [], [], [], [], [], [], []
     obs0 = np.array(obs, dtype=np.float32).reshape(C, 38)
     cur = obs0
     for t in range(steps):
@@ -83,6 +109,8 @@ def run(name, track, steps, policy, num_cars=1, discrete=False, reset_on_lap=Fal
         LAPS.append([info["cars"][c]["lap_timing"]["lap_count"] for c in range(C)])
         DIS.append([info["cars"][c]["disabled"] for c in range(C)])
         ONTRACK.append([info["cars"][c]["on_track"] for c in range(C)])
+        PERF.append([[info["cars"][c]["performance"][k] for k in ("current_max_speed", "estimated_0_100_time", "performance_valid")]
+                     for c in range(C)])
         ST.append(info["simulation_time"]); REASON.append(info["termination_reason"] or "")
         did_reset = False
         if te or tr:
@@ -97,7 +125,8 @@ def run(name, track, steps, policy, num_cars=1, discrete=False, reset_on_lap=Fal
     np.savez_compressed(os.path.join(OUT, f"traj_{name}.npz"), track=track, num_cars=C, discrete=discrete, reset_on_lap=reset_on_lap,
                         obs0=obs0, actions=np.array(A), obs=np.array(O), reward=np.array(R), terminated=np.array(TE), truncated=np.array(TR),
                         did_reset=np.array(RS), lap_count=np.array(LAPS), disabled=np.array(DIS), on_track=np.array(ONTRACK),
-                        sim_time=np.array(ST), reason=np.array(REASON))
+                        sim_time=np.array(ST), reason=np.array(REASON), performance=np.array(PERF, dtype=np.float64),
+                        start_pose=np.array([*(start_position or (0.0, 0.0)), start_angle], dtype=np.float64))
     print(f"{name}: {steps} steps, {int(np.sum(TE))} terminations, {int(np.sum(TR))} truncations, laps {np.max(LAPS)}, "
           f"disabled {int(np.sum(DIS[-1]))}, collision steps {int(np.sum(np.array(O)[:, :, 19] > 0))}, return {float(np.sum(R)):.2f}")
 
@@ -163,8 +192,9 @@ def dump_unit_kats():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    dump_constants_and_tracks()
-    dump_unit_kats()
+    if not REAL_BOX2D:                 # (pure-Python pins; the wall dump reads the stand-in's attributes)
+        dump_constants_and_tracks()
+        dump_unit_kats()
     run("nascar_full", "nascar", 1200, "full")
     run("nascar_zero", "nascar", 650, "zero")
     run("martinsville_drive", "martinsville", 2500, "drive", seed=1)
@@ -175,3 +205,6 @@ if __name__ == "__main__":
     run("nascar2_reverse", "nascar2", 2600, "reverse", seed=6)
     run("trioval_3cars_laplimit", "trioval", 3700, "controller", num_cars=3, reset_on_lap=True, seed=7)
     run("nascar_banked_controller", "nascar_banked", 2400, "controller", seed=8)      # the one track with banking (car.py:509-566)
+    # CarEnv(start_position=..., start_angle=...): a start off the racing line, pointing at the outer wall
+    run("nascar_startpose", "nascar", 900, "controller", seed=9, start_position=(30.0, -4.0), start_angle=0.35)
+    run("daytona_startpose_2cars", "daytona", 700, "drive", num_cars=2, seed=10, start_position=(-120.0, 6.0), start_angle=-0.2)

@@ -61,6 +61,7 @@ def lib():
         L.orc_env_create.argtypes = [vp, i, i]
         L.orc_env_free.argtypes = [vp]
         L.orc_env_reset.argtypes = [vp, i]
+        L.orc_env_set_start.argtypes = [vp, d, d, d]
         L.orc_env_walls.argtypes = [vp, P(f)]
         L.orc_action_continuous.argtypes = [f, f, P(f)]
         L.orc_action_discrete.argtypes = [i, P(f)]
@@ -136,11 +137,15 @@ class OracleTrack:
 class OracleEnv:
     """Sequential CPU CarEnv restatement: one env of ``num_cars`` cars."""
 
-    def __init__(self, track_text: str, num_cars: int = 1, reset_on_lap: bool = False, discrete: bool = False):
+    def __init__(self, track_text: str, num_cars: int = 1, reset_on_lap: bool = False, discrete: bool = False,
+                 start_position=(0.0, 0.0), start_angle: float = 0.0):
         self.track = OracleTrack(track_text)
         self.num_cars = num_cars
         self.discrete = discrete
         self._h = lib().orc_env_create(self.track._h, num_cars, int(reset_on_lap))
+        if tuple(start_position) != (0.0, 0.0) or start_angle != 0.0:
+            lib().orc_env_set_start(self._h, float(start_position[0]), float(start_position[1]), float(start_angle))
+            lib().orc_env_reset(self._h, 1)
         self.words = state_layout()["S_WORDS"]
 
     def reset(self, fresh: bool = True) -> np.ndarray:

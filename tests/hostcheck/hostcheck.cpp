@@ -31,7 +31,7 @@ void hc_env_reset(const float* blob, float* records, int C, int fresh, int track
     Track T = track_view(blob, blob);
     for (int i = 0; i < C; ++i) {
         float* R = records + i * NCG_RECORD_WORDS;
-        reset_record(R, T, fresh != 0, (uint32_t)track_id);
+        { StartPose sp; sp.x = 0.0f; sp.y = 0.0f; sp.a = 0.0f; reset_record(R, T, fresh != 0, (uint32_t)track_id, sp); }
         if (obs) {
             observe_state(R, obs + i * 38);
             unsigned tests = 0;

@@ -90,12 +90,14 @@ def test_engine_free_runs_the_reference_generated_trajectories(path):
     with np.load(path) as z:
         g = {k: z[k] for k in z.files}
     track, C = str(g["track"]), int(g["num_cars"])
-    eng = Engine(1, C, tracks=[track], discrete=bool(g["discrete"]), reset_on_lap=bool(g["reset_on_lap"]), auto_reset=False)
+    sp = g["start_pose"]
+    eng = Engine(1, C, tracks=[track], discrete=bool(g["discrete"]), reset_on_lap=bool(g["reset_on_lap"]), auto_reset=False,
+                 start_position=(float(sp[0]), float(sp[1])), start_angle=float(sp[2]))
     obs0 = eng.reset_host()
     assert np.abs(obs0.reshape(C, 38) - g["obs0"]).max() < 1e-6
     contact = np.nonzero((g["obs"][:, :, 19] > 0).any(axis=1))[0]
     n = int(contact[0]) if len(contact) else len(g["actions"])
-    assert n >= 200, (path, n)
+    assert n >= 60, (path, n)
     worst = 0.0
     for t in range(n):
         a = g["actions"][t]
@@ -107,4 +109,52 @@ def test_engine_free_runs_the_reference_generated_trajectories(path):
         if g["did_reset"][t]:
             eng.reset_host(fresh=False)
     print(os.path.basename(path), "steps compared", n, "of", len(g["actions"]), "max |dobs|", worst)
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["martinsville_laps", "nascar_full", "talladega_10cars", "nascar2_reverse", "nascar_startpose"])
+def test_info_dict_replays_the_reference_recorded_info(name):
+    """info["cars"][i]: lap_count, disabled, on_track and the validate_performance triple (600-sample velocity window) as
+    the reference's own CarEnv reported them (tests/golden, oracle/gen_golden.py), rebuilt by nascargymnasium_b200.info from
+    the engine's records and velocity ring.  The engine is teacher-forced from the (reference-pinned) oracle replay before
+    every step, so a lap completed after several wall contacts is still the same lap."""
+    from nascargymnasium_b200 import info as I
+    from nascargymnasium_b200.engine import Engine
+    from oracle import oracle as O
+    from tests import parity_util as P
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"traj_{name}.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    track, C = str(g["track"]), int(g["num_cars"])
+    sp = g["start_pose"]
+    kw = dict(start_position=(float(sp[0]), float(sp[1])), start_angle=float(sp[2]))
+    orc = O.OracleEnv(T.builtin_track_text(track), num_cars=C, reset_on_lap=bool(g["reset_on_lap"]), discrete=bool(g["discrete"]), **kw)
+    orc.reset()
+    eng = Engine(1, C, tracks=[track], discrete=bool(g["discrete"]), reset_on_lap=bool(g["reset_on_lap"]), auto_reset=False,
+                 track_info=True, **kw)
+    eng.reset_host()
+    n = min(len(g["actions"]), 2000)
+    laps_seen = dis_seen = 0
+    for t in range(n):
+        a = g["actions"][t]
+        recs = np.stack([P.oracle_to_record(orc.get_state(c)) for c in range(C)])
+        eng.set_state_host(recs)
+        orc.step(a if not g["discrete"] else a.astype(np.int64))
+        eng.step_host(a.astype(np.int32) if g["discrete"] else a.astype(np.float32))
+        info = I.env_info(eng.get_state_host(), hist=eng.velocity_history_host())
+        for c in range(C):
+            ci = info["cars"][c]
+            assert ci["lap_timing"]["lap_count"] == int(g["lap_count"][t][c]), (t, c)
+            assert ci["disabled"] == bool(g["disabled"][t][c]), (t, c)
+            assert ci["on_track"] == bool(g["on_track"][t][c]), (t, c)
+            mx, t100, ok = g["performance"][t][c]
+            pf = ci["performance"]
+            assert pf["current_max_speed"] == pytest.approx(mx, rel=1e-4, abs=1e-4), (t, c)
+            assert pf["estimated_0_100_time"] == pytest.approx(t100, abs=1e-9), (t, c)
+            assert pf["performance_valid"] == bool(ok), (t, c)
+        assert info["simulation_time"] == pytest.approx(float(g["sim_time"][t]), abs=1e-12)
+        laps_seen = max(laps_seen, int(g["lap_count"][t].max())); dis_seen = max(dis_seen, int(g["disabled"][t].sum()))
+        if g["did_reset"][t]:
+            orc.reset(fresh=False)
+            eng.reset_host(fresh=False)
+    print(name, "steps", n, "laps seen", laps_seen, "cars disabled", dis_seen)
     eng.close()

@@ -32,7 +32,9 @@ def test_oracle_reproduces_reference_trajectory(path):
     with np.load(path) as z:
         g = {k: z[k] for k in z.files}            # NpzFile re-inflates on every access
     track, C = str(g["track"]), int(g["num_cars"])
-    env = O.OracleEnv(T.builtin_track_text(track), num_cars=C, reset_on_lap=bool(g["reset_on_lap"]), discrete=bool(g["discrete"]))
+    sp = g["start_pose"]
+    env = O.OracleEnv(T.builtin_track_text(track), num_cars=C, reset_on_lap=bool(g["reset_on_lap"]), discrete=bool(g["discrete"]),
+                      start_position=(float(sp[0]), float(sp[1])), start_angle=float(sp[2]))
     obs0 = env.reset()
     assert np.abs(obs0 - g["obs0"]).max() < 1e-7
     n = len(g["actions"])
