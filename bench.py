@@ -402,6 +402,27 @@ def workload_text(envs, cars, track, mode, per_gpu=True):
             "16-ray observations written every step, same-step auto-reset")
 
 
+def config5_learner_loop(device: int):
+    """BASELINE config 5: the PPO collection loop (examples/ppo_rollout.py: 2x64 tanh actor-critic in torch, Discrete(5),
+    16384 envs on martinsville) over NascarVectorEnv.step_torch, observations never leaving the device; env-steps/s of the
+    rollout phase, policy inference included.  Run as the example itself, in a subprocess."""
+    cmd = [sys.executable, os.path.join(ROOT, "examples", "ppo_rollout.py"), "--envs", "16384", "--track", "martinsville", "--discrete", "1",
+           "--iters", "3", "--n-steps", "128"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(device)) if "CUDA_VISIBLE_DEVICES" in os.environ else str(device))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+        best = max(rows, key=lambda r: r["rollout_env_steps_per_s"])
+        return {"value": best["rollout_env_steps_per_s"], "unit": "env-steps/s", "envs": 16384, "n_steps": best["n_steps"],
+                "rollout_s": best["rollout_s"], "update_s": best["update_s"], "obs_device": best["obs_device"],
+                "workload": "PPO rollout collection, Discrete(5), 16384 single-car envs on martinsville.track, torch MLP policy in "
+                            "the loop, one CUDA graph per step (policy + env kernel + buffer writes), best of 3 iterations"}
+    except Exception as e:  # the learner example is informational: never fail the bench line over it
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def run_ours(args):
     b = Bench(args)
     world, rank = b.world, b.rank
@@ -443,6 +464,8 @@ def run_ours(args):
             for Es in (8192, 16384, 65536):
                 ex[f"daytona_{Es}"] = dict(b.measure(Es, 1, "daytona", 0, 200, 600, args.steps_per_launch, 3000), scaling="weak",
                                            workload=workload_text(Es, 1, "daytona", 0))
+        if world == 1 and rank == 0 and args.config5:
+            ex["config5"] = config5_learner_loop(b.local)
         line["workloads"] = ex
     line["gpu_launches"] = int(b.launches)
     if rank == 0 and world == 1:
@@ -495,6 +518,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--extras", type=int, default=1, help="1: also measure the driving distribution and BASELINE configs 3 and 4")
+    ap.add_argument("--config5", type=int, default=1, help="1: also run the PPO collection loop of BASELINE config 5 (N=1 only)")
     ap.add_argument("--sweep", type=int, default=1, help="1: also time the rollout kernel at 8192/16384/65536 envs (N=1 only)")
     ap.add_argument("--mode", type=int, default=0, help="synthetic action distribution: 0 = action_space.sample() (the metric), "
                     "1 = 'driving' (tb~U[0.2,1], steer~U[-0.2,0.6]: laps, wall contacts, episodes)")

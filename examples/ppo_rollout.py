@@ -106,8 +106,13 @@ def main():
             b_obs.index_copy_(0, t.view(1), obs.unsqueeze(0)); b_act.index_copy_(0, t.view(1), a.unsqueeze(0))
             b_logp.index_copy_(0, t.view(1), logp.unsqueeze(0)); b_val.index_copy_(0, t.view(1), val.unsqueeze(0))
         env_a = a.to(torch.int32) if discrete else a.clamp(-1.0, 1.0)
-        _obs, rew, te, tr, _final = venv.step_torch(env_a)          # writes the engine's buffers in place: _obs is `obs`
+        _obs, rew, te, tr, final = venv.step_torch(env_a)           # writes the engine's buffers in place: _obs is `obs`
         done = (te | tr).to(torch.float32)
+        # an episode cut by the 180 s limit is not a terminal state: bootstrap from the value of its last observation, as
+        # SB3's on-policy collector does for "TimeLimit.truncated" (final rows of envs that did not finish are stale and
+        # masked out; `rew` is a fresh tensor so the engine's buffer is left alone)
+        trunc_only = (tr != 0) & (te == 0)
+        rew = rew + torch.where(trunc_only, args.gamma * net.v(final).squeeze(-1), torch.zeros_like(rew))
         if isinstance(t, int):
             b_rew[t], b_done[t] = rew, done
         else:

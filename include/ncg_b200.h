@@ -114,7 +114,9 @@ typedef struct NcgConfig {
     int32_t discrete;        /* 0: actions float32 (E,C,2) in [-1,1]; 1: int32 (E,C) in 0..4 */
     int32_t reset_on_lap;    /* CarEnv(reset_on_lap=...) */
     int32_t auto_reset;      /* 1: envs that finish are reset inside the same step (VecEnv semantics) */
-    int32_t contacts;        /* 1: car-wall contact solver + TOI enabled (default); 0: contact-free integrator */
+    int32_t contacts;        /* 1: car-wall contact solver + TOI enabled (default), b2CollidePolygons as in Box2D 2.3.1+;
+                                2: the same with b2CollidePolygons as in Box2D 2.3.0 (edge-walk b2FindMaxSeparation,
+                                k_relativeTol/k_absoluteTol); 0: contact-free integrator */
     int32_t track_info;      /* 1: also keep what only the info dict needs: is_car_on_track() every step (NCG_F_ON_TRACK)
                                 and the 600-sample velocity history behind validate_performance (src/car.py:1060-1098) */
     float start_x, start_y;  /* CarEnv(start_position=...) (src/car_env.py:114, 391, 398); (0, 0) = the GRID segment's start */

@@ -144,6 +144,38 @@ NCG_HD float find_max_separation(int* edge, const Box& b1, const Xf& xf1, const 
     }
     *edge = best; return maxSep;
 }
+// Box2D 2.3.0's form of the same search (b2EdgeSeparation + hill climb from the edge facing the other centroid): the one
+// place the 2.3.x releases differ for this world, selectable because which one box2d-py 2.3.8 bundles cannot be checked
+// offline (NcgConfig.contacts = 2; oracle/b2lite.h g_collide_variant; profiles/r02_b2_version_study.json)
+NCG_HD float edge_separation230(const Box& b1, const Xf& xf1, int edge1, const Box& b2, const Xf& xf2) {
+    V2 n1w = mul(xf1.q, box_n(edge1));
+    V2 n1 = mulT(xf2.q, n1w);
+    int index = 0; float minDot = NCG_B2_MAXFLOAT;
+    for (int i = 0; i < 4; ++i) { float d = dot(box_v(b2, i), n1); if (d < minDot) { minDot = d; index = i; } }
+    V2 v1 = mul(xf1, box_v(b1, edge1)), v2 = mul(xf2, box_v(b2, index));
+    return dot(v2 - v1, n1w);
+}
+NCG_HDN float find_max_separation230(int* edgeOut, const Box& b1, const Xf& xf1, const Box& b2, const Xf& xf2) {
+    V2 d = mul(xf2, mk(0.0f, 0.0f)) - mul(xf1, mk(0.0f, 0.0f));
+    V2 dl = mulT(xf1.q, d);
+    int edge = 0; float maxDot = -NCG_B2_MAXFLOAT;
+    for (int i = 0; i < 4; ++i) { float dt = dot(box_n(i), dl); if (dt > maxDot) { maxDot = dt; edge = i; } }
+    float s = edge_separation230(b1, xf1, edge, b2, xf2);
+    int prevEdge = edge - 1 >= 0 ? edge - 1 : 3;
+    float sPrev = edge_separation230(b1, xf1, prevEdge, b2, xf2);
+    int nextEdge = edge + 1 < 4 ? edge + 1 : 0;
+    float sNext = edge_separation230(b1, xf1, nextEdge, b2, xf2);
+    int bestEdge, increment; float bestSep;
+    if (sPrev > s && sPrev > sNext) { increment = -1; bestEdge = prevEdge; bestSep = sPrev; }
+    else if (sNext > s) { increment = 1; bestEdge = nextEdge; bestSep = sNext; }
+    else { *edgeOut = edge; return s; }
+    for (;;) {
+        edge = increment == -1 ? (bestEdge - 1 >= 0 ? bestEdge - 1 : 3) : (bestEdge + 1 < 4 ? bestEdge + 1 : 0);
+        s = edge_separation230(b1, xf1, edge, b2, xf2);
+        if (s > bestSep) { bestEdge = edge; bestSep = s; } else break;
+    }
+    *edgeOut = bestEdge; return bestSep;
+}
 NCG_HD int clip_segment(ClipV out[2], const ClipV in[2], V2 normal, float offset, int vertexIndexA) {
     int n = 0;
     float d0 = dot(normal, in[0].v) - offset, d1 = dot(normal, in[1].v) - offset;
@@ -157,16 +189,17 @@ NCG_HD int clip_segment(ClipV out[2], const ClipV in[2], V2 normal, float offset
     }
     return n;
 }
-NCG_HD void collide_boxes(Manifold* m, const Box& bA, const Xf& xfA, const Box& bB, const Xf& xfB) {
+// v230: false = b2CollidePolygons of Box2D 2.3.1 and later (the default), true = of 2.3.0
+NCG_HD void collide_boxes(Manifold* m, const Box& bA, const Xf& xfA, const Box& bB, const Xf& xfB, bool v230 = false) {
     m->pc = 0;
     const float totalRadius = NCG_B2_POLY_RADIUS + NCG_B2_POLY_RADIUS;
-    int edgeA = 0; float sepA = find_max_separation(&edgeA, bA, xfA, bB, xfB);
+    int edgeA = 0; float sepA = v230 ? find_max_separation230(&edgeA, bA, xfA, bB, xfB) : find_max_separation(&edgeA, bA, xfA, bB, xfB);
     if (sepA > totalRadius) return;
-    int edgeB = 0; float sepB = find_max_separation(&edgeB, bB, xfB, bA, xfA);
+    int edgeB = 0; float sepB = v230 ? find_max_separation230(&edgeB, bB, xfB, bA, xfA) : find_max_separation(&edgeB, bB, xfB, bA, xfA);
     if (sepB > totalRadius) return;
     Box b1, b2; Xf xf1, xf2; int edge1, flip;
     const float k_tol = 0.1f * NCG_B2_LINEAR_SLOP;
-    if (sepB > sepA + k_tol) { b1 = bB; b2 = bA; xf1 = xfB; xf2 = xfA; edge1 = edgeB; m->type = FACE_B; flip = 1; }
+    if (v230 ? (sepB > 0.98f * sepA + 0.001f) : (sepB > sepA + k_tol)) { b1 = bB; b2 = bA; xf1 = xfB; xf2 = xfA; edge1 = edgeB; m->type = FACE_B; flip = 1; }
     else { b1 = bA; b2 = bB; xf1 = xfA; xf2 = xfB; edge1 = edgeA; m->type = FACE_A; flip = 0; }
     ClipV inc[2];
     {   // b2FindIncidentEdge

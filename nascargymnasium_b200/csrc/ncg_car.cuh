@@ -78,6 +78,7 @@ struct World {
     int ni; int isl[NCG_MAX_TOUCHING]; VC vc[NCG_MAX_TOUCHING]; PC pcs[NCG_MAX_TOUCHING];
     V2 pc_c; float pc_a; V2 pv; float pw;
     unsigned toi_events;
+    bool v230;                                  // b2CollidePolygons as in Box2D 2.3.0 (see collide_boxes)
 };
 NCG_HD Box car_box() { Box b; b.hx = NCG_CAR_HALF_LENGTH; b.hy = NCG_CAR_HALF_WIDTH; return b; }
 #define NCG_INV_MASS (1.0f / NCG_CAR_MASS)
@@ -173,7 +174,7 @@ NCG_HDN void w_update_contact(World& W, const Track& T, Contact& c) {
     c.enabled = true;
     bool was = c.touching;
     Xf xfB; Box bB; wall_get(T, c.wall, &xfB, &bB);
-    collide_boxes(&c.m, car_box(), W.b.xf, bB, xfB);
+    collide_boxes(&c.m, car_box(), W.b.xf, bB, xfB, W.v230);
     bool touching = c.m.pc > 0;
     for (int i = 0; i < c.m.pc; ++i) {
         c.m.ni[i] = 0.0f; c.m.ti[i] = 0.0f;
@@ -570,8 +571,8 @@ NCG_HD bool any_wall_overlap(const Track& T, const AABB& fat) {
 // overlaps a wall; continue from FindNewContacts.
 // (Track by value and the caller passes copies of its Body / Counters: nothing of the inlined fast path has its
 // address taken, so the fast path keeps all of it in registers.)
-NCG_HDN void step_with_contacts(Body& B, float* R, const Track T, float dt, bool resume, Counters* cnt) {
-    World W; W.b = B;
+NCG_HDN void step_with_contacts(Body& B, float* R, const Track T, float dt, bool resume, bool v230, Counters* cnt) {
+    World W; W.b = B; W.v230 = v230;
     w_load_contacts(W, R);
     float dtRatio = B.inv_dt0 * dt;
     if (!resume) {
@@ -588,7 +589,8 @@ NCG_HDN void step_with_contacts(Body& B, float* R, const Track T, float dt, bool
     cnt->toi_events += W.toi_events;
 }
 // b2World::Step
-NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts, Counters* cnt) {
+// contacts: 0 = contact-free integrator, 1 = Box2D 2.3.1+ collision, 2 = Box2D 2.3.0 collision (NcgConfig.contacts)
+NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, int contacts, Counters* cnt) {
     const float inv_dt = 1.0f / dt;
     const int nc = (int)(f2u(R[NCG_R_NCONTACT]) & 255u);
     bool slow = contacts && nc > 0;
@@ -611,7 +613,7 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, bool contacts
         }
     }
     // one cold block for both ways in (a copy of the body goes in and comes back: see step_with_contacts)
-    if (__builtin_expect(solver != 0, 0)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, solver == 2, &c2); B = b2; *cnt = c2; }
+    if (__builtin_expect(solver != 0, 0)) { Body b2 = B; Counters c2 = *cnt; step_with_contacts(b2, R, T, dt, solver == 2, contacts == 2, &c2); B = b2; *cnt = c2; }
     B.inv_dt0 = inv_dt;
     B.force = mk(0.0f, 0.0f); B.torque = 0.0f;
 }
@@ -878,7 +880,7 @@ NCG_HDN float banking_force(float bank) {
     return NCG_CAR_MASS * 9.81f * sb * 0.3f;
 }
 struct StepCtx { uint32_t fl, xf, laps_pre; bool dis_pre; float impulse; };
-NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, StepCtx* ctx,
+NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, int contacts, StepCtx* ctx,
                                Counters* cnt) {
     uint32_t fl = f2u(R[NCG_R_FLAGS]);
     uint32_t xf = 0;
@@ -1107,7 +1109,7 @@ NCG_HD float car_step_rules(float* R, const Track& T, const StepCtx* ctx, float*
     *xflags = xf;
     return reward;
 }
-NCG_HD float car_step(float* R, const Track& T, float thr_in, float brk_in, float steer_in, bool contacts, float* obs,
+NCG_HD float car_step(float* R, const Track& T, float thr_in, float brk_in, float steer_in, int contacts, float* obs,
                       uint32_t* xflags, Counters* cnt) {
     StepCtx ctx;
     car_step_dynamics(R, T, thr_in, brk_in, steer_in, contacts, &ctx, cnt);

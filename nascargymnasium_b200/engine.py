@@ -24,6 +24,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+# Which Box2D 2.3.x b2CollidePolygons the contact path follows (include/ncg_b200.h NcgConfig.contacts): box2d-py 2.3.8
+# bundles one of them and the two give different manifolds for ~2.6 % of touching box poses (profiles/r02_b2_version_study.json).
+# NCG_BOX2D=2.3.0 selects the older form for every engine created with contacts=True.
+DEFAULT_CONTACTS = 2 if os.environ.get("NCG_BOX2D", "").strip() == "2.3.0" else 1
+
+
 class NcgError(RuntimeError):
     pass
 
@@ -194,7 +200,8 @@ class Engine:
         self.num_envs, self.cars_per_env = int(num_envs), int(cars_per_env)
         self.num_cars = self.num_envs * self.cars_per_env
         self.discrete, self.device = bool(discrete), int(device)
-        cfg = _Config(device, num_envs, cars_per_env, int(discrete), int(reset_on_lap), int(auto_reset), int(contacts), int(track_info),
+        cfg = _Config(device, num_envs, cars_per_env, int(discrete), int(reset_on_lap), int(auto_reset),
+                      DEFAULT_CONTACTS if contacts is True else int(contacts), int(track_info),
                       float(start_position[0]), float(start_position[1]), float(start_angle))
         self.track_info = bool(track_info)
         h = ctypes.c_void_p()

@@ -129,11 +129,12 @@ class NascarVectorEnv:
         aux = self._aux.arrays
         a = np.asarray(actions)
         if self.validate_actions:
-            # CarEnv.step asserts action_space.contains(action) on every step (/root/reference/src/car_env.py:694)
+            # CarEnv.step asserts action_space.contains(action) on every step (/root/reference/src/car_env.py:694); two
+            # reductions without temporaries (a NaN makes min/max NaN and fails the comparison)
             if self.discrete:
-                assert a.dtype.kind in "iu" and a.size == aux["actions"].size and ((a >= 0) & (a < 5)).all(), "Invalid action"
+                assert a.dtype.kind in "iu" and a.size == aux["actions"].size and a.min() >= 0 and a.max() < 5, "Invalid action"
             else:
-                assert a.dtype == np.float32 and a.size == aux["actions"].size and (np.abs(a) <= 1.0).all(), "Invalid action"
+                assert a.dtype == np.float32 and a.size == aux["actions"].size and a.min() >= -1.0 and a.max() <= 1.0, "Invalid action"
         aux["actions"][...] = a.reshape(aux["actions"].shape)
         blk = self._next_result_block()
         spill = blk is None
@@ -166,7 +167,7 @@ class NascarVectorEnv:
             dev = f"cuda:{self.engine.device}"
             N, E = self.engine.num_cars, self.num_envs
             self._torch_bufs = dict(obs=torch.empty((N, K.OBS_DIM), dtype=torch.float32, device=dev),
-                                    final=torch.empty((N, K.OBS_DIM), dtype=torch.float32, device=dev),
+                                    final=torch.zeros((N, K.OBS_DIM), dtype=torch.float32, device=dev),
                                     rew=torch.empty(N, dtype=torch.float32, device=dev),
                                     te=torch.empty(E, dtype=torch.uint8, device=dev), tr=torch.empty(E, dtype=torch.uint8, device=dev),
                                     ep_return=torch.zeros(N, dtype=torch.float32, device=dev), ep_length=torch.zeros(E, dtype=torch.int32, device=dev),

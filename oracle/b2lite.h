@@ -187,7 +187,50 @@ static inline uint32_t mkKey(int indexA, int indexB, int typeA, int typeB) {
 }
 struct ClipVertex { V2 v; int indexA, indexB, typeA, typeB; };   // type: 0 vertex, 1 face
 
+// Which upstream minor's b2CollidePolygons is restated -- the one place where 2.3.x releases differ for this world:
+//   0 = v2.3.1 and later: b2FindMaxSeparation is a brute-force max over all edge normals, evaluated in poly2's frame,
+//       and the reference face flips to B when separationB > separationA + 0.1 * b2_linearSlop;
+//   1 = v2.3.0: b2EdgeSeparation per edge normal (support vertex of poly2, separation measured in world coordinates),
+//       b2FindMaxSeparation hill-climbs from the edge whose normal points most towards poly2's centroid, and the flip
+//       test is separationB > 0.98 * separationA + 0.001 (k_relativeTol / k_absoluteTol).
+// Which of the two box2d-py 2.3.8 bundles cannot be checked offline; tools/b2_version_study.py measures how often the
+// two disagree on this world's contacts, and tests/test_b2_variants.py keeps the goldens identical under both.
+static int g_collide_variant = 0;
+
+static inline f32 edgeSeparation230(const Poly& p1, const Xf& xf1, int edge1, const Poly& p2, const Xf& xf2) {
+    V2 normal1World = mul(xf1.q, p1.n[edge1]);
+    V2 normal1 = mulT(xf2.q, normal1World);
+    int index = 0; f32 minDot = kMaxFloat;
+    for (int i = 0; i < 4; ++i) { f32 d = dot(p2.v[i], normal1); if (d < minDot) { minDot = d; index = i; } }
+    V2 v1 = mul(xf1, p1.v[edge1]);
+    V2 v2 = mul(xf2, p2.v[index]);
+    return dot(v2 - v1, normal1World);
+}
+static inline f32 findMaxSeparation230(int* edgeIndex, const Poly& p1, const Xf& xf1, const Poly& p2, const Xf& xf2) {
+    // vector from the centroid of poly1 to the centroid of poly2 (SetAsBox: both centroids are the body origins)
+    V2 d = mul(xf2, mk(0.0f, 0.0f)) - mul(xf1, mk(0.0f, 0.0f));
+    V2 dLocal1 = mulT(xf1.q, d);
+    int edge = 0; f32 maxDot = -kMaxFloat;
+    for (int i = 0; i < 4; ++i) { f32 dt = dot(p1.n[i], dLocal1); if (dt > maxDot) { maxDot = dt; edge = i; } }
+    f32 s = edgeSeparation230(p1, xf1, edge, p2, xf2);
+    int prevEdge = edge - 1 >= 0 ? edge - 1 : 3;
+    f32 sPrev = edgeSeparation230(p1, xf1, prevEdge, p2, xf2);
+    int nextEdge = edge + 1 < 4 ? edge + 1 : 0;
+    f32 sNext = edgeSeparation230(p1, xf1, nextEdge, p2, xf2);
+    int bestEdge; f32 bestSeparation; int increment;
+    if (sPrev > s && sPrev > sNext) { increment = -1; bestEdge = prevEdge; bestSeparation = sPrev; }
+    else if (sNext > s) { increment = 1; bestEdge = nextEdge; bestSeparation = sNext; }
+    else { *edgeIndex = edge; return s; }
+    for (;;) {
+        if (increment == -1) edge = bestEdge - 1 >= 0 ? bestEdge - 1 : 3;
+        else edge = bestEdge + 1 < 4 ? bestEdge + 1 : 0;
+        s = edgeSeparation230(p1, xf1, edge, p2, xf2);
+        if (s > bestSeparation) { bestEdge = edge; bestSeparation = s; } else break;
+    }
+    *edgeIndex = bestEdge; return bestSeparation;
+}
 static inline f32 findMaxSeparation(int* edgeIndex, const Poly& p1, const Xf& xf1, const Poly& p2, const Xf& xf2) {
+    if (g_collide_variant == 1) return findMaxSeparation230(edgeIndex, p1, xf1, p2, xf2);
     Xf xf = mulT(xf2, xf1);
     int bestIndex = 0; f32 maxSep = -kMaxFloat;
     for (int i = 0; i < 4; ++i) {
@@ -223,7 +266,7 @@ static inline int clipSegmentToLine(ClipVertex vOut[2], const ClipVertex vIn[2],
     }
     return numOut;
 }
-// b2CollidePolygons (v2.3.1+: brute-force max separation, k_tol = 0.1*linearSlop)
+// b2CollidePolygons (variant 0: v2.3.1+, brute-force max separation, k_tol = 0.1*linearSlop; variant 1: v2.3.0)
 static inline void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xfA, const Poly& polyB, const Xf& xfB) {
     m->pointCount = 0;
     f32 totalRadius = polyA.radius + polyB.radius;
@@ -233,7 +276,8 @@ static inline void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xfA
     if (sepB > totalRadius) return;
     const Poly *poly1, *poly2; Xf xf1, xf2; int edge1; int flip;
     const f32 k_tol = 0.1f * kLinearSlop;
-    if (sepB > sepA + k_tol) { poly1 = &polyB; poly2 = &polyA; xf1 = xfB; xf2 = xfA; edge1 = edgeB; m->type = FACE_B; flip = 1; }
+    const bool flipToB = g_collide_variant == 1 ? (sepB > 0.98f * sepA + 0.001f) : (sepB > sepA + k_tol);
+    if (flipToB) { poly1 = &polyB; poly2 = &polyA; xf1 = xfB; xf2 = xfA; edge1 = edgeB; m->type = FACE_B; flip = 1; }
     else { poly1 = &polyA; poly2 = &polyB; xf1 = xfA; xf2 = xfB; edge1 = edgeA; m->type = FACE_A; flip = 0; }
     ClipVertex incident[2];
     findIncidentEdge(incident, *poly1, xf1, edge1, *poly2, xf2);

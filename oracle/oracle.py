@@ -86,6 +86,10 @@ def lib():
         L.orc_kat_tyres.argtypes = [P(d), d, d, d, d, d, P(d)]
         L.orc_kat_rpm.argtypes = [d, d, d]
         L.orc_kat_rpm.restype = d
+        L.orc_set_b2_variant.argtypes = [i]
+        L.orc_get_b2_variant.restype = i
+        L.orc_b2_collide.argtypes = [f] * 8 + [P(f)]
+        L.orc_b2_variant_study.argtypes = [vp, ctypes.c_long, ctypes.c_ulonglong, P(ctypes.c_long)]
         _lib = L
     return _lib
 
@@ -218,6 +222,25 @@ class OracleEnv:
             lib().orc_env_free(self._h)
         except Exception:
             pass
+
+
+def set_b2_variant(v: int) -> None:
+    """0: b2CollidePolygons as in Box2D 2.3.1+ (default); 1: as in 2.3.0 (see oracle/b2lite.h)."""
+    lib().orc_set_b2_variant(int(v))
+
+
+def b2_variant_study(env: "OracleEnv", n: int, seed: int = 0) -> dict:
+    c = (ctypes.c_long * 8)()
+    lib().orc_b2_variant_study(env._h, int(n), int(seed), c)
+    keys = ("samples", "touching", "touching_differs", "reference_face_differs", "point_count_differs", "feature_ids_differ",
+            "same_features_bits_differ", "worst_point_difference_nm")
+    return dict(zip(keys, [int(x) for x in c]))
+
+
+def b2_collide(car_pose, wall_pose, wall_half) -> np.ndarray:
+    out = np.zeros(12, dtype=np.float32)
+    lib().orc_b2_collide(*[float(x) for x in car_pose], *[float(x) for x in wall_pose], float(wall_half[0]), float(wall_half[1]), _fp(out))
+    return out
 
 
 def kat_tyres(friction4, dt, along, alat, speed, slip):

@@ -15,7 +15,7 @@ void hc_env_step(const float* blob, float* records, int C, const float* act3, in
     uint32_t xf[NCG_MAX_CARS];
     for (int i = 0; i < C; ++i) {
         float* R = records + i * NCG_RECORD_WORDS;
-        reward[i] = car_step(R, T, act3[i * 3], act3[i * 3 + 1], act3[i * 3 + 2], contacts != 0, obs + i * 38, &xf[i], &cnt);
+        reward[i] = car_step(R, T, act3[i * 3], act3[i * 3 + 1], act3[i * 3 + 2], contacts, obs + i * 38, &xf[i], &cnt);
         unsigned tests = 0;
         for (int k = 0; k < 16; ++k) cast_rays<1, false>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
         cnt.ray_tests += tests;

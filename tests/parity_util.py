@@ -314,12 +314,20 @@ def policy_actions(kind: str, rng, discrete: bool):
 
 
 def collect_cases(track: str, n_cases: int, kind: str = "drive", seed: int = 0, discrete: bool = False, every: int = 7,
-                  max_steps: int = 200000):
+                  max_steps: int = 200000, b2_variant: int = 0):
     """Run the oracle (one car) with a scripted policy and sample teacher-forcing cases along the way.
 
     Returns (records[n,128] float32, act3[n,3] float32, raw actions list, expected dict) where expected holds
     the oracle's results of stepping each sampled state once: records, obs, reward, terminated, truncated."""
     rng = np.random.default_rng(seed)
+    O.set_b2_variant(b2_variant)
+    try:
+        return _collect_cases(track, n_cases, kind, rng, discrete, every, max_steps)
+    finally:
+        O.set_b2_variant(0)
+
+
+def _collect_cases(track, n_cases, kind, rng, discrete, every, max_steps):
     env = O.OracleEnv(T.builtin_track_text(track), discrete=discrete)
     probe = O.OracleEnv(T.builtin_track_text(track), discrete=discrete)
     env.reset()
