@@ -83,7 +83,9 @@ def main():
 
     E, T, discrete = args.envs, args.n_steps, bool(args.discrete)
     track_file = None if args.track == "all" else f"tracks/{args.track}.track"
-    venv = NascarVectorEnv(E, track_file=track_file, discrete_action_space=discrete, device=local)
+    # (a captured step cannot contain the host-side re-grouping of envs that moved to another track: with --graph the envs of a
+    # --track all run keep the track they drew at reset)
+    venv = NascarVectorEnv(E, track_file=track_file, discrete_action_space=discrete, device=local, redraw_tracks=not args.graph)
     obs = venv.reset_torch()
     net = ActorCritic(38, 5 if discrete else 2, discrete).to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=args.lr, eps=1e-5)

@@ -218,6 +218,16 @@ int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset);
 int32_t ncg_plan_ctas(const int32_t* h_env_track, int32_t num_envs, int32_t cars_per_env, int32_t num_sms,
                       int32_t* h_first_env, int32_t* h_num_envs, int32_t capacity);
 
+/* CarEnv(track_file=None) for a batch (/root/reference/src/car_env.py:264-303, learn/ppo.py:65-77): with the redraw
+ * enabled, an env that finishes inside ncg_step / ncg_step_mapped (auto_reset on) does not restart on its own track: it
+ * moves to another of the uploaded tracks, drawn uniformly among the others (Philox keyed by `seed`, counter = (env, step
+ * index)), gets brand-new physics worlds there (fresh reset) and returns that track's reset observation.  The host
+ * re-groups the envs by track before the next launch; on the device-tensor path that costs one synchronisation of the
+ * caller's stream per step (so a redrawing engine cannot be captured in a CUDA graph).  ncg_rollout never redraws.
+ * ncg_get_env_tracks returns the current env -> track map (int32[E], host). */
+int ncg_set_track_redraw(NcgHandle* h, int32_t enable, uint64_t seed);
+int ncg_get_env_tracks(NcgHandle* h, int32_t* h_out);
+
 /* Offsets of ncg_rollout's synthetic action stream: the Philox counter of local car c at launch step t is
  * (car_base + c, step_base + t).  R ranks that own disjoint env slices (rank r: car_base = r * E * C) draw the streams
  * of one R*E-env job; a rank's slice is then bit-identical to the same envs inside a single larger engine.

@@ -29,7 +29,8 @@ struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, conta
 
 struct KParams {
     float* records; const float* blob; const long long* track_off;
-    const int2* cta_tab;                                   // per group: {first env, number of envs}; all of one track, <= 32 cars
+    const int2* cta_tab;                                   // per group: {first slot, number of envs}; all of one track, <= 32 cars
+    const int* slot_env;                                   // slot -> env, envs ordered by track; NULL = identity (the map is already sorted)
     const int2* pair_tab;                                  // two-physics-warp shape: per CTA the two groups it serves {g0, g1 or -1}
     const float* reset_obs;                                // [n_tracks][NCG_OBS_DIM]: the observation every reset_car yields on a track
     int E, C, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip, queue;
@@ -39,6 +40,9 @@ struct KParams {
     StartPose start;                                       // CarEnv(start_position, start_angle)
     float2* vel_hist;                                      // optional [N][NCG_VEL_HISTORY]: Car.velocity_history ring (info only)
     float* ep_return; int* ep_length; int* any_done;      // optional: episode return per car / length per env of finished envs
+    int redraw, n_tracks; unsigned redraw_step; unsigned long long redraw_seed;   // track_file=None: a finished env re-draws its track
+    int* env_track;                                        // [E] the env -> track map as the device sees it (redraw writes it)
+    int* redrawn;                                          // mapped host word: set when this launch moved an env
     DevStats* stats;
 };
 
@@ -77,8 +81,24 @@ __device__ __noinline__ void reset_in_place(float* R, const Track T, const Start
     reset_record(R, T, false, f2u(R[NCG_R_TRACK]), sp);
 }
 
+// CarEnv.reset() in random-track mode (car_env.py:264-303): the finished env moves to another track, drawn uniformly among
+// the others, and gets brand-new physics worlds (fresh reset) there.  The other track's table is read from global memory:
+// this runs once per episode.  The CTA that made the move does not step the env again (single-step launches only); the host
+// regroups the envs by track before the next launch.
+__device__ __noinline__ uint32_t redraw_track(uint32_t cur, int n_tracks, unsigned env, unsigned step, unsigned long long seed) {
+    if (n_tracks < 2) return cur;
+    uint32_t r[4]; philox4x32(env, step, 0x7472636bu, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const uint32_t k = r[0] % (uint32_t)(n_tracks - 1);
+    return k >= cur ? k + 1u : k;
+}
+__device__ __noinline__ void reset_on_track(float* R, const float* blob, const long long* track_off, uint32_t tid, const StartPose sp) {
+    const float* g = blob + track_off[tid];
+    const Track T = track_view(g, g);
+    reset_record(R, T, true, tid, sp);
+}
+
 struct SmemLayout {
-    int rec, obs, pose, flag, xf, act, otab, ray, rot, ctr, track, total;      // word offsets
+    int rec, obs, pose, flag, xf, gcar, act, otab, ray, rot, ctr, track, total;      // word offsets
 };
 // cpb = car slots of the CTA: 32 per physics warp
 __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb, int nb) {
@@ -89,6 +109,7 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb,
     L.pose = o; o += nb * cpb * 4;                 // [nb][cpb] float4 {x, y, angle, -}
     L.flag = o; o += nb * cpb;                     // [nb][cpb] u32: bit0 terminated, bit1 truncated
     L.xf = o; o += cpb;
+    L.gcar = o; o += cpb;                          // [cpb] global car index of a car slot
     o = (o + 3) & ~3;
     L.act = o; o += nb * cpb * 4;                  // [nb][cpb] float4 {throttle, brake, steer, -}: synthetic actions, made nb steps ahead
     L.otab = o; o += 2 * 40;                       // observation scale[38] (padded to 40) and lower clip bound[38]
@@ -128,6 +149,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     float4* s_pose = reinterpret_cast<float4*>(smem + L.pose);
     uint32_t* s_flag = reinterpret_cast<uint32_t*>(smem + L.flag);
     uint32_t* s_xf = reinterpret_cast<uint32_t*>(smem + L.xf);
+    int* s_gcar = reinterpret_cast<int*>(smem + L.gcar);
     float4* s_act = reinterpret_cast<float4*>(smem + L.act);
     float* s_otab = smem + L.otab;
     float* s_ray = smem + L.ray;
@@ -140,10 +162,16 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     if (PW == 1) g0 = p.cta_tab[blockIdx.x];
     else { const int2 pr = p.pair_tab[blockIdx.x]; g0 = p.cta_tab[pr.x]; if (pr.y >= 0) g1 = p.cta_tab[pr.y]; }
     const int n0 = g0.y * p.C, n1 = g1.y * p.C, n_all = n0 + n1;
-    const int cb0 = g0.x * p.C, cb1 = g1.x * p.C;
     const int N = p.E * p.C;
 #define SLOT_OF(ci) ((ci) < n0 ? (ci) : 32 + (ci) - n0)           /* dense car index of the CTA -> slot */
-#define GCAR_OF(ci) ((ci) < n0 ? cb0 + (ci) : cb1 + (ci) - n0)     /*                          -> global car */
+#define GCAR_OF(ci) (s_gcar[SLOT_OF(ci)])                          /*                          -> global car */
+    // a group is g.y consecutive entries of the slot list (envs ordered by track); without a list slot s is env s
+    for (int ci = threadIdx.x; ci < n_all; ci += NT) {
+        const int k = ci < n0 ? ci : ci - n0, le = k / p.C, sl = (ci < n0 ? g0.x : g1.x) + le;
+        s_gcar[SLOT_OF(ci)] = (p.slot_env ? p.slot_env[sl] : sl) * p.C + (k - le * p.C);
+    }
+    __syncthreads();
+    const int cb0 = s_gcar[0];                                       // the CTA's first car: its record names the CTA's track
 
     // ---- track table: staged by TMA when the whole CTA shares a track, else read through L1/L2
     const float* staged = nullptr;
@@ -167,7 +195,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     const bool synth = p.actions == nullptr;
     // the first PW ray warps make the synthetic actions (one per physics warp), two steps ahead of the physics warps
     const bool act_maker = synth && warp >= PW && warp < 2 * PW && lane < (warp == PW ? n0 : n1);
-    const int act_slot = (warp - PW) * 32 + lane; const unsigned act_car = p.car_base + (unsigned)((warp == PW ? cb0 : cb1) + lane);
+    const int act_slot = (warp - PW) * 32 + lane; const unsigned act_car = p.car_base + (unsigned)(act_maker ? s_gcar[act_slot] : 0);
     if (act_maker) {
         for (int t = 0; t < NB && t < p.T; ++t) {
             float thr, brk, st;
@@ -190,7 +218,8 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
 
     if (warp < PW) {
         // =============================================================== physics warps: one car per lane
-        const int car0 = warp == 0 ? cb0 : cb1, env0 = warp == 0 ? g0.x : g1.x;
+        const int gc = active ? s_gcar[slot] : 0;                // this lane's global car; its env: gc / C
+        const int ge = p.C == 1 ? gc : gc / p.C;
         float* R = s_rec + (active ? slot : 0) * REC_STRIDE;
         Counters cnt = {0, 0, 0, 0, 0};
         unsigned long long episodes = 0; double ret_sum = 0.0;
@@ -201,7 +230,6 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
             StepCtx ctx;
             if (active) {
                 float thr, brk, st;
-                const int gc = car0 + lane;
                 if (!synth) {
                     if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
                     else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
@@ -237,22 +265,30 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                 if (solo) env_decide(&xf, 1, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
                 else env_decide(s_xf + warp * 32 + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
                 car_finish(R, rew);
-                if (rew_out) rew_out[car0 + lane] = rew;
+                if (rew_out) rew_out[gc] = rew;
                 const bool done = te || tr;
                 if (solo || lane == le * p.C) {
-                    const int ge = env0 + le;
                     if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
                     else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
                     if (done) ++episodes;
                 }
                 if (__builtin_expect(done, 0)) {
                     ret_sum += (double)R[NCG_R_CUM_REWARD];
-                    if (p.ep_return) p.ep_return[car0 + lane] = R[NCG_R_CUM_REWARD];
-                    if (solo || lane == le * p.C) { if (p.ep_length) p.ep_length[env0 + le] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
+                    if (p.ep_return) p.ep_return[gc] = R[NCG_R_CUM_REWARD];
+                    if (solo || lane == le * p.C) { if (p.ep_length) p.ep_length[ge] = (int)f2u(R[NCG_R_STEP]); if (p.any_done) *p.any_done = 1; }
                 }
-                // ---- same-step auto-reset (CarPhysics.reset_car semantics)
-                if (__builtin_expect(done && do_reset, 0)) reset_in_place(R, T, p.start);
-                s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u);
+                // ---- same-step auto-reset: CarPhysics.reset_car on the same track, or (random-track mode, single-step
+                // launches) a fresh world on a newly drawn track; bits 8.. of the flag word name the track whose reset
+                // observation the ray warps hand out
+                uint32_t rtid = my_tid;
+                if (__builtin_expect(done && do_reset, 0)) {
+                    if (p.redraw) {
+                        rtid = redraw_track(my_tid, p.n_tracks, (unsigned)ge, p.redraw_step, p.redraw_seed);
+                        reset_on_track(R, p.blob, p.track_off, rtid, p.start);
+                        if (solo || lane == le * p.C) { p.env_track[ge] = (int)rtid; *p.redrawn = 1; }
+                    } else reset_in_place(R, T, p.start);
+                }
+                s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u) | (rtid << 8);
             }
             __syncwarp();
             __threadfence_block();
@@ -274,7 +310,6 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
         const int q = lane % LPC;
         const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // fixed mapping: a lane's rays are q0, q0+4, ... (90 deg apart)
         const int wslot0 = (warp - 1) * CPW;                     //                first car slot of this warp
-        const float* reset_row = p.reset_obs + (size_t)my_tid * NCG_OBS_DIM;
         const RaySet<RPL> rs = ray_set<RPL>(q0);
         // which (car, word pair) this lane stores in each pass of the row write-out: fixed for the launch.  PW == 1: a warp
         // writes the rows of its own CPW cars; PW == 2: the dense cars of the CTA are dealt over all ray lanes.
@@ -336,9 +371,10 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                     v.x = obs_word(row[0], s_otab[k], s_otab[40 + k]);
                     v.y = obs_word(row[1], s_otab[k + 1], s_otab[41 + k]);
                     const size_t o = ((size_t)GCAR_OF(ci) * NCG_OBS_DIM + k) >> 1;
-                    if (do_reset && s_flag[b * SLOTS + sl] != 0u) {
+                    const uint32_t fw = s_flag[b * SLOTS + sl];
+                    if (do_reset && (fw & 3u) != 0u) {
                         if (p.final_obs) reinterpret_cast<float2*>(p.final_obs)[o] = v;
-                        if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = __ldg(reinterpret_cast<const float2*>(reset_row + k));   // the track's reset observation
+                        if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = __ldg(reinterpret_cast<const float2*>(p.reset_obs + (size_t)(fw >> 8) * NCG_OBS_DIM + k));   // the (new) track's reset observation
                     } else if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = v;
                 }
             }
@@ -409,6 +445,11 @@ struct NcgHandle {
     std::vector<int> h_env_track;
     int2* d_cta_tab = nullptr; int n_ctas = 0; int cap_ctas = 0; bool cta_dirty = true;   // groups of <= 32 car slots (one CTA each, or two per CTA)
     int2* d_pair_tab = nullptr; int n_pairs = 0; int cap_pairs = 0;       // groups paired by track for the two-physics-warp shape
+    int* d_slot_env = nullptr; int cap_slots = 0; bool identity = true;   // slot -> env list (envs ordered by track); unused while the map is sorted
+    int* d_env_track = nullptr;                      // [E] device copy of the env -> track map; the redraw writes it
+    int redraw = 0; unsigned long long redraw_seed = 0; unsigned steps_taken = 0;
+    int* p_redrawn = nullptr;                        // page-locked, device-mapped: set by a step that moved an env to another track
+    std::vector<int> h_tmp_track;
     DevStats* d_stats = nullptr;
     bool was_reset = false;
     unsigned step_base = 0, car_base = 0;              // Philox counter offsets of ncg_rollout (ncg_set_rollout_base)
@@ -464,22 +505,46 @@ void plan_ctas(const int* env_track, int E, int C, int sms, std::vector<int2>& t
         e += n;
     }
 }
-// Rebuilt (host side, one small upload) whenever the env -> track map changes.
+// Rebuilt (host side, two small uploads) whenever the env -> track map changes.  Envs are ordered by track (a stable
+// counting sort: the slot list) and the groups are cut from that order, so every CTA serves one track whatever the map
+// looks like; the records themselves never move.  A map that is already sorted needs no list.
 int build_cta_table(NcgHandle* h) {
+    const int E = h->cfg.num_envs;
+    CUDA_TRY(cudaDeviceSynchronize());                    // no launch may still be reading the tables that are replaced here
+    const std::vector<int>& et = h->h_env_track;
+    bool sorted = true;
+    for (int e = 1; e < E && sorted; ++e) sorted = et[e] >= et[e - 1];
+    std::vector<int> slot_env, slot_track;
+    const int* seq = et.data();
+    if (!sorted) {
+        std::vector<int> start(h->n_tracks + 1, 0);
+        for (int e = 0; e < E; ++e) ++start[et[e] + 1];
+        for (int t = 0; t < h->n_tracks; ++t) start[t + 1] += start[t];
+        slot_env.resize(E); slot_track.resize(E);
+        for (int e = 0; e < E; ++e) { const int s = start[et[e]]++; slot_env[s] = e; slot_track[s] = et[e]; }
+        seq = slot_track.data();
+        if (E > h->cap_slots) {
+            cudaFree(h->d_slot_env); h->d_slot_env = nullptr; h->cap_slots = 0;
+            CUDA_TRY(cudaMalloc(&h->d_slot_env, (size_t)E * sizeof(int)));
+            h->cap_slots = E;
+        }
+        CUDA_TRY(cudaMemcpyAsync(h->d_slot_env, slot_env.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    h->identity = sorted;
     std::vector<int2> tab;
-    plan_ctas(h->h_env_track.data(), h->cfg.num_envs, h->cfg.cars_per_env, h->num_sms, tab);
+    plan_ctas(seq, E, h->cfg.cars_per_env, h->num_sms, tab);
     // (each table has its own capacity: the allocation only ever grows, and growing one never touches the other)
     if ((int)tab.size() > h->cap_ctas) {
         cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr; h->cap_ctas = 0;
         CUDA_TRY(cudaMalloc(&h->d_cta_tab, tab.size() * sizeof(int2)));
         h->cap_ctas = (int)tab.size();
     }
-    CUDA_TRY(cudaMemcpy(h->d_cta_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(h->d_cta_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     h->n_ctas = (int)tab.size();
     // neighbouring groups of one track, two by two (a group without such a neighbour stays alone)
     std::vector<int2> pairs;
     for (size_t g = 0; g < tab.size();) {
-        const bool two = g + 1 < tab.size() && h->h_env_track[tab[g + 1].x] == h->h_env_track[tab[g].x];
+        const bool two = g + 1 < tab.size() && seq[tab[g + 1].x] == seq[tab[g].x];
         pairs.push_back(make_int2((int)g, two ? (int)g + 1 : -1));
         g += two ? 2 : 1;
     }
@@ -488,14 +553,40 @@ int build_cta_table(NcgHandle* h) {
         CUDA_TRY(cudaMalloc(&h->d_pair_tab, pairs.size() * sizeof(int2)));
         h->cap_pairs = (int)pairs.size();
     }
-    CUDA_TRY(cudaMemcpy(h->d_pair_tab, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpyAsync(h->d_pair_tab, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_env_track, et.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // (pageable sources: the copies are staged before the calls return; the plan must be in place before the caller's
+    // stream runs the step)
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     h->n_pairs = (int)pairs.size();
     h->cta_dirty = false;
     return NCG_OK;
 }
 
+// Random-track mode: a step may have moved finished envs to other tracks (the kernel wrote the new ids to d_env_track and
+// raised the mapped flag).  Before the next launch the host map and the launch plan follow.  The flag is only meaningful
+// once the previous step has completed, hence the synchronisation of the caller's stream (the host-buffer paths have
+// already waited for it).
+int follow_redraws(NcgHandle* h, cudaStream_t s) {
+    if (!h->redraw) return NCG_OK;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (!*(volatile int*)h->p_redrawn) return NCG_OK;
+    *h->p_redrawn = 0;
+    h->h_tmp_track.resize(h->cfg.num_envs);
+    CUDA_TRY(cudaMemcpy(h->h_tmp_track.data(), h->d_env_track, (size_t)h->cfg.num_envs * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int e = 0; e < h->cfg.num_envs; ++e) {
+        const int t = h->h_tmp_track[e];
+        if (t >= 0 && t < h->n_tracks) h->h_env_track[e] = t;
+    }
+    h->cta_dirty = true;
+    return NCG_OK;
+}
+
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
+    { int rc = follow_redraws(h, s); if (rc) return rc; }
     if (h->cta_dirty) { int rc = build_cta_table(h); if (rc) return rc; }
+    p.redraw = (h->redraw && p.T == 1 && p.auto_reset && h->n_tracks > 1) ? 1 : 0;
+    p.redraw_step = h->steps_taken; h->steps_taken += (unsigned)p.T;
     const int sms = h->num_sms > 0 ? h->num_sms : 148;
     // rays per lane: 2 (8 ray warps per CTA) while the batch is at most one CTA per SM and latency-bound, 4 (4 ray warps,
     // better lane balance and fewer instructions per car-step) beyond that; measured in profiles/.  Two things that were
@@ -513,7 +604,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
         if (12 * waves2 < 10 * waves1) PW = 2;
     }
     { const char* pw = getenv("NCG_PHYS_WARPS"); if (pw && (atoi(pw) == 1 || atoi(pw) == 2)) PW = atoi(pw); }
-    p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab;
+    p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab; p.slot_env = h->identity ? nullptr : h->d_slot_env;
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
@@ -550,6 +641,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
 KParams base_params(NcgHandle* h) {
     KParams p; memset(&p, 0, sizeof(p));
     p.start = start_pose(h); p.vel_hist = h->d_vel_hist;
+    p.n_tracks = h->n_tracks; p.env_track = h->d_env_track; p.redraw_seed = h->redraw_seed; p.redrawn = h->p_redrawn;
     p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off; p.reset_obs = h->d_reset_obs;
     p.E = h->cfg.num_envs; p.C = h->cfg.cars_per_env; p.discrete = h->cfg.discrete; p.reset_on_lap = h->cfg.reset_on_lap;
     p.auto_reset = h->cfg.auto_reset; p.contacts = h->cfg.contacts; p.track_info = h->cfg.track_info; p.stats = h->d_stats; p.T = 1;
@@ -595,6 +687,10 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaMallocHost(&h->p_actions, N * 8)); CUDA_TRY(cudaMallocHost(&h->p_pack, h->pack_bytes)); CUDA_TRY(cudaMallocHost(&h->p_final, N * NCG_OBS_DIM * 4));
     h->p_obs = (float*)h->p_pack; h->p_reward = h->p_obs + N * NCG_OBS_DIM; h->p_flags = (uint8_t*)(h->p_reward + N);
     CUDA_TRY(cudaHostAlloc((void**)&h->p_any_done, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    CUDA_TRY(cudaHostAlloc((void**)&h->p_redrawn, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *h->p_redrawn = 0;
+    CUDA_TRY(cudaMalloc(&h->d_env_track, E * sizeof(int)));
+    CUDA_TRY(cudaMemset(h->d_env_track, 0, E * sizeof(int)));
     h->h_env_track.assign(E, 0);
     *out = h;
     return NCG_OK;
@@ -605,7 +701,8 @@ int ncg_destroy(NcgHandle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_vel_hist); cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
-    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab);
+    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); cudaFree(h->d_slot_env); cudaFree(h->d_env_track);
+    cudaFreeHost(h->p_redrawn);
     cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -867,6 +964,20 @@ int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset) {
 }
 
 int64_t ncg_launch_count(NcgHandle* h) { return h ? h->launches : 0; }
+
+int ncg_set_track_redraw(NcgHandle* h, int32_t enable, uint64_t seed) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    h->redraw = enable ? 1 : 0; h->redraw_seed = seed;
+    return NCG_OK;
+}
+
+int ncg_get_env_tracks(NcgHandle* h, int32_t* h_out) {
+    if (!h || !h_out) return fail(NCG_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->redraw) { CUDA_TRY(cudaDeviceSynchronize()); int rc = follow_redraws(h, h->stream); if (rc) return rc; }
+    for (int e = 0; e < h->cfg.num_envs; ++e) h_out[e] = h->h_env_track[e];
+    return NCG_OK;
+}
 
 int ncg_set_rollout_base(NcgHandle* h, uint32_t car_base, uint32_t step_base) {
     if (!h) return fail(NCG_E_INVALID, "null handle");

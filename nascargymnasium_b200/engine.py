@@ -70,7 +70,7 @@ EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_up
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
            "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs",
-           "ncg_get_velocity_history_host")
+           "ncg_get_velocity_history_host", "ncg_set_track_redraw", "ncg_get_env_tracks")
 
 _lib = None
 
@@ -111,6 +111,8 @@ def load_library():
     lib.ncg_set_rollout_base.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32]
     lib.ncg_set_episode_outputs.argtypes = [vp, vp, vp, vp]
     lib.ncg_get_velocity_history_host.argtypes = [vp, vp]
+    lib.ncg_set_track_redraw.argtypes = [vp, i32, u64]
+    lib.ncg_get_env_tracks.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -266,6 +268,15 @@ class Engine:
         self._dev(obs_last, torch.float32, N * 38, "obs_last")
         _check(self._lib.ncg_rollout(self._h, steps, seed, mode, self._ptr(obs_rollout), self._ptr(reward_rollout),
                                      self._ptr(done_rollout), self._ptr(obs_last), self._stream()))
+
+    def set_track_redraw(self, enable: bool, seed: int = 0):
+        """Random-track mode: finished envs restart on another track (ncg_set_track_redraw)."""
+        _check(self._lib.ncg_set_track_redraw(self._h, int(bool(enable)), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def env_tracks(self) -> np.ndarray:
+        out = np.empty(self.num_envs, dtype=np.int32)
+        _check(self._lib.ncg_get_env_tracks(self._h, _np_ptr(out)))
+        return out
 
     def set_rollout_base(self, car_base: int = 0, step_base: int = 0):
         """Philox counter offsets of rollout(): rank r of a sharded job passes car_base = r * num_cars."""

@@ -70,11 +70,15 @@ class NascarVectorEnv:
 
     def __init__(self, num_envs: int, track_file: Union[None, str, Sequence[str]] = None, num_cars: int = 1,
                  discrete_action_space: bool = False, reset_on_lap: bool = False, device: int = 0, track_info: bool = False,
-                 max_result_blocks: int = 64, validate_actions: bool = True):
+                 max_result_blocks: int = 64, validate_actions: bool = True, redraw_tracks: bool = True):
         self.validate_actions = bool(validate_actions)    # assert action_space.contains, like the reference's step()
         self.max_result_blocks = int(max_result_blocks)   # result buffers kept alive for the caller before step() copies
         if num_cars < 1 or num_cars > K.MAX_CARS:
             raise ValueError(f"Number of cars must be between 1 and {K.MAX_CARS}")
+        # track_file=None is the reference's random-track mode (car_env.py:243-303; learn/ppo.py:65-77 trains that way): an env
+        # draws a track at reset() and, when an episode ends, restarts on ANOTHER one.  redraw_tracks=False keeps every env on
+        # the track it drew at reset() (needed to capture step_torch in a CUDA graph: re-grouping envs is host work).
+        self.random_tracks = track_file is None
         if track_file is None:
             tracks = [f"tracks/{n}.track" for n in T.BUILTIN_TRACK_NAMES]
         elif isinstance(track_file, str):
@@ -90,8 +94,9 @@ class NascarVectorEnv:
         self.observation_space = _batched_space(self.single_observation_space, num_envs)
         self.engine = Engine(num_envs, num_cars, tracks=tracks, discrete=discrete_action_space, reset_on_lap=reset_on_lap,
                              auto_reset=True, device=device, track_info=track_info)
-        # envs sorted by track id so every CTA serves one track
-        self.track_id = (np.arange(num_envs, dtype=np.int64) * len(tracks) // num_envs).astype(np.int32)
+        self.redraw_tracks = bool(redraw_tracks) and self.random_tracks and len(tracks) > 1
+        # a list of tracks: equal blocks of envs per track; random mode: drawn per env at reset()
+        self._initial_track_id = (np.arange(num_envs, dtype=np.int64) * len(tracks) // num_envs).astype(np.int32)
         self._obs_shape = (num_envs, K.OBS_DIM) if num_cars == 1 else (num_envs, num_cars, K.OBS_DIM)
         self._rew_shape = (num_envs,) if num_cars == 1 else (num_envs, num_cars)
         self._aux, self._ring, self._ring_pos, self._spill = None, [], 0, None
@@ -99,8 +104,22 @@ class NascarVectorEnv:
         self.closed = False
 
     # ------------------------------------------------------------------ numpy API
+    @property
+    def track_id(self) -> np.ndarray:
+        """Current env -> track index (into self.tracks); in random-track mode it changes as episodes end."""
+        return self.engine.env_tracks()
+
+    def _draw_tracks(self, seed):
+        """reset(): every env of a random-track batch draws its own track (CarEnv._select_random_track); `seed` makes the
+        draw and the later re-draws reproducible (the reference seeds from pid + clock, i.e. not at all)."""
+        if not self.random_tracks:
+            return self._initial_track_id
+        rng = np.random.default_rng(seed)
+        self.engine.set_track_redraw(self.redraw_tracks, int(rng.integers(0, 2 ** 63)))
+        return rng.integers(0, len(self.tracks), size=self.num_envs).astype(np.int32)
+
     def reset(self, seed=None, options=None):
-        obs = self.engine.reset_host(track_id=self.track_id, fresh=True)
+        obs = self.engine.reset_host(track_id=self._draw_tracks(seed), fresh=True)
         return obs.reshape(self._obs_shape), {}
 
     def _next_result_block(self):
@@ -188,10 +207,10 @@ class NascarVectorEnv:
         """CUDA int32 tensor (E,): length in steps of the episode an env finished most recently."""
         return self._bufs()["ep_length"]
 
-    def reset_torch(self):
+    def reset_torch(self, seed=None):
         import torch
         b = self._bufs()
-        tid = torch.as_tensor(self.track_id, device=b["obs"].device)
+        tid = torch.as_tensor(self._draw_tracks(seed), device=b["obs"].device)
         self.engine.reset(obs=b["obs"].view(-1), track_id=tid, fresh=True)
         return b["obs"].view(self._obs_shape)
 

@@ -43,21 +43,29 @@ def main():
                 continue
             n_touch += 1
             w = exp["records"][i]
+            # discrete outcome first: contact list, touching set, point counts, feature ids.  A case where they differ is a
+            # threshold tie (a separation within rounding of b2_polygonRadius or of the reference-face tolerance); it is
+            # counted and left out of the per-field figures, which describe steps that solved the same constraints.
+            ncw = P._u(w, R["NCG_R_NCONTACT"])
+            same = P._u(got[i], R["NCG_R_NCONTACT"]) == ncw and P._u(got[i], R["NCG_R_MANIFOLD_PC"]) == P._u(w, R["NCG_R_MANIFOLD_PC"])
+            nt = bin((ncw >> 16) & 0xFFF).count("1")
+            for k in range(nt if same else 0):
+                M = R["NCG_R_MANIFOLD"] + 6 * k
+                same = same and P._u(got[i], M) == P._u(w, M) and P._u(got[i], M + 1) == P._u(w, M + 1)
+            if not same:
+                ids_bad += 1
+                continue
             for name, cnt in fields.items():
                 a, b = got[i, R[name]:R[name] + cnt].astype(np.float64), w[R[name]:R[name] + cnt].astype(np.float64)
                 d = np.abs(a - b)
                 k = int(d.argmax())
                 if d[k] > worst[name]["abs"]:
                     worst[name].update(abs=float(d[k]), scale=float(abs(b[k])))
-                worst[name]["rel"] = max(worst[name]["rel"], float((d / np.maximum(np.abs(b), 1e-6)).max()) if np.abs(b).max() > 1e-3 else 0.0)
-            ncw = P._u(w, R["NCG_R_NCONTACT"])
-            if P._u(got[i], R["NCG_R_NCONTACT"]) != ncw or P._u(got[i], R["NCG_R_MANIFOLD_PC"]) != P._u(w, R["NCG_R_MANIFOLD_PC"]):
-                ids_bad += 1
-                continue
-            for k in range(bin((ncw >> 16) & 0xFFF).count("1")):
+                big = np.abs(b) > 1e-2
+                if big.any():
+                    worst[name]["rel"] = max(worst[name]["rel"], float((d[big] / np.abs(b[big])).max()))
+            for k in range(nt):
                 M = R["NCG_R_MANIFOLD"] + 6 * k
-                if P._u(got[i], M) != P._u(w, M) or P._u(got[i], M + 1) != P._u(w, M + 1):
-                    ids_bad += 1
                 a, b = got[i, M + 2:M + 6].astype(np.float64), w[M + 2:M + 6].astype(np.float64)
                 d = np.abs(a - b)
                 j = int(d.argmax())
