@@ -468,7 +468,7 @@ def run_ours(args):
             ex["config5"] = config5_learner_loop(b.local)
         line["workloads"] = ex
     line["gpu_launches"] = int(b.launches)
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_baseline:
         tiers, best = cpu_tiers("daytona" if track == "all" else track, 1, args.seed)
         line["cpu_baseline"] = dict(tiers[best], tiers={str(k): v for k, v in tiers.items()})
     if rank == 0:
@@ -518,6 +518,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--extras", type=int, default=1, help="1: also measure the driving distribution and BASELINE configs 3 and 4")
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--config5", type=int, default=1, help="1: also run the PPO collection loop of BASELINE config 5 (N=1 only)")
     ap.add_argument("--sweep", type=int, default=1, help="1: also time the rollout kernel at 8192/16384/65536 envs (N=1 only)")
     ap.add_argument("--mode", type=int, default=0, help="synthetic action distribution: 0 = action_space.sample() (the metric), "

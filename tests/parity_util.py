@@ -174,10 +174,10 @@ def record_to_oracle(rec: np.ndarray) -> np.ndarray:
 FLOAT_FIELDS = {
     # name: (count, rtol, atol)   north_star: position, velocity and tyre state within 1e-4 relative
     "NCG_R_X": (2, 1e-4, 1e-4), "NCG_R_ANGLE": (1, 1e-4, 1e-5), "NCG_R_VX": (2, 1e-4, 1e-4), "NCG_R_OMEGA": (1, 1e-4, 1e-4),
-    "NCG_R_SLEEP": (1, 1e-5, 1e-6), "NCG_R_FAT_LX": (4, 1e-4, 1e-3), "NCG_R_INV_DT0": (1, 1e-6, 0), "NCG_R_IMPULSE": (1, 1e-3, 1e-1),
+    "NCG_R_SLEEP": (1, 1e-5, 1e-6), "NCG_R_FAT_LX": (4, 1e-4, 1e-3), "NCG_R_INV_DT0": (1, 1e-6, 0), "NCG_R_IMPULSE": (1, 1e-4, 1e-2),
     "NCG_R_RPM": (1, 1e-5, 1e-3), "NCG_R_PREV_VX": (2, 1e-4, 1e-4), "NCG_R_SLIP": (1, 1e-3, 1e-2), "NCG_R_FLAT": (1, 1e-4, 1e-1),
     "NCG_R_BANK": (1, 0, 0), "NCG_R_TYRE_TEMP": (4, 1e-4, 1e-4), "NCG_R_TYRE_WEAR": (4, 1e-4, 1e-6), "NCG_R_TYRE_LOAD": (4, 1e-4, 1e-2),
-    "NCG_R_CUM_IMPACT": (1, 1e-3, 1e-1), "NCG_R_STUCK_X": (2, 1e-4, 1e-4), "NCG_R_BACK": (2, 1e-3, 1e-3),
+    "NCG_R_CUM_IMPACT": (1, 1e-4, 1e-1), "NCG_R_STUCK_X": (2, 1e-4, 1e-4), "NCG_R_BACK": (2, 1e-3, 1e-3),
     "NCG_R_PROGRESS_PREV": (1, 1e-4, 1e-3), "NCG_R_PREV_X": (2, 1e-4, 1e-4), "NCG_R_CUM_REWARD": (1, 1e-4, 1e-4),
     "NCG_R_LAST_LAP": (2, 1e-5, 1e-5), "NCG_R_ODO": (1, 1e-4, 1e-3), "NCG_R_LAP_X": (2, 1e-4, 1e-4),
 }
@@ -191,11 +191,17 @@ def compare_records(got: np.ndarray, want: np.ndarray, contact_fields: bool = Tr
 
     `touching`: the step solved contact constraints.  Box2D's 2-point block solver accepts effective-mass matrices with
     condition numbers up to 1000 (b2ContactSolver: k_maxConditionNumber), which amplifies float32 rounding of its inputs
-    by that factor into the angular impulse, so on such steps the angular velocity is compared at 1e-3 rad/s absolute."""
+    by that factor into the angular impulse, so on such steps the angular velocity is compared at 3e-4 rad/s absolute
+    and the stored manifold impulses at 0.1 N s + 4e-4 relative.  Measured worst cases over 4332 contact-solving steps on five
+    tracks (tools/contact_worst_case.py -> profiles/r02_contact_worst_case.json): omega 1.7e-4 rad/s, angle 1.6e-4 rad,
+    velocity 1.1e-5 relative, position 7.6e-7 relative, manifold impulses 0.065 N s / 1.9e-4 relative, cumulative impact
+    2.3e-5 relative, listener impulse identical."""
     bad = []
     for name, (cnt, rtol, atol) in FLOAT_FIELDS.items():
         if touching and name == "NCG_R_OMEGA":
-            atol = 1e-3
+            atol = 3e-4
+        if touching and name == "NCG_R_ANGLE":
+            atol = 3e-4
         a, b = got[R[name]:R[name] + cnt].astype(np.float64), want[R[name]:R[name] + cnt].astype(np.float64)
         if not np.all(np.abs(a - b) <= atol + rtol * np.abs(b)):
             bad.append((name, a.copy(), b.copy()))
@@ -224,7 +230,7 @@ def compare_records(got: np.ndarray, want: np.ndarray, contact_fields: bool = Tr
                 if _u(got, M) != _u(want, M) or _u(got, M + 1) != _u(want, M + 1):
                     bad.append(("manifold keys", k))
                 a, b = got[M + 2:M + 6].astype(np.float64), want[M + 2:M + 6].astype(np.float64)
-                if not np.all(np.abs(a - b) <= 1.0 + 2e-3 * np.abs(b)):
+                if not np.all(np.abs(a - b) <= 0.1 + 4e-4 * np.abs(b)):
                     bad.append(("manifold impulses", a, b))
             na = (ncw >> 8) & 255
             for i in range(na):

@@ -48,11 +48,22 @@ def test_finished_envs_move_to_another_track_and_the_histogram_stays_uniform():
     orcs = {e: O.OracleEnv(T.builtin_track_text(T.BUILTIN_TRACK_NAMES[int(t1[e])]), discrete=True) for e in picks}
     for o in orcs.values():
         o.reset()
+    compared = 0
     for k in range(40):
         obs, rew, te, tr, info = v.step(acts[k])
-        for e, o in orcs.items():
-            oo, ro, _, _ = o.step([int(acts[k, e])])
-            assert np.abs(obs[e] - oo[0]).max() < 1e-4 and abs(rew[e] - ro[0]) < 1e-5, (k, e)
+        for e, o in list(orcs.items()):
+            oo, ro, teo, tro = o.step([int(acts[k, e])])
+            assert (bool(te[e]), bool(tr[e])) == (teo, tro), (k, e)
+            assert abs(rew[e] - ro[0]) < 1e-5, (k, e)
+            if teo or tro:
+                # (random steering at the start line of talladega / michigan / nascar2 / trioval ends an episode within a
+                # few steps: the reference's start-line overlap quirk) -- the env has moved on again
+                assert np.abs(info["final_obs_rows"][list(info["final_obs_index"]).index(e)] - oo[0]).max() < 1e-4
+                del orcs[e]
+                continue
+            assert np.abs(obs[e] - oo[0]).max() < 1e-4, (k, e)
+            compared += 1
+    assert compared > 100
     v.close()
 
 
