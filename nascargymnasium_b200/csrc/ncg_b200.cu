@@ -129,11 +129,17 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb,
 // 2: the CTA serves a pair of groups of one track -- two physics warps, 64 car slots, six ray warps that drain one ray
 // queue, one staged track table -- which puts four physics warps on an SM (2 CTAs x 256 threads x 128 registers) where
 // PW = 1 fits three (shared memory: three tables): at large batches a step is bound by the physics warps' dependent chains.
+// 4: one group again, its car slots spread over FOUR physics warps of eight lanes ("spread" shape, single-car envs, batches of at
+// most one CTA per SM): the four dependent chains run on the SM's four schedulers side by side, and a warp only walks the
+// union of the code paths of its own eight cars -- what a contact-heavy step (a few thousand divergent instructions per car)
+// is bound by; the contact-free chain is no shorter for it.
 template <int RPL, int MINB, int PW>
-__global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
+__global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
     constexpr int RW = PW == 2 ? 6 : 16 / RPL;      // ray warps
     constexpr int NT = 32 * (PW + RW);
-    constexpr int SLOTS = 32 * PW;                  // car slots: physics warp w owns slots 32w .. 32w+31
+    constexpr int GROUPS = PW == 2 ? 2 : 1;         // groups of the CTA table served by this CTA
+    constexpr int SLOTS = 32 * GROUPS;              // car slots: 32 per group
+    constexpr int LPW = PW == 4 ? 8 : 32;           // car slots per physics warp: warp w owns slots w*LPW .. w*LPW+LPW-1
     constexpr int LPC = 16 / RPL;                   // fixed ray mapping (PW == 1): lanes per car in a ray warp
     constexpr int CPW = 32 / LPC;                   //                              cars per ray warp
     extern __shared__ __align__(16) float smem[];
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
 
     // the groups of envs this CTA serves: n0 cars from global car cb0 in slots 0.., n1 cars from cb1 in slots 32..
     int2 g0, g1 = make_int2(0, 0);
-    if (PW == 1) g0 = p.cta_tab[blockIdx.x];
+    if (GROUPS == 1) g0 = p.cta_tab[blockIdx.x];
     else { const int2 pr = p.pair_tab[blockIdx.x]; g0 = p.cta_tab[pr.x]; if (pr.y >= 0) g1 = p.cta_tab[pr.y]; }
     const int n0 = g0.y * p.C, n1 = g1.y * p.C, n_all = n0 + n1;
     const int N = p.E * p.C;
@@ -193,8 +199,8 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     if (threadIdx.x < NCG_OBS_DIM) { s_otab[threadIdx.x] = obs_scale(threadIdx.x); s_otab[40 + threadIdx.x] = obs_lo(threadIdx.x); }
     if (threadIdx.x < 16) ray_rotation((int)threadIdx.x, &s_rot[2 * threadIdx.x], &s_rot[2 * threadIdx.x + 1]);
     const bool synth = p.actions == nullptr;
-    // the first PW ray warps make the synthetic actions (one per physics warp), two steps ahead of the physics warps
-    const bool act_maker = synth && warp >= PW && warp < 2 * PW && lane < (warp == PW ? n0 : n1);
+    // the first GROUPS ray warps make the synthetic actions (one per group), two steps ahead of the physics warps
+    const bool act_maker = synth && warp >= PW && warp < PW + GROUPS && lane < (warp == PW ? n0 : n1);
     const int act_slot = (warp - PW) * 32 + lane; const unsigned act_car = p.car_base + (unsigned)(act_maker ? s_gcar[act_slot] : 0);
     if (act_maker) {
         for (int t = 0; t < NB && t < p.T; ++t) {
@@ -207,8 +213,8 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
     if (p.stage) tma_wait(&s_mbar);
 
     // the car slot this thread serves: its lane (physics warps) or, with the fixed ray mapping, the car its rays belong to
-    const int slot = warp < PW ? warp * 32 + lane : (warp - 1) * CPW + lane / LPC;
-    const bool active = warp < PW ? lane < (warp == 0 ? n0 : n1) : (PW == 1 && slot < n0);
+    const int slot = warp < PW ? warp * LPW + lane : (warp - PW) * CPW + lane / LPC;
+    const bool active = warp < PW ? (PW == 2 ? lane < (warp == 0 ? n0 : n1) : (lane < LPW && slot < n0)) : (GROUPS == 1 && slot < n0);
     // track views are fixed for the launch (auto-reset keeps an env on its track): build them once
     const uint32_t my_tid = f2u(s_rec[NCG_R_TRACK]);              // slot 0: a CTA serves one track
     const float* gblob = p.blob + p.track_off[my_tid];
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                 const int le = solo ? lane : lane / p.C;
                 bool te, tr; int why;
                 if (solo) env_decide(&xf, 1, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
-                else env_decide(s_xf + warp * 32 + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
+                else env_decide(s_xf + warp * LPW + le * p.C, p.C, p.reset_on_lap != 0, f2u(R[NCG_R_STEP]), &te, &tr, &why);
                 car_finish(R, rew);
                 if (rew_out) rew_out[gc] = rew;
                 const bool done = te || tr;
@@ -309,15 +315,15 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
         const int rt = (warp - PW) * 32 + lane;                  // index among the CTA's ray lanes
         const int q = lane % LPC;
         const int q0 = RPL == 2 ? (q < 4 ? q : q + 4) : q;       // fixed mapping: a lane's rays are q0, q0+4, ... (90 deg apart)
-        const int wslot0 = (warp - 1) * CPW;                     //                first car slot of this warp
+        const int wslot0 = (warp - PW) * CPW;                    //                first car slot of this warp
         const RaySet<RPL> rs = ray_set<RPL>(q0);
         // which (car, word pair) this lane stores in each pass of the row write-out: fixed for the launch.  PW == 1: a warp
         // writes the rows of its own CPW cars; PW == 2: the dense cars of the CTA are dealt over all ray lanes.
-        constexpr int NIT = PW == 2 ? (SLOTS * (NCG_OBS_DIM / 2) + 32 * RW - 1) / (32 * RW) : (CPW * (NCG_OBS_DIM / 2) + 31) / 32;
+        constexpr int NIT = GROUPS == 2 ? (SLOTS * (NCG_OBS_DIM / 2) + 32 * RW - 1) / (32 * RW) : (CPW * (NCG_OBS_DIM / 2) + 31) / 32;
         uint32_t pair_sk[NIT];
 #pragma unroll
         for (int it = 0; it < NIT; ++it) {
-            if (PW == 2) {
+            if (GROUPS == 2) {
                 const int m = rt + 32 * RW * it;
                 pair_sk[it] = m < n_all * (NCG_OBS_DIM / 2) ? (uint32_t)(((m / (NCG_OBS_DIM / 2)) << 8) | ((m % (NCG_OBS_DIM / 2)) * 2)) : 0xFFFFFFFFu;
             } else {
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
         for (int t = 0, b = 0; t < p.T; ++t, b = b + 1 == NB ? 0 : b + 1) {
             float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
             bar_sync(BAR_POSE + b, NT);
-            if ((PW == 2 || p.queue) && !(p.debug_skip & 1)) {
+            if ((GROUPS == 2 || p.queue) && !(p.debug_skip & 1)) {
                 // every ray warp derives the cars' ray origins itself (same values to the same words: no barrier between
                 // the ray warps; nobody still reads last step's, every ray warp has passed that step's FULL barrier), then
                 // all ray lanes of the CTA drain one queue of 16 x n_all rays
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
                 float* o22 = s_obs + b * SLOTS * OBS_STRIDE + 22;
                 if (staged) cast_rays_queue<true>(T, s_ray, n_all, magic, n0, 32 - n0, rt, s_ctr + b, o22, OBS_STRIDE, s_rot, &tests);
                 else cast_rays_queue<false>(T, s_ray, n_all, magic, n0, 32 - n0, rt, s_ctr + b, o22, OBS_STRIDE, s_rot, &tests);
-            } else if (PW == 1 && active && !(p.debug_skip & 1)) {
+            } else if (GROUPS == 1 && active && !(p.debug_skip & 1)) {
                 const float4 ps = s_pose[b * SLOTS + slot];
                 float* dst = s_obs + (b * SLOTS + slot) * OBS_STRIDE + 22;
                 if (staged) cast_rays<RPL, true>(T, ps.x, ps.y, ps.z, rs, dst, &tests);
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (1 + 16 / RPL), MINB) ncg
             // leave them unchanged).
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
-                const int ci = (PW == 2 ? 0 : wslot0) + (int)(pair_sk[it] >> 8), k = (int)(pair_sk[it] & 255u);
+                const int ci = (GROUPS == 2 ? 0 : wslot0) + (int)(pair_sk[it] >> 8), k = (int)(pair_sk[it] & 255u);
                 if (pair_sk[it] != 0xFFFFFFFFu && ci < n_all) {
                     const int sl = SLOT_OF(ci);
                     const float* row = s_obs + (b * SLOTS + sl) * OBS_STRIDE + k;
@@ -603,7 +609,8 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
         const int waves1 = (h->n_ctas + 3 * sms - 1) / (3 * sms), waves2 = (h->n_pairs + 2 * sms - 1) / (2 * sms);
         if (12 * waves2 < 10 * waves1) PW = 2;
     }
-    { const char* pw = getenv("NCG_PHYS_WARPS"); if (pw && (atoi(pw) == 1 || atoi(pw) == 2)) PW = atoi(pw); }
+    { const char* pw = getenv("NCG_PHYS_WARPS"); if (pw && (atoi(pw) == 1 || atoi(pw) == 2 || atoi(pw) == 4)) PW = atoi(pw); }
+    if (PW == 4 && (h->cfg.cars_per_env != 1 || h->n_ctas > sms)) PW = 1;       // the spread shape: single-car envs, one CTA per SM
     p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab; p.slot_env = h->identity ? nullptr : h->d_slot_env;
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
@@ -620,18 +627,20 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && atoi(mb) >= 1 && atoi(mb) <= 3) minb = atoi(mb); }
     if (minb == 3 && RPL != 4) minb = 2;
     if (PW == 2) minb = 2;
+    if (PW == 4) minb = 1;
     const int nb = minb == 1 ? 3 : 2;                 // step buffers: NB of the kernel
-    smem = (size_t)smem_layout(mx, 32 * PW, nb).total * 4;
+    smem = (size_t)smem_layout(mx, PW == 2 ? 64 : 32, nb).total * 4;
     if (p.stage && h->max_smem > 0 && smem > (size_t)h->max_smem) {      // a user track too large to stage: read it through L1/L2
         p.stage = 0;
-        smem = (size_t)smem_layout(0, 32 * PW, nb).total * 4;
+        smem = (size_t)smem_layout(0, PW == 2 ? 64 : 32, nb).total * 4;
     }
-    void (*k)(KParams) = PW == 2 ? ncg_step_kernel<4, 2, 2>
+    void (*k)(KParams) = PW == 4 ? ncg_step_kernel<2, 1, 4> : PW == 2 ? ncg_step_kernel<4, 2, 2>
                        : minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1, 1> : ncg_step_kernel<2, 1, 1>)
                        : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2, 1> : ncg_step_kernel<2, 2, 1>)
                                    : ncg_step_kernel<4, 3, 1>;
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (PW == 2) k<<<h->n_pairs, 256, smem, s>>>(p);
+    if (PW == 4) k<<<h->n_ctas, 32 * (4 + 8), smem, s>>>(p);
+    else if (PW == 2) k<<<h->n_pairs, 256, smem, s>>>(p);
     else k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;

@@ -398,11 +398,12 @@ def _queue_variants_agree(monkeypatch, E, C):
     from nascargymnasium_b200.engine import Engine
     outs = []
     for queue, no_stage, rpl, pw in (("0", "0", "2", "1"), ("1", "0", "2", "1"), ("1", "0", "4", "1"), ("1", "1", "4", "1"), ("0", "0", "4", "1"),
-                                     ("1", "0", "4", "2"), ("1", "1", "4", "2")):
+                                     ("1", "0", "4", "2"), ("1", "1", "4", "2"), ("0", "0", "2", "4"), ("1", "1", "2", "4")):
         monkeypatch.setenv("NCG_RAY_QUEUE", queue)
         monkeypatch.setenv("NCG_NO_STAGE", no_stage)
         monkeypatch.setenv("NCG_RAYS_PER_LANE", rpl)
-        monkeypatch.setenv("NCG_PHYS_WARPS", pw)       # 2: a CTA serves two groups of envs (two physics warps, six ray warps)
+        monkeypatch.setenv("NCG_PHYS_WARPS", pw)       # 2: a CTA serves two groups of envs (two physics warps, six ray warps);
+        # 4: a group's cars spread over four physics warps of eight lanes (single-car envs; ignored for C = 3)
         eng = Engine(E, C, tracks=["daytona", "nascar2"], auto_reset=True)
         eng.reset_host(track_id=(np.arange(E) * 2 // E).astype(np.int32))
         obs = torch.zeros((200, E * C, 38), dtype=torch.float32, device="cuda:0")
