@@ -68,9 +68,9 @@ def test_finished_envs_move_to_another_track_and_the_histogram_stays_uniform():
 
 
 def test_redraw_on_the_device_tensor_path_and_staggered_episode_ends():
-    """step_torch in random-track mode: envs finish at different steps (half of them coast into the stuck rule, the others
-    keep driving), the map follows each time and every CTA keeps serving one track (results equal a fixed-track engine run
-    on the same (track, action) pairs until an env's first move)."""
+    """step_torch in random-track mode: envs finish at different steps (half of them coast into the stuck rule at step 600,
+    the others drive flat out and end whenever they hit a wall hard enough); the env -> track map follows every time, envs
+    that finished are on another track, envs that did not are where they were."""
     import torch
     from nascargymnasium_b200.vector_env import NascarVectorEnv
     E = 600
@@ -79,19 +79,22 @@ def test_redraw_on_the_device_tensor_path_and_staggered_episode_ends():
     t0 = v.track_id.copy()
     a = torch.zeros(E, dtype=torch.int32, device="cuda:0")
     a[E // 2:] = 1                                          # full throttle: these envs do not get stuck
-    moved_at = np.zeros(E, dtype=np.int64)
+    ever = torch.zeros(E, dtype=torch.uint8, device="cuda:0")       # finished at least once (accumulated on the device)
+    at600 = None
     for step in range(1, 640):
         obs, rew, te, tr, fin = v.step_torch(a)
-        if step in (600, 639):
-            torch.cuda.synchronize()
-            done = (te | tr).cpu().numpy().astype(bool)
-            moved_at[done & (moved_at == 0)] = step
+        ever |= te | tr
+        if step == 600:
+            at600 = (te | tr).clone()
+    torch.cuda.synchronize()
     t1 = v.track_id
+    ever, at600 = ever.cpu().numpy().astype(bool), at600.cpu().numpy().astype(bool)
     coasting = np.arange(E) < E // 2
-    assert (moved_at[coasting] == 600).all()
+    assert at600[coasting].all()                             # the stuck rule, all at once
     assert (t1[coasting] != t0[coasting]).all()
-    still = (~coasting) & (moved_at == 0)
-    assert (t1[still] == t0[still]).all()                    # envs that have not finished stay where they were
+    assert (t1[~ever] == t0[~ever]).all()                    # envs that have not finished stay where they were
+    once = ever & ~coasting
+    assert (t1[once] != t0[once]).mean() > 0.8               # (an env that finished twice may be back on its first track)
     assert torch.equal(v.episode_lengths[:E // 2].cpu(), torch.full((E // 2,), 600, dtype=torch.int32))
     v.close()
 
