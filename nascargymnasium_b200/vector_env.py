@@ -101,6 +101,7 @@ class NascarVectorEnv:
         self._rew_shape = (num_envs,) if num_cars == 1 else (num_envs, num_cars)
         self._aux, self._ring, self._ring_pos, self._spill = None, [], 0, None
         self._torch_bufs = None
+        self._fast = None
         self.closed = False
 
     # ------------------------------------------------------------------ numpy API
@@ -216,10 +217,29 @@ class NascarVectorEnv:
 
     def step_torch(self, actions):
         """actions: CUDA tensor float32 (E[,C],2) or int32 (E[,C]).  Returns views of internal CUDA buffers
-        (obs, reward, terminated, truncated, final_obs) that are overwritten by the next call."""
-        b = self._bufs()
-        self.engine.step(actions.contiguous().view(-1), b["obs"].view(-1), b["rew"], b["te"], b["tr"], b["final"].view(-1))
-        return b["obs"].view(self._obs_shape), b["rew"].view(self._rew_shape), b["te"], b["tr"], b["final"].view(self._obs_shape)
+        (obs, reward, terminated, truncated, final_obs) that are overwritten by the next call.  Nothing synchronises (except
+        in random-track mode, see ncg_set_track_redraw); the call costs a few microseconds of host time: the output
+        pointers and views are prepared once, only the action tensor is checked per call."""
+        f = self._fast
+        if f is None:
+            import ctypes
+            import torch
+            b = self._bufs()
+            eng = self.engine
+            f = self._fast = dict(
+                ptrs=[ctypes.c_void_p(b[k].data_ptr()) for k in ("obs", "rew", "te", "tr", "final")],
+                out=(b["obs"].view(self._obs_shape), b["rew"].view(self._rew_shape), b["te"], b["tr"], b["final"].view(self._obs_shape)),
+                dtype=torch.int32 if self.discrete else torch.float32, numel=eng.num_cars * (1 if self.discrete else 2),
+                stream=torch.cuda.current_stream, vp=ctypes.c_void_p, step=eng._lib.ncg_step, h=eng._h, dev=eng.device)
+        if not (actions.is_cuda and actions.dtype == f["dtype"] and actions.numel() == f["numel"] and actions.is_contiguous()
+                and actions.device.index == f["dev"]):
+            raise ValueError(f"actions: expected a contiguous {f['dtype']} CUDA tensor with {f['numel']} elements on cuda:{f['dev']}")
+        vp, p = f["vp"], f["ptrs"]
+        rc = f["step"](f["h"], vp(actions.data_ptr()), p[0], p[1], p[2], p[3], p[4], vp(f["stream"](f["dev"]).cuda_stream))
+        if rc:
+            from .engine import _check
+            _check(rc)
+        return f["out"]
 
     # ------------------------------------------------------------------ info on demand
     def get_info(self, env_index: int) -> dict:

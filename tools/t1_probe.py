@@ -20,27 +20,45 @@ def main():
     ap.add_argument("--envs", type=int, nargs="+", default=[4096, 16384, 65536])
     ap.add_argument("--track", default="daytona")
     ap.add_argument("--discrete", type=int, default=0)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=1000)
     args = ap.parse_args()
     out = []
     for E in args.envs:
         v = NascarVectorEnv(E, track_file=f"tracks/{args.track}.track", discrete_action_space=bool(args.discrete))
         v.reset_torch()
         g = torch.Generator(device="cuda").manual_seed(0)
+        # fresh actions every step (action_space.sample()): a short cycle of pre-drawn actions has a non-zero mean throttle and
+        # steer per car, drives every car into a wall within a few hundred steps and then times the contact path instead
+        n_sets = max(64, min(4096, (256 << 20) // (E * 8)))
         if args.discrete:
-            acts = torch.randint(0, 5, (64, E), device="cuda", generator=g, dtype=torch.int32)
+            acts = torch.randint(0, 5, (n_sets, E), device="cuda", generator=g, dtype=torch.int32)
         else:
-            acts = torch.rand((64, E, 2), device="cuda", generator=g) * 2 - 1
+            acts = torch.rand((n_sets, E, 2), device="cuda", generator=g) * 2 - 1
         for t in range(200):
-            v.step_torch(acts[t % 64])
+            v.step_torch(acts[t % n_sets])
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for t in range(args.steps):
-            v.step_torch(acts[t % 64])
+            v.step_torch(acts[t % n_sets])
         b.record()
         torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1e3 / args.steps
+        # where a single-step launch spends its time: the same loop without rays / without physics / without either
+        # (NCG_DEBUG_SKIP is read at every launch; timing only, the results are not a simulation)
+        skips = {}
+        for sk in (1, 2, 3):
+            os.environ["NCG_DEBUG_SKIP"] = str(sk)
+            for t in range(50):
+                v.step_torch(acts[t % n_sets])
+            torch.cuda.synchronize()
+            a.record()
+            for t in range(500):
+                v.step_torch(acts[t % n_sets])
+            b.record()
+            torch.cuda.synchronize()
+            skips[{1: "no_rays", 2: "no_physics", 3: "neither"}[sk]] = a.elapsed_time(b) * 1e3 / 500
+        os.environ.pop("NCG_DEBUG_SKIP", None)
         # the same step captured in a CUDA graph: the launch as the GPU sees it, without the Python / ctypes call
         static_a = acts[0].clone()
         side = torch.cuda.Stream()
@@ -57,12 +75,13 @@ def main():
         torch.cuda.synchronize()
         a.record()
         for t in range(args.steps):
+            static_a.copy_(acts[t % n_sets])
             g.replay()
         b.record()
         torch.cuda.synchronize()
         us_g = a.elapsed_time(b) * 1e3 / args.steps
         out.append({"envs": E, "track": args.track, "us_per_step": us, "us_per_step_graph": us_g, "car_steps_per_s": E / (us * 1e-6),
-                    "car_steps_per_s_graph": E / (us_g * 1e-6)})
+                    "car_steps_per_s_graph": E / (us_g * 1e-6), "us_per_step_debug_skip": skips})
         v.close()
     print(json.dumps(out))
 
