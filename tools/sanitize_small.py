@@ -18,4 +18,21 @@ v.reset()
 for _ in range(4):
     v.step(np.random.uniform(-1, 1, (12, 10, 2)).astype(np.float32))
 v.close()
+# interleaved env -> track map (slot list), random-track mode with a redraw, start pose, Box2D 2.3.0 contact form
+w = NascarVectorEnv(48, track_file=None, discrete_action_space=True)
+w.reset(seed=3)
+w.engine.set_state_host(w.engine.get_state_host())
+rec = w.engine.get_state_host()
+from nascargymnasium_b200 import layout as L
+rec.view(np.uint32)[:, L.R["NCG_R_STUCK_STEPS"]] = 599                      # every env finishes on the next step and moves to another track
+w.engine.set_state_host(rec)
+for _ in range(3):
+    w.step(np.zeros(48, dtype=np.int64))
+w.close()
+e2 = Engine(40, 1, tracks=["nascar"], contacts=2, start_position=(30.0, -4.0), start_angle=0.35, track_info=True)
+e2.reset_host()
+o2 = torch.empty((40, 38), device="cuda:0")
+e2.rollout(30, seed=2, mode=1, obs_last=o2.view(-1))
+torch.cuda.synchronize()
+e2.close()
 print("sanitize workload ok")
