@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
     // a group is g.y consecutive entries of the slot list (envs ordered by track); without a list slot s is env s
     for (int ci = threadIdx.x; ci < n_all; ci += NT) {
         const int k = ci < n0 ? ci : ci - n0, le = k / p.C, sl = (ci < n0 ? g0.x : g1.x) + le;
+        NCG_CHECK(sl >= 0 && sl < p.E && SLOT_OF(ci) < SLOTS, "slot list index / car slot");
         s_gcar[SLOT_OF(ci)] = (p.slot_env ? p.slot_env[sl] : sl) * p.C + (k - le * p.C);
+        NCG_CHECK(s_gcar[SLOT_OF(ci)] >= 0 && s_gcar[SLOT_OF(ci)] < N, "global car index");
     }
     __syncthreads();
     const int cb0 = s_gcar[0];                                       // the CTA's first car: its record names the CTA's track
@@ -217,6 +219,8 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
     const bool active = warp < PW ? (PW == 2 ? lane < (warp == 0 ? n0 : n1) : (lane < LPW && slot < n0)) : (GROUPS == 1 && slot < n0);
     // track views are fixed for the launch (auto-reset keeps an env on its track): build them once
     const uint32_t my_tid = f2u(s_rec[NCG_R_TRACK]);              // slot 0: a CTA serves one track
+    NCG_CHECK(my_tid < (uint32_t)p.n_tracks, "track id of the CTA");
+    NCG_CHECK(!active || warp >= PW || f2u(s_rec[slot * REC_STRIDE + NCG_R_TRACK]) == my_tid, "a CTA serves ONE track");
     const float* gblob = p.blob + p.track_off[my_tid];
     const Track T = track_view(staged ? staged : gblob, gblob);
     const bool do_reset = p.auto_reset != 0;

@@ -48,13 +48,17 @@ NCG_HD Track track_view(const float* staged, const float* global) {
 // the k-th wall of a grid cell's list (lists are padded to blocks of 4 by repeating a block's first wall, so a wall
 // can appear twice: every consumer is insensitive to duplicates)
 NCG_HD int cell_count_max(const Track& T, int cell) { return (int)(T.cells[cell] >> 16) * 4; }
-NCG_HD int cell_item(const Track& T, int cell, int k) { return (int)T.items[(T.cells[cell] & 0xFFFFu) * 4u + (uint32_t)k]; }
+NCG_HD int cell_item(const Track& T, int cell, int k) {
+    NCG_CHECK(cell >= 0 && cell < T.gnx * T.gny && k >= 0 && k < cell_count_max(T, cell), "grid cell / list index");
+    return (int)T.items[(T.cells[cell] & 0xFFFFu) * 4u + (uint32_t)k];
+}
 NCG_HD void wall_get(const Track& T, int i, Xf* xf, Box* b) {
+    NCG_CHECK(i >= 0 && i < T.n_walls, "wall index");
     const float* w = T.walls + i * WALL_STRIDE;
     xf->p = mk(w[0], w[1]); xf->q.c = w[2]; xf->q.s = w[3]; b->hx = w[7]; b->hy = w[5];      // w[4] is the rays' half-length
 }
 NCG_HD float wall_angle(const Track& T, int i) { return T.walls[i * WALL_STRIDE + 6]; }
-NCG_HD AABB wall_fat(const Track& T, int i) { const float* a = T.aabb + i * 4; AABB r; r.lx = a[0]; r.ly = a[1]; r.ux = a[2]; r.uy = a[3]; return r; }
+NCG_HD AABB wall_fat(const Track& T, int i) { NCG_CHECK(i >= 0 && i < T.n_walls, "wall AABB index"); const float* a = T.aabb + i * 4; AABB r; r.lx = a[0]; r.ly = a[1]; r.ux = a[2]; r.uy = a[3]; return r; }
 
 // ------------------------------------------------------------------ the per-car Box2D world
 struct Contact { int wall; bool touching, enabled, toiFlag, island; int toiCount; float toi; Manifold m; };
@@ -1179,6 +1183,7 @@ template <bool SH> struct RayMem {
         if (SH) { walls = (unsigned)__cvta_generic_to_shared(T.walls); cells = (unsigned)__cvta_generic_to_shared(T.cells); items = (unsigned)__cvta_generic_to_shared(T.items); }
     }
     __device__ __forceinline__ void wall(uint32_t wi, F4* a, F4* b) const {
+        NCG_CHECK(wi < (uint32_t)t->n_walls, "ray loop: wall index");
         if (SH) {
             const unsigned ad = walls + wi * (WALL_STRIDE * 4u);
             asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w) : "r"(ad));
@@ -1186,10 +1191,13 @@ template <bool SH> struct RayMem {
         } else { const float* w = t->walls + wi * WALL_STRIDE; *a = *reinterpret_cast<const F4*>(w); b->x = w[4]; b->y = w[5]; }
     }
     __device__ __forceinline__ uint32_t cell(int c) const {
+        NCG_CHECK(c >= 0 && c < t->gnx * t->gny, "ray loop: grid cell");
         if (SH) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(cells + 4u * (unsigned)c)); return v; }
         return t->cells[c];
     }
     __device__ __forceinline__ void block(int k, uint32_t* lo, uint32_t* hi) const {
+        // (k may be one past a cell's list -- the one-block-ahead fetch -- but never past the item array plus its pad block)
+        NCG_CHECK(k >= 0 && 4 * k <= (int)f2u(t->hdr[TH_NITEMS]), "ray loop: item block");
         if (SH) { asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(*lo), "=r"(*hi) : "r"(items + 8u * (unsigned)k)); return; }
         const uint32_t* q = reinterpret_cast<const uint32_t*>(t->items + 4 * k); *lo = q[0]; *hi = q[1];
     }

@@ -15,6 +15,17 @@
 #define NCG_HDN static
 #endif
 
+// Checked build (-DNCG_CHECKED, `NCG_CHECKED=1 python -c "from nascargymnasium_b200 import engine; engine.build_library()"` ->
+// libncg_b200_checked.so): every table / record / slot index of the step kernel is range-checked on the device and a violation
+// prints its site and traps.  tests/test_gpu_checked.py runs the launch shapes through it.  (compute-sanitizer is closed on
+// the measurement pool -- profiles/README.md -- so this is the memory-safety evidence that can be produced there.)
+#if defined(NCG_CHECKED) && defined(__CUDA_ARCH__)
+#include <stdio.h>
+#define NCG_CHECK(cond, what) do { if (!(cond)) { printf("NCG_CHECK failed: %s (%s:%d) block %d thread %d\n", what, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } } while (0)
+#else
+#define NCG_CHECK(cond, what) ((void)0)
+#endif
+
 namespace ncg {
 
 // 16-byte vector load type: CUDA's float4 on the device build, a plain struct in the host test build
