@@ -76,9 +76,10 @@ import glob
 import os
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "traj_*.npz")))
+GOLDEN += sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_real", "traj_*.npz")))   # real box2d-py, if ever recorded
 
 
-@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[5:-4] for p in GOLDEN])
+@pytest.mark.parametrize("path", GOLDEN, ids=[("real_" if "golden_real" in p else "") + os.path.basename(p)[5:-4] for p in GOLDEN])
 def test_engine_free_runs_the_reference_generated_trajectories(path):
     """tests/golden/traj_*.npz were produced by the reference's own src/car_env.py (oracle/gen_golden.py).  The CUDA engine
     replays their action streams WITHOUT teacher forcing: until the first wall contact of a trajectory (after which float32

@@ -18,6 +18,12 @@ from oracle import oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TRAJ = sorted(glob.glob(os.path.join(GOLD, "traj_*.npz")))
+# tests/golden_real/: the same trajectories recorded over REAL box2d-py (`python oracle/gen_golden.py --real-box2d` on a machine
+# that has it; none exists offline).  When present they are replayed too, contacts included: that pins oracle/b2lite.h itself.
+# NCG_BOX2D=2.3.0 replays them under the 2.3.0 form of b2CollidePolygons.
+TRAJ += sorted(glob.glob(os.path.join(os.path.dirname(GOLD), "golden_real", "traj_*.npz")))
+if os.environ.get("NCG_BOX2D", "").strip() == "2.3.0":
+    O.set_b2_variant(1)
 LAYOUT = O.state_layout()
 
 
@@ -27,7 +33,7 @@ def test_fixtures_present():
         assert os.path.exists(os.path.join(GOLD, f))
 
 
-@pytest.mark.parametrize("path", TRAJ, ids=[os.path.basename(p)[5:-4] for p in TRAJ])
+@pytest.mark.parametrize("path", TRAJ, ids=[("real_" if "golden_real" in p else "") + os.path.basename(p)[5:-4] for p in TRAJ])
 def test_oracle_reproduces_reference_trajectory(path):
     with np.load(path) as z:
         g = {k: z[k] for k in z.files}            # NpzFile re-inflates on every access

@@ -59,29 +59,7 @@ def main():
             torch.cuda.synchronize()
             skips[{1: "no_rays", 2: "no_physics", 3: "neither"}[sk]] = a.elapsed_time(b) * 1e3 / 500
         os.environ.pop("NCG_DEBUG_SKIP", None)
-        # the same step captured in a CUDA graph: the launch as the GPU sees it, without the Python / ctypes call
-        static_a = acts[0].clone()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                v.step_torch(static_a)
-        torch.cuda.current_stream().wait_stream(side)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            v.step_torch(static_a)
-        for _ in range(50):
-            g.replay()
-        torch.cuda.synchronize()
-        a.record()
-        for t in range(args.steps):
-            static_a.copy_(acts[t % n_sets])
-            g.replay()
-        b.record()
-        torch.cuda.synchronize()
-        us_g = a.elapsed_time(b) * 1e3 / args.steps
-        out.append({"envs": E, "track": args.track, "us_per_step": us, "us_per_step_graph": us_g, "car_steps_per_s": E / (us * 1e-6),
-                    "car_steps_per_s_graph": E / (us_g * 1e-6), "us_per_step_debug_skip": skips})
+        out.append({"envs": E, "track": args.track, "us_per_step": us, "car_steps_per_s": E / (us * 1e-6), "us_per_step_debug_skip": skips})
         v.close()
     print(json.dumps(out))
 
