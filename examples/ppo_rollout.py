@@ -6,8 +6,11 @@ from a vectorised env, then clipped-objective updates -- with `SubprocVecEnv([..
 
     python examples/ppo_rollout.py --envs 16384 --track martinsville --discrete 1 --iters 5
 
-Multi-GPU: launch with torchrun; each rank owns its own envs (no data-path collective) and the gradients are averaged
-with one all-reduce per minibatch (NCCL).  Prints one JSON line per iteration from rank 0.
+Multi-GPU: launch with torchrun; each rank owns its own envs (no data-path collective).  --sync gather (default): once per
+iteration the rollouts and episode statistics of every rank are gathered on the learner rank (rank 0) over NCCL
+(nascargymnasium_b200.distributed.gather_rollout / reduce_stats), rank 0 runs the clipped-objective updates on the whole
+batch and broadcasts the new weights.  --sync allreduce: every rank updates on its own rollouts and the gradients are
+averaged with one all-reduce per minibatch.  Prints one JSON line per iteration from rank 0.
 """
 from __future__ import annotations
 
@@ -68,6 +71,8 @@ def main():
     ap.add_argument("--clip", type=float, default=0.2)
     ap.add_argument("--ent-coef", type=float, default=0.002)        # learn/ppo.py:97
     ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--sync", default="gather", choices=["gather", "allreduce"], help="multi-GPU: gather rollouts to the learner "
+                    "rank and broadcast weights, or average gradients")
     ap.add_argument("--graph", type=int, default=1, help="1: capture one rollout step (policy + env kernel + bookkeeping) in a CUDA "
                     "graph and replay it, instead of launching ~60 small kernels per step from Python")
     args = ap.parse_args()
@@ -166,11 +171,19 @@ def main():
                 last = delta + args.gamma * args.lam * nonterm * last
                 adv[t] = last
             ret = adv + b_val
-        fo, fa = b_obs.reshape(-1, 38), b_act.reshape(-1) if discrete else b_act.reshape(-1, 2)
-        fl, fadv, fret = b_logp.reshape(-1), adv.reshape(-1), ret.reshape(-1)
-        n = fo.shape[0]
+        g_obs, g_act, g_logp, g_adv, g_ret = b_obs, b_act, b_logp, adv, ret
+        learner = True
+        if world > 1 and args.sync == "gather":
+            # the per-iteration exchange: (T, E_local, ...) tensors concatenated along the env axis on the learner rank
+            from nascargymnasium_b200 import distributed as D
+            g_obs, g_act, g_logp, g_adv, g_ret = (D.gather_rollout(x, dst=0) for x in (b_obs, b_act, b_logp, adv, ret))
+            learner = rank == 0
         loss_v = loss_p = torch.zeros((), device=dev)
-        for _ in range(args.epochs):
+        if learner:
+            fo, fa = g_obs.reshape(-1, 38), g_act.reshape(-1) if discrete else g_act.reshape(-1, 2)
+            fl, fadv, fret = g_logp.reshape(-1), g_adv.reshape(-1), g_ret.reshape(-1)
+            n = fo.shape[0]
+        for _ in range(args.epochs if learner else 0):
             perm = torch.randperm(n, device=dev)
             for mb in perm.chunk(args.minibatches):
                 logp, ent, v = net.evaluate(fo[mb], fa[mb])
@@ -182,20 +195,27 @@ def main():
                 loss = loss_p + 0.5 * loss_v - args.ent_coef * ent.mean()
                 opt.zero_grad(set_to_none=True)
                 loss.backward()
-                if world > 1:
+                if world > 1 and args.sync == "allreduce":
                     for p_ in net.parameters():
                         if p_.grad is not None:              # (log_std has no gradient with a categorical head)
                             dist.all_reduce(p_.grad, op=dist.ReduceOp.SUM)
                             p_.grad /= world
                 nn.utils.clip_grad_norm_(net.parameters(), 0.5)
                 opt.step()
+        if world > 1 and args.sync == "gather":
+            for p_ in net.parameters():
+                dist.broadcast(p_.data, src=0)
+            from nascargymnasium_b200 import distributed as D
+            tot = D.reduce_stats({"done_count": float(done_count), "done_returns": float(done_returns)}, device=dev)
+        else:
+            tot = {"done_count": float(done_count), "done_returns": float(done_returns)}
         torch.cuda.synchronize()
         t_upd = time.perf_counter() - t0
         if rank == 0:
             print(json.dumps({"iter": it, "envs_per_gpu": E, "n_gpus": world, "n_steps": T,
                               "rollout_env_steps_per_s": world * E * T / t_roll, "rollout_s": t_roll, "update_s": t_upd,
-                              "mean_step_reward": float(b_rew.mean()), "episodes_done": float(done_count),
-                              "mean_episode_return": float(done_returns / done_count.clamp(min=1)),
+                              "mean_step_reward": float(b_rew.mean()), "episodes_done": tot["done_count"],
+                              "mean_episode_return": tot["done_returns"] / max(tot["done_count"], 1.0), "sync": args.sync if world > 1 else None,
                               "policy_loss": float(loss_p.detach()), "value_loss": float(loss_v.detach()), "obs_device": str(obs.device)}), flush=True)
     venv.close()
     if world > 1:

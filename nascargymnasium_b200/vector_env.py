@@ -267,7 +267,7 @@ def make_sb3_vec_env(num_envs: int, track_file=None, discrete_action_space: bool
             self._actions = None
 
         def reset(self):
-            return venv.reset()[0]
+            return venv.reset(seed=getattr(self, "_seed", None))[0]
 
         def step_async(self, actions):
             self._actions = actions
@@ -285,19 +285,40 @@ def make_sb3_vec_env(num_envs: int, track_file=None, discrete_action_space: bool
         def close(self):
             venv.close()
 
+        # Per-env attributes the wrappers ask a (Subproc)VecEnv for.  There is no per-env Python object here, so the ones
+        # SB3's Monitor / VecNormalize / evaluation helpers read are answered per env; anything else is the batched env's
+        # own attribute, once per requested index (documented deviation: it is the same object for every index).
+        _PER_ENV = {"render_mode": None, "num_cars": 1, "discrete_action_space": discrete_action_space, "reset_on_lap": reset_on_lap}
+
         def get_attr(self, attr_name, indices=None):
-            return [getattr(venv, attr_name)] * len(self._get_indices(indices))
+            idx = list(self._get_indices(indices))
+            if attr_name == "track_file":
+                tid = venv.track_id
+                return [venv.tracks[int(tid[i])] for i in idx]
+            if attr_name in ("action_space", "observation_space"):
+                sp = venv.single_action_space if attr_name == "action_space" else venv.single_observation_space
+                return [sp for _ in idx]
+            if attr_name in self._PER_ENV:
+                return [self._PER_ENV[attr_name] for _ in idx]
+            if attr_name == "spec":
+                return [None for _ in idx]
+            return [getattr(venv, attr_name) for _ in idx]
 
         def set_attr(self, attr_name, value, indices=None):
             setattr(venv, attr_name, value)
 
         def env_method(self, method_name, *args, indices=None, **kwargs):
-            return [getattr(venv, method_name)(*args, **kwargs)] * len(self._get_indices(indices))
+            idx = list(self._get_indices(indices))
+            if method_name == "get_info":
+                return [venv.get_info(i) for i in idx]
+            out = getattr(venv, method_name)(*args, **kwargs)
+            return [out for _ in idx]
 
         def env_is_wrapped(self, wrapper_class, indices=None):
             return [False] * len(self._get_indices(indices))
 
         def seed(self, seed=None):
-            return [seed] * num_envs
+            self._seed = seed
+            return [None if seed is None else seed + i for i in range(num_envs)]
 
     return _SB3()

@@ -361,6 +361,13 @@ def test_sb3_vec_env_adapter_against_a_stub_of_the_sb3_base_class(monkeypatch):
     assert infos[1]["terminal_observation"].shape == (38,) and infos[1]["episode"]["l"] == 600
     assert infos[1]["TimeLimit.truncated"] is False and infos[0] == {}
     assert env.env_is_wrapped(None) == [False] * 32 and len(env.get_attr("num_envs")) == 32
+    # per-env answers for the attributes SB3's wrappers ask for
+    assert env.get_attr("track_file", indices=[0, 5]) == ["tracks/martinsville.track"] * 2
+    assert env.get_attr("render_mode") == [None] * 32 and env.get_attr("num_cars", 3) == [1]
+    assert env.get_attr("action_space", [1])[0].n == 5
+    info7 = env.env_method("get_info", indices=[7])[0]
+    assert info7["num_cars"] == 1 and "lap_timing" in info7["cars"][0]
+    assert env.seed(10)[:3] == [10, 11, 12]
     env.close()
 
 
