@@ -190,12 +190,16 @@ NCG_HD int clip_segment(ClipV out[2], const ClipV in[2], V2 normal, float offset
     return n;
 }
 // v230: false = b2CollidePolygons of Box2D 2.3.1 and later (the default), true = of 2.3.0
-NCG_HD void collide_boxes(Manifold* m, const Box& bA, const Xf& xfA, const Box& bB, const Xf& xfB, bool v230 = false) {
+// *sep (optional) receives a lower bound of the distance between the two boxes at these poses: the separation along the
+// face normal on which the test ended (a separating axis never overestimates the distance).
+NCG_HD void collide_boxes(Manifold* m, const Box& bA, const Xf& xfA, const Box& bB, const Xf& xfB, bool v230 = false, float* sep = nullptr) {
     m->pc = 0;
     const float totalRadius = NCG_B2_POLY_RADIUS + NCG_B2_POLY_RADIUS;
     int edgeA = 0; float sepA = v230 ? find_max_separation230(&edgeA, bA, xfA, bB, xfB) : find_max_separation(&edgeA, bA, xfA, bB, xfB);
+    if (sep) *sep = sepA;
     if (sepA > totalRadius) return;
     int edgeB = 0; float sepB = v230 ? find_max_separation230(&edgeB, bB, xfB, bA, xfA) : find_max_separation(&edgeB, bB, xfB, bA, xfA);
+    if (sep) *sep = fmaxb(sepA, sepB);
     if (sepB > totalRadius) return;
     Box b1, b2; Xf xf1, xf2; int edge1, flip;
     const float k_tol = 0.1f * NCG_B2_LINEAR_SLOP;

@@ -61,7 +61,8 @@ NCG_HD float wall_angle(const Track& T, int i) { return T.walls[i * WALL_STRIDE 
 NCG_HD AABB wall_fat(const Track& T, int i) { NCG_CHECK(i >= 0 && i < T.n_walls, "wall AABB index"); const float* a = T.aabb + i * 4; AABB r; r.lx = a[0]; r.ly = a[1]; r.ux = a[2]; r.uy = a[3]; return r; }
 
 // ------------------------------------------------------------------ the per-car Box2D world
-struct Contact { int wall; bool touching, enabled, toiFlag, island; int toiCount; float toi; Manifold m; };
+struct Contact { int wall; bool touching, enabled, toiFlag, island; int toiCount; float toi; Manifold m;
+                 float sep0; };      // lower bound of the car-wall distance at the pose Collide saw this step, or < 0: unknown
 struct VCPoint { V2 rA; float ni, ti, nm, tm, bias; };
 struct VC { VCPoint p[2]; V2 normal; float K[4], nmat[4]; int pc, ci; };
 struct PC { V2 lp[2], localNormal, localPoint; int type, pc, wall; };
@@ -178,7 +179,7 @@ NCG_HDN void w_update_contact(World& W, const Track& T, Contact& c) {
     c.enabled = true;
     bool was = c.touching;
     Xf xfB; Box bB; wall_get(T, c.wall, &xfB, &bB);
-    collide_boxes(&c.m, car_box(), W.b.xf, bB, xfB, W.v230);
+    collide_boxes(&c.m, car_box(), W.b.xf, bB, xfB, W.v230, &c.sep0);
     bool touching = c.m.pc > 0;
     for (int i = 0; i < c.m.pc; ++i) {
         c.m.ni[i] = 0.0f; c.m.ti[i] = 0.0f;
@@ -233,7 +234,7 @@ NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
         for (int j = W.nc; j > 0; --j) { W.c[j] = W.c[j - 1]; W.wallAlpha[j] = W.wallAlpha[j - 1]; }
         Contact& c = W.c[0];
         c.wall = found[i]; c.touching = false; c.enabled = true; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f;
-        c.m.pc = 0; c.m.type = FACE_A;
+        c.m.pc = 0; c.m.type = FACE_A; c.sep0 = -1.0f;
         W.wallAlpha[0] = 0.0f;
         ++W.nc;
     }
@@ -423,6 +424,16 @@ NCG_HDN void w_solve(World& W, const Track& T, float h, float dtRatio) {
 NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
     W.b.sweep.alpha0 = 0.0f;
     for (int i = 0; i < W.nc; ++i) { W.wallAlpha[i] = 0.0f; Contact& c = W.c[i]; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f; }
+    // Most broad-phase contacts of a step are walls the car merely passes: b2TimeOfImpact can only answer e_touching (the one
+    // answer that yields alpha < 1) if some separation it evaluates along the sweep comes down to `target`; every separation it
+    // evaluates is at least the distance at the start pose minus what a car point can travel in the step.  Collide measured a
+    // lower bound of that distance on a separating axis this very step (Contact::sep0, at the pose the sweep starts from), so
+    // while nothing has advanced the sweep yet a contact with  sep0 > target + tolerance + 2 * (|dc| + |da| * R) + 1 cm  keeps
+    // alpha = 1 without the GJK / root-finder query -- the same outcome, contact by contact (the parity tests compare the TOI
+    // counters and contact lists exactly).  R = the car's half diagonal.
+    const float toi_reach = 2.0f * (length(W.b.sweep.c - W.b.sweep.c0) + fabsf(W.b.sweep.a - W.b.sweep.a0) * 2.7114f)
+                            + (NCG_B2_LINEAR_SLOP + 0.25f * NCG_B2_LINEAR_SLOP) + 0.01f;
+    bool pristine = true;                                   // no TOI event has advanced the sweep or touched the contacts yet
     for (;;) {
         int minC = -1; float minAlpha = 1.0f;
         for (int i = 0; i < W.nc; ++i) {
@@ -433,6 +444,9 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
             if (c.toiFlag) alpha = c.toi;
             else {
                 if (!W.b.awake) continue;
+#ifndef NCG_NO_TOI_SHORTCUT      /* (tests/test_hostcheck.py builds the host compile both ways and demands identical records) */
+                if (pristine && c.sep0 > toi_reach) { c.toi = 1.0f; c.toiFlag = true; continue; }
+#endif
                 float alpha0 = W.b.sweep.alpha0;
                 if (W.b.sweep.alpha0 < W.wallAlpha[i]) { alpha0 = W.wallAlpha[i]; sweep_advance(W.b.sweep, alpha0); }
                 else if (W.wallAlpha[i] < W.b.sweep.alpha0) { alpha0 = W.b.sweep.alpha0; W.wallAlpha[i] = alpha0; }
@@ -447,6 +461,7 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
         }
         if (minC < 0 || 1.0f - 10.0f * NCG_B2_EPS < minAlpha) break;
         Contact& mc = W.c[minC];
+        pristine = false;
         Sweep backup = W.b.sweep; float backupWall = W.wallAlpha[minC];
         w_advance(W, minAlpha); W.wallAlpha[minC] = minAlpha;
         w_update_contact(W, T, mc);
@@ -515,7 +530,7 @@ NCG_HD void w_load_contacts(World& W, const float* R) {
         Contact& c = W.c[i];
         uint32_t ww = f2u(R[NCG_R_CONTACT_WALL + (i >> 1)]);
         c.wall = (int)((i & 1) ? (ww >> 16) : (ww & 0xFFFFu));
-        c.touching = ((tmask >> i) & 1u) != 0; c.enabled = true; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f;
+        c.touching = ((tmask >> i) & 1u) != 0; c.enabled = true; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f; c.sep0 = -1.0f;
         c.m.pc = 0; c.m.type = FACE_A; c.m.localNormal = mk(0.0f, 0.0f); c.m.localPoint = mk(0.0f, 0.0f);
         W.wallAlpha[i] = 0.0f;
         if (c.touching && k < NCG_MAX_TOUCHING) {

@@ -241,20 +241,22 @@ def compare_records(got: np.ndarray, want: np.ndarray, contact_fields: bool = Tr
 
 
 # ----------------------------------------------------------------------------- hostcheck (CPU compile of the device code)
-_HC = None
+_HC = {}
 
 
-def hostcheck():
-    global _HC
-    if _HC is None:
+def hostcheck(no_toi_shortcut: bool = False):
+    """The host compile of the device code (tests/hostcheck).  no_toi_shortcut: the same source with the TOI early-out of
+    w_solve_toi compiled out (-DNCG_NO_TOI_SHORTCUT), to prove the early-out changes nothing."""
+    key = bool(no_toi_shortcut)
+    if key not in _HC:
         src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
-        out = os.path.join(ROOT, "tests", "hostcheck", "_build", "libncg_hostcheck.so")
+        out = os.path.join(ROOT, "tests", "hostcheck", "_build", "libncg_hostcheck_notoi.so" if key else "libncg_hostcheck.so")
         deps = [src] + [os.path.join(ROOT, "nascargymnasium_b200", "csrc", f) for f in ("ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")] + \
                [os.path.join(ROOT, "include", "ncg_b200.h")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
-                                   "-Wno-unknown-pragmas", "-o", out, src])
+                                   "-Wno-unknown-pragmas"] + (["-DNCG_NO_TOI_SHORTCUT"] if key else []) + ["-o", out, src])
         lib = ctypes.CDLL(out)
         fp, ip = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)
         lib.hc_env_step.argtypes = [fp, fp, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp, fp, ip, ip, ip,
@@ -267,8 +269,8 @@ def hostcheck():
         lib.hc_nearest_segment.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_int, fp]
         lib.hc_on_track.argtypes = [fp, ctypes.c_float, ctypes.c_float]
         lib.hc_synthetic_action.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int, fp]
-        _HC = lib
-    return _HC
+        _HC[key] = lib
+    return _HC[key]
 
 
 def _fp(a):
@@ -278,7 +280,9 @@ def _fp(a):
 class HostCheckEnv:
     """One env of C cars stepped by the host compile of the device code."""
 
-    def __init__(self, track_name: str, num_cars: int = 1, reset_on_lap: bool = False, contacts: bool = True):
+    def __init__(self, track_name: str, num_cars: int = 1, reset_on_lap: bool = False, contacts: bool = True,
+                 no_toi_shortcut: bool = False):
+        self.lib = hostcheck(no_toi_shortcut)
         self.table = T.get_track_table(track_name)
         self.blob = np.ascontiguousarray(self.table.blob)
         self.C = num_cars
@@ -289,7 +293,7 @@ class HostCheckEnv:
 
     def reset(self, fresh=True):
         obs = np.zeros((self.C, 38), dtype=np.float32)
-        hostcheck().hc_env_reset(_fp(self.blob), _fp(self.records), self.C, int(fresh), 0, _fp(obs))
+        self.lib.hc_env_reset(_fp(self.blob), _fp(self.records), self.C, int(fresh), 0, _fp(obs))
         return obs
 
     def step(self, act3):
@@ -297,7 +301,7 @@ class HostCheckEnv:
         obs = np.zeros((self.C, 38), dtype=np.float32)
         rew = np.zeros(self.C, dtype=np.float32)
         te, tr, why = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        hostcheck().hc_env_step(_fp(self.blob), _fp(self.records), self.C, _fp(act3), int(self.contacts), int(self.reset_on_lap),
+        self.lib.hc_env_step(_fp(self.blob), _fp(self.records), self.C, _fp(act3), int(self.contacts), int(self.reset_on_lap),
                                 _fp(obs), _fp(rew), ctypes.byref(te), ctypes.byref(tr), ctypes.byref(why), self.counters)
         return obs, rew, bool(te.value), bool(tr.value), why.value
 

@@ -176,3 +176,31 @@ def test_nearest_segment_candidate_mask_is_exact():
             hc.hc_nearest_segment(P._fp(blob), x, y, 1, P._fp(a))
             hc.hc_nearest_segment(P._fp(blob), x, y, 0, P._fp(b))
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, x, y, a, b)
+
+
+@pytest.mark.parametrize("track,kind", [("martinsville", "drive"), ("daytona", "drive"), ("michigan", "drive"), ("trioval", "drive")])
+def test_toi_early_out_changes_nothing(track, kind):
+    """w_solve_toi skips the b2TimeOfImpact query for a broad-phase contact whose start-of-step separation (measured by Collide
+    on a separating axis) exceeds what the car can travel in the step.  The claim is that the outcome is the same contact by
+    contact: the device source compiled with and without the early-out must produce bit-identical records, observations and
+    TOI counters over long free runs with lots of wall contact."""
+    rng = np.random.default_rng(3)
+    a = P.HostCheckEnv(track)
+    b = P.HostCheckEnv(track, no_toi_shortcut=True)
+    a.reset(); b.reset()
+    touching_steps = skipped_possible = 0
+    for t in range(6000):
+        act = P.policy_actions(kind, rng, False)
+        tb, st = act
+        act3 = np.array([max(tb, 0.0), max(-tb, 0.0), st], dtype=np.float32)
+        oa, ra, tea, tra, _ = a.step(act3)
+        ob, rb, teb, trb, _ = b.step(act3)
+        assert np.array_equal(a.records.view(np.uint32), b.records.view(np.uint32)), t
+        assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32)) and (tea, tra) == (teb, trb), t
+        nc = int(a.records.view(np.uint32)[0, L.R["NCG_R_NCONTACT"]])
+        touching_steps += 1 if (nc >> 16) & 0xFFF else 0
+        skipped_possible += 1 if (nc & 255) else 0
+        if tea or tra:
+            a.reset(fresh=False); b.reset(fresh=False)
+    assert list(a.counters) == list(b.counters)                   # incl. TOI events and contact steps
+    assert skipped_possible > 500, (touching_steps, skipped_possible)
