@@ -18,7 +18,9 @@ from . import track as T
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # NCG_CHECKED=1: the range-checked build of the same source (csrc/ncg_defs.cuh NCG_CHECK), a debugging aid, several times slower
 _CHECKED = os.environ.get("NCG_CHECKED", "") not in ("", "0")
-_SO = os.path.join(_PKG, "libncg_b200_checked.so" if _CHECKED else "libncg_b200.so")
+# NCG_VARIANT=name NCG_DEFINES="-DX -DY": an A/B build of the same source under another file name (measurement only)
+_VARIANT = os.environ.get("NCG_VARIANT", "").strip()
+_SO = os.path.join(_PKG, f"libncg_b200_{_VARIANT}.so" if _VARIANT else ("libncg_b200_checked.so" if _CHECKED else "libncg_b200.so"))
 _CSRC = os.path.join(_PKG, "csrc")
 _SOURCES = ("ncg_b200.cu", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
 
@@ -46,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not have_src:
         raise NcgError("CUDA sources missing and no prebuilt libncg_b200.so")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-DNCG_CHECKED"] if _CHECKED else []) + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [nvcc] + NVCC_FLAGS + (["-DNCG_CHECKED"] if _CHECKED else []) + (os.environ.get("NCG_DEFINES", "").split() if _VARIANT else []) + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", _SO + ".tmp", os.path.join(_CSRC, "ncg_b200.cu")]
     subprocess.check_call(cmd)
     os.replace(_SO + ".tmp", _SO)
