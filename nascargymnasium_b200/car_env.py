@@ -41,8 +41,10 @@ class CarEnv(_Base):
             if len(car_names) != num_cars:
                 raise ValueError(f"Number of car names ({len(car_names)}) must match number of cars ({num_cars})")
             self.car_names = list(car_names)
-        if render_mode == "human":
-            raise NotImplementedError("render_mode='human' (pygame window) is outside the accelerated path; use render_mode=None")
+        # render_mode="human": the window is the reference's own pygame Renderer, fed from the engine's records through
+        # render_bridge.frame_kwargs; it is created at the first render() and needs the reference tree + pygame importable
+        self._renderer = None
+        self._last_rewards, self._last_actions = None, None
         self.render_mode = render_mode
         self.discrete_action_space = discrete_action_space
         self.num_cars = num_cars
@@ -130,6 +132,7 @@ class CarEnv(_Base):
         else:
             a = np.asarray(action, dtype=np.float32).reshape(self.num_cars, 2)
         obs, rew, te, tr, _ = self._engine.step_host(a)
+        self._last_rewards, self._last_actions = rew, a
         recs = self._engine.get_state_host()
         terminated, truncated = bool(te[0]), bool(tr[0])
         self._update_mirrors(recs, rew, terminated, truncated)
@@ -166,13 +169,35 @@ class CarEnv(_Base):
             p["bodies_in_world"] = n_bodies
         return info
 
+    def render_state(self) -> Dict[str, Any]:
+        """What CarEnv.render passes to Renderer.render_frame (car_env.py:1387-1401), from the engine's records."""
+        from . import render_bridge as RB
+        if self._engine is None or not self._was_reset:
+            raise RuntimeError("Environment not properly initialized. Call reset() first.")
+        tab = self._engine.tables[self._track_index]
+        return RB.frame_kwargs(self._engine.get_state_host(), tab.seg64, tab.track.total_length, self.car_names, self.followed_car_index,
+                               self._last_rewards, self._last_actions, self.reset_on_lap, self.track_file)
+
     def render(self):
-        return None
+        if self.render_mode != "human":
+            return None
+        from . import render_bridge as RB
+        if self._renderer is None:
+            try:
+                self._renderer = RB.make_reference_renderer(self.track_file, self.metadata["render_fps"])
+            except ImportError as e:
+                raise NotImplementedError("render_mode='human' draws with the reference's own pygame Renderer (src/renderer.py): put the "
+                                          f"NascarGymnasium tree on sys.path and install pygame ({e}); render_state() gives the frame data") from e
+        if self._was_reset:
+            self._renderer.render_frame(**self.render_state())
 
     def check_quit_requested(self) -> bool:
         return False
 
     def close(self) -> None:
+        if self._renderer is not None:
+            self._renderer.close()
+            self._renderer = None
         if self._engine is not None:
             self._engine.close()
             self._engine = None
