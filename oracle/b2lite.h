@@ -1059,4 +1059,329 @@ struct World {
     }
 };
 
+// ------------------------------------------------------------------ optional shared world (default off)
+// The reference gives every car a private b2World (src/car_env.py:389-394), so cars never touch each other.  This is the
+// Box2D semantics of putting the C cars of an env into ONE world instead: car-vs-car contacts between dynamic boxes, solved
+// with full two-body rows together with each car's wall contacts, islands built over touching car-car contacts.  There is no
+// reference behaviour to pin; the arithmetic is b2ContactSolver's general form and the orderings that Box2D leaves to its
+// contact lists are fixed here as follows (the CUDA engine does the same):
+//   * a car-car contact exists while the two fat AABBs overlap, is created after Solve / after the TOI phase like
+//     b2ContactManager::FindNewContacts does, and is destroyed in Collide;
+//   * an island = the cars connected by touching car-car contacts; its constraint order is every member's wall contacts
+//     (members in ascending car index, each car's own list order), then the car-car contacts in ascending (i, j);
+//   * TOI: Box2D skips contacts between two non-bullet dynamic bodies, so the continuous phase stays per car against walls.
+// Listener: a car-car contact reports to both cars like a wall contact does (key = -1 - other car; the normal points away
+// from the reporting car).
+struct PairContact { int i, j; bool touching; Manifold m; };
+struct PairVC { VelocityConstraint vc; PositionConstraint pc; int i, j; };
+
+struct SharedWorld {
+    std::vector<World*> cars;
+    std::vector<PairContact> pairs;             // ascending (i, j)
+    f32 friction, restitution;                  // b2MixFriction / b2MixRestitution of two car fixtures
+
+    void clear() { pairs.clear(); }
+    int find(int i, int j) const { for (size_t k = 0; k < pairs.size(); ++k) if (pairs[k].i == i && pairs[k].j == j) return (int)k; return -1; }
+    // b2ContactManager::FindNewContacts for the car proxies against each other
+    void findNewPairs() {
+        int n = (int)cars.size();
+        for (int i = 0; i < n; ++i) for (int j = i + 1; j < n; ++j) {
+            if (!overlap(cars[i]->carFat, cars[j]->carFat)) continue;
+            if (find(i, j) >= 0) continue;
+            PairContact pc; pc.i = i; pc.j = j; pc.touching = false; pc.m.pointCount = 0; pc.m.type = FACE_A;
+            size_t pos = 0; while (pos < pairs.size() && (pairs[pos].i < i || (pairs[pos].i == i && pairs[pos].j < j))) ++pos;
+            pairs.insert(pairs.begin() + pos, pc);
+        }
+    }
+    // b2Contact::Update for a car-car contact
+    void updatePair(PairContact& p) {
+        World& A = *cars[p.i]; World& B = *cars[p.j];
+        Manifold old = p.m;
+        bool was = p.touching;
+        collidePolygons(&p.m, A.carPoly, A.xf, B.carPoly, B.xf);
+        bool touching = p.m.pointCount > 0;
+        for (int a = 0; a < p.m.pointCount; ++a) {
+            MPoint* mp2 = p.m.points + a; mp2->normalImpulse = 0.0f; mp2->tangentImpulse = 0.0f;
+            for (int b = 0; b < old.pointCount; ++b) if (old.points[b].key == mp2->key) {
+                mp2->normalImpulse = old.points[b].normalImpulse; mp2->tangentImpulse = old.points[b].tangentImpulse; break;
+            }
+        }
+        if (touching != was) { A.setAwake(true); B.setAwake(true); }
+        p.touching = touching;
+        if (!was && touching) {
+            WorldManifold wm; wm.initialize(&p.m, A.xf, A.carPoly.radius, B.xf, B.carPoly.radius);
+            if (A.listener) A.listener->beginContact(-1 - p.j, wm.normal);
+            if (B.listener) B.listener->beginContact(-1 - p.i, -wm.normal);
+        }
+        if (was && !touching) { if (A.listener) A.listener->endContact(-1 - p.j); if (B.listener) B.listener->endContact(-1 - p.i); }
+    }
+    void collidePairs() {
+        for (size_t k = 0; k < pairs.size();) {
+            PairContact& p = pairs[k];
+            World& A = *cars[p.i]; World& B = *cars[p.j];
+            if (!A.awake && !B.awake) { ++k; continue; }
+            if (!overlap(A.carFat, B.carFat)) {
+                if (p.touching) { if (A.listener) A.listener->endContact(-1 - p.j); if (B.listener) B.listener->endContact(-1 - p.i); }
+                pairs.erase(pairs.begin() + k);
+                continue;
+            }
+            updatePair(p);
+            ++k;
+        }
+    }
+    // ---- two-body rows (b2ContactSolver, both bodies dynamic)
+    std::vector<PairVC> rows;
+    void rowsInit(const std::vector<int>& isl, f32 dtRatio) {
+        rows.clear();
+        for (int k : isl) {
+            PairContact& p = pairs[k]; PairVC r; r.i = p.i; r.j = p.j;
+            VelocityConstraint& vc = r.vc; PositionConstraint& pc = r.pc;
+            vc.friction = friction; vc.restitution = restitution; vc.contactIndex = k; vc.pointCount = p.m.pointCount;
+            for (int q = 0; q < 4; ++q) { vc.K[q] = 0.0f; vc.nm[q] = 0.0f; }
+            pc.localNormal = p.m.localNormal; pc.localPoint = p.m.localPoint; pc.pointCount = p.m.pointCount; pc.type = p.m.type; pc.wall = -1;
+            for (int a = 0; a < p.m.pointCount; ++a) {
+                VCPoint& cp = vc.points[a];
+                cp.normalImpulse = dtRatio * p.m.points[a].normalImpulse; cp.tangentImpulse = dtRatio * p.m.points[a].tangentImpulse;
+                cp.rA = mk(0, 0); cp.rB = mk(0, 0); cp.normalMass = 0.0f; cp.tangentMass = 0.0f; cp.velocityBias = 0.0f;
+                pc.localPoints[a] = p.m.points[a].localPoint;
+            }
+            rows.push_back(r);
+        }
+    }
+    void rowsInitVelocity() {
+        for (PairVC& r : rows) {
+            World& A = *cars[r.i]; World& B = *cars[r.j];
+            VelocityConstraint& vc = r.vc; PairContact& p = pairs[vc.contactIndex];
+            f32 mA = A.invMass, mB = B.invMass, iA = A.invI, iB = B.invI;
+            V2 cA = A.pc_c, cB = B.pc_c; f32 aA = A.pc_a, aB = B.pc_a; V2 vA = A.pv, vB = B.pv; f32 wA = A.pw, wB = B.pw;
+            Xf xfA, xfB; xfA.q.set(aA); xfB.q.set(aB);
+            xfA.p = cA - mul(xfA.q, A.sweep.localCenter); xfB.p = cB - mul(xfB.q, B.sweep.localCenter);
+            WorldManifold wm; wm.initialize(&p.m, xfA, A.carPoly.radius, xfB, B.carPoly.radius);
+            vc.normal = wm.normal;
+            for (int a = 0; a < vc.pointCount; ++a) {
+                VCPoint& cp = vc.points[a];
+                cp.rA = wm.points[a] - cA; cp.rB = wm.points[a] - cB;
+                f32 rnA = cross(cp.rA, vc.normal), rnB = cross(cp.rB, vc.normal);
+                f32 kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                cp.normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+                V2 tangent = cross(vc.normal, 1.0f);
+                f32 rtA = cross(cp.rA, tangent), rtB = cross(cp.rB, tangent);
+                f32 kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+                cp.tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+                cp.velocityBias = 0.0f;
+                f32 vRel = dot(vc.normal, vB + cross(wB, cp.rB) - vA - cross(wA, cp.rA));
+                if (vRel < -kVelocityThreshold) cp.velocityBias = -vc.restitution * vRel;
+            }
+            if (vc.pointCount == 2) {
+                VCPoint& p1 = vc.points[0]; VCPoint& p2 = vc.points[1];
+                f32 rn1A = cross(p1.rA, vc.normal), rn1B = cross(p1.rB, vc.normal);
+                f32 rn2A = cross(p2.rA, vc.normal), rn2B = cross(p2.rB, vc.normal);
+                f32 k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+                f32 k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+                f32 k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+                if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+                    vc.K[0] = k11; vc.K[1] = k12; vc.K[2] = k12; vc.K[3] = k22;
+                    f32 det = k11 * k22 - k12 * k12;
+                    if (det != 0.0f) det = 1.0f / det;
+                    vc.nm[0] = det * k22; vc.nm[2] = -det * k12; vc.nm[1] = -det * k12; vc.nm[3] = det * k11;
+                } else vc.pointCount = 1;
+            }
+        }
+    }
+    static void applyPair(World& A, World& B, V2 P, V2 rA, V2 rB) {
+        A.pv = A.pv - A.invMass * P; A.pw -= A.invI * cross(rA, P);
+        B.pv = B.pv + B.invMass * P; B.pw += B.invI * cross(rB, P);
+    }
+    void rowsWarmStart() {
+        for (PairVC& r : rows) {
+            World& A = *cars[r.i]; World& B = *cars[r.j]; VelocityConstraint& vc = r.vc;
+            V2 tangent = cross(vc.normal, 1.0f);
+            for (int a = 0; a < vc.pointCount; ++a) {
+                VCPoint& cp = vc.points[a];
+                V2 P = cp.normalImpulse * vc.normal + cp.tangentImpulse * tangent;
+                applyPair(A, B, P, cp.rA, cp.rB);
+            }
+        }
+    }
+    void rowsSolveVelocity() {
+        for (PairVC& r : rows) {
+            World& A = *cars[r.i]; World& B = *cars[r.j]; VelocityConstraint& vc = r.vc;
+            V2 normal = vc.normal, tangent = cross(normal, 1.0f);
+            for (int a = 0; a < vc.pointCount; ++a) {
+                VCPoint& cp = vc.points[a];
+                V2 dv = B.pv + cross(B.pw, cp.rB) - A.pv - cross(A.pw, cp.rA);
+                f32 vt = dot(dv, tangent) - 0.0f;
+                f32 lambda = cp.tangentMass * (-vt);
+                f32 maxFriction = vc.friction * cp.normalImpulse;
+                f32 newImpulse = clampf(cp.tangentImpulse + lambda, -maxFriction, maxFriction);
+                lambda = newImpulse - cp.tangentImpulse; cp.tangentImpulse = newImpulse;
+                applyPair(A, B, lambda * tangent, cp.rA, cp.rB);
+            }
+            if (vc.pointCount == 1) {
+                VCPoint& cp = vc.points[0];
+                V2 dv = B.pv + cross(B.pw, cp.rB) - A.pv - cross(A.pw, cp.rA);
+                f32 vn = dot(dv, normal);
+                f32 lambda = -cp.normalMass * (vn - cp.velocityBias);
+                f32 newImpulse = fmax2(cp.normalImpulse + lambda, 0.0f);
+                lambda = newImpulse - cp.normalImpulse; cp.normalImpulse = newImpulse;
+                applyPair(A, B, lambda * normal, cp.rA, cp.rB);
+            } else if (vc.pointCount == 2) {
+                VCPoint& cp1 = vc.points[0]; VCPoint& cp2 = vc.points[1];
+                V2 a = mk(cp1.normalImpulse, cp2.normalImpulse);
+                V2 dv1 = B.pv + cross(B.pw, cp1.rB) - A.pv - cross(A.pw, cp1.rA);
+                V2 dv2 = B.pv + cross(B.pw, cp2.rB) - A.pv - cross(A.pw, cp2.rA);
+                f32 vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+                V2 b = mk(vn1 - cp1.velocityBias, vn2 - cp2.velocityBias);
+                b = b - mk(vc.K[0] * a.x + vc.K[2] * a.y, vc.K[1] * a.x + vc.K[3] * a.y);
+                V2 x; bool ok = false;
+                for (;;) {
+                    x = -mk(vc.nm[0] * b.x + vc.nm[2] * b.y, vc.nm[1] * b.x + vc.nm[3] * b.y);
+                    if (x.x >= 0.0f && x.y >= 0.0f) { ok = true; break; }
+                    x.x = -cp1.normalMass * b.x; x.y = 0.0f; vn2 = vc.K[1] * x.x + b.y;
+                    if (x.x >= 0.0f && vn2 >= 0.0f) { ok = true; break; }
+                    x.x = 0.0f; x.y = -cp2.normalMass * b.y; vn1 = vc.K[2] * x.y + b.x;
+                    if (x.y >= 0.0f && vn1 >= 0.0f) { ok = true; break; }
+                    x.x = 0.0f; x.y = 0.0f; vn1 = b.x; vn2 = b.y;
+                    if (vn1 >= 0.0f && vn2 >= 0.0f) { ok = true; break; }
+                    break;
+                }
+                if (ok) {
+                    V2 d = x - a; V2 P1 = d.x * normal, P2 = d.y * normal;
+                    A.pv = A.pv - A.invMass * (P1 + P2); A.pw -= A.invI * (cross(cp1.rA, P1) + cross(cp2.rA, P2));
+                    B.pv = B.pv + B.invMass * (P1 + P2); B.pw += B.invI * (cross(cp1.rB, P1) + cross(cp2.rB, P2));
+                    cp1.normalImpulse = x.x; cp2.normalImpulse = x.y;
+                }
+            }
+        }
+    }
+    void rowsStore() {
+        for (PairVC& r : rows) { Manifold& m = pairs[r.vc.contactIndex].m; for (int a = 0; a < r.vc.pointCount; ++a) { m.points[a].normalImpulse = r.vc.points[a].normalImpulse; m.points[a].tangentImpulse = r.vc.points[a].tangentImpulse; } }
+    }
+    bool rowsSolvePosition() {
+        f32 minSeparation = 0.0f;
+        for (PairVC& r : rows) {
+            World& A = *cars[r.i]; World& B = *cars[r.j]; PositionConstraint& pc = r.pc;
+            f32 mA = A.invMass, iA = A.invI, mB = B.invMass, iB = B.invI;
+            V2 cA = A.pc_c, cB = B.pc_c; f32 aA = A.pc_a, aB = B.pc_a;
+            for (int a = 0; a < pc.pointCount; ++a) {
+                Xf xfA, xfB; xfA.q.set(aA); xfB.q.set(aB);
+                xfA.p = cA - mul(xfA.q, A.sweep.localCenter); xfB.p = cB - mul(xfB.q, B.sweep.localCenter);
+                V2 normal, point; f32 separation;
+                if (pc.type == FACE_A) {
+                    normal = mul(xfA.q, pc.localNormal);
+                    V2 planePoint = mul(xfA, pc.localPoint), clipPoint = mul(xfB, pc.localPoints[a]);
+                    separation = dot(clipPoint - planePoint, normal) - A.carPoly.radius - B.carPoly.radius;
+                    point = clipPoint;
+                } else {
+                    normal = mul(xfB.q, pc.localNormal);
+                    V2 planePoint = mul(xfB, pc.localPoint), clipPoint = mul(xfA, pc.localPoints[a]);
+                    separation = dot(clipPoint - planePoint, normal) - A.carPoly.radius - B.carPoly.radius;
+                    point = clipPoint; normal = -normal;
+                }
+                V2 rA = point - cA, rB = point - cB;
+                minSeparation = fmin2(minSeparation, separation);
+                f32 C = clampf(kBaumgarte * (separation + kLinearSlop), -kMaxLinearCorrection, 0.0f);
+                f32 rnA = cross(rA, normal), rnB = cross(rB, normal);
+                f32 K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                f32 impulse = K > 0.0f ? -C / K : 0.0f;
+                V2 P = impulse * normal;
+                cA = cA - mA * P; aA -= iA * cross(rA, P);
+                cB = cB + mB * P; aB += iB * cross(rB, P);
+            }
+            A.pc_c = cA; A.pc_a = aA; B.pc_c = cB; B.pc_a = aB;
+        }
+        return minSeparation >= -3.0f * kLinearSlop;
+    }
+    void rowsReport() {
+        for (PairVC& r : rows) {
+            f32 ni[2] = {0.0f, 0.0f};
+            for (int a = 0; a < r.vc.pointCount; ++a) ni[a] = r.vc.points[a].normalImpulse;
+            if (cars[r.i]->listener) cars[r.i]->listener->postSolve(-1 - r.j, r.vc.pointCount, ni);
+            if (cars[r.j]->listener) cars[r.j]->listener->postSolve(-1 - r.i, r.vc.pointCount, ni);
+        }
+    }
+    // b2Island::Solve for the cars `mem` (ascending) joined by the touching pair contacts `isl` (ascending)
+    void solveIsland(const std::vector<int>& mem, const std::vector<int>& isl, f32 h, int velIters, int posIters, f32 dtRatio) {
+        for (int k : mem) {
+            World& W = *cars[k];
+            W.setAwake(true);
+            W.islandContacts.clear();
+            for (size_t c = 0; c < W.contacts.size(); ++c) if (W.contacts[c].enabled && W.contacts[c].touching) W.islandContacts.push_back((int)c);
+            W.pc_c = W.sweep.c; W.pc_a = W.sweep.a; W.pv = W.v; W.pw = W.w;
+            W.sweep.c0 = W.sweep.c; W.sweep.a0 = W.sweep.a;
+            W.pv = W.pv + h * (1.0f * mk(0.0f, 0.0f) + W.invMass * W.force);
+            W.pw += h * W.invI * W.torque;
+            W.pv = (1.0f / (1.0f + h * 0.0f)) * W.pv;
+            W.pw *= 1.0f / (1.0f + h * 0.0f);
+            W.solverInit(true, dtRatio);
+        }
+        rowsInit(isl, dtRatio);
+        for (int k : mem) cars[k]->initializeVelocityConstraints();
+        rowsInitVelocity();
+        for (int k : mem) cars[k]->warmStart();
+        rowsWarmStart();
+        for (int it = 0; it < velIters; ++it) { for (int k : mem) cars[k]->solveVelocityConstraints(); rowsSolveVelocity(); }
+        for (int k : mem) cars[k]->storeImpulses();
+        rowsStore();
+        for (int k : mem) cars[k]->integratePositions(h);
+        bool positionSolved = false;
+        for (int it = 0; it < posIters; ++it) {
+            bool ok = true;
+            for (int k : mem) ok = cars[k]->solvePositionConstraints(kBaumgarte, -3.0f) && ok;
+            ok = rowsSolvePosition() && ok;
+            if (ok) { positionSolved = true; break; }
+        }
+        f32 minSleepTime = kMaxFloat;
+        for (int k : mem) {
+            World& W = *cars[k];
+            W.sweep.c = W.pc_c; W.sweep.a = W.pc_a; W.v = W.pv; W.w = W.pw;
+            W.synchronizeTransform();
+        }
+        for (int k : mem) cars[k]->report();
+        rowsReport();
+        const f32 linTolSqr = kLinearSleepTol * kLinearSleepTol, angTolSqr = kAngularSleepTol * kAngularSleepTol;
+        for (int k : mem) {
+            World& W = *cars[k];
+            if (W.w * W.w > angTolSqr || dot(W.v, W.v) > linTolSqr) { W.sleepTime = 0.0f; minSleepTime = 0.0f; }
+            else { W.sleepTime += h; minSleepTime = fmin2(minSleepTime, W.sleepTime); }
+        }
+        if (minSleepTime >= kTimeToSleep && positionSolved) for (int k : mem) cars[k]->setAwake(false);
+        for (int k : mem) { cars[k]->synchronizeFixtures(); cars[k]->findNewContacts(); }
+    }
+    // b2World::Step of the shared world
+    void step(f32 dt, int velIters, int posIters) {
+        int n = (int)cars.size();
+        f32 inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+        bool anyNew = false;
+        for (World* W : cars) if (W->newFixture) { W->findNewContacts(); W->newFixture = false; anyNew = true; }
+        if (anyNew) findNewPairs();
+        for (World* W : cars) W->collide();
+        collidePairs();
+        // islands: union of cars over touching car-car contacts
+        std::vector<int> root(n); for (int i = 0; i < n; ++i) root[i] = i;
+        auto findr = [&](int x) { while (root[x] != x) x = root[x]; return x; };
+        for (PairContact& p : pairs) if (p.touching) { int a = findr(p.i), b = findr(p.j); if (a != b) root[a > b ? a : b] = (a > b ? b : a); }
+        std::vector<bool> done(n, false);
+        for (int i = 0; i < n; ++i) {
+            if (done[i]) continue;
+            std::vector<int> mem, isl;
+            for (int k = i; k < n; ++k) if (!done[k] && findr(k) == findr(i)) mem.push_back(k);
+            for (int k : mem) done[k] = true;
+            for (size_t q = 0; q < pairs.size(); ++q) if (pairs[q].touching && findr(pairs[q].i) == findr(i)) isl.push_back((int)q);
+            if (isl.empty()) {
+                World& W = *cars[i];
+                if (W.stepComplete && dt > 0.0f) W.solve(dt, velIters, posIters, W.inv_dt0 * dt);
+                continue;
+            }
+            bool anyAwake = false; for (int k : mem) anyAwake = anyAwake || cars[k]->awake;
+            if (!anyAwake) { for (int k : mem) cars[k]->findNewContacts(); continue; }
+            solveIsland(mem, isl, dt, velIters, posIters, cars[mem[0]]->inv_dt0 * dt);
+        }
+        findNewPairs();
+        for (World* W : cars) { if (dt > 0.0f) W->solveTOI(dt, velIters); }
+        findNewPairs();
+        for (World* W : cars) { if (dt > 0.0f) W->inv_dt0 = inv_dt; W->force = mk(0.0f, 0.0f); W->torque = 0.0f; }
+    }
+};
+
 }  // namespace b2

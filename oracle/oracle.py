@@ -62,6 +62,9 @@ def lib():
         L.orc_env_free.argtypes = [vp]
         L.orc_env_reset.argtypes = [vp, i]
         L.orc_env_set_start.argtypes = [vp, d, d, d]
+        L.orc_env_set_car_contacts.argtypes = [vp, i, d, d]
+        L.orc_env_num_pairs.argtypes = [vp, i]
+        L.orc_env_num_pairs.restype = i
         L.orc_env_walls.argtypes = [vp, P(f)]
         L.orc_action_continuous.argtypes = [f, f, P(f)]
         L.orc_action_discrete.argtypes = [i, P(f)]
@@ -142,13 +145,14 @@ class OracleEnv:
     """Sequential CPU CarEnv restatement: one env of ``num_cars`` cars."""
 
     def __init__(self, track_text: str, num_cars: int = 1, reset_on_lap: bool = False, discrete: bool = False,
-                 start_position=(0.0, 0.0), start_angle: float = 0.0):
+                 start_position=(0.0, 0.0), start_angle: float = 0.0, car_contacts: bool = False, grid=(8.0, 3.0)):
         self.track = OracleTrack(track_text)
         self.num_cars = num_cars
         self.discrete = discrete
         self._h = lib().orc_env_create(self.track._h, num_cars, int(reset_on_lap))
-        if tuple(start_position) != (0.0, 0.0) or start_angle != 0.0:
+        if tuple(start_position) != (0.0, 0.0) or start_angle != 0.0 or car_contacts:
             lib().orc_env_set_start(self._h, float(start_position[0]), float(start_position[1]), float(start_angle))
+            lib().orc_env_set_car_contacts(self._h, int(car_contacts), float(grid[0]), float(grid[1]))
             lib().orc_env_reset(self._h, 1)
         self.words = state_layout()["S_WORDS"]
 
@@ -213,6 +217,10 @@ class OracleEnv:
 
     def impulse(self, car: int = 0) -> float:
         return lib().orc_env_impulse(self._h, car)
+
+    def num_pairs(self, touching_only: bool = False) -> int:
+        """car-car contacts of the shared world (car_contacts=True)."""
+        return lib().orc_env_num_pairs(self._h, int(touching_only))
 
     def num_contacts(self, car: int = 0):
         return lib().orc_env_num_contacts(self._h, car), lib().orc_env_num_touching(self._h, car)
