@@ -121,6 +121,11 @@ typedef struct NcgConfig {
                                 and the 600-sample velocity history behind validate_performance (src/car.py:1060-1098) */
     float start_x, start_y;  /* CarEnv(start_position=...) (src/car_env.py:114, 391, 398); (0, 0) = the GRID segment's start */
     float start_angle;       /* CarEnv(start_angle=...), radians */
+    int32_t car_contacts;    /* 0 (default): every car has its own world, as in the reference (src/car_env.py:389-394).  1: the
+                                cars of an env share ONE Box2D world and collide with each other (no reference
+                                behaviour; Box2D semantics, restated in oracle/b2lite.h SharedWorld) */
+    float grid_dx, grid_dy;  /* car_contacts only: start grid, car k at (-(k / 2) * grid_dx, +-grid_dy / 2) in the start frame
+                                (e.g. 8 m, 3 m; the fat AABBs of neighbours must not overlap at rest) */
 } NcgConfig;
 
 typedef struct NcgHandle NcgHandle;

@@ -32,7 +32,12 @@ class CarEnv(_Base):
 
     def __init__(self, render_mode: Optional[str] = None, track_file: Optional[str] = None,
                  start_position: Optional[Tuple[float, float]] = None, start_angle: float = 0.0, reset_on_lap: bool = False,
-                 discrete_action_space: bool = False, num_cars: int = 1, car_names: Optional[list] = None, device: int = 0):
+                 discrete_action_space: bool = False, num_cars: int = 1, car_names: Optional[list] = None, device: int = 0,
+                 car_contacts: bool = False, start_grid: Tuple[float, float] = (8.0, 3.0)):
+        # car_contacts (NOT a reference kwarg, default off = the reference's behaviour: every car alone in its own b2World,
+        # car_env.py:389-394): the cars share one world, start on a two-wide grid (rows start_grid[0] m apart, lanes
+        # start_grid[1] m apart) and collide with each other (NcgConfig.car_contacts)
+        self.car_contacts, self.start_grid = bool(car_contacts), (float(start_grid[0]), float(start_grid[1]))
         if num_cars < 1 or num_cars > K.MAX_CARS:
             raise ValueError(f"Number of cars must be between 1 and {K.MAX_CARS}")
         if car_names is None:
@@ -97,7 +102,8 @@ class CarEnv(_Base):
         if self._engine is None:
             self._engine = Engine(1, self.num_cars, tracks=self._tracks, discrete=self.discrete_action_space,
                                   reset_on_lap=self.reset_on_lap, auto_reset=False, device=self._device, track_info=True,
-                                  start_position=self.start_position, start_angle=self.start_angle)
+                                  start_position=self.start_position, start_angle=self.start_angle,
+                                  car_contacts=self.car_contacts, grid=self.start_grid)
 
     # ------------------------------------------------------------------ gym API
     def reset(self, seed: Optional[int] = None, options: Optional[Dict] = None):

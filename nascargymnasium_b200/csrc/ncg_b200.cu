@@ -38,6 +38,8 @@ struct KParams {
     int T; unsigned long long seed; int mode; unsigned step_base; unsigned car_base;
     float* obs_roll; float* rew_roll; uint8_t* done_roll;
     StartPose start;                                       // CarEnv(start_position, start_angle)
+    int car_contacts; float grid_dx, grid_dy;              // optional shared world: the cars of an env collide (default off)
+    float* cc_pairs; World* cc_worlds;                     //   [E][NCG_CC_STRIDE] pair tables; [N] per-car Worlds (scratch of the joint step)
     float2* vel_hist;                                      // optional [N][NCG_VEL_HISTORY]: Car.velocity_history ring (info only)
     float* ep_return; int* ep_length; int* any_done;      // optional: episode return per car / length per env of finished envs
     int redraw, n_tracks; unsigned redraw_step; unsigned long long redraw_seed;   // track_file=None: a finished env re-draws its track
@@ -79,6 +81,10 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
 // computed once per track (ncg_reset_obs_kernel) instead of once per reset.
 __device__ __noinline__ void reset_in_place(float* R, const Track T, const StartPose sp) {
     reset_record(R, T, false, f2u(R[NCG_R_TRACK]), sp);
+}
+// the start pose of car k of an env: the env's start pose, or its slot on the start grid of the shared world
+__device__ __forceinline__ StartPose start_of(const StartPose sp, int k, int car_contacts, float gdx, float gdy) {
+    return car_contacts ? cc_start_pose(sp, k, gdx, gdy) : sp;
 }
 
 // CarEnv.reset() in random-track mode (car_env.py:264-303): the finished env moves to another track, drawn uniformly among
@@ -246,7 +252,36 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
                 } else { const float4 a = s_act[b * SLOTS + slot]; thr = a.x; brk = a.y; st = a.z; }
                 // Car.velocity_history (car.py:384-386): the speed update_physics saw, i.e. before b2World.Step (info only)
                 if (p.vel_hist) p.vel_hist[(size_t)gc * NCG_VEL_HISTORY + f2u(R[NCG_R_STEP]) % NCG_VEL_HISTORY] = make_float2(R[NCG_R_VX], R[NCG_R_VY]);
-                if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts, &ctx, &cnt);
+                if (!p.car_contacts) { if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts, &ctx, &cnt); }
+                else {
+                    // shared world: an env that has car-car contacts is stepped by its first car's lane over the per-car
+                    // Worlds (global scratch), the others hand their bodies over and take them back; envs without any
+                    // keep the per-lane step.  Every lane of an env takes the same branch (the pair count is the env's).
+                    const int k = gc - ge * p.C;                                   // car index inside the env
+                    const unsigned envmask = ((1u << p.C) - 1u) << (lane - k);
+                    float* PT = p.cc_pairs + (size_t)ge * NCG_CC_STRIDE;
+                    const bool joint = f2u(PT[NCG_CC_COUNT]) != 0u;
+                    Body W; DynPre pre;
+                    car_dyn_pre(R, T, thr, brk, st, &W, &pre);
+                    if (!joint) body_step(W, R, T, NCG_DT, p.contacts, &cnt);
+                    else {
+                        World* Wk = p.cc_worlds + gc;
+                        Wk->b = W; Wk->v230 = p.contacts == 2;
+                        w_load_contacts(*Wk, R);
+                        __syncwarp(envmask);
+                        if (k == 0) shared_world_step(p.cc_worlds + (size_t)ge * p.C, p.C, PT, T, NCG_DT, &cnt);
+                        __syncwarp(envmask);
+                        w_store_contacts(*Wk, R);
+                        W = Wk->b; W.inv_dt0 = 1.0f / NCG_DT; W.force = mk(0.0f, 0.0f); W.torque = 0.0f;
+                    }
+                    car_dyn_post(R, W, pre, &ctx, &cnt);
+                    __syncwarp(envmask);
+                    if (!joint && k == 0) {                                        // FindNewContacts among the env's cars
+                        AABB fat[NCG_MAX_CARS];
+                        for (int c = 0; c < p.C; ++c) { const float* Rc = R + c * REC_STRIDE; fat[c].lx = Rc[NCG_R_FAT_LX]; fat[c].ly = Rc[NCG_R_FAT_LY]; fat[c].ux = Rc[NCG_R_FAT_UX]; fat[c].uy = Rc[NCG_R_FAT_UY]; }
+                        cc_find_new_pairs(fat, p.C, PT);
+                    }
+                }
                 s_pose[b * SLOTS + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
             }
             if (threadIdx.x == 0) s_ctr[b] = 32 * RW;           // ray queue: every ray lane starts on job = its index
@@ -294,11 +329,15 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
                 if (__builtin_expect(done && do_reset, 0)) {
                     if (p.redraw) {
                         rtid = redraw_track(my_tid, p.n_tracks, (unsigned)ge, p.redraw_step, p.redraw_seed);
-                        reset_on_track(R, p.blob, p.track_off, rtid, p.start);
-                        if (solo || lane == le * p.C) { p.env_track[ge] = (int)rtid; *p.redrawn = 1; }
-                    } else reset_in_place(R, T, p.start);
+                        reset_on_track(R, p.blob, p.track_off, rtid, start_of(p.start, gc - ge * p.C, p.car_contacts, p.grid_dx, p.grid_dy));
+                        if (solo || lane == le * p.C) {
+                            p.env_track[ge] = (int)rtid; *p.redrawn = 1;
+                            if (p.car_contacts) for (int w_ = 0; w_ < NCG_CC_STRIDE; ++w_) p.cc_pairs[(size_t)ge * NCG_CC_STRIDE + w_] = 0.0f;   // a new world
+                        }
+                    } else reset_in_place(R, T, start_of(p.start, gc - ge * p.C, p.car_contacts, p.grid_dx, p.grid_dy));
                 }
-                s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u) | (rtid << 8);
+                // (bits 8..: the row of reset_obs to hand out: one per track, or per (track, car of the env) on a start grid)
+                s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u) | ((p.car_contacts ? rtid * (uint32_t)p.C + (uint32_t)(gc - ge * p.C) : rtid) << 8);
             }
             __syncwarp();
             __threadfence_block();
@@ -406,10 +445,13 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
 }
 
 // the observation of the reset state of each track; one warp per track
-__global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, const long long* track_off, float* reset_obs, const StartPose sp) {
+__global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, const long long* track_off, float* reset_obs, const StartPose sp0,
+                                                            int rc, float gdx, float gdy) {
     __shared__ float s_rec[NCG_RECORD_WORDS];
     __shared__ float s_o[40];
-    const int lane = threadIdx.x, tid = blockIdx.x;
+    // one block per row: (track, car k of the env) with rc = cars per env on a start grid, else rc = 1
+    const int lane = threadIdx.x, tid = blockIdx.x / rc;
+    const StartPose sp = rc > 1 ? cc_start_pose(sp0, blockIdx.x % rc, gdx, gdy) : sp0;
     const float* g = blob + track_off[tid];
     Track T = track_view(g, g);
     if (lane == 0) { reset_record(s_rec, T, true, (uint32_t)tid, sp); observe_state(s_rec, s_o); }
@@ -417,12 +459,13 @@ __global__ void __launch_bounds__(32) ncg_reset_obs_kernel(const float* blob, co
     unsigned tests = 0;
     if (lane < 16) cast_rays<1, false>(T, s_rec[NCG_R_X], s_rec[NCG_R_Y], s_rec[NCG_R_ANGLE], lane, s_o + 22, &tests);
     __syncwarp();
-    for (int k = lane; k < NCG_OBS_DIM; k += 32) reset_obs[(size_t)tid * NCG_OBS_DIM + k] = s_o[k];
+    for (int k = lane; k < NCG_OBS_DIM; k += 32) reset_obs[(size_t)blockIdx.x * NCG_OBS_DIM + k] = s_o[k];
 }
 
 // reset of masked envs + their initial observation; one warp per car (rays over lanes)
 __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const float* blob, const long long* track_off, int E, int C,
-                                                         const uint8_t* mask, const int* track_id, int fresh, float* obs, const StartPose sp) {
+                                                         const uint8_t* mask, const int* track_id, int fresh, float* obs, const StartPose sp0,
+                                                         int car_contacts, float gdx, float gdy, float* cc_pairs) {
     const int lane = threadIdx.x & 31;
     const int car = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (car >= E * C) return;
@@ -434,7 +477,9 @@ __global__ void __launch_bounds__(256) ncg_reset_kernel(float* records, const fl
     uint32_t tid = track_id ? (uint32_t)track_id[env] : f2u(R[NCG_R_TRACK]);
     const float* g = blob + track_off[tid];
     Track T = track_view(g, g);
+    const StartPose sp = car_contacts ? cc_start_pose(sp0, car - env * C, gdx, gdy) : sp0;
     if (lane == 0) { reset_record(R, T, fresh != 0, tid, sp); observe_state(R, so); }
+    if (car_contacts && fresh && car == env * C) for (int w_ = lane; w_ < NCG_CC_STRIDE; w_ += 32) cc_pairs[(size_t)env * NCG_CC_STRIDE + w_] = 0.0f;
     __syncwarp();
     if (obs) {
         unsigned tests = 0;
@@ -450,6 +495,7 @@ struct NcgHandle {
     NcgConfig cfg; int N;
     float* d_records = nullptr; float* d_blob = nullptr; long long* d_track_off = nullptr; int n_tracks = 0;
     float* d_reset_obs = nullptr;
+    float* d_cc_pairs = nullptr; void* d_cc_worlds = nullptr;   // car_contacts only: pair tables, per-car World scratch
     float2* d_vel_hist = nullptr;                    // track_info only: the last NCG_VEL_HISTORY pre-step velocities of every car
     std::vector<long long> h_track_off; std::vector<unsigned> h_stage_words;
     std::vector<int> h_env_track;
@@ -654,6 +700,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
 KParams base_params(NcgHandle* h) {
     KParams p; memset(&p, 0, sizeof(p));
     p.start = start_pose(h); p.vel_hist = h->d_vel_hist;
+    p.car_contacts = h->cfg.car_contacts; p.grid_dx = h->cfg.grid_dx; p.grid_dy = h->cfg.grid_dy; p.cc_pairs = h->d_cc_pairs; p.cc_worlds = (World*)h->d_cc_worlds;
     p.n_tracks = h->n_tracks; p.env_track = h->d_env_track; p.redraw_seed = h->redraw_seed; p.redrawn = h->p_redrawn;
     p.records = h->d_records; p.blob = h->d_blob; p.track_off = h->d_track_off; p.reset_obs = h->d_reset_obs;
     p.E = h->cfg.num_envs; p.C = h->cfg.cars_per_env; p.discrete = h->cfg.discrete; p.reset_on_lap = h->cfg.reset_on_lap;
@@ -673,6 +720,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     if (!cfg || !out) return fail(NCG_E_INVALID, "null argument");
     if (cfg->cars_per_env < 1 || cfg->cars_per_env > NCG_MAX_CARS) return fail(NCG_E_INVALID, "Number of cars must be between 1 and 10");
     if (cfg->num_envs < 1) return fail(NCG_E_INVALID, "num_envs must be >= 1");
+    if (cfg->car_contacts && !(cfg->grid_dx > 0.0f && cfg->grid_dy > 0.0f)) return fail(NCG_E_INVALID, "car_contacts needs a start grid: grid_dx, grid_dy > 0");
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(NCG_E_INVALID, "no such CUDA device");
@@ -689,6 +737,10 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaMalloc(&h->d_records, N * NCG_RECORD_WORDS * 4));
     CUDA_TRY(cudaMemset(h->d_records, 0, N * NCG_RECORD_WORDS * 4));
     if (cfg->track_info) CUDA_TRY(cudaMalloc(&h->d_vel_hist, N * NCG_VEL_HISTORY * sizeof(float2)));
+    if (cfg->car_contacts) {
+        CUDA_TRY(cudaMalloc(&h->d_cc_pairs, E * NCG_CC_STRIDE * 4)); CUDA_TRY(cudaMemset(h->d_cc_pairs, 0, E * NCG_CC_STRIDE * 4));
+        CUDA_TRY(cudaMalloc(&h->d_cc_worlds, N * sizeof(World)));
+    }
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(DevStats)));
     CUDA_TRY(cudaMemset(h->d_stats, 0, sizeof(DevStats)));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -712,7 +764,7 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
 int ncg_destroy(NcgHandle* h) {
     if (!h) return NCG_OK;
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->d_vel_hist); cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
+    cudaFree(h->d_cc_pairs); cudaFree(h->d_cc_worlds); cudaFree(h->d_vel_hist); cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
     cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); cudaFree(h->d_slot_env); cudaFree(h->d_env_track);
     cudaFreeHost(h->p_redrawn);
@@ -736,8 +788,9 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
     h->h_stage_words.clear();
     for (int i = 0; i < n_tracks; ++i) { uint32_t w; memcpy(&w, h_blob + h_offsets[i] + TH_STAGE_WORDS, 4); h->h_stage_words.push_back(w); }
     h->n_tracks = n_tracks;
-    CUDA_TRY(cudaMalloc(&h->d_reset_obs, (size_t)n_tracks * NCG_OBS_DIM * 4));
-    ncg_reset_obs_kernel<<<n_tracks, 32>>>(h->d_blob, h->d_track_off, h->d_reset_obs, start_pose(h));
+    const int rc = h->cfg.car_contacts ? h->cfg.cars_per_env : 1;             // reset rows per track (a start grid: one per car of an env)
+    CUDA_TRY(cudaMalloc(&h->d_reset_obs, (size_t)n_tracks * rc * NCG_OBS_DIM * 4));
+    ncg_reset_obs_kernel<<<n_tracks * rc, 32>>>(h->d_blob, h->d_track_off, h->d_reset_obs, start_pose(h), rc, h->cfg.grid_dx, h->cfg.grid_dy);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     ++h->launches;
@@ -763,7 +816,8 @@ int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id
     const int threads = 256, cars_per_block = threads / 32;
     const int grid = (h->N + cars_per_block - 1) / cars_per_block;
     ncg_reset_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(h->d_records, h->d_blob, h->d_track_off, h->cfg.num_envs, h->cfg.cars_per_env,
-                                                                d_env_mask, d_track_id, fresh, d_obs, start_pose(h));
+                                                                d_env_mask, d_track_id, fresh, d_obs, start_pose(h),
+                                                                h->cfg.car_contacts, h->cfg.grid_dx, h->cfg.grid_dy, h->d_cc_pairs);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     h->was_reset = true;

@@ -637,6 +637,296 @@ NCG_HD void body_step(Body& B, float* R, const Track& T, float dt, int contacts,
     B.force = mk(0.0f, 0.0f); B.torque = 0.0f;
 }
 
+// (x, y, a): CarEnv(start_position=..., start_angle=...) (car_env.py:114-115, 391, 398); float32 as Box2D takes them
+struct StartPose { float x, y, a; };
+
+// ------------------------------------------------------------------ optional shared world: the cars of an env collide
+// (NcgConfig.car_contacts, default off).  The reference gives every car a private b2World, so there is no
+// reference behaviour: this is Box2D's semantics for ONE world holding the env's cars -- car-vs-car contacts between dynamic
+// boxes, two-body solver rows, islands over touching car-car contacts -- restated in oracle/b2lite.h (SharedWorld), whose
+// orderings this follows line by line.  An env that has car-car contacts is stepped by ONE lane (its first car's) over the
+// per-car Worlds, which then live in a global-memory scratch; envs without any keep the per-lane path.
+// Pair table of an env: NCG_CC_STRIDE words; pair (i < j) at 8 * pair_index: {flags | pc << 8, key0, key1, ni0, ti0, ni1, ti1, -},
+// word NCG_CC_COUNT = number of existing pairs.
+#define NCG_MAX_PAIRS 45
+#define NCG_CC_COUNT (8 * NCG_MAX_PAIRS)
+#define NCG_CC_STRIDE (8 * NCG_MAX_PAIRS + 8)
+#define NCG_MAX_PAIR_ROWS 12          /* touching car-car contacts solved per env and step (more: counted as overflow) */
+enum { PAIR_EXISTS = 1u, PAIR_TOUCHING = 2u };
+NCG_HD int pair_index(int i, int j, int C) { return i * (2 * C - i - 1) / 2 + (j - i - 1); }
+struct PVCPoint { V2 rA, rB; float ni, ti, nm, tm, bias; };
+struct PairRow { PVCPoint p[2]; V2 normal; float K[4], nmat[4]; int pc, i, j, pid; Manifold m; };
+// CarEnv start grid of the shared world: car k at (-(k / 2) * dx, +-dy / 2) in the start frame
+NCG_HD StartPose cc_start_pose(const StartPose sp, int k, float gdx, float gdy) {
+    const double lx = -(double)(k / 2) * (double)gdx, ly = (k % 2 == 0 ? 0.5 : -0.5) * (double)gdy;
+    const double c = cos((double)sp.a), s_ = sin((double)sp.a);
+    StartPose o; o.a = sp.a;
+    o.x = (float)((double)sp.x + c * lx - s_ * ly);
+    o.y = (float)((double)sp.y + s_ * lx + c * ly);
+    return o;
+}
+NCG_HDN void cc_find_new_pairs(const AABB* fat, int C, float* PT) {
+    uint32_t n = f2u(PT[NCG_CC_COUNT]);
+    for (int i = 0; i < C; ++i) for (int j = i + 1; j < C; ++j) {
+        float* P = PT + 8 * pair_index(i, j, C);
+        if (f2u(P[0]) & PAIR_EXISTS) continue;
+        if (!aabb_overlap(fat[i], fat[j])) continue;
+        P[0] = u2f(PAIR_EXISTS); P[1] = u2f(0u); P[2] = u2f(0u); P[3] = P[4] = P[5] = P[6] = 0.0f;
+        ++n;
+    }
+    PT[NCG_CC_COUNT] = u2f(n);
+}
+NCG_HD void cc_apply(World& A, World& B, V2 P, V2 rA, V2 rB) {
+    A.pv = A.pv - NCG_INV_MASS * P; A.pw -= NCG_INV_I * cross(rA, P);
+    B.pv = B.pv + NCG_INV_MASS * P; B.pw += NCG_INV_I * cross(rB, P);
+}
+// b2Island::Solve of the cars mem[0..nm) (ascending) joined by rows[ridx[0..nr)] (ascending pair index)
+NCG_HDN void cc_solve_island(World* Ws, const Track& T, const int* mem, int nm, PairRow* rows, const int* ridx, int nr, float* PT, float h) {
+    const float mA = NCG_INV_MASS, mB = NCG_INV_MASS, iA = NCG_INV_I, iB = NCG_INV_I;
+    const float friction = sqrtf(NCG_CAR_FRICTION * NCG_CAR_FRICTION), restitution = NCG_CAR_RESTITUTION;
+    const float dtRatio = Ws[mem[0]].b.inv_dt0 * h;
+    for (int q = 0; q < nm; ++q) {
+        World& W = Ws[mem[q]]; Body& B = W.b;
+        b_set_awake(B, true);
+        W.ni = 0;
+        for (int c = 0; c < W.nc; ++c) if (W.c[c].enabled && W.c[c].touching) { if (W.ni < NCG_MAX_TOUCHING) W.isl[W.ni++] = c; else B.overflow = true; }
+        B.sweep.c0 = B.sweep.c; B.sweep.a0 = B.sweep.a;
+        b_integrate_velocity(B, h);
+        W.pc_c = B.sweep.c; W.pc_a = B.sweep.a; W.pv = B.v; W.pw = B.w;
+        s_init(W, true, dtRatio);
+    }
+    for (int q = 0; q < nr; ++q) {          // rowsInit: warm-start impulses
+        PairRow& r = rows[ridx[q]];
+        r.pc = r.m.pc;
+        for (int k = 0; k < 4; ++k) { r.K[k] = 0.0f; r.nmat[k] = 0.0f; }
+        for (int a = 0; a < r.m.pc; ++a) { r.p[a].ni = dtRatio * r.m.ni[a]; r.p[a].ti = dtRatio * r.m.ti[a]; r.p[a].nm = r.p[a].tm = r.p[a].bias = 0.0f; }
+    }
+    for (int q = 0; q < nm; ++q) s_init_velocity(Ws[mem[q]], T);
+    for (int q = 0; q < nr; ++q) {          // rowsInitVelocity
+        PairRow& r = rows[ridx[q]]; World& A = Ws[r.i]; World& B = Ws[r.j];
+        Xf xfA, xfB; xfA.q = rot(A.pc_a); xfA.p = A.pc_c - mul(xfA.q, mk(0.0f, 0.0f)); xfB.q = rot(B.pc_a); xfB.p = B.pc_c - mul(xfB.q, mk(0.0f, 0.0f));
+        V2 pts[2]; world_manifold(&r.normal, pts, r.m, xfA, xfB);
+        for (int a = 0; a < r.pc; ++a) {
+            PVCPoint& cp = r.p[a];
+            cp.rA = pts[a] - A.pc_c; cp.rB = pts[a] - B.pc_c;
+            float rnA = cross(cp.rA, r.normal), rnB = cross(cp.rB, r.normal);
+            float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+            cp.nm = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+            V2 tangent = cross(r.normal, 1.0f);
+            float rtA = cross(cp.rA, tangent), rtB = cross(cp.rB, tangent);
+            float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+            cp.tm = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+            cp.bias = 0.0f;
+            float vRel = dot(r.normal, B.pv + cross(B.pw, cp.rB) - A.pv - cross(A.pw, cp.rA));
+            if (vRel < -NCG_B2_VEL_THRESHOLD) cp.bias = -restitution * vRel;
+        }
+        if (r.pc == 2) {
+            float rn1A = cross(r.p[0].rA, r.normal), rn1B = cross(r.p[0].rB, r.normal), rn2A = cross(r.p[1].rA, r.normal), rn2B = cross(r.p[1].rB, r.normal);
+            float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B, k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+            float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+            if (k11 * k11 < 1000.0f * (k11 * k22 - k12 * k12)) {
+                r.K[0] = k11; r.K[1] = k12; r.K[2] = k12; r.K[3] = k22;
+                float det = k11 * k22 - k12 * k12;
+                if (det != 0.0f) det = 1.0f / det;
+                r.nmat[0] = det * k22; r.nmat[2] = -det * k12; r.nmat[1] = -det * k12; r.nmat[3] = det * k11;
+            } else r.pc = 1;
+        }
+    }
+    for (int q = 0; q < nm; ++q) s_warm_start(Ws[mem[q]]);
+    for (int q = 0; q < nr; ++q) {
+        PairRow& r = rows[ridx[q]]; V2 tangent = cross(r.normal, 1.0f);
+        for (int a = 0; a < r.pc; ++a) cc_apply(Ws[r.i], Ws[r.j], r.p[a].ni * r.normal + r.p[a].ti * tangent, r.p[a].rA, r.p[a].rB);
+    }
+    for (int it = 0; it < NCG_VEL_ITERS; ++it) {
+        for (int q = 0; q < nm; ++q) s_solve_velocity(Ws[mem[q]]);
+        for (int q = 0; q < nr; ++q) {      // rowsSolveVelocity
+            PairRow& r = rows[ridx[q]]; World& A = Ws[r.i]; World& B = Ws[r.j];
+            V2 normal = r.normal, tangent = cross(normal, 1.0f);
+            for (int a = 0; a < r.pc; ++a) {
+                PVCPoint& cp = r.p[a];
+                V2 dv = B.pv + cross(B.pw, cp.rB) - A.pv - cross(A.pw, cp.rA);
+                float vt = dot(dv, tangent) - 0.0f;
+                float lambda = cp.tm * (-vt);
+                float maxF = friction * cp.ni;
+                float ni = clampb(cp.ti + lambda, -maxF, maxF);
+                lambda = ni - cp.ti; cp.ti = ni;
+                cc_apply(A, B, lambda * tangent, cp.rA, cp.rB);
+            }
+            if (r.pc == 1) {
+                PVCPoint& cp = r.p[0];
+                V2 dv = B.pv + cross(B.pw, cp.rB) - A.pv - cross(A.pw, cp.rA);
+                float vn = dot(dv, normal);
+                float lambda = -cp.nm * (vn - cp.bias);
+                float ni = fmaxb(cp.ni + lambda, 0.0f);
+                lambda = ni - cp.ni; cp.ni = ni;
+                cc_apply(A, B, lambda * normal, cp.rA, cp.rB);
+            } else if (r.pc == 2) {
+                PVCPoint& c1 = r.p[0]; PVCPoint& c2 = r.p[1];
+                V2 a = mk(c1.ni, c2.ni);
+                V2 dv1 = B.pv + cross(B.pw, c1.rB) - A.pv - cross(A.pw, c1.rA), dv2 = B.pv + cross(B.pw, c2.rB) - A.pv - cross(A.pw, c2.rA);
+                float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
+                V2 b = mk(vn1 - c1.bias, vn2 - c2.bias);
+                b = b - mk(r.K[0] * a.x + r.K[2] * a.y, r.K[1] * a.x + r.K[3] * a.y);
+                V2 x; bool ok = false;
+                for (;;) {
+                    x = -mk(r.nmat[0] * b.x + r.nmat[2] * b.y, r.nmat[1] * b.x + r.nmat[3] * b.y);
+                    if (x.x >= 0.0f && x.y >= 0.0f) { ok = true; break; }
+                    x.x = -c1.nm * b.x; x.y = 0.0f; vn2 = r.K[1] * x.x + b.y;
+                    if (x.x >= 0.0f && vn2 >= 0.0f) { ok = true; break; }
+                    x.x = 0.0f; x.y = -c2.nm * b.y; vn1 = r.K[2] * x.y + b.x;
+                    if (x.y >= 0.0f && vn1 >= 0.0f) { ok = true; break; }
+                    x.x = 0.0f; x.y = 0.0f; vn1 = b.x; vn2 = b.y;
+                    if (vn1 >= 0.0f && vn2 >= 0.0f) { ok = true; break; }
+                    break;
+                }
+                if (ok) {
+                    V2 d = x - a; V2 P1 = d.x * normal, P2 = d.y * normal;
+                    A.pv = A.pv - mA * (P1 + P2); A.pw -= iA * (cross(c1.rA, P1) + cross(c2.rA, P2));
+                    B.pv = B.pv + mB * (P1 + P2); B.pw += iB * (cross(c1.rB, P1) + cross(c2.rB, P2));
+                    c1.ni = x.x; c2.ni = x.y;
+                }
+            }
+        }
+    }
+    for (int q = 0; q < nm; ++q) s_store_impulses(Ws[mem[q]]);
+    for (int q = 0; q < nr; ++q) {          // rowsStore: warm-start impulses of the next step
+        PairRow& r = rows[ridx[q]]; float* P = PT + 8 * r.pid;
+        for (int a = 0; a < r.pc; ++a) { P[3 + 2 * a] = r.p[a].ni; P[4 + 2 * a] = r.p[a].ti; }
+    }
+    for (int q = 0; q < nm; ++q) s_integrate(Ws[mem[q]], h);
+    bool positionSolved = false;
+    for (int it = 0; it < NCG_POS_ITERS; ++it) {
+        bool ok = true;
+        for (int q = 0; q < nm; ++q) ok = s_solve_position(Ws[mem[q]], T, NCG_B2_BAUMGARTE, -3.0f) && ok;
+        float minSep = 0.0f;
+        for (int q = 0; q < nr; ++q) {      // rowsSolvePosition
+            PairRow& r = rows[ridx[q]]; World& A = Ws[r.i]; World& B = Ws[r.j];
+            V2 cA = A.pc_c, cB = B.pc_c; float aA = A.pc_a, aB = B.pc_a;
+            for (int a = 0; a < r.m.pc; ++a) {
+                Xf xfA, xfB; xfA.q = rot(aA); xfA.p = cA - mul(xfA.q, mk(0.0f, 0.0f)); xfB.q = rot(aB); xfB.p = cB - mul(xfB.q, mk(0.0f, 0.0f));
+                V2 normal, point; float separation;
+                if (r.m.type == FACE_A) {
+                    normal = mul(xfA.q, r.m.localNormal);
+                    V2 planePoint = mul(xfA, r.m.localPoint), clip = mul(xfB, r.m.lp[a]);
+                    separation = dot(clip - planePoint, normal) - NCG_B2_POLY_RADIUS - NCG_B2_POLY_RADIUS;
+                    point = clip;
+                } else {
+                    normal = mul(xfB.q, r.m.localNormal);
+                    V2 planePoint = mul(xfB, r.m.localPoint), clip = mul(xfA, r.m.lp[a]);
+                    separation = dot(clip - planePoint, normal) - NCG_B2_POLY_RADIUS - NCG_B2_POLY_RADIUS;
+                    point = clip; normal = -normal;
+                }
+                V2 rA = point - cA, rB = point - cB;
+                minSep = fminb(minSep, separation);
+                float Cc = clampb(NCG_B2_BAUMGARTE * (separation + NCG_B2_LINEAR_SLOP), -NCG_B2_MAX_LIN_CORR, 0.0f);
+                float rnA = cross(rA, normal), rnB = cross(rB, normal);
+                float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                float impulse = K > 0.0f ? -Cc / K : 0.0f;
+                V2 P = impulse * normal;
+                cA = cA - mA * P; aA -= iA * cross(rA, P);
+                cB = cB + mB * P; aB += iB * cross(rB, P);
+            }
+            A.pc_c = cA; A.pc_a = aA; B.pc_c = cB; B.pc_a = aB;
+        }
+        ok = (minSep >= -3.0f * NCG_B2_LINEAR_SLOP) && ok;
+        if (ok) { positionSolved = true; break; }
+    }
+    for (int q = 0; q < nm; ++q) { World& W = Ws[mem[q]]; Body& B = W.b; B.sweep.c = W.pc_c; B.sweep.a = W.pc_a; B.v = W.pv; B.w = W.pw; b_sync_transform(B); }
+    for (int q = 0; q < nm; ++q) if (Ws[mem[q]].ni > 0) s_report(Ws[mem[q]]);
+    for (int q = 0; q < nr; ++q) {          // rowsReport: both cars' listeners
+        PairRow& r = rows[ridx[q]];
+        l_post_solve(Ws[r.i], r.pc, r.p[0].ni, r.pc > 1 ? r.p[1].ni : 0.0f);
+        l_post_solve(Ws[r.j], r.pc, r.p[0].ni, r.pc > 1 ? r.p[1].ni : 0.0f);
+    }
+    float minSleep = NCG_B2_MAXFLOAT;
+    for (int q = 0; q < nm; ++q) {
+        Body& B = Ws[mem[q]].b;
+        if (B.w * B.w > NCG_B2_ANG_SLEEP_TOL * NCG_B2_ANG_SLEEP_TOL || dot(B.v, B.v) > NCG_B2_LIN_SLEEP_TOL * NCG_B2_LIN_SLEEP_TOL) { B.sleepTime = 0.0f; minSleep = 0.0f; }
+        else { B.sleepTime += h; minSleep = fminb(minSleep, B.sleepTime); }
+    }
+    if (minSleep >= NCG_B2_TIME_TO_SLEEP && positionSolved) for (int q = 0; q < nm; ++q) b_set_awake(Ws[mem[q]].b, false);
+    for (int q = 0; q < nm; ++q) { b_sync_fixtures(Ws[mem[q]].b); w_find_new_contacts(Ws[mem[q]], T); }
+}
+// b2World::Step of the shared world of one env: Ws[0..C) hold the cars' bodies (forces applied) and wall contacts
+NCG_HDN void shared_world_step(World* Ws, int C, float* PT, const Track T, float dt, Counters* cnt) {
+    const bool v230 = Ws[0].v230;
+    for (int k = 0; k < C; ++k) { Ws[k].toi_events = 0; if (Ws[k].b.newFixture) { w_find_new_contacts(Ws[k], T); Ws[k].b.newFixture = false; } }
+    for (int k = 0; k < C; ++k) w_collide(Ws[k], T);
+    // ---- Collide of the car-car contacts (ascending pair index = ascending (i, j))
+    PairRow rows[NCG_MAX_PAIR_ROWS]; int nrows = 0;
+    uint32_t count = f2u(PT[NCG_CC_COUNT]);
+    for (int i = 0; i < C; ++i) for (int j = i + 1; j < C; ++j) {
+        const int pid = pair_index(i, j, C);
+        float* P = PT + 8 * pid;
+        const uint32_t fl = f2u(P[0]);
+        if (!(fl & PAIR_EXISTS)) continue;
+        World& A = Ws[i]; World& B = Ws[j];
+        const bool was = (fl & PAIR_TOUCHING) != 0;
+        if (!A.b.awake && !B.b.awake) continue;
+        if (!aabb_overlap(A.b.fat, B.b.fat)) {
+            if (was) { l_end(A, -1 - j); l_end(B, -1 - i); }
+            P[0] = u2f(0u); --count;
+            continue;
+        }
+        Manifold m;
+        collide_boxes(&m, car_box(), A.b.xf, car_box(), B.b.xf, v230);
+        const int opc = (int)((fl >> 8) & 3u);
+        const uint32_t okey[2] = {f2u(P[1]), f2u(P[2])}; const float oni[2] = {P[3], P[5]}, oti[2] = {P[4], P[6]};
+        for (int a = 0; a < m.pc; ++a) {
+            m.ni[a] = 0.0f; m.ti[a] = 0.0f;
+            for (int b = 0; b < opc; ++b) if (okey[b] == m.key[a]) { m.ni[a] = oni[b]; m.ti[a] = oti[b]; break; }
+        }
+        const bool touching = m.pc > 0;
+        if (touching != was) { b_set_awake(A.b, true); b_set_awake(B.b, true); }
+        if (!was && touching) { V2 n, pts[2]; world_manifold(&n, pts, m, A.b.xf, B.b.xf); l_begin(A, -1 - j, n); l_begin(B, -1 - i, -n); }
+        if (was && !touching) { l_end(A, -1 - j); l_end(B, -1 - i); }
+        P[0] = u2f(PAIR_EXISTS | (touching ? PAIR_TOUCHING : 0u) | ((uint32_t)m.pc << 8));
+        P[1] = u2f(m.pc > 0 ? m.key[0] : 0u); P[2] = u2f(m.pc > 1 ? m.key[1] : 0u);
+        P[3] = m.pc > 0 ? m.ni[0] : 0.0f; P[4] = m.pc > 0 ? m.ti[0] : 0.0f; P[5] = m.pc > 1 ? m.ni[1] : 0.0f; P[6] = m.pc > 1 ? m.ti[1] : 0.0f;
+        if (touching) {
+            if (nrows < NCG_MAX_PAIR_ROWS) { PairRow& r = rows[nrows++]; r.m = m; r.i = i; r.j = j; r.pid = pid; }
+            else A.b.overflow = true;
+        }
+    }
+    PT[NCG_CC_COUNT] = u2f(count);
+    // ---- Solve: islands = cars connected by touching car-car contacts (root = the lowest car index)
+    int root[NCG_MAX_CARS];
+    for (int k = 0; k < C; ++k) root[k] = k;
+    for (int q = 0; q < nrows; ++q) {
+        int a = rows[q].i, b = rows[q].j;
+        while (root[a] != a) a = root[a];
+        while (root[b] != b) b = root[b];
+        if (a != b) { if (a > b) root[a] = b; else root[b] = a; }
+    }
+    for (int k = 0; k < C; ++k) { int r = k; while (root[r] != r) r = root[r]; root[k] = r; }
+    for (int i = 0; i < C; ++i) {
+        if (root[i] != i) continue;
+        int mem[NCG_MAX_CARS], nm = 0, ridx[NCG_MAX_PAIR_ROWS], nr = 0;
+        for (int k = i; k < C; ++k) if (root[k] == i) mem[nm++] = k;
+        for (int q = 0; q < nrows; ++q) if (root[rows[q].i] == i) ridx[nr++] = q;
+        if (nr == 0) {
+            World& W = Ws[i];
+            w_solve(W, T, dt, W.b.inv_dt0 * dt);
+            w_find_new_contacts(W, T);
+            continue;
+        }
+        bool anyAwake = false;
+        for (int q = 0; q < nm; ++q) anyAwake = anyAwake || Ws[mem[q]].b.awake;
+        if (!anyAwake) { for (int q = 0; q < nm; ++q) w_find_new_contacts(Ws[mem[q]], T); continue; }
+        cc_solve_island(Ws, T, mem, nm, rows, ridx, nr, PT, dt);
+    }
+    // ---- continuous phase: per car against walls (Box2D skips contacts between two non-bullet dynamic bodies)
+    for (int k = 0; k < C; ++k) w_solve_toi(Ws[k], T, dt);
+    AABB fat[NCG_MAX_CARS];
+    for (int k = 0; k < C; ++k) {
+        fat[k] = Ws[k].b.fat;
+        int nt = 0; for (int c = 0; c < Ws[k].nc; ++c) nt += Ws[k].c[c].touching ? 1 : 0;
+        if (nt) cnt->contact_steps++;
+        cnt->toi_events += Ws[k].toi_events;
+    }
+    cc_find_new_pairs(fat, C, PT);
+}
+
 // ------------------------------------------------------------------ tyres (tyre.py, tyre_manager.py)
 NCG_HD float tyre_grip(float T, float wear) {
     float tg;
@@ -808,8 +1098,6 @@ NCG_HDN bool on_track(const Track T, float x, float y) {
 
 // ------------------------------------------------------------------ reset (car_env.py:316-535)
 // fresh: new Box2D world (CarPhysics.__init__); otherwise CarPhysics.reset_car + Car.reset on the existing world.
-// (sx, sy, sa): CarEnv(start_position=..., start_angle=...) (car_env.py:114-115, 391, 398); float32 as Box2D takes them
-struct StartPose { float x, y, a; };
 NCG_HD void reset_record(float* R, const Track& T, bool fresh, uint32_t track_id, const StartPose sp) {
     uint32_t fl;
     if (fresh) {
@@ -899,8 +1187,11 @@ NCG_HDN float banking_force(float bank) {
     return NCG_CAR_MASS * 9.81f * sb * 0.3f;
 }
 struct StepCtx { uint32_t fl, xf, laps_pre; bool dis_pre; float impulse; };
-NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, int contacts, StepCtx* ctx,
-                               Counters* cnt) {
+// car_dyn_pre: everything of CarPhysics.step before b2World.Step (inputs, forces, tyres): leaves the loaded body with its
+// force / torque in *Wout.  car_dyn_post: the record takes the stepped body.  car_step_dynamics = pre, body_step, post; the
+// shared-world mode (cars of an env collide, optional) steps all bodies of an env between the two halves.
+struct DynPre { uint32_t fl, xf, laps_pre; bool dis_pre; };
+NCG_HD void car_dyn_pre(float* R, const Track& T, float thr_in, float brk_in, float steer_in, Body* Wout, DynPre* pre) {
     uint32_t fl = f2u(R[NCG_R_FLAGS]);
     uint32_t xf = 0;
     const bool dis_pre = (fl & NCG_F_DISABLED) != 0;
@@ -1023,11 +1314,21 @@ NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_
             b_apply_torque(W, (dav - W.w) * NCG_CAR_MASS * 0.8f);
         }
     }
-    // ---- b2World.Step (car_physics.py:363)
-    body_step(W, R, T, NCG_DT, contacts, cnt);
+    *Wout = W; pre->fl = fl; pre->xf = xf; pre->laps_pre = laps_pre; pre->dis_pre = dis_pre;
+}
+NCG_HD void car_dyn_post(float* R, Body& W, const DynPre& pre, StepCtx* ctx, Counters* cnt) {
+    uint32_t fl = pre.fl;
     b_store(W, R, &fl);
     if (W.overflow) cnt->overflow++;
-    ctx->fl = fl; ctx->xf = xf; ctx->laps_pre = laps_pre; ctx->dis_pre = dis_pre; ctx->impulse = W.impulse;
+    ctx->fl = fl; ctx->xf = pre.xf; ctx->laps_pre = pre.laps_pre; ctx->dis_pre = pre.dis_pre; ctx->impulse = W.impulse;
+}
+NCG_HD void car_step_dynamics(float* R, const Track& T, float thr_in, float brk_in, float steer_in, int contacts, StepCtx* ctx,
+                               Counters* cnt) {
+    Body W; DynPre pre;
+    car_dyn_pre(R, T, thr_in, brk_in, steer_in, &W, &pre);
+    // ---- b2World.Step (car_physics.py:363)
+    body_step(W, R, T, NCG_DT, contacts, cnt);
+    car_dyn_post(R, W, pre, ctx, cnt);
 }
 // RAW: obs[0..21] receives observe_raw's values (the caller normalises them when it stores the row)
 template <bool RAW>

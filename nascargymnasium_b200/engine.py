@@ -59,7 +59,8 @@ class _Config(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int32), ("num_envs", ctypes.c_int32), ("cars_per_env", ctypes.c_int32),
                 ("discrete", ctypes.c_int32), ("reset_on_lap", ctypes.c_int32), ("auto_reset", ctypes.c_int32),
                 ("contacts", ctypes.c_int32), ("track_info", ctypes.c_int32),
-                ("start_x", ctypes.c_float), ("start_y", ctypes.c_float), ("start_angle", ctypes.c_float)]
+                ("start_x", ctypes.c_float), ("start_y", ctypes.c_float), ("start_angle", ctypes.c_float),
+                ("car_contacts", ctypes.c_int32), ("grid_dx", ctypes.c_float), ("grid_dy", ctypes.c_float)]
 
 
 class Stats(ctypes.Structure):
@@ -201,7 +202,8 @@ class Engine:
 
     def __init__(self, num_envs: int, cars_per_env: int = 1, tracks: Sequence[str] = ("nascar",), discrete: bool = False,
                  reset_on_lap: bool = False, auto_reset: bool = True, contacts: bool = True, device: int = 0,
-                 track_info: bool = False, start_position=(0.0, 0.0), start_angle: float = 0.0):
+                 track_info: bool = False, start_position=(0.0, 0.0), start_angle: float = 0.0, car_contacts: bool = False,
+                 grid=(8.0, 3.0)):
         lib = load_library()
         self._lib = lib
         self.num_envs, self.cars_per_env = int(num_envs), int(cars_per_env)
@@ -209,7 +211,8 @@ class Engine:
         self.discrete, self.device = bool(discrete), int(device)
         cfg = _Config(device, num_envs, cars_per_env, int(discrete), int(reset_on_lap), int(auto_reset),
                       DEFAULT_CONTACTS if contacts is True else int(contacts), int(track_info),
-                      float(start_position[0]), float(start_position[1]), float(start_angle))
+                      float(start_position[0]), float(start_position[1]), float(start_angle),
+                      int(bool(car_contacts)), float(grid[0]), float(grid[1]))
         self.track_info = bool(track_info)
         h = ctypes.c_void_p()
         _check(lib.ncg_create(ctypes.byref(cfg), ctypes.byref(h)))

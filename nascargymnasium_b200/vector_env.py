@@ -70,7 +70,8 @@ class NascarVectorEnv:
 
     def __init__(self, num_envs: int, track_file: Union[None, str, Sequence[str]] = None, num_cars: int = 1,
                  discrete_action_space: bool = False, reset_on_lap: bool = False, device: int = 0, track_info: bool = False,
-                 max_result_blocks: int = 64, validate_actions: bool = True, redraw_tracks: bool = True):
+                 max_result_blocks: int = 64, validate_actions: bool = True, redraw_tracks: bool = True,
+                 car_contacts: bool = False, start_grid=(8.0, 3.0)):
         self.validate_actions = bool(validate_actions)    # assert action_space.contains, like the reference's step()
         self.max_result_blocks = int(max_result_blocks)   # result buffers kept alive for the caller before step() copies
         if num_cars < 1 or num_cars > K.MAX_CARS:
@@ -93,7 +94,7 @@ class NascarVectorEnv:
         self.action_space = _batched_space(self.single_action_space, num_envs)
         self.observation_space = _batched_space(self.single_observation_space, num_envs)
         self.engine = Engine(num_envs, num_cars, tracks=tracks, discrete=discrete_action_space, reset_on_lap=reset_on_lap,
-                             auto_reset=True, device=device, track_info=track_info)
+                             auto_reset=True, device=device, track_info=track_info, car_contacts=car_contacts, grid=start_grid)
         self.redraw_tracks = bool(redraw_tracks) and self.random_tracks and len(tracks) > 1
         # a list of tracks: equal blocks of envs per track; random mode: drawn per env at reset()
         self._initial_track_id = (np.arange(num_envs, dtype=np.int64) * len(tracks) // num_envs).astype(np.int32)

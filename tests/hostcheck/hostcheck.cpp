@@ -27,6 +27,58 @@ void hc_env_step(const float* blob, float* records, int C, const float* act3, in
     if (counters) { counters[0] = cnt.ray_tests; counters[1] = cnt.contact_steps; counters[2] = cnt.toi_events; counters[3] = cnt.overflow; counters[4] = cnt.laps; }
 }
 
+// The same env step in the optional shared-world mode (the cars of the env collide): what the kernel's physics warp does
+// with its lanes, done here one car after the other.  pairs: the env's pair table [NCG_CC_STRIDE] floats.
+void hc_env_step_cc(const float* blob, float* records, int C, const float* act3, int contacts, int reset_on_lap, float* pairs,
+                    float* obs, float* reward, int* terminated, int* truncated, int* reason, unsigned long long* counters) {
+    Track T = track_view(blob, blob);
+    Counters cnt = {0, 0, 0, 0, 0};
+    uint32_t xf[NCG_MAX_CARS];
+    static World Ws[NCG_MAX_CARS];
+    Body W[NCG_MAX_CARS]; DynPre pre[NCG_MAX_CARS]; StepCtx ctx[NCG_MAX_CARS];
+    const bool joint = f2u(pairs[NCG_CC_COUNT]) != 0u;
+    for (int i = 0; i < C; ++i) car_dyn_pre(records + i * NCG_RECORD_WORDS, T, act3[i * 3], act3[i * 3 + 1], act3[i * 3 + 2], &W[i], &pre[i]);
+    if (!joint) { for (int i = 0; i < C; ++i) body_step(W[i], records + i * NCG_RECORD_WORDS, T, NCG_DT, contacts, &cnt); }
+    else {
+        for (int i = 0; i < C; ++i) { Ws[i].b = W[i]; Ws[i].v230 = contacts == 2; w_load_contacts(Ws[i], records + i * NCG_RECORD_WORDS); }
+        shared_world_step(Ws, C, pairs, T, NCG_DT, &cnt);
+        for (int i = 0; i < C; ++i) { w_store_contacts(Ws[i], records + i * NCG_RECORD_WORDS); W[i] = Ws[i].b; W[i].inv_dt0 = 1.0f / NCG_DT; W[i].force = mk(0.0f, 0.0f); W[i].torque = 0.0f; }
+    }
+    for (int i = 0; i < C; ++i) car_dyn_post(records + i * NCG_RECORD_WORDS, W[i], pre[i], &ctx[i], &cnt);
+    if (!joint) {
+        AABB fat[NCG_MAX_CARS];
+        for (int c = 0; c < C; ++c) { const float* Rc = records + c * NCG_RECORD_WORDS; fat[c].lx = Rc[NCG_R_FAT_LX]; fat[c].ly = Rc[NCG_R_FAT_LY]; fat[c].ux = Rc[NCG_R_FAT_UX]; fat[c].uy = Rc[NCG_R_FAT_UY]; }
+        cc_find_new_pairs(fat, C, pairs);
+    }
+    for (int i = 0; i < C; ++i) {
+        float* R = records + i * NCG_RECORD_WORDS;
+        reward[i] = car_step_rules<false>(R, T, &ctx[i], obs + i * 38, &xf[i], &cnt);
+        unsigned tests = 0;
+        for (int k = 0; k < 16; ++k) cast_rays<1, false>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
+        cnt.ray_tests += tests;
+    }
+    bool te, tr; int why;
+    env_decide(xf, C, reset_on_lap != 0, f2u(records[NCG_R_STEP]), &te, &tr, &why);
+    for (int i = 0; i < C; ++i) car_finish(records + i * NCG_RECORD_WORDS, reward[i]);
+    *terminated = te; *truncated = tr; *reason = why;
+    if (counters) { counters[0] = cnt.ray_tests; counters[1] = cnt.contact_steps; counters[2] = cnt.toi_events; counters[3] = cnt.overflow; counters[4] = cnt.laps; }
+}
+void hc_env_reset_cc(const float* blob, float* records, int C, int fresh, int track_id, float gdx, float gdy, float* pairs, float* obs) {
+    Track T = track_view(blob, blob);
+    StartPose sp0; sp0.x = 0.0f; sp0.y = 0.0f; sp0.a = 0.0f;
+    for (int i = 0; i < C; ++i) {
+        float* R = records + i * NCG_RECORD_WORDS;
+        reset_record(R, T, fresh != 0, (uint32_t)track_id, cc_start_pose(sp0, i, gdx, gdy));
+        if (obs) {
+            observe_state(R, obs + i * 38);
+            unsigned tests = 0;
+            for (int k = 0; k < 16; ++k) cast_rays<1, false>(T, R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], k, obs + i * 38 + 22, &tests);
+        }
+    }
+    if (fresh) for (int w = 0; w < NCG_CC_STRIDE; ++w) pairs[w] = 0.0f;
+}
+int hc_cc_stride() { return NCG_CC_STRIDE; }
+
 void hc_env_reset(const float* blob, float* records, int C, int fresh, int track_id, float* obs) {
     Track T = track_view(blob, blob);
     for (int i = 0; i < C; ++i) {

@@ -269,6 +269,9 @@ def hostcheck(no_toi_shortcut: bool = False):
         lib.hc_nearest_segment.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_int, fp]
         lib.hc_on_track.argtypes = [fp, ctypes.c_float, ctypes.c_float]
         lib.hc_synthetic_action.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int, fp]
+        lib.hc_env_step_cc.argtypes = [fp, fp, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp, fp, fp, ip, ip, ip,
+                                       ctypes.POINTER(ctypes.c_ulonglong)]
+        lib.hc_env_reset_cc.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, fp, fp]
         _HC[key] = lib
     return _HC[key]
 
@@ -281,8 +284,10 @@ class HostCheckEnv:
     """One env of C cars stepped by the host compile of the device code."""
 
     def __init__(self, track_name: str, num_cars: int = 1, reset_on_lap: bool = False, contacts: bool = True,
-                 no_toi_shortcut: bool = False):
+                 no_toi_shortcut: bool = False, car_contacts: bool = False, grid=(8.0, 3.0)):
         self.lib = hostcheck(no_toi_shortcut)
+        self.car_contacts, self.grid = car_contacts, grid
+        self.pairs = np.zeros(self.lib.hc_cc_stride(), dtype=np.float32)
         self.table = T.get_track_table(track_name)
         self.blob = np.ascontiguousarray(self.table.blob)
         self.C = num_cars
@@ -293,7 +298,10 @@ class HostCheckEnv:
 
     def reset(self, fresh=True):
         obs = np.zeros((self.C, 38), dtype=np.float32)
-        self.lib.hc_env_reset(_fp(self.blob), _fp(self.records), self.C, int(fresh), 0, _fp(obs))
+        if self.car_contacts:
+            self.lib.hc_env_reset_cc(_fp(self.blob), _fp(self.records), self.C, int(fresh), 0, self.grid[0], self.grid[1], _fp(self.pairs), _fp(obs))
+        else:
+            self.lib.hc_env_reset(_fp(self.blob), _fp(self.records), self.C, int(fresh), 0, _fp(obs))
         return obs
 
     def step(self, act3):
@@ -301,8 +309,12 @@ class HostCheckEnv:
         obs = np.zeros((self.C, 38), dtype=np.float32)
         rew = np.zeros(self.C, dtype=np.float32)
         te, tr, why = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        self.lib.hc_env_step(_fp(self.blob), _fp(self.records), self.C, _fp(act3), int(self.contacts), int(self.reset_on_lap),
-                                _fp(obs), _fp(rew), ctypes.byref(te), ctypes.byref(tr), ctypes.byref(why), self.counters)
+        if self.car_contacts:
+            self.lib.hc_env_step_cc(_fp(self.blob), _fp(self.records), self.C, _fp(act3), int(self.contacts), int(self.reset_on_lap),
+                                    _fp(self.pairs), _fp(obs), _fp(rew), ctypes.byref(te), ctypes.byref(tr), ctypes.byref(why), self.counters)
+        else:
+            self.lib.hc_env_step(_fp(self.blob), _fp(self.records), self.C, _fp(act3), int(self.contacts), int(self.reset_on_lap),
+                                 _fp(obs), _fp(rew), ctypes.byref(te), ctypes.byref(tr), ctypes.byref(why), self.counters)
         return obs, rew, bool(te.value), bool(tr.value), why.value
 
 
