@@ -22,7 +22,7 @@ _CHECKED = os.environ.get("NCG_CHECKED", "") not in ("", "0")
 _VARIANT = os.environ.get("NCG_VARIANT", "").strip()
 _SO = os.path.join(_PKG, f"libncg_b200_{_VARIANT}.so" if _VARIANT else ("libncg_b200_checked.so" if _CHECKED else "libncg_b200.so"))
 _CSRC = os.path.join(_PKG, "csrc")
-_SOURCES = ("ncg_b200.cu", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
+_SOURCES = ("ncg_b200.cu", "ncg_b200_cc.cu", "ncg_step.cuh", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -49,7 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise NcgError("CUDA sources missing and no prebuilt libncg_b200.so")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-DNCG_CHECKED"] if _CHECKED else []) + (os.environ.get("NCG_DEFINES", "").split() if _VARIANT else []) + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", _SO + ".tmp", os.path.join(_CSRC, "ncg_b200.cu")]
+          ["--threads", "2", "-o", _SO + ".tmp", os.path.join(_CSRC, "ncg_b200.cu"), os.path.join(_CSRC, "ncg_b200_cc.cu")]
     subprocess.check_call(cmd)
     os.replace(_SO + ".tmp", _SO)
     return _SO

@@ -141,3 +141,50 @@ def test_car_contacts_off_is_bit_identical_and_on_conserves_momentum():
     assert d.min() > 1.9                                      # two car boxes (5.04 x 2.0 m) cannot be closer than a car width
     assert not np.array_equal(rec.reshape(E * C, -1).view(np.uint32), outs[0].view(np.uint32))
     eng.close()
+
+
+def _kin(rec, C):
+    return rec.reshape(-1, C, rec.shape[-1])[0][:, [R["NCG_R_X"], R["NCG_R_Y"], R["NCG_R_ANGLE"], R["NCG_R_VX"], R["NCG_R_VY"], R["NCG_R_OMEGA"]]].astype(np.float64)
+
+
+@pytest.mark.gpu
+def test_engine_known_answers_of_the_shared_world():
+    """The analytic cases of tests/test_oracle_carcar.py on the CUDA engine itself: a central rear-end hit between equal masses
+    (e = 0.1: closing 10 m/s -> separating 1 m/s, 5.5 / 4.5 m/s), both listeners report m (1 + e) v / 2, and a chain of three
+    (car 4 hits car 2, which then hits car 0) moves momentum forward without creating any."""
+    from nascargymnasium_b200.engine import Engine
+    M = 1500.0
+    C = 6
+    eng = Engine(2, C, tracks=["daytona"], auto_reset=False, car_contacts=True)
+    eng.reset_host()
+    rec = eng.get_state_host().reshape(2, C, -1)
+    rec[0, 2, R["NCG_R_VX"]] = 10.0                             # env 0: car 2 runs into the standing car 0
+    rec[1, 4, R["NCG_R_VX"]] = 14.0                             # env 1: car 4 -> car 2 -> car 0
+    eng.set_state_host(rec.reshape(2 * C, -1))
+    z = np.zeros((2, C, 2), dtype=np.float32)
+    hit, imp, moved0 = None, 0.0, None
+    for t in range(120):
+        before = eng.get_state_host().reshape(2, C, -1)
+        obs, rew, te, tr, _ = eng.step_host(z)
+        after = eng.get_state_host().reshape(2, C, -1)
+        obs = obs.reshape(2, C, 38)
+        if hit is None and after[0, 0, R["NCG_R_VX"]] > 1.0:
+            hit = t
+            kb, ka = _kin(before[0:1], C), _kin(after[0:1], C)
+            assert ka[0, 3] == pytest.approx(5.5, abs=0.08) and ka[2, 3] == pytest.approx(4.5, abs=0.08)
+            assert ka[0, 3] - ka[2, 3] == pytest.approx(0.1 * (kb[2, 3] - kb[0, 3]), abs=0.02)
+            assert abs(ka[0, 4]) < 1e-3 and abs(ka[0, 5]) < 1e-3
+            assert np.allclose(ka[[1, 3, 5]], kb[[1, 3, 5]], atol=1e-4)
+            imp = obs[0, 0, 19] * 50000.0
+            assert obs[0, 2, 19] == pytest.approx(obs[0, 0, 19], rel=1e-6)
+            assert abs(obs[0, 0, 20]) == pytest.approx(1.0, abs=0.02) and abs(obs[0, 2, 20]) < 0.02
+        if moved0 is None and after[1, 0, R["NCG_R_VX"]] > 1.0:
+            moved0 = t
+        px = M * after[1, :, R["NCG_R_VX"]].astype(np.float64).sum()
+        assert px < M * 14.0 + 1.0                              # momentum is handed on, never created
+    assert hit is not None and 15 < hit < 25
+    assert imp == pytest.approx(M * 1.1 * 10.0 / 2.0, rel=0.03)
+    assert moved0 is not None and moved0 > hit                  # the second link of the chain is hit later
+    last = eng.get_state_host().reshape(2, C, -1)[1]
+    assert last[0, R["NCG_R_X"]] > 0.5 and last[2, R["NCG_R_X"]] > -8.0 + 0.5 and last[0, R["NCG_R_X"]] - last[2, R["NCG_R_X"]] > 5.0
+    eng.close()
