@@ -114,13 +114,17 @@ namespace {
 StartPose start_pose(const NcgHandle* h) { StartPose sp; sp.x = h->cfg.start_x; sp.y = h->cfg.start_y; sp.a = h->cfg.start_angle; return sp; }
 
 // Whole envs per CTA: at most CPB car slots, fewer when that spreads a small batch over all SMs (4096 single-car
-// envs: 28 per CTA = 147 CTAs on 148 SMs instead of 128 CTAs of 32).
+// envs: 28 per CTA = 147 CTAs on 148 SMs instead of 128 CTAs of 32).  Beyond two CTAs per SM the groups are full: a CTA's
+// step costs about the same with 24 cars as with 32 (measured in the dispersed steady state, tools/ab_group.sh: 20480 envs
+// 1.15 G car-steps/s with groups of 32 vs 1.03 G with 28, 40960 envs 1.42 vs 1.26 G; at 8192 and fewer, spreading still wins
+// by 2 %), so fewer CTAs win.
 int envs_per_cta(int E, int C, int sms) {
     const int epb_max = CPB / C;                               // C <= 10 < CPB
     const int min_ctas = (E + epb_max - 1) / epb_max;
     if (sms <= 0) sms = 148;
     const int target = ((min_ctas + sms - 1) / sms) * sms;     // whole waves of one CTA per SM
-    int epb = (E + target - 1) / target;
+    int epb = min_ctas > 2 * sms ? epb_max : (E + target - 1) / target;
+    { const char* v = getenv("NCG_GROUP_ENVS"); if (v && atoi(v) > 0) epb = atoi(v); }       // A/B runs
     if (epb < 1) epb = 1;
     if (epb > epb_max) epb = epb_max;
     return epb;
@@ -139,7 +143,7 @@ void plan_ctas(const int* env_track, int E, int C, int sms, std::vector<int2>& t
     const int epb_max = CPB / C;
     if (sms <= 0) sms = 148;
     const int waves = (count_ctas(env_track, E, epb_max) + sms - 1) / sms;
-    while (epb < epb_max && count_ctas(env_track, E, epb) > waves * sms) ++epb;
+    if (!getenv("NCG_GROUP_ENVS")) while (epb < epb_max && count_ctas(env_track, E, epb) > waves * sms) ++epb;
     tab.clear();
     int e = 0;
     while (e < E) {
@@ -245,7 +249,8 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     int PW = 1;
     if (h->n_ctas > 2 * sms) {
         const int waves1 = (h->n_ctas + 3 * sms - 1) / (3 * sms), waves2 = (h->n_pairs + 2 * sms - 1) / (2 * sms);
-        if (12 * waves2 < 10 * waves1) PW = 2;
+        // (single-car envs: the pair shape with eight ray warps; fitted over 12288..131072 envs, tools/ab_pw.sh)
+        if ((h->cfg.cars_per_env == 1 ? 13 : 12) * waves2 < 10 * waves1) PW = 2;
     }
     { const char* pw = getenv("NCG_PHYS_WARPS"); if (pw && (atoi(pw) == 1 || atoi(pw) == 2 || atoi(pw) == 4)) PW = atoi(pw); }
     const bool cc = h->cfg.car_contacts != 0;                // shared world: one shape (an env's cars sit in one physics warp)
@@ -275,7 +280,14 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
         p.stage = 0;
         smem = (size_t)smem_layout(0, PW == 2 ? 64 : 32, nb).total * 4;
     }
-    void (*k)(KParams) = PW == 4 ? ncg_step_kernel<2, 1, 4> : PW == 2 ? ncg_step_kernel<4, 2, 2>
+    // the pair shape's ray warps: eight (320 threads x 96 registers) for single-car envs, six (256 x 128) otherwise.  At large
+    // batches a step waits for the ray warps while the physics warps idle half of the time (tools/timeline_probe.py), so two more
+    // ray warps per CTA pay for the physics warps' spills: +10 % at 16384 and 65536 single-car envs; ten ray warps at 80
+    // registers lose it again (1.32 vs 1.41 G at 65536), and ten-car envs on talladega, whose physics warps do the env phase and
+    // frequent resets on top, lose 18 % with eight (1.07 vs 1.30 G).  NCG_PAIR_RW8 = 0 | 1 overrides.
+    int pair_rw8 = h->cfg.cars_per_env == 1 ? 1 : 0;
+    { const char* v = getenv("NCG_PAIR_RW8"); if (v) pair_rw8 = atoi(v) ? 1 : 0; }
+    void (*k)(KParams) = PW == 4 ? ncg_step_kernel<2, 1, 4> : PW == 2 ? (pair_rw8 ? ncg_step_kernel<2, 2, 2> : ncg_step_kernel<4, 2, 2>)
                        : minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1, 1> : ncg_step_kernel<2, 1, 1>)
                        : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2, 1> : ncg_step_kernel<2, 2, 1>)
                                    : ncg_step_kernel<4, 3, 1>;
@@ -287,7 +299,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     }
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (PW == 4) k<<<h->n_ctas, 32 * (4 + 8), smem, s>>>(p);
-    else if (PW == 2) k<<<h->n_pairs, 256, smem, s>>>(p);
+    else if (PW == 2) k<<<h->n_pairs, pair_rw8 ? 320 : 256, smem, s>>>(p);
     else k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
@@ -311,6 +323,10 @@ KParams base_params(NcgHandle* h) {
 extern "C" {
 
 const char* ncg_last_error(void) { return g_err.c_str(); }
+#ifdef NCG_TIMELINE
+int ncg_debug_timeline(long long* out) { return cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)) == cudaSuccess ? 0 : 1; }
+int ncg_debug_cta_cycles(long long* out) { return cudaMemcpyFromSymbol(out, g_cta_cycles, sizeof(g_cta_cycles)) == cudaSuccess ? 0 : 1; }
+#endif
 int ncg_version(void) { return 1; }
 
 int ncg_create(const NcgConfig* cfg, NcgHandle** out) {

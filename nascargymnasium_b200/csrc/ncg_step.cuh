@@ -11,6 +11,27 @@ using namespace ncg;
 
 namespace {
 
+// NCG_TIMELINE (variant build, measurement only): clock64 stamps of one CTA's warps per step and phase
+#ifdef NCG_TIMELINE
+__device__ long long g_timeline[12][128][6];
+__device__ __forceinline__ long long tl_clock() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory"); return c; }
+#define TL(ev) do { const long long c_ = tl_clock(); if (blockIdx.x == 5 && lane == 0 && t < 128 && warp < 12) g_timeline[warp][t][ev] = c_; } while (0)
+// a stamp taken after a barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on until its next memory access, so the clock is
+// read under a predicate that depends on a shared-memory load issued after the barrier
+__device__ __forceinline__ long long tl_clock_after(const float* sm) {
+    long long c = 0; const float x = *(const volatile float*)sm;
+    asm volatile("{ .reg .pred p; setp.neu.f32 p, %1, 0f7FC01234; @p mov.u64 %0, %%clock64; }" : "+l"(c) : "f"(x) : "memory");
+    return c;
+}
+#define TLB(ev) do { const long long c_ = tl_clock_after(smem); if (blockIdx.x == 5 && lane == 0 && t < 128 && warp < 12) g_timeline[warp][t][ev] = c_; } while (0)
+__device__ long long g_cta_cycles[4096][4];     // per CTA: {kernel cycles, physics-warp wait cycles, ray warp 1 wait cycles, -}
+#define TLWAIT(stmt) do { const long long w0_ = tl_clock(); stmt; tl_wait += tl_clock_after(smem) - w0_; } while (0)
+#else
+#define TL(ev) do { } while (0)
+#define TLB(ev) do { } while (0)
+#define TLWAIT(stmt) do { stmt; } while (0)
+#endif
+
 struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, contact_steps, toi_events, overflow; double return_sum; };
 
 struct KParams {
@@ -128,8 +149,8 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb,
 // CC = the optional shared world (NcgConfig.car_contacts): a separate instantiation, so that the default kernels carry none of
 // its code (measured: as a run-time branch it cost the default path 2 % contact-free and 12 % with the driving distribution).
 template <int RPL, int MINB, int PW, bool CC = false>
-__global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
-    constexpr int RW = PW == 2 ? 6 : 16 / RPL;      // ray warps
+__global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
+    constexpr int RW = PW == 2 ? (RPL == 2 ? 8 : 6) : 16 / RPL;      // ray warps (PW == 2: RPL only picks six or eight of them, the rays come from the queue)
     constexpr int NT = 32 * (PW + RW);
     constexpr int GROUPS = PW == 2 ? 2 : 1;         // groups of the CTA table served by this CTA
     constexpr int SLOTS = 32 * GROUPS;              // car slots: 32 per group
@@ -144,6 +165,9 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
     constexpr int BAR_POSE = 1, BAR_FULL = 1 + NB, BAR_EMPTY = 1 + 2 * NB;
     const SmemLayout L = smem_layout(0, SLOTS, NB);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef NCG_TIMELINE
+    long long tl_wait = 0; const long long tl_k0 = tl_clock();
+#endif
     float* s_rec = smem + L.rec;
     float* s_obs = smem + L.obs;
     float4* s_pose = reinterpret_cast<float4*>(smem + L.pose);
@@ -228,7 +252,9 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
         Counters cnt = {0, 0, 0, 0, 0};
         unsigned long long episodes = 0; double ret_sum = 0.0;
         for (int t = 0, b = 0; t < p.T; ++t, b = b + 1 == NB ? 0 : b + 1) {
-            if (t >= NB) bar_sync(BAR_EMPTY + b, NT);           // the ray warps have drained buffer b (step t-NB)
+            TL(0);
+            TLWAIT(if (t >= NB) bar_sync(BAR_EMPTY + b, NT));   // the ray warps have drained buffer b (step t-NB)
+            TL(1);
             float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
             float rew = 0.0f;
             StepCtx ctx;
@@ -277,6 +303,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
             __syncwarp();
             __threadfence_block();
             bar_arrive(BAR_POSE + b, NT);
+            TL(2);
             // single-car envs (C == 1, uniform) decide from the car's own result word: no exchange through shared memory,
             // no division by C, and the multi-car loops of env_decide unroll away
             const bool solo = p.C == 1;
@@ -290,6 +317,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
                     R[NCG_R_FLAGS] = u2f(fl);
                 }
             }
+            TL(3);
             if (!solo) __syncwarp();
             // ---- env phase (every car of an env computes the same decision from the env's xf words)
             if (active) {
@@ -330,6 +358,7 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
             __syncwarp();
             __threadfence_block();
             bar_arrive(BAR_FULL + b, NT);
+            TL(4);
         }
         // ---- counters
         unsigned long long v[7] = {active ? (unsigned long long)p.T : 0ull, episodes, cnt.laps, 0ull, cnt.contact_steps, cnt.toi_events, cnt.overflow};
@@ -366,7 +395,9 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
         const unsigned magic = (131072u + (unsigned)n_all - 1u) / (unsigned)n_all;
         for (int t = 0, b = 0; t < p.T; ++t, b = b + 1 == NB ? 0 : b + 1) {
             float* obs_out = p.obs_roll ? p.obs_roll + (size_t)t * N * NCG_OBS_DIM : p.obs;
-            bar_sync(BAR_POSE + b, NT);
+            TL(0);
+            TLWAIT(bar_sync(BAR_POSE + b, NT));
+            TL(1);
             if ((GROUPS == 2 || p.queue) && !(p.debug_skip & 1)) {
                 // every ray warp derives the cars' ray origins itself (same values to the same words: no barrier between
                 // the ray warps; nobody still reads last step's, every ray warp has passed that step's FULL barrier), then
@@ -392,7 +423,9 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
                 action_synthetic(p.seed, act_car, p.step_base + (unsigned)(t + NB), p.mode, p.discrete != 0, &thr, &brk, &st);
                 s_act[b * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
             }
-            bar_sync(BAR_FULL + b, NT);
+            TL(2);
+            TLWAIT(bar_sync(BAR_FULL + b, NT));
+            TL(3);
             __syncwarp();
             // ---- observation rows shared -> HBM: 38 consecutive floats per car, written as float2 (a row is 19 float2,
             // so a pair never straddles two cars and every store is 8-byte aligned).  Words 0..21 arrive raw from the
@@ -415,12 +448,18 @@ __global__ void __launch_bounds__(PW == 2 ? 256 : 32 * (PW + 16 / RPL), MINB) nc
                     } else if (obs_out) reinterpret_cast<float2*>(obs_out)[o] = v;
                 }
             }
+            TL(5);
             if (t + NB < p.T) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NT); }
+            TL(4);
         }
         ray_tests = tests;
         for (int o = 16; o > 0; o >>= 1) ray_tests += __shfl_down_sync(0xffffffffu, ray_tests, o);
         if (lane == 0 && ray_tests) atomicAdd(((unsigned long long*)p.stats) + 3, ray_tests);
     }
+#ifdef NCG_TIMELINE
+    if (lane == 0 && warp < 3 && blockIdx.x < 4096) g_cta_cycles[blockIdx.x][1 + warp] = tl_wait;
+    if (threadIdx.x == 0 && blockIdx.x < 4096) g_cta_cycles[blockIdx.x][0] = tl_clock() - tl_k0;
+#endif
     // ---- records shared -> HBM
     __syncthreads();
     for (int i = threadIdx.x; i < n_all * (NCG_RECORD_WORDS / 4); i += NT) {

@@ -404,8 +404,10 @@ def _queue_variants_agree(monkeypatch, E, C):
     import torch
     from nascargymnasium_b200.engine import Engine
     outs = []
-    for queue, no_stage, rpl, pw in (("0", "0", "2", "1"), ("1", "0", "2", "1"), ("1", "0", "4", "1"), ("1", "1", "4", "1"), ("0", "0", "4", "1"),
-                                     ("1", "0", "4", "2"), ("1", "1", "4", "2"), ("0", "0", "2", "4"), ("1", "1", "2", "4")):
+    for queue, no_stage, rpl, pw, rw8 in (("0", "0", "2", "1", "0"), ("1", "0", "2", "1", "0"), ("1", "0", "4", "1", "0"), ("1", "1", "4", "1", "0"),
+                                          ("0", "0", "4", "1", "0"), ("1", "0", "4", "2", "0"), ("1", "1", "4", "2", "0"), ("1", "0", "4", "2", "1"),
+                                          ("1", "1", "4", "2", "1"), ("0", "0", "2", "4", "0"), ("1", "1", "2", "4", "0")):
+        monkeypatch.setenv("NCG_PAIR_RW8", rw8)        # the pair shape with eight ray warps (96 registers) instead of six
         monkeypatch.setenv("NCG_RAY_QUEUE", queue)
         monkeypatch.setenv("NCG_NO_STAGE", no_stage)
         monkeypatch.setenv("NCG_RAYS_PER_LANE", rpl)
