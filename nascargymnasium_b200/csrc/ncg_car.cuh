@@ -421,6 +421,32 @@ NCG_HDN void w_solve(World& W, const Track& T, float h, float dtRatio) {
     }
 }
 // b2World::SolveTOI + b2Island::SolveTOI
+// A lower bound of the distance between the car box and a (static) wall box over the WHOLE sweep c0,a0 -> c,a, on the wall's
+// own face normals as separating axes.  Along the unit axis u the separation is d(t) - r(t) - h: d = u.(car centre - wall
+// centre) is linear in t, so >= min(d0, d1); r = the car box's support radius along u, a maximum of sinusoids in the heading
+// of amplitude R (half diagonal), so over the heading interval r <= max(r0, r1) + R da^2 / 8.  The distance of two convex
+// shapes is at least their separation on any axis.
+NCG_HD float sweep_face_bound(const Sweep& s, const Rot q1, const Xf& xfB, const Box& bB) {
+    const Rot q0 = rot(s.a0);
+    const float da = s.a - s.a0, curv = 2.7114f * da * da * 0.125f;
+    const V2 r0 = s.c0 - xfB.p, r1 = s.c - xfB.p;
+    float best = -NCG_B2_MAXFLOAT;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const V2 u = k == 0 ? mk(xfB.q.c, xfB.q.s) : mk(-xfB.q.s, xfB.q.c);
+        const float h = k == 0 ? bB.hx : bB.hy;
+        const float d0 = dot(u, r0), d1 = dot(u, r1);
+        const V2 m0 = mulT(q0, u), m1 = mulT(q1, u);                   // the axis in the car's frame at both ends
+        const float sup0 = fabsf(m0.x) * NCG_CAR_HALF_LENGTH + fabsf(m0.y) * NCG_CAR_HALF_WIDTH;
+        const float sup1 = fabsf(m1.x) * NCG_CAR_HALF_LENGTH + fabsf(m1.y) * NCG_CAR_HALF_WIDTH;
+        const float r = fmaxb(sup0, sup1) + curv + h;
+        best = fmaxb(best, fmaxb(fminb(d0, d1) - r, -fmaxb(d0, d1) - r));
+    }
+    return best;
+}
+#if !defined(__CUDA_ARCH__)
+static unsigned long long g_toi_full = 0, g_toi_skip_reach = 0, g_toi_skip_face = 0;      // host compile: how the queries were answered
+#endif
 NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
     W.b.sweep.alpha0 = 0.0f;
     for (int i = 0; i < W.nc; ++i) { W.wallAlpha[i] = 0.0f; Contact& c = W.c[i]; c.toiFlag = false; c.island = false; c.toiCount = 0; c.toi = 1.0f; }
@@ -445,7 +471,28 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
             else {
                 if (!W.b.awake) continue;
 #ifndef NCG_NO_TOI_SHORTCUT      /* (tests/test_hostcheck.py builds the host compile both ways and demands identical records) */
-                if (pristine && c.sep0 > toi_reach) { c.toi = 1.0f; c.toiFlag = true; continue; }
+                if (pristine && c.sep0 > toi_reach) {
+#if !defined(__CUDA_ARCH__)
+                    ++g_toi_skip_reach;
+#endif
+                    c.toi = 1.0f; c.toiFlag = true; continue;
+                }
+                // A car that scrapes along a wall keeps ~1.5 cm between the core shapes (the position solver's resting
+                // penetration) and does not come closer during the step: the same argument with a sharper bound -- the
+                // separation on the wall's face normals over the whole sweep -- answers those without the query too.  The
+                // margin covers the rounding of both computations (coordinates of ~1e3 m carry 1e-4 m).
+                if (pristine) {
+                    Xf xfW; Box bW; wall_get(T, c.wall, &xfW, &bW);
+                    if (sweep_face_bound(W.b.sweep, W.b.xf.q, xfW, bW) > NCG_B2_LINEAR_SLOP + 0.25f * NCG_B2_LINEAR_SLOP + 1e-3f) {
+#if !defined(__CUDA_ARCH__)
+                        ++g_toi_skip_face;
+#endif
+                        c.toi = 1.0f; c.toiFlag = true; continue;
+                    }
+                }
+#endif
+#if !defined(__CUDA_ARCH__)
+                ++g_toi_full;
 #endif
                 float alpha0 = W.b.sweep.alpha0;
                 if (W.b.sweep.alpha0 < W.wallAlpha[i]) { alpha0 = W.wallAlpha[i]; sweep_advance(W.b.sweep, alpha0); }

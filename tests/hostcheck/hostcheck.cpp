@@ -160,6 +160,7 @@ void hc_nearest_segment(const float* blob, float x, float y, int masked, float* 
 }
 void hc_sincos_heading(float a, float* out2) { sincos_heading(a, out2, out2 + 1); }
 int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }
+void hc_toi_counters(unsigned long long* out3) { out3[0] = g_toi_full; out3[1] = g_toi_skip_reach; out3[2] = g_toi_skip_face; }
 void hc_synthetic_action(unsigned long long seed, unsigned car, unsigned step, int mode, int discrete, float* out3) {
     action_synthetic(seed, car, step, mode, discrete != 0, out3, out3 + 1, out3 + 2);
 }
