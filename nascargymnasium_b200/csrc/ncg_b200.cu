@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "ncg_car.cuh"
 
 using namespace ncg;
@@ -26,6 +27,13 @@ namespace {
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+// NVTX ranges around the launches of the C ABI (tracing), opt-in with NCG_NVTX=1 so that the default path pays nothing:
+// `nsys`/`ncu --nvtx` then show ncg_reset / ncg_step / ncg_rollout next to the caller's own ranges.
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) { static const bool en = [] { const char* v = getenv("NCG_NVTX"); return v && atoi(v) != 0; }(); on = en; if (on) nvtxRangePushA(name); }
+    ~NvtxRange() { if (on) nvtxRangePop(); }
+};
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(NCG_E_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
 }  // namespace
@@ -231,6 +239,7 @@ int follow_redraws(NcgHandle* h, cudaStream_t s) {
 }
 
 int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
+    NvtxRange nvtx_(p.T == 1 ? "ncg_step" : "ncg_rollout");
     { int rc = follow_redraws(h, s); if (rc) return rc; }
     if (h->cta_dirty) { int rc = build_cta_table(h); if (rc) return rc; }
     p.redraw = (h->redraw && p.T == 1 && p.auto_reset && h->n_tracks > 1) ? 1 : 0;
@@ -411,6 +420,7 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
 }
 
 int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id, int32_t fresh, float* d_obs, void* stream) {
+    NvtxRange nvtx_("ncg_reset");
     if (!h) return fail(NCG_E_INVALID, "null handle");
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called before ncg_reset");
     CUDA_TRY(cudaSetDevice(h->cfg.device));

@@ -426,7 +426,7 @@ NCG_HDN void w_solve(World& W, const Track& T, float h, float dtRatio) {
 // centre) is linear in t, so >= min(d0, d1); r = the car box's support radius along u, a maximum of sinusoids in the heading
 // of amplitude R (half diagonal), so over the heading interval r <= max(r0, r1) + R da^2 / 8.  The distance of two convex
 // shapes is at least their separation on any axis.
-NCG_HD float sweep_face_bound(const Sweep& s, const Rot q1, const Xf& xfB, const Box& bB) {
+NCG_HD float sweep_face_bound(const Sweep& s, const Rot q1, const Xf& xfB, const Box& bB, float enough) {
     const Rot q0 = rot(s.a0);
     const float da = s.a - s.a0, curv = 2.7114f * da * da * 0.125f;
     const V2 r0 = s.c0 - xfB.p, r1 = s.c - xfB.p;
@@ -442,6 +442,25 @@ NCG_HD float sweep_face_bound(const Sweep& s, const Rot q1, const Xf& xfB, const
         const float r = fmaxb(sup0, sup1) + curv + h;
         best = fmaxb(best, fmaxb(fminb(d0, d1) - r, -fmaxb(d0, d1) - r));
     }
+    if (best > enough) return best;                                    // (most scraping contacts: decided on the wall's axes)
+#ifndef NCG_NO_TOI_CAR_AXES
+    // the car's own face normals (a wall corner against the car's side: the inner wall of a bend).  In the car's frame the
+    // wall centre is D(t) = R(a(t))^T (p - c(t)), per component |D''| <= da^2 |p - c|max + 2 |da| |dc|, and the wall box's
+    // support radius along a car axis is again a maximum of sinusoids in the heading, of amplitude <= hx + hy.
+    const V2 D0 = mulT(q0, -1.0f * r0), D1 = mulT(q1, -1.0f * r1);
+    const float ada = fabsf(da);
+    const float wmax = fmaxb(length(r0), length(r1)), dd = (da * da * wmax + 2.0f * ada * length(s.c - s.c0)) * 0.125f;
+    const V2 ex0 = mulT(q0, mk(xfB.q.c, xfB.q.s)), ex1 = mulT(q1, mk(xfB.q.c, xfB.q.s));      // the wall's x axis in the car's frame; its y axis is (-ex.y, ex.x)
+    const float scurv = (bB.hx + bB.hy) * da * da * 0.125f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float a0 = k == 0 ? D0.x : D0.y, a1 = k == 0 ? D1.x : D1.y;
+        const float s0 = k == 0 ? fabsf(ex0.x) * bB.hx + fabsf(ex0.y) * bB.hy : fabsf(ex0.y) * bB.hx + fabsf(ex0.x) * bB.hy;
+        const float s1 = k == 0 ? fabsf(ex1.x) * bB.hx + fabsf(ex1.y) * bB.hy : fabsf(ex1.y) * bB.hx + fabsf(ex1.x) * bB.hy;
+        const float r = fmaxb(s0, s1) + scurv + dd + (k == 0 ? NCG_CAR_HALF_LENGTH : NCG_CAR_HALF_WIDTH);
+        best = fmaxb(best, fmaxb(fminb(a0, a1) - r, -fmaxb(a0, a1) - r));
+    }
+#endif
     return best;
 }
 #if !defined(__CUDA_ARCH__)
@@ -483,7 +502,8 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
                 // margin covers the rounding of both computations (coordinates of ~1e3 m carry 1e-4 m).
                 if (pristine) {
                     Xf xfW; Box bW; wall_get(T, c.wall, &xfW, &bW);
-                    if (sweep_face_bound(W.b.sweep, W.b.xf.q, xfW, bW) > NCG_B2_LINEAR_SLOP + 0.25f * NCG_B2_LINEAR_SLOP + 1e-3f) {
+                    const float enough = NCG_B2_LINEAR_SLOP + 0.25f * NCG_B2_LINEAR_SLOP + 1e-3f;
+                    if (sweep_face_bound(W.b.sweep, W.b.xf.q, xfW, bW, enough) > enough) {
 #if !defined(__CUDA_ARCH__)
                         ++g_toi_skip_face;
 #endif

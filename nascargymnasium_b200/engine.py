@@ -25,7 +25,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 _SOURCES = ("ncg_b200.cu", "ncg_b200_cc.cu", "ncg_step.cuh", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 # Which Box2D 2.3.x b2CollidePolygons the contact path follows (include/ncg_b200.h NcgConfig.contacts): box2d-py 2.3.8
