@@ -97,6 +97,7 @@ struct NcgHandle {
     std::vector<int> h_env_track;
     int2* d_cta_tab = nullptr; int n_ctas = 0; int cap_ctas = 0; bool cta_dirty = true;   // groups of <= 32 car slots (one CTA each, or two per CTA)
     int2* d_pair_tab = nullptr; int n_pairs = 0; int cap_pairs = 0;       // groups paired by track for the two-physics-warp shape
+    int2* d_cta_stage = nullptr; int2* d_pair_stage = nullptr;            // per group / pair: where its track's table is, bytes to stage
     int* d_slot_env = nullptr; int cap_slots = 0; bool identity = true;   // slot -> env list (envs ordered by track); unused while the map is sorted
     int* d_env_track = nullptr;                      // [E] device copy of the env -> track map; the redraw writes it
     int redraw = 0; unsigned long long redraw_seed = 0; unsigned steps_taken = 0;
@@ -191,12 +192,17 @@ int build_cta_table(NcgHandle* h) {
     plan_ctas(seq, E, h->cfg.cars_per_env, h->num_sms, tab);
     // (each table has its own capacity: the allocation only ever grows, and growing one never touches the other)
     if ((int)tab.size() > h->cap_ctas) {
-        cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr; h->cap_ctas = 0;
+        cudaFree(h->d_cta_tab); h->d_cta_tab = nullptr; h->cap_ctas = 0; cudaFree(h->d_cta_stage); h->d_cta_stage = nullptr;
         CUDA_TRY(cudaMalloc(&h->d_cta_tab, tab.size() * sizeof(int2)));
+        CUDA_TRY(cudaMalloc(&h->d_cta_stage, tab.size() * sizeof(int2)));
         h->cap_ctas = (int)tab.size();
     }
     CUDA_TRY(cudaMemcpyAsync(h->d_cta_tab, tab.data(), tab.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     h->n_ctas = (int)tab.size();
+    auto stage_of = [&](int g) { const int t = seq[tab[g].x]; return make_int2((int)h->h_track_off[t], (int)(h->h_stage_words[t] * 4u)); };
+    std::vector<int2> stage(tab.size());
+    for (size_t g = 0; g < tab.size(); ++g) stage[g] = stage_of((int)g);
+    CUDA_TRY(cudaMemcpyAsync(h->d_cta_stage, stage.data(), stage.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     // neighbouring groups of one track, two by two (a group without such a neighbour stays alone)
     std::vector<int2> pairs;
     for (size_t g = 0; g < tab.size();) {
@@ -205,11 +211,15 @@ int build_cta_table(NcgHandle* h) {
         g += two ? 2 : 1;
     }
     if ((int)pairs.size() > h->cap_pairs) {
-        cudaFree(h->d_pair_tab); h->d_pair_tab = nullptr; h->cap_pairs = 0;
+        cudaFree(h->d_pair_tab); h->d_pair_tab = nullptr; h->cap_pairs = 0; cudaFree(h->d_pair_stage); h->d_pair_stage = nullptr;
         CUDA_TRY(cudaMalloc(&h->d_pair_tab, pairs.size() * sizeof(int2)));
+        CUDA_TRY(cudaMalloc(&h->d_pair_stage, pairs.size() * sizeof(int2)));
         h->cap_pairs = (int)pairs.size();
     }
     CUDA_TRY(cudaMemcpyAsync(h->d_pair_tab, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    std::vector<int2> pstage(pairs.size());
+    for (size_t q = 0; q < pairs.size(); ++q) pstage[q] = stage_of(pairs[q].x);
+    CUDA_TRY(cudaMemcpyAsync(h->d_pair_stage, pstage.data(), pstage.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_env_track, et.data(), (size_t)E * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     // (pageable sources: the copies are staged before the calls return; the plan must be in place before the caller's
     // stream runs the step)
@@ -265,7 +275,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     const bool cc = h->cfg.car_contacts != 0;                // shared world: one shape (an env's cars sit in one physics warp)
     if (cc) PW = 1;
     if (PW == 4 && (h->cfg.cars_per_env != 1 || h->n_ctas > sms)) PW = 1;       // the spread shape: single-car envs, one CTA per SM
-    p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab; p.slot_env = h->identity ? nullptr : h->d_slot_env;
+    p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab; p.cta_stage = h->d_cta_stage; p.pair_stage = h->d_pair_stage; p.slot_env = h->identity ? nullptr : h->d_slot_env;
     { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
@@ -334,6 +344,7 @@ extern "C" {
 const char* ncg_last_error(void) { return g_err.c_str(); }
 #ifdef NCG_TIMELINE
 int ncg_debug_timeline(long long* out) { return cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)) == cudaSuccess ? 0 : 1; }
+int ncg_debug_launch_ns(unsigned long long* out, int reset) { if (reset) { static unsigned long long init[4096][2]; for (int i = 0; i < 4096; ++i) { init[i][0] = ~0ull; init[i][1] = 0; } return cudaMemcpyToSymbol(g_launch_ns, init, sizeof(init)) == cudaSuccess ? 0 : 1; } return cudaMemcpyFromSymbol(out, g_launch_ns, sizeof(g_launch_ns)) == cudaSuccess ? 0 : 1; }
 int ncg_debug_cta_cycles(long long* out) { return cudaMemcpyFromSymbol(out, g_cta_cycles, sizeof(g_cta_cycles)) == cudaSuccess ? 0 : 1; }
 #endif
 int ncg_version(void) { return 1; }
@@ -388,7 +399,7 @@ int ncg_destroy(NcgHandle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_cc_pairs); cudaFree(h->d_cc_worlds); cudaFree(h->d_vel_hist); cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
-    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); cudaFree(h->d_slot_env); cudaFree(h->d_env_track);
+    cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); cudaFree(h->d_cta_stage); cudaFree(h->d_pair_stage); cudaFree(h->d_slot_env); cudaFree(h->d_env_track);
     cudaFreeHost(h->p_redrawn);
     cudaFreeHost(h->p_actions); cudaFreeHost(h->p_pack); cudaFreeHost(h->p_final); cudaFreeHost(h->p_any_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -410,6 +421,7 @@ int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offset
     h->h_stage_words.clear();
     for (int i = 0; i < n_tracks; ++i) { uint32_t w; memcpy(&w, h_blob + h_offsets[i] + TH_STAGE_WORDS, 4); h->h_stage_words.push_back(w); }
     h->n_tracks = n_tracks;
+    h->cta_dirty = true;                                                      // the plan carries table offsets
     const int rc = h->cfg.car_contacts ? h->cfg.cars_per_env : 1;             // reset rows per track (a start grid: one per car of an env)
     CUDA_TRY(cudaMalloc(&h->d_reset_obs, (size_t)n_tracks * rc * NCG_OBS_DIM * 4));
     ncg_reset_obs_kernel<<<n_tracks * rc, 32>>>(h->d_blob, h->d_track_off, h->d_reset_obs, start_pose(h), rc, h->cfg.grid_dx, h->cfg.grid_dy);

@@ -24,7 +24,9 @@ __device__ __forceinline__ long long tl_clock_after(const float* sm) {
     return c;
 }
 #define TLB(ev) do { const long long c_ = tl_clock_after(smem); if (blockIdx.x == 5 && lane == 0 && t < 128 && warp < 12) g_timeline[warp][t][ev] = c_; } while (0)
-__device__ long long g_cta_cycles[4096][4];     // per CTA: {kernel cycles, physics-warp wait cycles, ray warp 1 wait cycles, -}
+__device__ long long g_cta_cycles[4096][5];
+__device__ unsigned long long g_launch_ns[4096][2];   // per launch (index = step_base & 4095): first CTA start, last CTA end (globaltimer, ns)
+__device__ __forceinline__ unsigned long long tl_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }     // per CTA: {kernel cycles, physics-warp wait cycles, ray warp 1 wait cycles, -}
 #define TLWAIT(stmt) do { const long long w0_ = tl_clock(); stmt; tl_wait += tl_clock_after(smem) - w0_; } while (0)
 #else
 #define TL(ev) do { } while (0)
@@ -39,6 +41,7 @@ struct KParams {
     const int2* cta_tab;                                   // per group: {first slot, number of envs}; all of one track, <= 32 cars
     const int* slot_env;                                   // slot -> env, envs ordered by track; NULL = identity (the map is already sorted)
     const int2* pair_tab;                                  // two-physics-warp shape: per CTA the two groups it serves {g0, g1 or -1}
+    const int2* cta_stage; const int2* pair_stage;         // per group / per pair: {word offset of the track's table in blob, bytes to stage}
     const float* reset_obs;                                // [n_tracks][NCG_OBS_DIM]: the observation every reset_car yields on a track
     int E, C, discrete, reset_on_lap, auto_reset, contacts, stage, track_info, debug_skip, queue;
     const void* actions; float* obs; float* reward; uint8_t* term; uint8_t* trunc; float* final_obs;
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifdef NCG_TIMELINE
     long long tl_wait = 0; const long long tl_k0 = tl_clock();
+    if (threadIdx.x == 0) atomicMin(&g_launch_ns[p.step_base & 4095][0], tl_ns());
 #endif
     float* s_rec = smem + L.rec;
     float* s_obs = smem + L.obs;
@@ -181,6 +185,17 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     int* s_ctr = reinterpret_cast<int*>(smem + L.ctr);
     float* s_track = smem + L.track;
 
+    // ---- track table: staged by TMA when the whole CTA shares a track (else read through L1/L2).  Issued first: where the
+    // table is and how much of it to stage comes with the launch plan (one independent load), not from the first record's
+    // track id -> offset table -> table header, a chain of three dependent global loads (1.5 us of a single-step launch).
+    const float* staged = nullptr;
+    if (p.stage) {
+        if (threadIdx.x == 0) {
+            const int2 sg = (GROUPS == 1 ? p.cta_stage : p.pair_stage)[blockIdx.x];
+            tma_issue(s_track, p.blob + sg.x, (unsigned)sg.y, &s_mbar);
+        }
+        staged = s_track;
+    }
     // the groups of envs this CTA serves: n0 cars from global car cb0 in slots 0.., n1 cars from cb1 in slots 32..
     int2 g0, g1 = make_int2(0, 0);
     if (GROUPS == 1) g0 = p.cta_tab[blockIdx.x];
@@ -199,16 +214,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     __syncthreads();
     const int cb0 = s_gcar[0];                                       // the CTA's first car: its record names the CTA's track
 
-    // ---- track table: staged by TMA when the whole CTA shares a track, else read through L1/L2
-    const float* staged = nullptr;
-    if (p.stage) {
-        if (threadIdx.x == 0) {
-            const uint32_t tid = f2u(p.records[(size_t)cb0 * NCG_RECORD_WORDS + NCG_R_TRACK]);
-            const float* g = p.blob + p.track_off[tid];
-            tma_issue(s_track, g, f2u(__ldg(g + TH_STAGE_WORDS)) * 4u, &s_mbar);
-        }
-        staged = s_track;
-    }
+    // (the track table's bulk copy was issued at the top of the kernel)
     // ---- records HBM -> shared (coalesced float4 reads, scalar shared stores into the padded rows)
     for (int i = threadIdx.x; i < n_all * (NCG_RECORD_WORDS / 4); i += NT) {
         const int ci = i >> 5;
@@ -458,15 +464,22 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     }
 #ifdef NCG_TIMELINE
     if (lane == 0 && warp < 3 && blockIdx.x < 4096) g_cta_cycles[blockIdx.x][1 + warp] = tl_wait;
-    if (threadIdx.x == 0 && blockIdx.x < 4096) g_cta_cycles[blockIdx.x][0] = tl_clock() - tl_k0;
+    if (threadIdx.x == 0 && blockIdx.x < 4096) { g_cta_cycles[blockIdx.x][0] = tl_clock() - tl_k0; g_cta_cycles[blockIdx.x][4] = tl_k0; }
 #endif
     // ---- records shared -> HBM
     __syncthreads();
+#ifdef NCG_TIMELINE
+    if (threadIdx.x == 0 && blockIdx.x == 5) g_timeline[11][127][0] = tl_clock();
+#endif
     for (int i = threadIdx.x; i < n_all * (NCG_RECORD_WORDS / 4); i += NT) {
         const int ci = i >> 5;
         const float* d = s_rec + SLOT_OF(ci) * REC_STRIDE + (i & 31) * 4;
         reinterpret_cast<float4*>(p.records + (size_t)GCAR_OF(ci) * NCG_RECORD_WORDS)[i & 31] = make_float4(d[0], d[1], d[2], d[3]);
     }
+#ifdef NCG_TIMELINE
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMax(&g_launch_ns[p.step_base & 4095][1], tl_ns());
+#endif
 #undef SLOT_OF
 #undef GCAR_OF
 }
