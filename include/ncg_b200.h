@@ -209,6 +209,12 @@ int ncg_get_state(NcgHandle* h, float* d_records, void* stream);
 int ncg_set_state(NcgHandle* h, const float* d_records, void* stream);
 int ncg_get_state_host(NcgHandle* h, float* h_records);
 int ncg_set_state_host(NcgHandle* h, const float* h_records);
+/* NcgConfig.car_contacts only: the rest of an env's state, the car-car contact table of its shared world (which pairs of cars
+ * have a contact, touching or not, feature ids and warm-start impulses), NCG_CAR_PAIR_WORDS 32-bit words per env.  A checkpoint
+ * of a shared-world engine is ncg_get_state_host + ncg_get_car_pairs_host; NCG_E_STATE without car_contacts. */
+#define NCG_CAR_PAIR_WORDS 368
+int ncg_get_car_pairs_host(NcgHandle* h, float* h_pairs);
+int ncg_set_car_pairs_host(NcgHandle* h, const float* h_pairs);
 
 /* Car.velocity_history (src/car.py:173, 384-386, 1058): the velocity (vx, vy) update_physics saw on each of the last
  * NCG_VEL_HISTORY steps of the running episode, a ring indexed by (episode step mod NCG_VEL_HISTORY);

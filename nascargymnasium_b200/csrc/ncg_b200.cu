@@ -644,6 +644,24 @@ int ncg_set_state_host(NcgHandle* h, const float* h_records) {
     return NCG_OK;
 }
 
+static_assert(NCG_CAR_PAIR_WORDS == NCG_CC_STRIDE, "include/ncg_b200.h and csrc/ncg_car.cuh disagree on the pair table");
+int ncg_get_car_pairs_host(NcgHandle* h, float* h_pairs) {
+    if (!h || !h_pairs) return fail(NCG_E_INVALID, "null argument");
+    if (!h->d_cc_pairs) return fail(NCG_E_STATE, "the car-car contact table exists only with NcgConfig.car_contacts = 1");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h_pairs, h->d_cc_pairs, (size_t)h->cfg.num_envs * NCG_CC_STRIDE * 4, cudaMemcpyDeviceToHost));
+    return NCG_OK;
+}
+int ncg_set_car_pairs_host(NcgHandle* h, const float* h_pairs) {
+    if (!h || !h_pairs) return fail(NCG_E_INVALID, "null argument");
+    if (!h->d_cc_pairs) return fail(NCG_E_STATE, "the car-car contact table exists only with NcgConfig.car_contacts = 1");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpy(h->d_cc_pairs, h_pairs, (size_t)h->cfg.num_envs * NCG_CC_STRIDE * 4, cudaMemcpyHostToDevice));
+    return NCG_OK;
+}
+
 int ncg_get_velocity_history_host(NcgHandle* h, float* h_out) {
     if (!h || !h_out) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_vel_hist) return fail(NCG_E_STATE, "the velocity history is kept only with NcgConfig.track_info = 1");

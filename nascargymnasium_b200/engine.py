@@ -76,7 +76,8 @@ EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_up
            "ncg_rollout", "ncg_step_host", "ncg_reset_host", "ncg_get_state", "ncg_set_state", "ncg_get_state_host",
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
            "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs",
-           "ncg_get_velocity_history_host", "ncg_set_track_redraw", "ncg_get_env_tracks")
+           "ncg_get_velocity_history_host", "ncg_set_track_redraw", "ncg_get_env_tracks", "ncg_get_car_pairs_host",
+           "ncg_set_car_pairs_host")
 
 _lib = None
 
@@ -117,6 +118,8 @@ def load_library():
     lib.ncg_set_rollout_base.argtypes = [vp, ctypes.c_uint32, ctypes.c_uint32]
     lib.ncg_set_episode_outputs.argtypes = [vp, vp, vp, vp]
     lib.ncg_get_velocity_history_host.argtypes = [vp, vp]
+    lib.ncg_get_car_pairs_host.argtypes = [vp, vp]
+    lib.ncg_set_car_pairs_host.argtypes = [vp, vp]
     lib.ncg_set_track_redraw.argtypes = [vp, i32, u64]
     lib.ncg_get_env_tracks.argtypes = [vp, vp]
     _lib = lib
@@ -387,6 +390,18 @@ class Engine:
         if records.size != self.num_cars * L.RECORD_WORDS:
             raise ValueError("records: wrong number of elements")
         _check(self._lib.ncg_set_state_host(self._h, _np_ptr(records)))
+
+    def get_car_pairs_host(self) -> np.ndarray:
+        """car_contacts only: the car-car contact tables of the shared worlds, (E, NCG_CAR_PAIR_WORDS) float32 (raw words)."""
+        out = np.empty((self.num_envs, L.DEFS["NCG_CAR_PAIR_WORDS"]), dtype=np.float32)
+        _check(self._lib.ncg_get_car_pairs_host(self._h, _np_ptr(out)))
+        return out
+
+    def set_car_pairs_host(self, pairs: np.ndarray) -> None:
+        pairs = np.ascontiguousarray(pairs, dtype=np.float32)
+        if pairs.size != self.num_envs * L.DEFS["NCG_CAR_PAIR_WORDS"]:
+            raise ValueError("pairs: wrong number of elements")
+        _check(self._lib.ncg_set_car_pairs_host(self._h, _np_ptr(pairs)))
 
     def velocity_history_host(self) -> np.ndarray:
         """(N, 600, 2) ring of the pre-step velocities of the running episode (track_info engines only)."""

@@ -188,3 +188,32 @@ def test_engine_known_answers_of_the_shared_world():
     last = eng.get_state_host().reshape(2, C, -1)[1]
     assert last[0, R["NCG_R_X"]] > 0.5 and last[2, R["NCG_R_X"]] > -8.0 + 0.5 and last[0, R["NCG_R_X"]] - last[2, R["NCG_R_X"]] > 5.0
     eng.close()
+
+
+@pytest.mark.gpu
+def test_checkpoint_of_a_shared_world_engine_in_the_middle_of_a_contact():
+    """get_state_host + get_car_pairs_host is the whole state: an engine restored from them in the middle of a car-car contact
+    continues bit for bit like the one that kept running."""
+    from nascargymnasium_b200.engine import Engine
+    rng = np.random.default_rng(1)
+    E, C = 8, 4
+    a_eng = Engine(E, C, tracks=["daytona"], auto_reset=False, car_contacts=True)
+    b_eng = Engine(E, C, tracks=["daytona"], auto_reset=False, car_contacts=True)
+    a_eng.reset_host(); b_eng.reset_host()
+    touched = 0
+    for t in range(220):
+        a = np.broadcast_to(_actions("rear_end", C, t, rng), (E, C, 2)).copy()
+        a_eng.step_host(a)
+        pairs = a_eng.get_car_pairs_host()
+        touched += 1 if (pairs.view(np.uint32)[0, 0::8][:45] & 2).any() else 0
+        if touched == 4:
+            break
+    assert touched == 4
+    b_eng.set_state_host(a_eng.get_state_host()); b_eng.set_car_pairs_host(pairs)
+    for t in range(60):
+        a = np.broadcast_to(_actions("rear_end", C, t, rng), (E, C, 2)).copy()
+        oa = a_eng.step_host(a)[0]; ob = b_eng.step_host(a)[0]
+        assert np.array_equal(oa.view(np.uint32), ob.view(np.uint32)), t
+    assert np.array_equal(a_eng.get_state_host().view(np.uint32), b_eng.get_state_host().view(np.uint32))
+    assert np.array_equal(a_eng.get_car_pairs_host().view(np.uint32), b_eng.get_car_pairs_host().view(np.uint32))
+    a_eng.close(); b_eng.close()
