@@ -13,7 +13,10 @@
 // (cp.async.bulk + mbarrier).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 #include <nvtx3/nvToolsExt.h>
 #include "ncg_car.cuh"
@@ -108,6 +111,8 @@ struct NcgHandle {
     unsigned step_base = 0, car_base = 0;              // Philox counter offsets of ncg_rollout (ncg_set_rollout_base)
     float* d_ep_return = nullptr; int* d_ep_length = nullptr; int* d_ep_any = nullptr;   // ncg_set_episode_outputs
     int rays_per_lane = 0; int num_sms = 0; int max_smem = 0;
+    // diagnostic overrides, read once at ncg_create (-1 = not set): a launch does not scan the environment
+    int ov_phys_warps = -1, ov_no_stage = -1, ov_ray_queue = -1, ov_min_blocks = -1, ov_pair_rw8 = -1;
     long long launches = 0;
     // host-buffer path
     cudaStream_t stream = nullptr;
@@ -271,12 +276,12 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
         // (single-car envs: the pair shape with eight ray warps; fitted over 12288..131072 envs, tools/ab_pw.sh)
         if ((h->cfg.cars_per_env == 1 ? 13 : 12) * waves2 < 10 * waves1) PW = 2;
     }
-    { const char* pw = getenv("NCG_PHYS_WARPS"); if (pw && (atoi(pw) == 1 || atoi(pw) == 2 || atoi(pw) == 4)) PW = atoi(pw); }
+    if (h->ov_phys_warps == 1 || h->ov_phys_warps == 2 || h->ov_phys_warps == 4) PW = h->ov_phys_warps;
     const bool cc = h->cfg.car_contacts != 0;                // shared world: one shape (an env's cars sit in one physics warp)
     if (cc) PW = 1;
     if (PW == 4 && (h->cfg.cars_per_env != 1 || h->n_ctas > sms)) PW = 1;       // the spread shape: single-car envs, one CTA per SM
     p.cta_tab = h->d_cta_tab; p.pair_tab = h->d_pair_tab; p.cta_stage = h->d_cta_stage; p.pair_stage = h->d_pair_stage; p.slot_env = h->identity ? nullptr : h->d_slot_env;
-    { const char* ns = getenv("NCG_NO_STAGE"); p.stage = (ns && atoi(ns)) ? 0 : 1; }
+    p.stage = h->ov_no_stage > 0 ? 0 : 1;
     unsigned mx = 0;
     if (p.stage) for (unsigned w : h->h_stage_words) mx = w > mx ? w : mx;
     size_t smem = 0;        // (set below, once the shape is known: the number of step buffers depends on it)
@@ -284,11 +289,11 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     // issue-bound, i.e. with three resident CTAs per SM (measured on B200, daytona: +22 % at 65536 envs, +9 % at 16384,
     // -5 % at 8192 and -7 % at 4096, where a step is bound by latency and the queue's claims and job set-up only add to it)
     p.queue = h->n_ctas > 2 * sms ? 1 : 0;
-    { const char* q = getenv("NCG_RAY_QUEUE"); if (q) p.queue = atoi(q) ? 1 : 0; }
+    if (h->ov_ray_queue >= 0) p.queue = h->ov_ray_queue ? 1 : 0;
     // resident CTAs per SM the register allocation allows: as many as the batch has use for, up to what shared memory
     // (~72 KB per CTA) admits; the 4-rays-per-lane shape (160 threads) fits three
     int minb = h->n_ctas <= sms ? 1 : (h->n_ctas <= 2 * sms || RPL != 4 ? 2 : 3);
-    { const char* mb = getenv("NCG_MIN_BLOCKS"); if (mb && atoi(mb) >= 1 && atoi(mb) <= 3) minb = atoi(mb); }
+    if (h->ov_min_blocks >= 1 && h->ov_min_blocks <= 3) minb = h->ov_min_blocks;
     if (minb == 3 && RPL != 4) minb = 2;
     if (PW == 2) minb = 2;
     if (PW == 4) minb = 1;
@@ -305,7 +310,7 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
     // registers lose it again (1.32 vs 1.41 G at 65536), and ten-car envs on talladega, whose physics warps do the env phase and
     // frequent resets on top, lose 18 % with eight (1.07 vs 1.30 G).  NCG_PAIR_RW8 = 0 | 1 overrides.
     int pair_rw8 = h->cfg.cars_per_env == 1 ? 1 : 0;
-    { const char* v = getenv("NCG_PAIR_RW8"); if (v) pair_rw8 = atoi(v) ? 1 : 0; }
+    if (h->ov_pair_rw8 >= 0) pair_rw8 = h->ov_pair_rw8 ? 1 : 0;
     void (*k)(KParams) = PW == 4 ? ncg_step_kernel<2, 1, 4> : PW == 2 ? (pair_rw8 ? ncg_step_kernel<2, 2, 2> : ncg_step_kernel<4, 2, 2>)
                        : minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1, 1> : ncg_step_kernel<2, 1, 1>)
                        : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2, 1> : ncg_step_kernel<2, 2, 1>)
@@ -316,7 +321,13 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
         ++h->launches;
         return NCG_OK;
     }
-    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // the kernel's dynamic shared memory limit: a driver call, made only when a launch needs more than any before it
+        // (the attribute belongs to the function, not to the handle: raised, never lowered; per device)
+        static std::mutex mu; static std::map<std::pair<const void*, int>, int> limit;
+        std::lock_guard<std::mutex> lock(mu);
+        int& have = limit[std::make_pair((const void*)k, h->cfg.device)];
+        if ((int)smem > have) { CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); have = (int)smem; }
+    }
     if (PW == 4) k<<<h->n_ctas, 32 * (4 + 8), smem, s>>>(p);
     else if (PW == 2) k<<<h->n_pairs, pair_rw8 ? 320 : 256, smem, s>>>(p);
     else k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
@@ -362,6 +373,9 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     CUDA_TRY(cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     h->cfg = *cfg; h->N = cfg->num_envs * cfg->cars_per_env;
+    { auto ov = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : -1; };
+      h->ov_phys_warps = ov("NCG_PHYS_WARPS"); h->ov_no_stage = ov("NCG_NO_STAGE"); h->ov_ray_queue = ov("NCG_RAY_QUEUE");
+      h->ov_min_blocks = ov("NCG_MIN_BLOCKS"); h->ov_pair_rw8 = ov("NCG_PAIR_RW8"); }
     const char* g = getenv("NCG_RAYS_PER_LANE");
     int rpl = g ? atoi(g) : 0;
     if (rpl != 2 && rpl != 4) rpl = 0;                            // 0 = chosen per launch from the batch size

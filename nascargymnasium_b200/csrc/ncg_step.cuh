@@ -215,6 +215,16 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     const int cb0 = s_gcar[0];                                       // the CTA's first car: its record names the CTA's track
 
     // (the track table's bulk copy was issued at the top of the kernel)
+    // the car slot this thread serves: its lane (physics warps) or, with the fixed ray mapping, the car its rays belong to
+    const int slot = warp < PW ? warp * LPW + lane : (warp - PW) * CPW + lane / LPC;
+    const bool active = warp < PW ? (PW == 2 ? lane < (warp == 0 ? n0 : n1) : (lane < LPW && slot < n0)) : (GROUPS == 1 && slot < n0);
+    // the caller's action of this lane's car (single-step launches): asked for now, while the records and the table are on
+    // their way -- with mapped host memory (ncg_step_mapped) it crosses PCIe, ~2 us that would otherwise sit in front of the dynamics
+    const bool synth = p.actions == nullptr;
+    float2 act_c = make_float2(0.0f, 0.0f); int act_d = 0;
+    if (!synth && warp < PW && active) {
+        if (p.discrete) act_d = ((const int*)p.actions)[s_gcar[slot]]; else act_c = ((const float2*)p.actions)[s_gcar[slot]];
+    }
     // ---- records HBM -> shared (coalesced float4 reads, scalar shared stores into the padded rows)
     for (int i = threadIdx.x; i < n_all * (NCG_RECORD_WORDS / 4); i += NT) {
         const int ci = i >> 5;
@@ -224,7 +234,6 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     }
     if (threadIdx.x < NCG_OBS_DIM) { s_otab[threadIdx.x] = obs_scale(threadIdx.x); s_otab[40 + threadIdx.x] = obs_lo(threadIdx.x); }
     if (threadIdx.x < 16) ray_rotation((int)threadIdx.x, &s_rot[2 * threadIdx.x], &s_rot[2 * threadIdx.x + 1]);
-    const bool synth = p.actions == nullptr;
     // the first GROUPS ray warps make the synthetic actions (one per group), two steps ahead of the physics warps
     const bool act_maker = synth && warp >= PW && warp < PW + GROUPS && lane < (warp == PW ? n0 : n1);
     const int act_slot = (warp - PW) * 32 + lane; const unsigned act_car = p.car_base + (unsigned)(act_maker ? s_gcar[act_slot] : 0);
@@ -238,9 +247,6 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     __syncthreads();
     if (p.stage) tma_wait(&s_mbar);
 
-    // the car slot this thread serves: its lane (physics warps) or, with the fixed ray mapping, the car its rays belong to
-    const int slot = warp < PW ? warp * LPW + lane : (warp - PW) * CPW + lane / LPC;
-    const bool active = warp < PW ? (PW == 2 ? lane < (warp == 0 ? n0 : n1) : (lane < LPW && slot < n0)) : (GROUPS == 1 && slot < n0);
     // track views are fixed for the launch (auto-reset keeps an env on its track): build them once
     const uint32_t my_tid = f2u(s_rec[NCG_R_TRACK]);              // slot 0: a CTA serves one track
     NCG_CHECK(my_tid < (uint32_t)p.n_tracks, "track id of the CTA");
@@ -267,8 +273,9 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
             if (active) {
                 float thr, brk, st;
                 if (!synth) {
-                    if (p.discrete) action_discrete(((const int*)p.actions)[gc], &thr, &brk, &st);
-                    else { float2 a = ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
+                    // (t == 0: asked for at the top of the kernel; launches with caller actions are single steps)
+                    if (p.discrete) action_discrete(t == 0 ? act_d : ((const int*)p.actions)[gc], &thr, &brk, &st);
+                    else { const float2 a = t == 0 ? act_c : ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
                 } else { const float4 a = s_act[b * SLOTS + slot]; thr = a.x; brk = a.y; st = a.z; }
                 // Car.velocity_history (car.py:384-386): the speed update_physics saw, i.e. before b2World.Step (info only)
                 if (p.vel_hist) p.vel_hist[(size_t)gc * NCG_VEL_HISTORY + f2u(R[NCG_R_STEP]) % NCG_VEL_HISTORY] = make_float2(R[NCG_R_VX], R[NCG_R_VY]);

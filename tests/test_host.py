@@ -206,6 +206,20 @@ def test_launch_plan_keeps_ctas_on_one_track_and_fills_the_sms():
     assert first.tolist() == [0] and count.tolist() == [1]
 
 
+def test_launch_plan_uses_full_groups_beyond_two_ctas_per_sm():
+    """Up to two CTAs per SM a batch is spread over all SMs; beyond, a CTA's step costs about the same with 24 cars as with 32
+    (measured in the dispersed steady state, tools/ab_group.sh), so the groups are full and the CTAs as few as possible."""
+    from nascargymnasium_b200 import engine
+    for E in (8192, 6144):                                     # <= 2 groups of 32 per SM: spread
+        first, count = engine.plan_ctas(np.zeros(E, np.int32), 1, 148)
+        assert count.sum() == E and count.max() < 32 and len(count) <= 2 * 148
+    for E in (12288, 20480, 40960, 65536):
+        first, count = engine.plan_ctas(np.zeros(E, np.int32), 1, 148)
+        assert count.sum() == E and (count == 32).all() and len(count) == E // 32
+    first, count = engine.plan_ctas(np.zeros(8192, np.int32), 10, 148)          # ten-car envs: three envs (30 car slots) per group
+    assert count.sum() == 8192 and count.max() == 3 and (count[:-1] == 3).all()
+
+
 def test_launch_plan_does_not_spill_into_an_extra_wave_on_the_track_mix():
     from nascargymnasium_b200 import engine
     tid = (np.arange(4096) * 8 // 4096).astype(np.int32)         # BASELINE config 4 mix at 4096 envs: 8 blocks of 512

@@ -12,10 +12,13 @@ def region(f, line):
     if f == "ncg_b2.cuh":
         return "b2 geometry (collide / GJK / TOI root finder)"
     if f == "ncg_car.cuh":
-        if line >= 1155: return "sensor rays"
-        if line >= 1010: return "rules (lap timer, disable, reward, obs words)"
-        if line >= 620: return "dynamics (forces, tyres, nearest segment)"
-        if line >= 590: return "body_step fast path"
+        # (line ranges of csrc/ncg_car.cuh as of round 2's final source: step_with_contacts 660, body_step 679, shared world
+        # 706-996, tyres 997, car_dyn_pre 1261, car_step_rules 1402, sensor rays 1542)
+        if line >= 1540: return "sensor rays"
+        if line >= 1401: return "rules (lap timer, disable, reward, obs words)"
+        if line >= 997: return "dynamics (forces, tyres, nearest segment)"
+        if line >= 706: return "shared world (car-car, optional)"
+        if line >= 679: return "body_step fast path"
         return "contact world (collide, solver, TOI driver, load/store)"
     if f == "ncg_b200.cu": return "kernel body (barriers, loads, stores)"
     return "other (" + str(f) + ")"
