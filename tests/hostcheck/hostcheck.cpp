@@ -160,6 +160,14 @@ void hc_nearest_segment(const float* blob, float x, float y, int masked, float* 
 }
 void hc_sincos_heading(float a, float* out2) { sincos_heading(a, out2, out2 + 1); }
 int hc_on_track(const float* blob, float x, float y) { Track T = track_view(blob, blob); return on_track(T, x, y) ? 1 : 0; }
+// sweep_face_bound (the exact TOI early-out's lower bound of the car-wall distance over a whole sweep); in: c0x c0y a0 c1x c1y a1,
+// wall: px py angle hx hy
+float hc_sweep_face_bound(const float* sw6, const float* wall5) {
+    Sweep s; s.c0 = mk(sw6[0], sw6[1]); s.a0 = sw6[2]; s.c = mk(sw6[3], sw6[4]); s.a = sw6[5]; s.alpha0 = 0.0f;
+    Xf xfB; xfB.p = mk(wall5[0], wall5[1]); xfB.q = rot(wall5[2]);
+    Box bB; bB.hx = wall5[3]; bB.hy = wall5[4];
+    return sweep_face_bound(s, rot(s.a), xfB, bB, 1e30f);
+}
 void hc_toi_counters(unsigned long long* out3) { out3[0] = g_toi_full; out3[1] = g_toi_skip_reach; out3[2] = g_toi_skip_face; }
 void hc_synthetic_action(unsigned long long seed, unsigned car, unsigned step, int mode, int discrete, float* out3) {
     action_synthetic(seed, car, step, mode, discrete != 0, out3, out3 + 1, out3 + 2);

@@ -269,6 +269,8 @@ def hostcheck(no_toi_shortcut: bool = False):
         lib.hc_nearest_segment.argtypes = [fp, ctypes.c_float, ctypes.c_float, ctypes.c_int, fp]
         lib.hc_on_track.argtypes = [fp, ctypes.c_float, ctypes.c_float]
         lib.hc_synthetic_action.argtypes = [ctypes.c_ulonglong, ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_int, fp]
+        lib.hc_sweep_face_bound.argtypes = [fp, fp]
+        lib.hc_sweep_face_bound.restype = ctypes.c_float
         lib.hc_env_step_cc.argtypes = [fp, fp, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp, fp, fp, ip, ip, ip,
                                        ctypes.POINTER(ctypes.c_ulonglong)]
         lib.hc_env_reset_cc.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, fp, fp]
