@@ -384,15 +384,20 @@ class Bench:
         t0 = time.perf_counter()
         for s in range(5, steps + 5):
             venv.step(acts[s])
+        venv.engine.resident_pause()           # (inside the timed region: the resident step kernel leaves, records back in HBM)
         self.torch.cuda.synchronize()
         dt = self.max_ranks(time.perf_counter() - t0)
         self.launches += venv.engine.launch_count - l0
+        res = venv.engine.resident_stats
         venv.close()
         return {"value": self.world * N * steps / dt, "unit": UNIT, "h2d_bytes_per_step": N * 2 * 4,
                 "d2h_bytes_per_step": N * 38 * 4 + N * 4 + 2 * E, "steps": steps,
-                "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated; actions are copied into "
-                       "page-locked memory the kernel reads across PCIe, results are written by the kernel into page-locked host "
-                       "buffers and returned without a further copy"}
+                "resident": {"steps_through_mailbox": res["steps"], "host_us_per_step": round(res["host_us_per_step"], 2),
+                             "device_us_per_step": round(res["device_us_per_step"], 2)},
+                "api": "NascarVectorEnv.step(numpy actions) -> numpy obs/reward/terminated/truncated; actions are checked and copied "
+                       "into page-locked memory the kernel reads across PCIe, results are written by the kernel into page-locked host "
+                       "buffers and returned without a further copy; the step kernel stays resident between the steps of the loop "
+                       "and takes one mailbox command per step (steps_through_mailbox of them; NCG_RESIDENT=0: one launch per step)"}
 
 
 def workload_text(envs, cars, track, mode, per_gpu=True):

@@ -202,6 +202,14 @@ int ncg_host_free(void* p);
 int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
                     uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done);
 
+/* ncg_step_mapped for a binding whose caller owns the action array: src_actions (pageable host memory, float32[E*C*2] or
+ * int32[E*C]) is copied into the mapped buffer h_actions and, with validate != 0, checked in the same pass the way CarEnv.step
+ * asserts action_space.contains(action) (src/car_env.py:694): continuous values in [-1, 1] and not NaN, discrete values in 0..4.
+ * A failed check returns NCG_E_INVALID ("Invalid action") and steps nothing. */
+int ncg_step_mapped_from(NcgHandle* h, const void* src_actions, int32_t validate, void* h_actions, float* h_obs, float* h_reward,
+                         uint8_t* h_terminated, uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length,
+                         int32_t* any_done);
+
 /* Raw records, NCG_RECORD_WORDS words per car, car-major; d_records float32[n_cars*128].  ncg_set_state* read the
  * env -> track map out of the records (word NCG_R_TRACK of each env's first car), reject ids that were not uploaded
  * (nothing is written then) and re-plan the launch; the device variant synchronises `stream` once to do so. */
@@ -254,6 +262,21 @@ int ncg_set_episode_outputs(NcgHandle* h, float* d_ep_return, int32_t* d_ep_leng
 
 /* Number of kernels this library has launched on the handle (for bench.py's gpu_launches). */
 int64_t ncg_launch_count(NcgHandle* h);
+
+/* ncg_step_mapped's resident mode: for a host-driven step loop the library keeps ONE launch of the step kernel on the SMs
+ * (records and track table in shared memory) and feeds it a command per step through a mailbox in page-locked memory, instead of
+ * launching per step; the kernel leaves by itself when no step arrives for NCG_RESIDENT_IDLE_US (default 1000; a caller that
+ * lets that happen three times in a row gets per-step launches for a while, doubling) and every other entry point of this header
+ * ends it first, so it is invisible except in time.  Batches without a resident kernel (more CTAs than
+ * fit on the SMs at once, car_contacts, track redraw) and NCG_RESIDENT=0 take per-step launches.  While it is resident, CUDA calls
+ * that synchronise the device (cudaMalloc, cudaHostAlloc, cudaDeviceSynchronize ...) wait for that idle time: a caller about to
+ * make one can end the launch at once with ncg_resident_pause (the next ncg_step_mapped starts it again). */
+int ncg_resident_pause(NcgHandle* h);
+
+/* Diagnostics of ncg_step_mapped's resident mode (ends a running resident launch): out4 = {nanoseconds spent inside
+ * ncg_step_mapped from entry to the kernel's done word, steps taken through the mailbox, nanoseconds on the device from "command
+ * seen" to "done word raised", steps counted there}. */
+int ncg_debug_resident(NcgHandle* h, unsigned long long* out4);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,7 @@
 // (cp.async.bulk + mbarrier).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <string>
@@ -25,6 +26,10 @@ using namespace ncg;
 
 // ncg_b200_cc.cu: launches ncg_step_kernel<4, 2, 1, true>; returns NULL or the CUDA error string
 extern "C" __attribute__((visibility("hidden"))) const char* ncg_cc_launch(const void* kparams, size_t kparams_bytes, int n_ctas, int smem_bytes, cudaStream_t stream);
+
+// ncg_b200_res.cu: launches the resident variant ncg_step_kernel<RPL, MINB, 1, false, true>; NULL, or why it was not launched
+extern "C" __attribute__((visibility("hidden"))) const char* ncg_res_launch(const void* kparams, size_t kparams_bytes, int rpl, int minb, int n_ctas,
+                                                                            int num_sms, int smem_bytes, cudaStream_t stream);
 
 namespace {
 
@@ -121,6 +126,16 @@ struct NcgHandle {
     void* p_actions = nullptr; float* p_obs = nullptr; float* p_final = nullptr; float* p_reward = nullptr; uint8_t* p_flags = nullptr;
     void* d_pack = nullptr; void* p_pack = nullptr; size_t pack_bytes = 0;
     int* p_any_done = nullptr;                       // page-locked, device-mapped flag word of ncg_step_mapped
+    // resident mode of ncg_step_mapped (ncg_b200_res.cu): the mailbox.  p_res: [0] command word, [16] {done seq, left-by-itself flag}
+    // (words of 4 bytes, its own cache line), [32] the word the device relay starts from, [64..] the result-slot table
+    int res_enabled = 1; bool res_running = false; unsigned res_seq = 0, res_gen = 0; int res_slots = 0;
+    unsigned long long res_idle_ns = 1000000ull;
+    int res_idle_exits = 0, res_backoff = 0, res_backoff_len = 256;     // a caller that is slower than the idle time gets per-step launches
+    unsigned long long* p_res = nullptr; unsigned long long* d_res = nullptr;
+    const void* res_fixed[4] = {nullptr, nullptr, nullptr, nullptr};   // what the running kernel was launched with: actions, final_obs, ep_return, ep_length
+    const void* res_slot_ptrs[NCG_RES_SLOTS][4];
+    long long res_launches = 0;
+    unsigned long long res_wait_ns = 0, res_steps = 0, res_dev_ns = 0, res_dev_steps = 0;   // diagnostics (ncg_debug_resident)
 };
 
 namespace {
@@ -253,12 +268,14 @@ int follow_redraws(NcgHandle* h, cudaStream_t s) {
     return NCG_OK;
 }
 
-int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
-    NvtxRange nvtx_(p.T == 1 ? "ncg_step" : "ncg_rollout");
+#define NCG_RES_UNSUPPORTED 1000      /* launch_step(resident): this batch has no resident kernel; the caller launches per step */
+#define NCG_RES_SKIP 1001             /* res_step: not this time (the caller steps slower than the kernel's idle time) */
+int launch_step(NcgHandle* h, KParams& p, cudaStream_t s, bool resident = false) {
+    NvtxRange nvtx_(resident ? "ncg_step_resident" : p.T == 1 ? "ncg_step" : "ncg_rollout");
     { int rc = follow_redraws(h, s); if (rc) return rc; }
     if (h->cta_dirty) { int rc = build_cta_table(h); if (rc) return rc; }
-    p.redraw = (h->redraw && p.T == 1 && p.auto_reset && h->n_tracks > 1) ? 1 : 0;
-    p.redraw_step = h->steps_taken; h->steps_taken += (unsigned)p.T;
+    p.redraw = (!resident && h->redraw && p.T == 1 && p.auto_reset && h->n_tracks > 1) ? 1 : 0;
+    p.redraw_step = h->steps_taken; if (!resident) h->steps_taken += (unsigned)p.T;
     const int sms = h->num_sms > 0 ? h->num_sms : 148;
     // rays per lane: 2 (8 ray warps per CTA) while the batch is at most one CTA per SM and latency-bound, 4 (4 ray warps,
     // better lane balance and fewer instructions per car-step) beyond that; measured in profiles/.  Two things that were
@@ -315,6 +332,13 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s) {
                        : minb == 1 ? (RPL == 4 ? ncg_step_kernel<4, 1, 1> : ncg_step_kernel<2, 1, 1>)
                        : minb == 2 ? (RPL == 4 ? ncg_step_kernel<4, 2, 1> : ncg_step_kernel<2, 2, 1>)
                                    : ncg_step_kernel<4, 3, 1>;
+    if (resident) {                                   // the resident variant lives in its own translation unit (ncg_b200_res.cu)
+        if (cc || PW != 1) return NCG_RES_UNSUPPORTED;
+        const char* err = ncg_res_launch(&p, sizeof(p), RPL, minb, h->n_ctas, sms, (int)smem, s);
+        if (err) { g_err = err; return NCG_RES_UNSUPPORTED; }
+        ++h->launches; ++h->res_launches;
+        return NCG_OK;
+    }
     if (cc) {                                         // the shared-world variant lives in its own translation unit (ncg_b200_cc.cu)
         const char* err = ncg_cc_launch(&p, sizeof(p), h->n_ctas, (int)smem, s);
         if (err) return fail(NCG_E_CUDA, std::string("shared-world step kernel: ") + err);
@@ -348,6 +372,112 @@ KParams base_params(NcgHandle* h) {
     return p;
 }
 
+// ---- resident mode of ncg_step_mapped ------------------------------------------------------------------------------------
+// Every other entry point that looks at or changes device state ends the resident launch first (RES_STOP): the records live in
+// the kernel's shared memory while it runs and return to HBM when it leaves.
+int res_stop(NcgHandle* h) {
+    if (!h->res_running) return NCG_OK;
+    volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
+    const unsigned long long idle_word = ((unsigned long long)h->res_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16);
+    if (!done[1]) *reinterpret_cast<volatile unsigned long long*>(h->p_res) = idle_word | (NCG_RES_OP_EXIT << 8);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    h->res_running = false; done[1] = 0;
+    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = idle_word;
+    { unsigned long long d[2] = {0, 0}; if (e == cudaSuccess && cudaMemcpy(d, h->d_res + 18, 16, cudaMemcpyDeviceToHost) == cudaSuccess) { h->res_dev_ns += d[0]; h->res_dev_steps += d[1]; } }
+    if (e != cudaSuccess) return fail(NCG_E_CUDA, std::string("resident step kernel: ") + cudaGetErrorString(e));
+    return NCG_OK;
+}
+#define RES_STOP(h) do { if ((h)->res_running) { int rc_ = res_stop(h); if (rc_) return rc_; } } while (0)
+
+KParams base_params(NcgHandle* h);
+// launch the resident kernel for the caller's fixed buffers; NCG_RES_UNSUPPORTED = this batch has none
+int res_start(NcgHandle* h, const void* h_actions, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length) {
+    KParams p = base_params(h);
+    p.actions = h_actions; p.final_obs = h_final_obs; p.ep_return = h_ep_return; p.ep_length = h_ep_length; p.any_done = h->p_any_done;
+    p.T = 0x7fffffff;
+    p.res_host_cmd = h->p_res; p.res_host_done = reinterpret_cast<volatile unsigned*>(h->p_res + 16); p.res_host_tab = h->p_res + 64;
+    p.res_dev_cmd = h->d_res; p.res_done_ctr = h->d_res + 16; p.res_dev_tab = h->d_res + 64;
+    p.res_seq0 = h->res_seq; p.res_idle_ns = h->res_idle_ns;
+    const unsigned long long idle_word = ((unsigned long long)h->res_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16);
+    volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
+    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = idle_word; done[0] = h->res_seq; done[1] = 0;
+    h->p_res[32] = idle_word;
+    CUDA_TRY(cudaMemcpyAsync(h->d_res, h->p_res + 32, 8, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemsetAsync(h->d_res + 16, 0, 32, h->stream));         // (d_res + 20..: NCG_RES_TIMELINE sums, kept across launches)
+    int rc = launch_step(h, p, h->stream, true);
+    if (rc) return rc;
+    h->res_running = true;
+    h->res_fixed[0] = h_actions; h->res_fixed[1] = h_final_obs; h->res_fixed[2] = h_ep_return; h->res_fixed[3] = h_ep_length;
+    return NCG_OK;
+}
+// one step through the mailbox; NCG_RES_UNSUPPORTED = not taken (the caller launches the step kernel instead)
+int res_step(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+             float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
+    if (h->redraw || h->cfg.car_contacts) return NCG_RES_UNSUPPORTED;
+    if (h->res_running && (h->res_fixed[0] != h_actions || h->res_fixed[1] != h_final_obs || h->res_fixed[2] != h_ep_return || h->res_fixed[3] != h_ep_length)) RES_STOP(h);
+    // the result slot of this set of buffers (callers rotate a few blocks so that returned arrays stay valid)
+    const void* want[4] = {h_obs, h_reward, h_terminated, h_truncated};
+    int slot = -1;
+    for (int i = 0; i < h->res_slots && slot < 0; ++i) if (!memcmp(h->res_slot_ptrs[i], want, sizeof(want))) slot = i;
+    if (slot < 0) {
+        if (h->res_slots == NCG_RES_SLOTS) { h->res_slots = 0; ++h->res_gen; }      // table full: a new generation, the device drops its copy
+        slot = h->res_slots++;
+        memcpy(h->res_slot_ptrs[slot], want, sizeof(want));
+        for (int k = 0; k < 4; ++k) reinterpret_cast<volatile unsigned long long*>(h->p_res + 64)[slot * 4 + k] = (unsigned long long)(uintptr_t)want[k];
+    }
+    volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
+    *(volatile int*)h->p_any_done = 0;
+    const unsigned seq = h->res_seq + 1u;
+    const unsigned long long cmd = ((unsigned long long)seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16) | (unsigned)slot;
+    const auto t_start = std::chrono::steady_clock::now();
+    if (h->res_running && done[1]) {
+        // it left by itself: nobody stepped for res_idle_ns.  A caller that keeps doing that (a policy that takes longer than
+        // the idle time per step) gains nothing from a resident kernel and its own GPU work would wait for the SMs: after three
+        // idle exits in a row the next res_backoff_len steps are launched one by one, twice as many every time it happens again
+        RES_STOP(h);
+        if (++h->res_idle_exits >= 3) {
+            h->res_idle_exits = 0; h->res_backoff = h->res_backoff_len;
+            if (h->res_backoff_len < 65536) h->res_backoff_len *= 2;
+            return NCG_RES_SKIP;
+        }
+    } else if (h->res_running) h->res_idle_exits = 0;
+    for (;;) {
+        if (h->res_running && done[1]) RES_STOP(h);
+        if (!h->res_running) { int rc = res_start(h, h_actions, h_final_obs, h_ep_return, h_ep_length); if (rc) return rc; }
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);                        // actions and table rows before the command
+        *reinterpret_cast<volatile unsigned long long*>(h->p_res) = cmd;
+        bool left = false;
+        for (unsigned spins = 1;; ++spins) {
+            if (done[0] == seq) break;
+            if (done[1]) { left = true; break; }
+            __builtin_ia32_pause();
+            if ((spins & 0xfffu) == 0u) {
+                const cudaError_t q = cudaStreamQuery(h->stream);
+                if (q != cudaErrorNotReady) {
+                    if (done[0] == seq) break;
+                    if (q != cudaSuccess) { h->res_running = false; return fail(NCG_E_CUDA, std::string("resident step kernel: ") + cudaGetErrorString(q)); }
+                    left = true; break;                                 // the kernel has ended without answering: start it again
+                }
+                if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(20)) {
+                    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = cmd | (NCG_RES_OP_EXIT << 8);
+                    h->res_enabled = 0;
+                    return fail(NCG_E_CUDA, "resident step kernel did not answer within 20 s");
+                }
+            }
+        }
+        if (!left) break;
+        { cudaError_t e = cudaStreamSynchronize(h->stream); h->res_running = false; done[1] = 0;
+          { unsigned long long d[2] = {0, 0}; if (e == cudaSuccess && cudaMemcpy(d, h->d_res + 18, 16, cudaMemcpyDeviceToHost) == cudaSuccess) { h->res_dev_ns += d[0]; h->res_dev_steps += d[1]; } }
+          if (e != cudaSuccess) return fail(NCG_E_CUDA, std::string("resident step kernel: ") + cudaGetErrorString(e)); }
+        if (done[0] == seq) break;
+    }
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    h->res_wait_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_start).count(); ++h->res_steps;
+    h->res_seq = seq;
+    if (any_done) *any_done = *(volatile int*)h->p_any_done;
+    return NCG_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -359,6 +489,26 @@ int ncg_debug_launch_ns(unsigned long long* out, int reset) { if (reset) { stati
 int ncg_debug_cta_cycles(long long* out) { return cudaMemcpyFromSymbol(out, g_cta_cycles, sizeof(g_cta_cycles)) == cudaSuccess ? 0 : 1; }
 #endif
 int ncg_version(void) { return 1; }
+// diagnostics of the resident mode: {ns ncg_step_mapped spent from entry to the done word, steps taken through the mailbox,
+// ns on the device from "command seen by CTA 0" to "done word raised", steps counted there (updated when a resident launch ends)}
+#ifdef NCG_RES_TIMELINE
+int ncg_debug_resident_timeline(NcgHandle* h, unsigned long long* out16) {
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
+    CUDA_TRY(cudaMemcpy(out16, h->d_res + 20, 16 * 8, cudaMemcpyDeviceToHost));
+    return NCG_OK;
+}
+#endif
+int ncg_resident_pause(NcgHandle* h) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
+    return NCG_OK;
+}
+int ncg_debug_resident(NcgHandle* h, unsigned long long* out4) {
+    if (!h || !out4) return fail(NCG_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
+    out4[0] = h->res_wait_ns; out4[1] = h->res_steps; out4[2] = h->res_dev_ns; out4[3] = h->res_dev_steps;
+    return NCG_OK;
+}
 
 int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     if (!cfg || !out) return fail(NCG_E_INVALID, "null argument");
@@ -401,6 +551,12 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
     CUDA_TRY(cudaHostAlloc((void**)&h->p_any_done, 64, cudaHostAllocMapped | cudaHostAllocPortable));
     CUDA_TRY(cudaHostAlloc((void**)&h->p_redrawn, 64, cudaHostAllocMapped | cudaHostAllocPortable));
     *h->p_redrawn = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&h->p_res, 1024, cudaHostAllocMapped | cudaHostAllocPortable)); memset(h->p_res, 0, 1024);
+    CUDA_TRY(cudaMalloc(&h->d_res, 1024)); CUDA_TRY(cudaMemset(h->d_res, 0, 1024));
+    { const char* v = getenv("NCG_RESIDENT"); if (v) h->res_enabled = atoi(v) != 0;
+      const char* u = getenv("NCG_RESIDENT_IDLE_US"); if (u && atoll(u) > 0) h->res_idle_ns = (unsigned long long)atoll(u) * 1000ull;
+      // a launch shape forced for an A/B run is a request for the per-step launches
+      if (h->ov_phys_warps >= 0 || h->ov_ray_queue >= 0 || h->ov_min_blocks >= 0 || h->ov_no_stage >= 0 || h->rays_per_lane) h->res_enabled = v && atoi(v) != 0; }
     CUDA_TRY(cudaMalloc(&h->d_env_track, E * sizeof(int)));
     CUDA_TRY(cudaMemset(h->d_env_track, 0, E * sizeof(int)));
     h->h_env_track.assign(E, 0);
@@ -411,6 +567,8 @@ int ncg_create(const NcgConfig* cfg, NcgHandle** out) {
 int ncg_destroy(NcgHandle* h) {
     if (!h) return NCG_OK;
     cudaSetDevice(h->cfg.device);
+    if (h->res_running) res_stop(h);
+    cudaFreeHost(h->p_res); cudaFree(h->d_res);
     cudaFree(h->d_cc_pairs); cudaFree(h->d_cc_worlds); cudaFree(h->d_vel_hist); cudaFree(h->d_records); cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_stats); cudaFree(h->d_reset_obs);
     cudaFree(h->d_actions); cudaFree(h->d_pack); cudaFree(h->d_final);
     cudaFree(h->d_mask); cudaFree(h->d_tid); cudaFree(h->d_cta_tab); cudaFree(h->d_pair_tab); cudaFree(h->d_cta_stage); cudaFree(h->d_pair_stage); cudaFree(h->d_slot_env); cudaFree(h->d_env_track);
@@ -423,7 +581,7 @@ int ncg_destroy(NcgHandle* h) {
 
 int ncg_upload_tracks(NcgHandle* h, const float* h_blob, const int64_t* h_offsets, int32_t n_tracks) {
     if (!h || !h_blob || !h_offsets || n_tracks < 1) return fail(NCG_E_INVALID, "bad track upload");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     for (int i = 0; i <= n_tracks; ++i) if (h_offsets[i] % 4) return fail(NCG_E_INVALID, "track offsets must be multiples of 4 words");
     cudaFree(h->d_blob); cudaFree(h->d_track_off); cudaFree(h->d_reset_obs); h->d_blob = nullptr; h->d_track_off = nullptr; h->d_reset_obs = nullptr;
     size_t words = (size_t)h_offsets[n_tracks];
@@ -449,7 +607,7 @@ int ncg_reset(NcgHandle* h, const uint8_t* d_env_mask, const int32_t* d_track_id
     NvtxRange nvtx_("ncg_reset");
     if (!h) return fail(NCG_E_INVALID, "null handle");
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called before ncg_reset");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     if (!h->was_reset && (d_env_mask || !fresh)) return fail(NCG_E_STATE, "the first reset must be a full fresh reset");
     const int E = h->cfg.num_envs;
     std::vector<int> ids; std::vector<uint8_t> mk;
@@ -481,7 +639,7 @@ int ncg_step(NcgHandle* h, const void* d_actions, float* d_obs, float* d_reward,
              float* d_final_obs, void* stream) {
     if (!h || !d_actions || !d_obs || !d_reward) return fail(NCG_E_INVALID, "null argument");
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     KParams p = base_params(h);
     p.actions = d_actions; p.obs = d_obs; p.reward = d_reward; p.term = d_terminated; p.trunc = d_truncated; p.final_obs = d_final_obs;
     p.ep_return = h->d_ep_return; p.ep_length = h->d_ep_length; p.any_done = h->d_ep_any;
@@ -492,7 +650,7 @@ int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float*
                 uint8_t* d_done_rollout, float* d_obs_last, void* stream) {
     if (!h || steps < 1) return fail(NCG_E_INVALID, "bad rollout arguments");
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     KParams p = base_params(h);
     p.T = steps; p.seed = seed; p.mode = mode; p.step_base = h->step_base; p.car_base = h->car_base; p.auto_reset = 1;
     p.obs_roll = d_obs_rollout; p.rew_roll = d_reward_rollout; p.done_roll = d_done_rollout; p.obs = d_obs_last; p.reward = nullptr;
@@ -504,7 +662,7 @@ int ncg_rollout(NcgHandle* h, int32_t steps, uint64_t seed, int32_t mode, float*
 
 int ncg_reset_host(NcgHandle* h, const uint8_t* h_env_mask, const int32_t* h_track_id, int32_t fresh, float* h_obs) {
     if (!h) return fail(NCG_E_INVALID, "null handle");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     const size_t E = h->cfg.num_envs;
     if (h_track_id) for (size_t e = 0; e < E; ++e) if ((!h_env_mask || h_env_mask[e]) && (h_track_id[e] < 0 || h_track_id[e] >= h->n_tracks)) return fail(NCG_E_INVALID, "track id out of range");
     if (h_env_mask) CUDA_TRY(cudaMemcpyAsync(h->d_mask, h_env_mask, E, cudaMemcpyHostToDevice, h->stream));
@@ -539,7 +697,7 @@ int ncg_step_host(NcgHandle* h, const void* h_actions, float* h_obs, float* h_re
                   float* h_final_obs) {
     if (!h || !h_actions || !h_obs || !h_reward || !h_terminated || !h_truncated) return fail(NCG_E_INVALID, "null argument");
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     const size_t N = h->N, E = h->cfg.num_envs, abytes = h->cfg.discrete ? N * 4 : N * 8;
     memcpy(h->p_actions, h_actions, abytes);
     int done = 0;
@@ -565,7 +723,7 @@ int ncg_host_buffers(NcgHandle* h, void** actions, float** obs, float** reward, 
 int ncg_step_pinned(NcgHandle* h, int32_t want_final, int32_t* any_done) {
     if (!h) return fail(NCG_E_INVALID, "null handle");
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     return step_pinned(h, want_final != 0, any_done);
 }
 
@@ -595,6 +753,14 @@ int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_
     if (!h || !h_actions || !h_obs || !h_reward || !h_terminated || !h_truncated) return fail(NCG_E_INVALID, "null argument");
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (h->res_enabled && h->res_backoff > 0) --h->res_backoff;
+    else if (h->res_enabled) {
+        // host-driven loop: the resident kernel takes the step through its mailbox (no launch, no staging, no record traffic)
+        const int rc = res_step(h, h_actions, h_obs, h_reward, h_terminated, h_truncated, h_final_obs, h_ep_return, h_ep_length, any_done);
+        if (rc != NCG_RES_UNSUPPORTED && rc != NCG_RES_SKIP) return rc;
+        if (rc == NCG_RES_UNSUPPORTED) h->res_enabled = 0;     // this batch has no resident kernel: per-step launches from here on
+    }
+    RES_STOP(h);
     KParams p = base_params(h);
     p.actions = h_actions; p.obs = h_obs; p.reward = h_reward; p.term = h_terminated; p.trunc = h_truncated; p.final_obs = h_final_obs;
     p.ep_return = h_ep_return; p.ep_length = h_ep_length; p.any_done = h->p_any_done;
@@ -606,16 +772,36 @@ int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_
     return NCG_OK;
 }
 
+// ncg_step_mapped with the caller's own action array staged into the mapped buffer and range-checked in the same pass
+// (CarEnv.step asserts action_space.contains(action), /root/reference/src/car_env.py:694): nothing is stepped when the check fails.
+int ncg_step_mapped_from(NcgHandle* h, const void* src_actions, int32_t validate, void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
+                         uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
+    if (!h || !src_actions || !h_actions) return fail(NCG_E_INVALID, "null argument");
+    const size_t N = (size_t)h->N;
+    if (h->cfg.discrete) {
+        const int32_t* s = static_cast<const int32_t*>(src_actions); int32_t* d = static_cast<int32_t*>(h_actions);
+        uint32_t bad = 0;
+        for (size_t i = 0; i < N; ++i) { const int32_t v = s[i]; bad |= (uint32_t)v > 4u; d[i] = v; }
+        if (validate && bad) return fail(NCG_E_INVALID, "Invalid action");
+    } else {
+        const float* s = static_cast<const float*>(src_actions); float* d = static_cast<float*>(h_actions);
+        int ok = 1;
+        for (size_t i = 0; i < 2 * N; ++i) { const float v = s[i]; ok &= (v >= -1.0f) & (v <= 1.0f); d[i] = v; }      // (a NaN fails both comparisons)
+        if (validate && !ok) return fail(NCG_E_INVALID, "Invalid action");
+    }
+    return ncg_step_mapped(h, h_actions, h_obs, h_reward, h_terminated, h_truncated, h_final_obs, h_ep_return, h_ep_length, any_done);
+}
+
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream) {
     if (!h || !d_records) return fail(NCG_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     CUDA_TRY(cudaMemcpyAsync(d_records, h->d_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return NCG_OK;
 }
 int ncg_set_state(NcgHandle* h, const float* d_records, void* stream) {
     if (!h || !d_records) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called first");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     // the records carry the env -> track map (word NCG_R_TRACK of each env's first car): read it from the caller's copy,
     // range-check it and let the CTA table follow, as ncg_set_state_host does -- a CTA stages ONE track table and would
     // otherwise step foreign records against the wrong walls.  One synchronisation of the caller's stream.
@@ -634,7 +820,7 @@ int ncg_set_state(NcgHandle* h, const float* d_records, void* stream) {
 }
 int ncg_get_state_host(NcgHandle* h, float* h_records) {
     if (!h || !h_records) return fail(NCG_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(h_records, h->d_records, (size_t)h->N * NCG_RECORD_WORDS * 4, cudaMemcpyDeviceToHost));
     return NCG_OK;
@@ -642,7 +828,7 @@ int ncg_get_state_host(NcgHandle* h, float* h_records) {
 int ncg_set_state_host(NcgHandle* h, const float* h_records) {
     if (!h || !h_records) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_blob) return fail(NCG_E_STATE, "ncg_upload_tracks must be called first");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     for (int e = 0; e < h->cfg.num_envs; ++e) {
         uint32_t t; memcpy(&t, h_records + (size_t)e * h->cfg.cars_per_env * NCG_RECORD_WORDS + NCG_R_TRACK, 4);
         if ((int)t < 0 || (int)t >= h->n_tracks) return fail(NCG_E_INVALID, "record names a track id that was not uploaded");
@@ -662,7 +848,7 @@ static_assert(NCG_CAR_PAIR_WORDS == NCG_CC_STRIDE, "include/ncg_b200.h and csrc/
 int ncg_get_car_pairs_host(NcgHandle* h, float* h_pairs) {
     if (!h || !h_pairs) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_cc_pairs) return fail(NCG_E_STATE, "the car-car contact table exists only with NcgConfig.car_contacts = 1");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(h_pairs, h->d_cc_pairs, (size_t)h->cfg.num_envs * NCG_CC_STRIDE * 4, cudaMemcpyDeviceToHost));
     return NCG_OK;
@@ -670,7 +856,7 @@ int ncg_get_car_pairs_host(NcgHandle* h, float* h_pairs) {
 int ncg_set_car_pairs_host(NcgHandle* h, const float* h_pairs) {
     if (!h || !h_pairs) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_cc_pairs) return fail(NCG_E_STATE, "the car-car contact table exists only with NcgConfig.car_contacts = 1");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(h->d_cc_pairs, h_pairs, (size_t)h->cfg.num_envs * NCG_CC_STRIDE * 4, cudaMemcpyHostToDevice));
     return NCG_OK;
@@ -679,7 +865,7 @@ int ncg_set_car_pairs_host(NcgHandle* h, const float* h_pairs) {
 int ncg_get_velocity_history_host(NcgHandle* h, float* h_out) {
     if (!h || !h_out) return fail(NCG_E_INVALID, "null argument");
     if (!h->d_vel_hist) return fail(NCG_E_STATE, "the velocity history is kept only with NcgConfig.track_info = 1");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaMemcpy(h_out, h->d_vel_hist, (size_t)h->N * NCG_VEL_HISTORY * sizeof(float2), cudaMemcpyDeviceToHost));
     return NCG_OK;
@@ -687,7 +873,7 @@ int ncg_get_velocity_history_host(NcgHandle* h, float* h_out) {
 
 int ncg_read_stats(NcgHandle* h, NcgStats* out, int32_t reset) {
     if (!h || !out) return fail(NCG_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     DevStats s;
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(&s, h->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
@@ -707,7 +893,7 @@ int ncg_set_track_redraw(NcgHandle* h, int32_t enable, uint64_t seed) {
 
 int ncg_get_env_tracks(NcgHandle* h, int32_t* h_out) {
     if (!h || !h_out) return fail(NCG_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     if (h->redraw) { CUDA_TRY(cudaDeviceSynchronize()); int rc = follow_redraws(h, h->stream); if (rc) return rc; }
     for (int e = 0; e < h->cfg.num_envs; ++e) h_out[e] = h->h_env_track[e];
     return NCG_OK;

@@ -34,6 +34,15 @@ __device__ __forceinline__ unsigned long long tl_ns() { unsigned long long t; as
 #define TLWAIT(stmt) do { stmt; } while (0)
 #endif
 
+// NCG_RES_TIMELINE (variant build, measurement only): clock64 sums of CTA 0's phases of a resident step, in res_done_ctr[4 + k]
+#ifdef NCG_RES_TIMELINE
+#ifndef NCG_RES_TL_CTA
+#define NCG_RES_TL_CTA 0
+#endif
+#define RTL(k) do { if (RES && blockIdx.x == NCG_RES_TL_CTA && lane == 0) { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); atomicAdd(p.res_done_ctr + 4 + (k), (unsigned long long)(c_ - *(volatile long long*)&s_res_t0)); } } while (0)
+#else
+#define RTL(k) do { } while (0)
+#endif
 struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, contact_steps, toi_events, overflow; double return_sum; };
 
 struct KParams {
@@ -56,7 +65,18 @@ struct KParams {
     int* env_track;                                        // [E] the env -> track map as the device sees it (redraw writes it)
     int* redrawn;                                          // mapped host word: set when this launch moved an env
     DevStats* stats;
+    // resident mode (ncg_b200_res.cu, RES = true): the kernel stays on the SMs between the steps of a host-driven loop and is
+    // fed through a mailbox in page-locked host memory
+    const unsigned long long* res_host_cmd;                // mapped host word: seq << 32 | table generation << 16 | op << 8 | result slot
+    unsigned long long* res_dev_cmd;                       // the same word, relayed to device memory by CTA 0
+    const unsigned long long* res_host_tab;                // mapped host [NCG_RES_SLOTS][4]: obs, reward, terminated, truncated of a result slot
+    unsigned long long* res_dev_tab;                       // device copy of the rows CTA 0 has seen
+    unsigned long long* res_done_ctr;                      // CTAs that have finished a step, summed over the launch
+    volatile unsigned* res_host_done;                      // mapped host: [0] last completed seq, [1] the kernel left by itself (idle)
+    unsigned res_seq0; unsigned long long res_idle_ns;     // seq of the last step before this launch; idle time after which the kernel leaves
 };
+#define NCG_RES_SLOTS 16
+#define NCG_RES_OP_EXIT 1u
 
 #define CPB 32                    /* car slots per CTA = lanes of the physics warp */
 #define REC_STRIDE 129            /* shared-memory row stride of a record (odd: conflict-free column access) */
@@ -83,6 +103,52 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
     while (!ok) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok) : "r"(mb) : "memory");
+    }
+}
+
+// ---- resident mode: the mailbox.  The host posts one 64-bit command word per step into page-locked memory; lane 0 of CTA 0's
+// physics warp (the "dispatcher") polls it across PCIe and relays it through a device word every CTA polls in L2, so that the
+// decision "step seq" / "leave" is taken once for the whole grid (a CTA that timed out on its own while another one saw the
+// next command would leave the batch half stepped).
+__device__ __forceinline__ unsigned long long res_ld_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long res_ld_acq(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void res_st_rel(unsigned long long* p, unsigned long long v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long res_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
+// returns the command of step `want` or an exit word (op != 0); gen / valid: which rows of the result-slot table the device copy holds
+__device__ __noinline__ unsigned long long res_dispatch(const KParams& p, unsigned want, unsigned& gen, unsigned& valid) {
+    const unsigned long long t0 = res_ns();
+    unsigned long long c;
+    for (;;) {
+        c = res_ld_sys(p.res_host_cmd);
+        if (((c >> 8) & 0xffu) != 0u) break;                                   // the host asks the kernel to leave
+        if ((unsigned)(c >> 32) == want) {
+            p.res_done_ctr[1] = res_ns();                                      // (diagnostic: when the grid learnt of the step)
+            __threadfence_system();
+            const unsigned g = (unsigned)(c >> 16) & 0xffffu, slot = (unsigned)c & (NCG_RES_SLOTS - 1);
+            if (g != gen) { gen = g; valid = 0u; }
+            if (!((valid >> slot) & 1u)) {
+                for (int k = 0; k < 4; ++k) p.res_dev_tab[slot * 4 + k] = res_ld_sys(p.res_host_tab + slot * 4 + k);
+                valid |= 1u << slot;
+            }
+            break;
+        }
+        if (res_ns() - t0 > p.res_idle_ns) {                                   // nobody stepped for a while: give the SMs back
+            c = ((unsigned long long)(want - 1u) << 32) | (NCG_RES_OP_EXIT << 8);
+            p.res_host_done[1] = 1u;
+            break;
+        }
+    }
+    res_st_rel(p.res_dev_cmd, c);
+    return c;
+}
+__device__ __noinline__ unsigned long long res_wait(const KParams& p, unsigned want) {
+    const unsigned long long t0 = res_ns();
+    for (;;) {
+        const unsigned long long c = res_ld_acq(p.res_dev_cmd);
+        if (((c >> 8) & 0xffu) != 0u || (unsigned)(c >> 32) == want) return c;
+        // (never expected: CTA 0 relays every command and its own exit; a bound so that no CTA can spin for ever)
+        if (res_ns() - t0 > p.res_idle_ns + 10000000000ull) return ((unsigned long long)(want - 1u) << 32) | (NCG_RES_OP_EXIT << 8);
+        __nanosleep(32);
     }
 }
 
@@ -151,8 +217,12 @@ __host__ __device__ inline SmemLayout smem_layout(unsigned stage_words, int cpb,
 // is bound by; the contact-free chain is no shorter for it.
 // CC = the optional shared world (NcgConfig.car_contacts): a separate instantiation, so that the default kernels carry none of
 // its code (measured: as a run-time branch it cost the default path 2 % contact-free and 12 % with the driving distribution).
-template <int RPL, int MINB, int PW, bool CC = false>
+// RES = resident mode (its own translation unit, ncg_b200_res.cu; PW = 1 shapes): the step loop has no end, every step waits for
+// a command of the host's mailbox, reads the caller's actions from mapped host memory, writes its results into the result slot the
+// command names and reports completion through a grid-wide counter whose last arrival raises the host's done word.
+template <int RPL, int MINB, int PW, bool CC = false, bool RES = false>
 __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 16 / RPL), MINB) ncg_step_kernel(KParams p) {
+    static_assert(!RES || (PW == 1 && !CC), "resident mode: one physics warp per CTA, no shared world");
     constexpr int RW = PW == 2 ? (RPL == 2 ? 8 : 6) : 16 / RPL;      // ray warps (PW == 2: RPL only picks six or eight of them, the rays come from the queue)
     constexpr int NT = 32 * (PW + RW);
     constexpr int GROUPS = PW == 2 ? 2 : 1;         // groups of the CTA table served by this CTA
@@ -162,10 +232,14 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     constexpr int CPW = 32 / LPC;                   //                              cars per ray warp
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned long long s_mbar;
+    __shared__ float* s_res_obs[3]; __shared__ int s_res_exit;          // RES only (unreferenced otherwise)
+#ifdef NCG_RES_TIMELINE
+    __shared__ long long s_res_t0;
+#endif
     // step buffers between the physics and the ray warps: three when a CTA has an SM to itself (the physics warp then
     // never waits for a drained buffer; shared memory is not the limit there), two otherwise
     constexpr int NB = MINB == 1 ? 3 : 2;
-    constexpr int BAR_POSE = 1, BAR_FULL = 1 + NB, BAR_EMPTY = 1 + 2 * NB;
+    constexpr int BAR_POSE = 1, BAR_FULL = 1 + NB, BAR_EMPTY = 1 + 2 * NB, BAR_RES = 1 + 3 * NB;
     const SmemLayout L = smem_layout(0, SLOTS, NB);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifdef NCG_TIMELINE
@@ -222,7 +296,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     // their way -- with mapped host memory (ncg_step_mapped) it crosses PCIe, ~2 us that would otherwise sit in front of the dynamics
     const bool synth = p.actions == nullptr;
     float2 act_c = make_float2(0.0f, 0.0f); int act_d = 0;
-    if (!synth && warp < PW && active) {
+    if (!RES && !synth && warp < PW && active) {
         if (p.discrete) act_d = ((const int*)p.actions)[s_gcar[slot]]; else act_c = ((const float2*)p.actions)[s_gcar[slot]];
     }
     // ---- records HBM -> shared (coalesced float4 reads, scalar shared stores into the padded rows)
@@ -234,6 +308,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
     }
     if (threadIdx.x < NCG_OBS_DIM) { s_otab[threadIdx.x] = obs_scale(threadIdx.x); s_otab[40 + threadIdx.x] = obs_lo(threadIdx.x); }
     if (threadIdx.x < 16) ray_rotation((int)threadIdx.x, &s_rot[2 * threadIdx.x], &s_rot[2 * threadIdx.x + 1]);
+    if (RES && threadIdx.x == 0) s_res_exit = 0;
     // the first GROUPS ray warps make the synthetic actions (one per group), two steps ahead of the physics warps
     const bool act_maker = synth && warp >= PW && warp < PW + GROUPS && lane < (warp == PW ? n0 : n1);
     const int act_slot = (warp - PW) * 32 + lane; const unsigned act_car = p.car_base + (unsigned)(act_maker ? s_gcar[act_slot] : 0);
@@ -263,20 +338,58 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
         float* R = s_rec + (active ? slot : 0) * REC_STRIDE;
         Counters cnt = {0, 0, 0, 0, 0};
         unsigned long long episodes = 0; double ret_sum = 0.0;
+        int steps_done = p.T;
+        unsigned res_gen = 0xffffffffu, res_valid = 0u;          // RES, the dispatcher's view of the result-slot table
+        uint8_t* term_out = p.term; uint8_t* trunc_out = p.trunc;
         for (int t = 0, b = 0; t < p.T; ++t, b = b + 1 == NB ? 0 : b + 1) {
             TL(0);
             TLWAIT(if (t >= NB) bar_sync(BAR_EMPTY + b, NT));   // the ray warps have drained buffer b (step t-NB)
             TL(1);
             float* rew_out = p.rew_roll ? p.rew_roll + (size_t)t * N : p.reward;
+            if (RES) {
+                // ---- the mailbox: wait for the command of this step (or for the word that ends the launch)
+                const unsigned want = p.res_seq0 + (unsigned)t + 1u;
+                unsigned long long c = 0;
+                if (lane == 0) c = blockIdx.x == 0 ? res_dispatch(p, want, res_gen, res_valid) : res_wait(p, want);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (((c >> 8) & 0xffu) != 0u) {
+                    // leave: take the ray warps' outstanding "drained" arrivals, then wake them on the pose barrier with the exit flag up
+                    for (int s = t - NB + 1 > 0 ? t - NB + 1 : 0; s < t; ++s) bar_sync(BAR_EMPTY + s % NB, NT);
+                    if (lane == 0) s_res_exit = 1;
+                    __syncwarp();
+                    __threadfence_block();
+                    bar_arrive(BAR_POSE + b, NT);
+                    steps_done = t;
+                    break;
+                }
+#ifdef NCG_RES_TIMELINE
+                if (blockIdx.x == NCG_RES_TL_CTA && lane == 0) { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory"); s_res_t0 = c_; }
+                __syncwarp();
+#endif
+                // the caller's actions (mapped host memory, written before the command) and the result slot's pointers
+                // (ld.global.cv: fetched again from host memory on every step, never from a cache line of the step before)
+                if (active) {
+                    if (p.discrete) act_d = __ldcv((const int*)p.actions + gc); else act_c = __ldcv((const float2*)p.actions + gc);
+                }
+                const unsigned long long* row = p.res_dev_tab + ((unsigned)c & (NCG_RES_SLOTS - 1)) * 4;
+                const unsigned long long q0 = __ldcg(row), q1 = __ldcg(row + 1), q2 = __ldcg(row + 2), q3 = __ldcg(row + 3);
+                if (lane == 0) s_res_obs[b] = reinterpret_cast<float*>(q0);
+                rew_out = reinterpret_cast<float*>(q1); term_out = reinterpret_cast<uint8_t*>(q2); trunc_out = reinterpret_cast<uint8_t*>(q3);
+            }
             float rew = 0.0f;
             StepCtx ctx;
             if (active) {
                 float thr, brk, st;
-                if (!synth) {
+                if (RES) { if (p.discrete) action_discrete(act_d, &thr, &brk, &st); else action_continuous(act_c.x, act_c.y, &thr, &brk, &st); }
+                else if (!synth) {
                     // (t == 0: asked for at the top of the kernel; launches with caller actions are single steps)
                     if (p.discrete) action_discrete(t == 0 ? act_d : ((const int*)p.actions)[gc], &thr, &brk, &st);
                     else { const float2 a = t == 0 ? act_c : ((const float2*)p.actions)[gc]; action_continuous(a.x, a.y, &thr, &brk, &st); }
                 } else { const float4 a = s_act[b * SLOTS + slot]; thr = a.x; brk = a.y; st = a.z; }
+#ifdef NCG_RES_TIMELINE
+                if (RES && thr == 12345.0f) s_res_exit = 2;      // (a use of the action before the stamp)
+                RTL(0);
+#endif
                 // Car.velocity_history (car.py:384-386): the speed update_physics saw, i.e. before b2World.Step (info only)
                 if (p.vel_hist) p.vel_hist[(size_t)gc * NCG_VEL_HISTORY + f2u(R[NCG_R_STEP]) % NCG_VEL_HISTORY] = make_float2(R[NCG_R_VX], R[NCG_R_VY]);
                 if (!CC) { if (!(p.debug_skip & 2)) car_step_dynamics(R, T, thr, brk, st, p.contacts, &ctx, &cnt); }
@@ -313,9 +426,12 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
             }
             if (threadIdx.x == 0) s_ctr[b] = 32 * RW;           // ray queue: every ray lane starts on job = its index
             // the pose exists: let the ray warps start while this warp does the rest of the step
+            RTL(9);
             __syncwarp();
             __threadfence_block();
+            RTL(10);
             bar_arrive(BAR_POSE + b, NT);
+            RTL(1);
             TL(2);
             // single-car envs (C == 1, uniform) decide from the car's own result word: no exchange through shared memory,
             // no division by C, and the multi-car loops of env_decide unroll away
@@ -343,7 +459,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 const bool done = te || tr;
                 if (solo || lane == le * p.C) {
                     if (p.done_roll) p.done_roll[(size_t)t * p.E + ge] = (uint8_t)((te ? 1 : 0) | (tr ? 2 : 0));
-                    else { if (p.term) p.term[ge] = te ? 1 : 0; if (p.trunc) p.trunc[ge] = tr ? 1 : 0; }
+                    else { if (term_out) term_out[ge] = te ? 1 : 0; if (trunc_out) trunc_out[ge] = tr ? 1 : 0; }
                     if (done) ++episodes;
                 }
                 if (__builtin_expect(done, 0)) {
@@ -369,12 +485,14 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 s_flag[b * SLOTS + slot] = (te ? 1u : 0u) | (tr ? 2u : 0u) | ((CC ? rtid * (uint32_t)p.C + (uint32_t)(gc - ge * p.C) : rtid) << 8);
             }
             __syncwarp();
-            __threadfence_block();
+            RTL(2);
+            __threadfence_block();     // (RES: rewards and flags went to mapped host memory; the ray warps' signaller orders them, below)
+            RTL(3);
             bar_arrive(BAR_FULL + b, NT);
             TL(4);
         }
         // ---- counters
-        unsigned long long v[7] = {active ? (unsigned long long)p.T : 0ull, episodes, cnt.laps, 0ull, cnt.contact_steps, cnt.toi_events, cnt.overflow};
+        unsigned long long v[7] = {active ? (unsigned long long)steps_done : 0ull, episodes, cnt.laps, 0ull, cnt.contact_steps, cnt.toi_events, cnt.overflow};
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             unsigned long long x = v[k];
@@ -411,6 +529,10 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
             TL(0);
             TLWAIT(bar_sync(BAR_POSE + b, NT));
             TL(1);
+            if (RES) {
+                if (*(volatile int*)&s_res_exit) break;
+                obs_out = *(float* volatile*)&s_res_obs[b];
+            }
             if ((GROUPS == 2 || p.queue) && !(p.debug_skip & 1)) {
                 // every ray warp derives the cars' ray origins itself (same values to the same words: no barrier between
                 // the ray warps; nobody still reads last step's, every ray warp has passed that step's FULL barrier), then
@@ -437,9 +559,11 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 s_act[b * SLOTS + act_slot] = make_float4(thr, brk, st, 0.0f);
             }
             TL(2);
+            if (warp == PW) RTL(4);
             TLWAIT(bar_sync(BAR_FULL + b, NT));
             TL(3);
             __syncwarp();
+            if (warp == PW) RTL(5);
             // ---- observation rows shared -> HBM: 38 consecutive floats per car, written as float2 (a row is 19 float2,
             // so a pair never straddles two cars and every store is 8-byte aligned).  Words 0..21 arrive raw from the
             // physics warp and are scaled and clipped here; the ray words are already in [0,1] (scale 1, lower bound 0
@@ -462,6 +586,23 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 }
             }
             TL(5);
+            if (RES) {
+                // the step is complete for the host once every CTA's rows are on their way: the ray warps meet, one thread
+                // orders the CTA's writes before its count, and the grid's last arrival raises the host's done word
+                if (warp == PW) RTL(6);
+                bar_sync(BAR_RES, 32 * RW);
+                if (warp == PW) RTL(7);
+                if (warp == PW && lane == 0) {
+                    __threadfence_system();
+                    RTL(8);
+                    const unsigned long long old = atomicAdd(p.res_done_ctr, 1ull);
+                    if (old + 1ull == (unsigned long long)gridDim.x * (unsigned long long)(t + 1)) {
+                        __threadfence_system();
+                        p.res_host_done[0] = p.res_seq0 + (unsigned)t + 1u;
+                        p.res_done_ctr[2] += res_ns() - *(volatile unsigned long long*)(p.res_done_ctr + 1); p.res_done_ctr[3] += 1ull;   // (diagnostic: command seen -> done raised)
+                    }
+                }
+            }
             if (t + NB < p.T) { __threadfence_block(); bar_arrive(BAR_EMPTY + b, NT); }
             TL(4);
         }

@@ -22,7 +22,7 @@ _CHECKED = os.environ.get("NCG_CHECKED", "") not in ("", "0")
 _VARIANT = os.environ.get("NCG_VARIANT", "").strip()
 _SO = os.path.join(_PKG, f"libncg_b200_{_VARIANT}.so" if _VARIANT else ("libncg_b200_checked.so" if _CHECKED else "libncg_b200.so"))
 _CSRC = os.path.join(_PKG, "csrc")
-_SOURCES = ("ncg_b200.cu", "ncg_b200_cc.cu", "ncg_step.cuh", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
+_SOURCES = ("ncg_b200.cu", "ncg_b200_cc.cu", "ncg_b200_res.cu", "ncg_step.cuh", "ncg_car.cuh", "ncg_b2.cuh", "ncg_defs.cuh")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
@@ -49,7 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise NcgError("CUDA sources missing and no prebuilt libncg_b200.so")
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-DNCG_CHECKED"] if _CHECKED else []) + (os.environ.get("NCG_DEFINES", "").split() if _VARIANT else []) + (["-Xptxas", "-v"] if verbose else []) + \
-          ["--threads", "2", "-o", _SO + ".tmp", os.path.join(_CSRC, "ncg_b200.cu"), os.path.join(_CSRC, "ncg_b200_cc.cu")]
+          ["--threads", "3", "-o", _SO + ".tmp", os.path.join(_CSRC, "ncg_b200.cu"), os.path.join(_CSRC, "ncg_b200_cc.cu"), os.path.join(_CSRC, "ncg_b200_res.cu")]
     subprocess.check_call(cmd)
     os.replace(_SO + ".tmp", _SO)
     return _SO
@@ -77,7 +77,7 @@ EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_up
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
            "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs",
            "ncg_get_velocity_history_host", "ncg_set_track_redraw", "ncg_get_env_tracks", "ncg_get_car_pairs_host",
-           "ncg_set_car_pairs_host")
+           "ncg_set_car_pairs_host", "ncg_debug_resident", "ncg_resident_pause", "ncg_step_mapped_from")
 
 _lib = None
 
@@ -122,6 +122,9 @@ def load_library():
     lib.ncg_set_car_pairs_host.argtypes = [vp, vp]
     lib.ncg_set_track_redraw.argtypes = [vp, i32, u64]
     lib.ncg_get_env_tracks.argtypes = [vp, vp]
+    lib.ncg_debug_resident.argtypes = [vp, vp]
+    lib.ncg_resident_pause.argtypes = [vp]
+    lib.ncg_step_mapped_from.argtypes = [vp, vp, i32] + [vp] * 8 + [ctypes.POINTER(i32)]
     _lib = lib
     return lib
 
@@ -196,8 +199,22 @@ class HostBlock:
             self.ptrs[name] = ctypes.c_void_p(base + off)
         self._base_refs = {k: sys.getrefcount(a) for k, a in self._flat.items()}
 
+        self.views, self._view_refs = (), ()
+
+    def cache_views(self, views) -> None:
+        """Shaped views of the arrays that a binding hands out on every step (made once instead of per step); `busy()` then
+        also looks at who else holds THEM."""
+        self.views = tuple(views)
+        self._base_refs = {k: sys.getrefcount(a) for k, a in self._flat.items()}
+        self._view_refs = self._view_counts()
+
+    def _view_counts(self):
+        return [sys.getrefcount(v) for v in self.views]
+
     def busy(self) -> bool:
-        return any(sys.getrefcount(a) > self._base_refs[k] for k, a in self._flat.items())
+        if any(sys.getrefcount(a) > self._base_refs[k] for k, a in self._flat.items()):
+            return True
+        return self._view_counts() != self._view_refs
 
 
 class Engine:
@@ -361,12 +378,14 @@ class Engine:
 
     def result_block(self) -> "HostBlock":
         """A fresh set of mapped host result buffers for step_mapped."""
+        self._lib.ncg_resident_pause(self._h)        # (page-locked allocations synchronise the device: do not wait for a resident kernel's idle time)
         N, E = self.num_cars, self.num_envs
         return HostBlock([("obs", (N, 38), np.float32), ("reward", (N,), np.float32), ("terminated", (E,), np.uint8),
                           ("truncated", (E,), np.uint8)])
 
     def aux_block(self) -> "HostBlock":
         """Mapped host buffers for the actions and the rarely read per-episode outputs of step_mapped."""
+        self._lib.ncg_resident_pause(self._h)
         N, E = self.num_cars, self.num_envs
         act = ("actions", (N,), np.int32) if self.discrete else ("actions", (N, 2), np.float32)
         return HostBlock([act, ("final_obs", (N, 38), np.float32), ("ep_return", (N,), np.float32), ("ep_length", (E,), np.int32)])
@@ -413,6 +432,18 @@ class Engine:
         s = Stats()
         _check(self._lib.ncg_read_stats(self._h, ctypes.byref(s), int(reset)))
         return s.as_dict()
+
+    def resident_pause(self) -> None:
+        """End a resident launch of the step kernel now (ncg_resident_pause): before CUDA calls that synchronise the device."""
+        _check(self._lib.ncg_resident_pause(self._h))
+
+    @property
+    def resident_stats(self) -> dict:
+        """Diagnostics of the resident step kernel behind step_mapped (ends a running resident launch)."""
+        out = np.zeros(4, dtype=np.uint64)
+        _check(self._lib.ncg_debug_resident(self._h, _np_ptr(out)))
+        w, n, d, m = (int(x) for x in out)
+        return {"steps": n, "host_us_per_step": w / max(n, 1) / 1e3, "device_us_per_step": d / max(m, 1) / 1e3, "device_steps": m}
 
     @property
     def launch_count(self) -> int:

@@ -134,39 +134,58 @@ class NascarVectorEnv:
                 return blk
         if len(self._ring) >= self.max_result_blocks:
             return None
-        blk = self.engine.result_block()
+        blk = self._new_result_block()
         self._ring.insert(self._ring_pos + 1, blk)
         self._ring_pos += 1
         return blk
 
+    def _new_result_block(self):
+        """Result buffers with the views step() hands out and the argument list of the C call, both made once."""
+        blk = self.engine.result_block()
+        r = blk.arrays
+        blk.cache_views((r["obs"].reshape(self._obs_shape), r["reward"].reshape(self._rew_shape),
+                         r["terminated"].view(np.bool_), r["truncated"].view(np.bool_)))
+        a, p = self._aux.ptrs, blk.ptrs
+        blk.call_args = (a["actions"], p["obs"], p["reward"], p["terminated"], p["truncated"], a["final_obs"], a["ep_return"], a["ep_length"])
+        return blk
+
     def step(self, actions):
         """actions: (E[,C],2) float32 in [-1,1] or (E[,C]) ints.  Host buffers in, host buffers out.  The actions are
-        written into a page-locked buffer the kernel reads directly; observations, rewards and flags are written by the
-        kernel straight into page-locked result buffers (ncg_step_mapped), which are handed out without a copy and not
-        reused while the caller still references them."""
+        checked and copied into a page-locked buffer the kernel reads directly (one pass, in the library); observations,
+        rewards and flags are written by the kernel straight into page-locked result buffers (ncg_step_mapped_from), which are
+        handed out without a copy and not reused while the caller still references them."""
         if self._aux is None:
+            import ctypes
             self._aux = self.engine.aux_block()
-            self._ring, self._ring_pos = [self.engine.result_block() for _ in range(2)], 0
+            self._ring, self._ring_pos = [self._new_result_block() for _ in range(2)], 0
+            self._act_dtype = np.dtype(np.int32 if self.discrete else np.float32)
+            self._done_flag = ctypes.c_int32(0)
+            self._done_ref = ctypes.byref(self._done_flag)
+            self._step_c = self.engine._lib.ncg_step_mapped_from
         aux = self._aux.arrays
-        a = np.asarray(actions)
-        if self.validate_actions:
-            # CarEnv.step asserts action_space.contains(action) on every step (/root/reference/src/car_env.py:694); two
-            # reductions without temporaries (a NaN makes min/max NaN and fails the comparison)
-            if self.discrete:
-                assert a.dtype.kind in "iu" and a.size == aux["actions"].size and a.min() >= 0 and a.max() < 5, "Invalid action"
-            else:
-                assert a.dtype == np.float32 and a.size == aux["actions"].size and a.min() >= -1.0 and a.max() <= 1.0, "Invalid action"
-        aux["actions"][...] = a.reshape(aux["actions"].shape)
+        a = actions if type(actions) is np.ndarray else np.asarray(actions)
+        if a.dtype != self._act_dtype or not a.flags.c_contiguous or a.size != aux["actions"].size:
+            # CarEnv.step asserts action_space.contains(action) on every step (/root/reference/src/car_env.py:694)
+            if self.validate_actions:
+                if self.discrete:
+                    assert a.dtype.kind in "iu" and a.size == aux["actions"].size and a.min() >= 0 and a.max() < 5, "Invalid action"
+                else:
+                    assert a.dtype == np.float32 and a.size == aux["actions"].size, "Invalid action"
+            a = np.ascontiguousarray(a, dtype=self._act_dtype).reshape(aux["actions"].shape)
         blk = self._next_result_block()
         spill = blk is None
         if spill:                                   # the caller holds max_result_blocks results: fall back to copying
             if self._spill is None:
-                self._spill = self.engine.result_block()
+                self._spill = self._new_result_block()
             blk = self._spill
-        any_done = self.engine.step_mapped(self._aux, blk)
-        r = blk.arrays
-        obs, rew = r["obs"].reshape(self._obs_shape), r["reward"].reshape(self._rew_shape)
-        te, tr = r["terminated"].view(np.bool_), r["truncated"].view(np.bool_)
+        rc = self._step_c(self.engine._h, a.__array_interface__["data"][0], 1 if self.validate_actions else 0, *blk.call_args, self._done_ref)
+        if rc:
+            if self.engine._lib.ncg_last_error() == b"Invalid action":
+                raise AssertionError("Invalid action")
+            from .engine import _check
+            _check(rc)
+        any_done = self._done_flag.value
+        obs, rew, te, tr = blk.views
         if spill:
             obs, rew, te, tr = obs.copy(), rew.copy(), te.copy(), tr.copy()
         info = {}

@@ -15,8 +15,10 @@ for _ in range(3):
 eng.close()
 v = NascarVectorEnv(12, track_file="tracks/talladega.track", num_cars=10)
 v.reset()
-for _ in range(4):
+for i in range(8):                 # (through the resident step kernel; the state read in the middle ends and restarts it)
     v.step(np.random.uniform(-1, 1, (12, 10, 2)).astype(np.float32))
+    if i == 3:
+        v.engine.set_state_host(v.engine.get_state_host())
 v.close()
 # interleaved env -> track map (slot list), random-track mode with a redraw, start pose, Box2D 2.3.0 contact form
 w = NascarVectorEnv(48, track_file=None, discrete_action_space=True)
