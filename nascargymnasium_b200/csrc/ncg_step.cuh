@@ -593,7 +593,9 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 bar_sync(BAR_RES, 32 * RW);
                 if (warp == PW) RTL(7);
                 if (warp == PW && lane == 0) {
-                    __threadfence_system();
+                    // (release at GPU scope, cumulative over the barrier above: the CTA's writes are ordered before its count; the
+                    // grid's last arrival, which has observed every count, is the one thread that pays for the system-scope fence)
+                    __threadfence();
                     RTL(8);
                     const unsigned long long old = atomicAdd(p.res_done_ctr, 1ull);
                     if (old + 1ull == (unsigned long long)gridDim.x * (unsigned long long)(t + 1)) {
