@@ -202,6 +202,18 @@ int ncg_host_free(void* p);
 int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
                     uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done);
 
+/* ncg_step_mapped in two halves, for a binding that has per-step work of its own (choosing the next result buffer, building
+ * the objects it returns) to do while the GPU steps: ncg_step_mapped_post stages and checks src_actions like
+ * ncg_step_mapped_from (src_actions may be NULL: the actions are already in b->actions) and hands the step to the GPU,
+ * ncg_step_mapped_wait returns when its results are readable.  Exactly one wait per post; any other entry point called in
+ * between completes the posted step first.  The buffers are those of ncg_step_mapped (final_obs, ep_return, ep_length may be NULL). */
+typedef struct NcgMappedBuffers {
+    void* actions; float* obs; float* reward; uint8_t* terminated; uint8_t* truncated;
+    float* final_obs; float* ep_return; int32_t* ep_length;
+} NcgMappedBuffers;
+int ncg_step_mapped_post(NcgHandle* h, const void* src_actions, int32_t validate, const NcgMappedBuffers* b);
+int ncg_step_mapped_wait(NcgHandle* h, int32_t* any_done);
+
 /* ncg_step_mapped for a binding whose caller owns the action array: src_actions (pageable host memory, float32[E*C*2] or
  * int32[E*C]) is copied into the mapped buffer h_actions and, with validate != 0, checked in the same pass the way CarEnv.step
  * asserts action_space.contains(action) (src/car_env.py:694): continuous values in [-1, 1] and not NaN, discrete values in 0..4.

@@ -136,6 +136,9 @@ struct NcgHandle {
     const void* res_slot_ptrs[NCG_RES_SLOTS][4];
     long long res_launches = 0;
     unsigned long long res_wait_ns = 0, res_steps = 0, res_dev_ns = 0, res_dev_steps = 0;   // diagnostics (ncg_debug_resident)
+    // a step posted by ncg_step_mapped_post and not yet waited for: 0 none, 1 in the resident kernel's mailbox, 2 a launched kernel
+    int pend_kind = 0; unsigned pend_seq = 0; unsigned long long pend_cmd = 0; NcgMappedBuffers pend_buf;
+    std::chrono::steady_clock::time_point pend_t0;
 };
 
 namespace {
@@ -375,7 +378,9 @@ KParams base_params(NcgHandle* h) {
 // ---- resident mode of ncg_step_mapped ------------------------------------------------------------------------------------
 // Every other entry point that looks at or changes device state ends the resident launch first (RES_STOP): the records live in
 // the kernel's shared memory while it runs and return to HBM when it leaves.
+int res_wait(NcgHandle* h, int32_t* any_done);
 int res_stop(NcgHandle* h) {
+    if (h->pend_kind == 1) { int rc = res_wait(h, nullptr); if (rc) return rc; }      // (a posted step completes before anything else touches the state)
     if (!h->res_running) return NCG_OK;
     volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
     const unsigned long long idle_word = ((unsigned long long)h->res_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16);
@@ -410,26 +415,12 @@ int res_start(NcgHandle* h, const void* h_actions, float* h_final_obs, float* h_
     h->res_fixed[0] = h_actions; h->res_fixed[1] = h_final_obs; h->res_fixed[2] = h_ep_return; h->res_fixed[3] = h_ep_length;
     return NCG_OK;
 }
-// one step through the mailbox; NCG_RES_UNSUPPORTED = not taken (the caller launches the step kernel instead)
-int res_step(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
-             float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
+// post one step into the mailbox (the kernel is started if it is not running); NCG_RES_UNSUPPORTED / NCG_RES_SKIP = not taken
+// (the caller launches the step kernel instead).  res_wait spins on the done word.
+int res_post(NcgHandle* h, const NcgMappedBuffers& B) {
     if (h->redraw || h->cfg.car_contacts) return NCG_RES_UNSUPPORTED;
-    if (h->res_running && (h->res_fixed[0] != h_actions || h->res_fixed[1] != h_final_obs || h->res_fixed[2] != h_ep_return || h->res_fixed[3] != h_ep_length)) RES_STOP(h);
-    // the result slot of this set of buffers (callers rotate a few blocks so that returned arrays stay valid)
-    const void* want[4] = {h_obs, h_reward, h_terminated, h_truncated};
-    int slot = -1;
-    for (int i = 0; i < h->res_slots && slot < 0; ++i) if (!memcmp(h->res_slot_ptrs[i], want, sizeof(want))) slot = i;
-    if (slot < 0) {
-        if (h->res_slots == NCG_RES_SLOTS) { h->res_slots = 0; ++h->res_gen; }      // table full: a new generation, the device drops its copy
-        slot = h->res_slots++;
-        memcpy(h->res_slot_ptrs[slot], want, sizeof(want));
-        for (int k = 0; k < 4; ++k) reinterpret_cast<volatile unsigned long long*>(h->p_res + 64)[slot * 4 + k] = (unsigned long long)(uintptr_t)want[k];
-    }
+    if (h->res_running && (h->res_fixed[0] != B.actions || h->res_fixed[1] != B.final_obs || h->res_fixed[2] != B.ep_return || h->res_fixed[3] != B.ep_length)) RES_STOP(h);
     volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
-    *(volatile int*)h->p_any_done = 0;
-    const unsigned seq = h->res_seq + 1u;
-    const unsigned long long cmd = ((unsigned long long)seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16) | (unsigned)slot;
-    const auto t_start = std::chrono::steady_clock::now();
     if (h->res_running && done[1]) {
         // it left by itself: nobody stepped for res_idle_ns.  A caller that keeps doing that (a policy that takes longer than
         // the idle time per step) gains nothing from a resident kernel and its own GPU work would wait for the SMs: after three
@@ -441,11 +432,31 @@ int res_step(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward,
             return NCG_RES_SKIP;
         }
     } else if (h->res_running) h->res_idle_exits = 0;
+    // the result slot of this set of buffers (callers rotate a few blocks so that returned arrays stay valid)
+    const void* want[4] = {B.obs, B.reward, B.terminated, B.truncated};
+    int slot = -1;
+    for (int i = 0; i < h->res_slots && slot < 0; ++i) if (!memcmp(h->res_slot_ptrs[i], want, sizeof(want))) slot = i;
+    if (slot < 0) {
+        if (h->res_slots == NCG_RES_SLOTS) { h->res_slots = 0; ++h->res_gen; }      // table full: a new generation, the device drops its copy
+        slot = h->res_slots++;
+        memcpy(h->res_slot_ptrs[slot], want, sizeof(want));
+        for (int k = 0; k < 4; ++k) reinterpret_cast<volatile unsigned long long*>(h->p_res + 64)[slot * 4 + k] = (unsigned long long)(uintptr_t)want[k];
+    }
+    *(volatile int*)h->p_any_done = 0;
+    h->pend_seq = h->res_seq + 1u;
+    h->pend_cmd = ((unsigned long long)h->pend_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16) | (unsigned)slot;
+    h->pend_buf = B; h->pend_t0 = std::chrono::steady_clock::now();
+    if (!h->res_running) { int rc = res_start(h, B.actions, B.final_obs, B.ep_return, B.ep_length); if (rc) return rc; }
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);                            // actions and table rows before the command
+    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = h->pend_cmd;
+    h->pend_kind = 1;
+    return NCG_OK;
+}
+int res_wait(NcgHandle* h, int32_t* any_done) {
+    volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
+    const unsigned seq = h->pend_seq;
+    h->pend_kind = 0;
     for (;;) {
-        if (h->res_running && done[1]) RES_STOP(h);
-        if (!h->res_running) { int rc = res_start(h, h_actions, h_final_obs, h_ep_return, h_ep_length); if (rc) return rc; }
-        __atomic_thread_fence(__ATOMIC_SEQ_CST);                        // actions and table rows before the command
-        *reinterpret_cast<volatile unsigned long long*>(h->p_res) = cmd;
         bool left = false;
         for (unsigned spins = 1;; ++spins) {
             if (done[0] == seq) break;
@@ -458,21 +469,25 @@ int res_step(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward,
                     if (q != cudaSuccess) { h->res_running = false; return fail(NCG_E_CUDA, std::string("resident step kernel: ") + cudaGetErrorString(q)); }
                     left = true; break;                                 // the kernel has ended without answering: start it again
                 }
-                if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(20)) {
-                    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = cmd | (NCG_RES_OP_EXIT << 8);
+                if (std::chrono::steady_clock::now() - h->pend_t0 > std::chrono::seconds(20)) {
+                    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = h->pend_cmd | (NCG_RES_OP_EXIT << 8);
                     h->res_enabled = 0;
                     return fail(NCG_E_CUDA, "resident step kernel did not answer within 20 s");
                 }
             }
         }
         if (!left) break;
+        // it left by itself between two looks at the mailbox (idle time-out): the command is still there for a new launch
         { cudaError_t e = cudaStreamSynchronize(h->stream); h->res_running = false; done[1] = 0;
           { unsigned long long d[2] = {0, 0}; if (e == cudaSuccess && cudaMemcpy(d, h->d_res + 18, 16, cudaMemcpyDeviceToHost) == cudaSuccess) { h->res_dev_ns += d[0]; h->res_dev_steps += d[1]; } }
           if (e != cudaSuccess) return fail(NCG_E_CUDA, std::string("resident step kernel: ") + cudaGetErrorString(e)); }
         if (done[0] == seq) break;
+        { const NcgMappedBuffers& B = h->pend_buf; int rc = res_start(h, B.actions, B.final_obs, B.ep_return, B.ep_length); if (rc) return rc == NCG_RES_UNSUPPORTED ? fail(NCG_E_CUDA, "resident step kernel could not be started again") : rc; }
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        *reinterpret_cast<volatile unsigned long long*>(h->p_res) = h->pend_cmd;
     }
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
-    h->res_wait_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_start).count(); ++h->res_steps;
+    h->res_wait_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - h->pend_t0).count(); ++h->res_steps;
     h->res_seq = seq;
     if (any_done) *any_done = *(volatile int*)h->p_any_done;
     return NCG_OK;
@@ -746,50 +761,68 @@ int ncg_host_free(void* p) {
     return NCG_OK;
 }
 
-// One step with every buffer in page-locked, device-mapped host memory: the kernel reads the actions and writes
-// observations / rewards / flags over PCIe itself, so a step is one launch and one stream synchronise.
-int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
-                    float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
-    if (!h || !h_actions || !h_obs || !h_reward || !h_terminated || !h_truncated) return fail(NCG_E_INVALID, "null argument");
+// One step with every buffer in page-locked, device-mapped host memory: the kernel reads the actions and writes observations /
+// rewards / flags over PCIe itself.  Posting and waiting are separate calls so that a binding can do its own per-step
+// bookkeeping while the GPU works; ncg_step_mapped / ncg_step_mapped_from are post + wait.
+int ncg_step_mapped_post(NcgHandle* h, const void* src_actions, int32_t validate, const NcgMappedBuffers* b) {
+    if (!h || !b || !b->actions || !b->obs || !b->reward || !b->terminated || !b->truncated) return fail(NCG_E_INVALID, "null argument");
     if (!h->was_reset) return fail(NCG_E_STATE, "Environment not properly initialized. Call reset() first.");
+    if (h->pend_kind) return fail(NCG_E_STATE, "a posted step has not been waited for");
+    if (src_actions) {
+        // the caller's own action array, staged into the mapped buffer and range-checked in the same pass (CarEnv.step asserts
+        // action_space.contains(action), /root/reference/src/car_env.py:694): nothing is stepped when the check fails
+        const size_t N = (size_t)h->N;
+        if (h->cfg.discrete) {
+            const int32_t* s = static_cast<const int32_t*>(src_actions); int32_t* d = static_cast<int32_t*>(b->actions);
+            uint32_t bad = 0;
+            for (size_t i = 0; i < N; ++i) { const int32_t v = s[i]; bad |= (uint32_t)v > 4u; d[i] = v; }
+            if (validate && bad) return fail(NCG_E_INVALID, "Invalid action");
+        } else {
+            const float* s = static_cast<const float*>(src_actions); float* d = static_cast<float*>(b->actions);
+            int ok = 1;
+            for (size_t i = 0; i < 2 * N; ++i) { const float v = s[i]; ok &= (v >= -1.0f) & (v <= 1.0f); d[i] = v; }      // (a NaN fails both comparisons)
+            if (validate && !ok) return fail(NCG_E_INVALID, "Invalid action");
+        }
+    }
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     if (h->res_enabled && h->res_backoff > 0) --h->res_backoff;
     else if (h->res_enabled) {
         // host-driven loop: the resident kernel takes the step through its mailbox (no launch, no staging, no record traffic)
-        const int rc = res_step(h, h_actions, h_obs, h_reward, h_terminated, h_truncated, h_final_obs, h_ep_return, h_ep_length, any_done);
+        const int rc = res_post(h, *b);
         if (rc != NCG_RES_UNSUPPORTED && rc != NCG_RES_SKIP) return rc;
         if (rc == NCG_RES_UNSUPPORTED) h->res_enabled = 0;     // this batch has no resident kernel: per-step launches from here on
     }
     RES_STOP(h);
     KParams p = base_params(h);
-    p.actions = h_actions; p.obs = h_obs; p.reward = h_reward; p.term = h_terminated; p.trunc = h_truncated; p.final_obs = h_final_obs;
-    p.ep_return = h_ep_return; p.ep_length = h_ep_length; p.any_done = h->p_any_done;
+    p.actions = b->actions; p.obs = b->obs; p.reward = b->reward; p.term = b->terminated; p.trunc = b->truncated; p.final_obs = b->final_obs;
+    p.ep_return = b->ep_return; p.ep_length = b->ep_length; p.any_done = h->p_any_done;
     *h->p_any_done = 0;
     int rc = launch_step(h, p, h->stream);
     if (rc) return rc;
+    h->pend_kind = 2;
+    return NCG_OK;
+}
+int ncg_step_mapped_wait(NcgHandle* h, int32_t* any_done) {
+    if (!h) return fail(NCG_E_INVALID, "null handle");
+    if (!h->pend_kind) return fail(NCG_E_STATE, "no step has been posted");
+    if (h->pend_kind == 1) return res_wait(h, any_done);
+    h->pend_kind = 0;
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (any_done) *any_done = *h->p_any_done;
     return NCG_OK;
 }
-
-// ncg_step_mapped with the caller's own action array staged into the mapped buffer and range-checked in the same pass
-// (CarEnv.step asserts action_space.contains(action), /root/reference/src/car_env.py:694): nothing is stepped when the check fails.
+int ncg_step_mapped(NcgHandle* h, const void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                    float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
+    const NcgMappedBuffers b = {const_cast<void*>(h_actions), h_obs, h_reward, h_terminated, h_truncated, h_final_obs, h_ep_return, h_ep_length};
+    const int rc = ncg_step_mapped_post(h, nullptr, 0, &b);
+    return rc ? rc : ncg_step_mapped_wait(h, any_done);
+}
 int ncg_step_mapped_from(NcgHandle* h, const void* src_actions, int32_t validate, void* h_actions, float* h_obs, float* h_reward, uint8_t* h_terminated,
                          uint8_t* h_truncated, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, int32_t* any_done) {
-    if (!h || !src_actions || !h_actions) return fail(NCG_E_INVALID, "null argument");
-    const size_t N = (size_t)h->N;
-    if (h->cfg.discrete) {
-        const int32_t* s = static_cast<const int32_t*>(src_actions); int32_t* d = static_cast<int32_t*>(h_actions);
-        uint32_t bad = 0;
-        for (size_t i = 0; i < N; ++i) { const int32_t v = s[i]; bad |= (uint32_t)v > 4u; d[i] = v; }
-        if (validate && bad) return fail(NCG_E_INVALID, "Invalid action");
-    } else {
-        const float* s = static_cast<const float*>(src_actions); float* d = static_cast<float*>(h_actions);
-        int ok = 1;
-        for (size_t i = 0; i < 2 * N; ++i) { const float v = s[i]; ok &= (v >= -1.0f) & (v <= 1.0f); d[i] = v; }      // (a NaN fails both comparisons)
-        if (validate && !ok) return fail(NCG_E_INVALID, "Invalid action");
-    }
-    return ncg_step_mapped(h, h_actions, h_obs, h_reward, h_terminated, h_truncated, h_final_obs, h_ep_return, h_ep_length, any_done);
+    if (!src_actions) return fail(NCG_E_INVALID, "null argument");
+    const NcgMappedBuffers b = {h_actions, h_obs, h_reward, h_terminated, h_truncated, h_final_obs, h_ep_return, h_ep_length};
+    const int rc = ncg_step_mapped_post(h, src_actions, validate, &b);
+    return rc ? rc : ncg_step_mapped_wait(h, any_done);
 }
 
 int ncg_get_state(NcgHandle* h, float* d_records, void* stream) {

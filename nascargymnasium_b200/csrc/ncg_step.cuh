@@ -113,6 +113,10 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
 __device__ __forceinline__ unsigned long long res_ld_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned long long res_ld_acq(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void res_st_rel(unsigned long long* p, unsigned long long v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+// (acquire-release fences: __threadfence_system() / __threadfence() are the sequentially consistent MEMBAR.SC.*, which this
+// release -> count -> acquire -> release chain does not need)
+__device__ __forceinline__ void res_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+__device__ __forceinline__ void res_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long res_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
 // returns the command of step `want` or an exit word (op != 0); gen / valid: which rows of the result-slot table the device copy holds
 __device__ __noinline__ unsigned long long res_dispatch(const KParams& p, unsigned want, unsigned& gen, unsigned& valid) {
@@ -123,7 +127,7 @@ __device__ __noinline__ unsigned long long res_dispatch(const KParams& p, unsign
         if (((c >> 8) & 0xffu) != 0u) break;                                   // the host asks the kernel to leave
         if ((unsigned)(c >> 32) == want) {
             p.res_done_ctr[1] = res_ns();                                      // (diagnostic: when the grid learnt of the step)
-            __threadfence_system();
+            res_fence_sys();
             const unsigned g = (unsigned)(c >> 16) & 0xffffu, slot = (unsigned)c & (NCG_RES_SLOTS - 1);
             if (g != gen) { gen = g; valid = 0u; }
             if (!((valid >> slot) & 1u)) {
@@ -595,11 +599,11 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 if (warp == PW && lane == 0) {
                     // (release at GPU scope, cumulative over the barrier above: the CTA's writes are ordered before its count; the
                     // grid's last arrival, which has observed every count, is the one thread that pays for the system-scope fence)
-                    __threadfence();
+                    res_fence_gpu();
                     RTL(8);
                     const unsigned long long old = atomicAdd(p.res_done_ctr, 1ull);
                     if (old + 1ull == (unsigned long long)gridDim.x * (unsigned long long)(t + 1)) {
-                        __threadfence_system();
+                        res_fence_sys();
                         p.res_host_done[0] = p.res_seq0 + (unsigned)t + 1u;
                         p.res_done_ctr[2] += res_ns() - *(volatile unsigned long long*)(p.res_done_ctr + 1); p.res_done_ctr[3] += 1ull;   // (diagnostic: command seen -> done raised)
                     }

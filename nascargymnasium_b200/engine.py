@@ -63,6 +63,11 @@ class _Config(ctypes.Structure):
                 ("car_contacts", ctypes.c_int32), ("grid_dx", ctypes.c_float), ("grid_dy", ctypes.c_float)]
 
 
+class MappedBuffers(ctypes.Structure):
+    """NcgMappedBuffers of include/ncg_b200.h: the buffers of one ncg_step_mapped_post."""
+    _fields_ = [(k, ctypes.c_void_p) for k in ("actions", "obs", "reward", "terminated", "truncated", "final_obs", "ep_return", "ep_length")]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("car_steps", ctypes.c_uint64), ("episodes", ctypes.c_uint64), ("laps", ctypes.c_uint64),
                 ("ray_tests", ctypes.c_uint64), ("contact_steps", ctypes.c_uint64), ("toi_events", ctypes.c_uint64),
@@ -77,7 +82,7 @@ EXPORTS = ("ncg_last_error", "ncg_version", "ncg_create", "ncg_destroy", "ncg_up
            "ncg_set_state_host", "ncg_read_stats", "ncg_launch_count", "ncg_host_buffers", "ncg_step_pinned", "ncg_host_alloc",
            "ncg_host_free", "ncg_step_mapped", "ncg_plan_ctas", "ncg_set_rollout_base", "ncg_set_episode_outputs",
            "ncg_get_velocity_history_host", "ncg_set_track_redraw", "ncg_get_env_tracks", "ncg_get_car_pairs_host",
-           "ncg_set_car_pairs_host", "ncg_debug_resident", "ncg_resident_pause", "ncg_step_mapped_from")
+           "ncg_set_car_pairs_host", "ncg_debug_resident", "ncg_resident_pause", "ncg_step_mapped_from", "ncg_step_mapped_post", "ncg_step_mapped_wait")
 
 _lib = None
 
@@ -125,6 +130,8 @@ def load_library():
     lib.ncg_debug_resident.argtypes = [vp, vp]
     lib.ncg_resident_pause.argtypes = [vp]
     lib.ncg_step_mapped_from.argtypes = [vp, vp, i32] + [vp] * 8 + [ctypes.POINTER(i32)]
+    lib.ncg_step_mapped_post.argtypes = [vp, vp, i32, vp]
+    lib.ncg_step_mapped_wait.argtypes = [vp, vp]
     _lib = lib
     return lib
 

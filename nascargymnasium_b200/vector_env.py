@@ -124,14 +124,21 @@ class NascarVectorEnv:
         obs = self.engine.reset_host(track_id=self._draw_tracks(seed), fresh=True)
         return obs.reshape(self._obs_shape), {}
 
-    def _next_result_block(self):
-        """Result buffers nobody holds views of any more: the next one of the ring, or a new one while the caller keeps
-        earlier results alive (so returned arrays are never overwritten -- copy semantics without the copy)."""
+    def _free_result_block(self, exclude=None):
+        """The next block of the ring nobody holds views of any more (and that is not `exclude`), or None."""
         for _ in range(len(self._ring)):
             self._ring_pos = (self._ring_pos + 1) % len(self._ring)
             blk = self._ring[self._ring_pos]
-            if not blk.busy():
+            if blk is not exclude and not blk.busy():
                 return blk
+        return None
+
+    def _next_result_block(self):
+        """Result buffers nobody holds views of any more: the next one of the ring, or a new one while the caller keeps
+        earlier results alive (so returned arrays are never overwritten -- copy semantics without the copy)."""
+        blk = self._free_result_block()
+        if blk is not None:
+            return blk
         if len(self._ring) >= self.max_result_blocks:
             return None
         blk = self._new_result_block()
@@ -140,28 +147,34 @@ class NascarVectorEnv:
         return blk
 
     def _new_result_block(self):
-        """Result buffers with the views step() hands out and the argument list of the C call, both made once."""
+        """Result buffers with the views step() hands out and the argument block of the C call, both made once."""
+        import ctypes
+        from .engine import MappedBuffers
         blk = self.engine.result_block()
         r = blk.arrays
         blk.cache_views((r["obs"].reshape(self._obs_shape), r["reward"].reshape(self._rew_shape),
                          r["terminated"].view(np.bool_), r["truncated"].view(np.bool_)))
         a, p = self._aux.ptrs, blk.ptrs
-        blk.call_args = (a["actions"], p["obs"], p["reward"], p["terminated"], p["truncated"], a["final_obs"], a["ep_return"], a["ep_length"])
+        blk.cbuf = MappedBuffers(a["actions"].value, p["obs"].value, p["reward"].value, p["terminated"].value, p["truncated"].value,
+                                 a["final_obs"].value, a["ep_return"].value, a["ep_length"].value)
+        blk.cref = ctypes.byref(blk.cbuf)
         return blk
 
     def step(self, actions):
         """actions: (E[,C],2) float32 in [-1,1] or (E[,C]) ints.  Host buffers in, host buffers out.  The actions are
         checked and copied into a page-locked buffer the kernel reads directly (one pass, in the library); observations,
-        rewards and flags are written by the kernel straight into page-locked result buffers (ncg_step_mapped_from), which are
-        handed out without a copy and not reused while the caller still references them."""
+        rewards and flags are written by the kernel straight into page-locked result buffers, which are handed out without a
+        copy and not reused while the caller still references them.  The step is posted (ncg_step_mapped_post), the result
+        block of the NEXT step is chosen while the GPU works, then the results are waited for (ncg_step_mapped_wait)."""
         if self._aux is None:
             import ctypes
             self._aux = self.engine.aux_block()
-            self._ring, self._ring_pos = [self._new_result_block() for _ in range(2)], 0
+            self._ring, self._ring_pos = [self._new_result_block() for _ in range(3)], 0
             self._act_dtype = np.dtype(np.int32 if self.discrete else np.float32)
             self._done_flag = ctypes.c_int32(0)
             self._done_ref = ctypes.byref(self._done_flag)
-            self._step_c = self.engine._lib.ncg_step_mapped_from
+            self._post_c, self._wait_c = self.engine._lib.ncg_step_mapped_post, self.engine._lib.ncg_step_mapped_wait
+            self._next_blk = None
         aux = self._aux.arrays
         a = actions if type(actions) is np.ndarray else np.asarray(actions)
         if a.dtype != self._act_dtype or not a.flags.c_contiguous or a.size != aux["actions"].size:
@@ -172,16 +185,26 @@ class NascarVectorEnv:
                 else:
                     assert a.dtype == np.float32 and a.size == aux["actions"].size, "Invalid action"
             a = np.ascontiguousarray(a, dtype=self._act_dtype).reshape(aux["actions"].shape)
-        blk = self._next_result_block()
+        blk, self._next_blk = self._next_blk, None
+        if blk is None:
+            blk = self._next_result_block()
         spill = blk is None
         if spill:                                   # the caller holds max_result_blocks results: fall back to copying
             if self._spill is None:
                 self._spill = self._new_result_block()
             blk = self._spill
-        rc = self._step_c(self.engine._h, a.__array_interface__["data"][0], 1 if self.validate_actions else 0, *blk.call_args, self._done_ref)
+        h = self.engine._h
+        rc = self._post_c(h, a.__array_interface__["data"][0], 1 if self.validate_actions else 0, blk.cref)
         if rc:
             if self.engine._lib.ncg_last_error() == b"Invalid action":
                 raise AssertionError("Invalid action")
+            from .engine import _check
+            _check(rc)
+        # (while the GPU steps) the block of the next step, among those that exist: a block that is free now stays free, the caller
+        # can only get hold of the one being filled
+        self._next_blk = self._free_result_block(exclude=blk)
+        rc = self._wait_c(h, self._done_ref)
+        if rc:
             from .engine import _check
             _check(rc)
         any_done = self._done_flag.value
