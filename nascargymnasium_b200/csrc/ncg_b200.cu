@@ -13,6 +13,7 @@
 // (cp.async.bulk + mbarrier).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <emmintrin.h>
 #include <chrono>
 #include <map>
 #include <mutex>
@@ -396,7 +397,9 @@ int res_stop(NcgHandle* h) {
 
 KParams base_params(NcgHandle* h);
 // launch the resident kernel for the caller's fixed buffers; NCG_RES_UNSUPPORTED = this batch has none
-int res_start(NcgHandle* h, const void* h_actions, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length) {
+// first_cmd: the command the kernel finds in the mailbox when it starts (posted BEFORE the launch: under a tool that makes launches
+// synchronous -- ncu, a sanitizer -- the launch only returns when the kernel has left, i.e. after it has taken that step and idled out)
+int res_start(NcgHandle* h, const void* h_actions, float* h_final_obs, float* h_ep_return, int32_t* h_ep_length, unsigned long long first_cmd) {
     KParams p = base_params(h);
     p.actions = h_actions; p.final_obs = h_final_obs; p.ep_return = h_ep_return; p.ep_length = h_ep_length; p.any_done = h->p_any_done;
     p.T = 0x7fffffff;
@@ -405,8 +408,10 @@ int res_start(NcgHandle* h, const void* h_actions, float* h_final_obs, float* h_
     p.res_seq0 = h->res_seq; p.res_idle_ns = h->res_idle_ns;
     const unsigned long long idle_word = ((unsigned long long)h->res_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16);
     volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
-    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = idle_word; done[0] = h->res_seq; done[1] = 0;
+    done[0] = h->res_seq; done[1] = 0;
     h->p_res[32] = idle_word;
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);                            // actions and table rows before the command
+    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = first_cmd;
     CUDA_TRY(cudaMemcpyAsync(h->d_res, h->p_res + 32, 8, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaMemsetAsync(h->d_res + 16, 0, 32, h->stream));         // (d_res + 20..: NCG_RES_TIMELINE sums, kept across launches)
     int rc = launch_step(h, p, h->stream, true);
@@ -446,9 +451,11 @@ int res_post(NcgHandle* h, const NcgMappedBuffers& B) {
     h->pend_seq = h->res_seq + 1u;
     h->pend_cmd = ((unsigned long long)h->pend_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16) | (unsigned)slot;
     h->pend_buf = B; h->pend_t0 = std::chrono::steady_clock::now();
-    if (!h->res_running) { int rc = res_start(h, B.actions, B.final_obs, B.ep_return, B.ep_length); if (rc) return rc; }
-    __atomic_thread_fence(__ATOMIC_SEQ_CST);                            // actions and table rows before the command
-    *reinterpret_cast<volatile unsigned long long*>(h->p_res) = h->pend_cmd;
+    if (!h->res_running) { int rc = res_start(h, B.actions, B.final_obs, B.ep_return, B.ep_length, h->pend_cmd); if (rc) return rc; }
+    else {
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);                        // actions and table rows before the command
+        *reinterpret_cast<volatile unsigned long long*>(h->p_res) = h->pend_cmd;
+    }
     h->pend_kind = 1;
     return NCG_OK;
 }
@@ -482,9 +489,7 @@ int res_wait(NcgHandle* h, int32_t* any_done) {
           { unsigned long long d[2] = {0, 0}; if (e == cudaSuccess && cudaMemcpy(d, h->d_res + 18, 16, cudaMemcpyDeviceToHost) == cudaSuccess) { h->res_dev_ns += d[0]; h->res_dev_steps += d[1]; } }
           if (e != cudaSuccess) return fail(NCG_E_CUDA, std::string("resident step kernel: ") + cudaGetErrorString(e)); }
         if (done[0] == seq) break;
-        { const NcgMappedBuffers& B = h->pend_buf; int rc = res_start(h, B.actions, B.final_obs, B.ep_return, B.ep_length); if (rc) return rc == NCG_RES_UNSUPPORTED ? fail(NCG_E_CUDA, "resident step kernel could not be started again") : rc; }
-        __atomic_thread_fence(__ATOMIC_SEQ_CST);
-        *reinterpret_cast<volatile unsigned long long*>(h->p_res) = h->pend_cmd;
+        { const NcgMappedBuffers& B = h->pend_buf; int rc = res_start(h, B.actions, B.final_obs, B.ep_return, B.ep_length, h->pend_cmd); if (rc) return rc == NCG_RES_UNSUPPORTED ? fail(NCG_E_CUDA, "resident step kernel could not be started again") : rc; }
     }
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
     h->res_wait_ns += (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - h->pend_t0).count(); ++h->res_steps;
@@ -506,7 +511,7 @@ int ncg_debug_cta_cycles(long long* out) { return cudaMemcpyFromSymbol(out, g_ct
 int ncg_version(void) { return 1; }
 // diagnostics of the resident mode: {ns ncg_step_mapped spent from entry to the done word, steps taken through the mailbox,
 // ns on the device from "command seen by CTA 0" to "done word raised", steps counted there (updated when a resident launch ends)}
-#ifdef NCG_RES_TIMELINE
+#if defined(NCG_RES_TIMELINE) || defined(NCG_RES_TIMELINE2)
 int ncg_debug_resident_timeline(NcgHandle* h, unsigned long long* out16) {
     CUDA_TRY(cudaSetDevice(h->cfg.device)); RES_STOP(h);
     CUDA_TRY(cudaMemcpy(out16, h->d_res + 20, 16 * 8, cudaMemcpyDeviceToHost));
@@ -771,16 +776,40 @@ int ncg_step_mapped_post(NcgHandle* h, const void* src_actions, int32_t validate
     if (src_actions) {
         // the caller's own action array, staged into the mapped buffer and range-checked in the same pass (CarEnv.step asserts
         // action_space.contains(action), /root/reference/src/car_env.py:694): nothing is stepped when the check fails
+        // Streaming (non-temporal) stores: the GPU reads these lines across PCIe a microsecond later, and lines left dirty in this
+        // core's cache have to be snooped out of it one by one (measured: the physics warps' action fetch 5.9 us instead of 1.5).
         const size_t N = (size_t)h->N;
+        const bool aligned = (reinterpret_cast<uintptr_t>(b->actions) & 15u) == 0;
         if (h->cfg.discrete) {
             const int32_t* s = static_cast<const int32_t*>(src_actions); int32_t* d = static_cast<int32_t*>(b->actions);
-            uint32_t bad = 0;
-            for (size_t i = 0; i < N; ++i) { const int32_t v = s[i]; bad |= (uint32_t)v > 4u; d[i] = v; }
+            uint32_t bad = 0; size_t i = 0;
+            if (aligned) {
+                __m128i acc = _mm_setzero_si128(); const __m128i four = _mm_set1_epi32(4), zero = _mm_setzero_si128();
+                for (; i + 4 <= N; i += 4) {
+                    const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + i));
+                    acc = _mm_or_si128(acc, _mm_or_si128(_mm_cmpgt_epi32(v, four), _mm_cmplt_epi32(v, zero)));
+                    _mm_stream_si128(reinterpret_cast<__m128i*>(d + i), v);
+                }
+                bad |= (uint32_t)_mm_movemask_epi8(acc);
+            }
+            for (; i < N; ++i) { const int32_t v = s[i]; bad |= (uint32_t)v > 4u; d[i] = v; }
+            _mm_sfence();
             if (validate && bad) return fail(NCG_E_INVALID, "Invalid action");
         } else {
             const float* s = static_cast<const float*>(src_actions); float* d = static_cast<float*>(b->actions);
-            int ok = 1;
-            for (size_t i = 0; i < 2 * N; ++i) { const float v = s[i]; ok &= (v >= -1.0f) & (v <= 1.0f); d[i] = v; }      // (a NaN fails both comparisons)
+            int ok = 1; size_t i = 0;
+            if (aligned) {
+                const __m128 lo = _mm_set1_ps(-1.0f), hi = _mm_set1_ps(1.0f);
+                __m128 acc = _mm_cmpeq_ps(lo, lo);
+                for (; i + 4 <= 2 * N; i += 4) {
+                    const __m128 v = _mm_loadu_ps(s + i);
+                    acc = _mm_and_ps(acc, _mm_and_ps(_mm_cmpge_ps(v, lo), _mm_cmple_ps(v, hi)));      // (a NaN fails both comparisons)
+                    _mm_stream_ps(d + i, v);
+                }
+                ok &= _mm_movemask_ps(acc) == 0xF;
+            }
+            for (; i < 2 * N; ++i) { const float v = s[i]; ok &= (v >= -1.0f) & (v <= 1.0f); d[i] = v; }
+            _mm_sfence();
             if (validate && !ok) return fail(NCG_E_INVALID, "Invalid action");
         }
     }

@@ -43,6 +43,16 @@ __device__ __forceinline__ unsigned long long tl_ns() { unsigned long long t; as
 #else
 #define RTL(k) do { } while (0)
 #endif
+// NCG_RES_TIMELINE2 (variant build): the same from the ray warps only -- %globaltimer since CTA 0 saw the command, stamped by
+// lane 0 of one CTA's first ray warp, so that the physics warp runs exactly the code of the default build
+#ifdef NCG_RES_TIMELINE2
+#ifndef NCG_RES_TL_CTA
+#define NCG_RES_TL_CTA 5
+#endif
+#define RTG(k) do { if (RES && blockIdx.x == NCG_RES_TL_CTA && warp == PW && lane == 0) atomicAdd(p.res_done_ctr + 4 + (k), res_ns() - *(volatile unsigned long long*)(p.res_done_ctr + 1)); } while (0)
+#else
+#define RTG(k) do { } while (0)
+#endif
 struct DevStats { unsigned long long car_steps, episodes, laps, ray_tests, contact_steps, toi_events, overflow; double return_sum; };
 
 struct KParams {
@@ -111,7 +121,7 @@ __device__ __forceinline__ void tma_wait(unsigned long long* mbar) {
 // decision "step seq" / "leave" is taken once for the whole grid (a CTA that timed out on its own while another one saw the
 // next command would leave the batch half stepped).
 __device__ __forceinline__ unsigned long long res_ld_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ unsigned long long res_ld_acq(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned long long res_ld_gpu(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void res_st_rel(unsigned long long* p, unsigned long long v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 // (acquire-release fences: __threadfence_system() / __threadfence() are the sequentially consistent MEMBAR.SC.*, which this
 // release -> count -> acquire -> release chain does not need)
@@ -121,16 +131,18 @@ __device__ __forceinline__ unsigned long long res_ns() { unsigned long long t; a
 // returns the command of step `want` or an exit word (op != 0); gen / valid: which rows of the result-slot table the device copy holds
 __device__ __noinline__ unsigned long long res_dispatch(const KParams& p, unsigned want, unsigned& gen, unsigned& valid) {
     const unsigned long long t0 = res_ns();
-    unsigned long long c;
+    unsigned long long c, seen = 0;
     for (;;) {
         c = res_ld_sys(p.res_host_cmd);
         if (((c >> 8) & 0xffu) != 0u) break;                                   // the host asks the kernel to leave
         if ((unsigned)(c >> 32) == want) {
-            p.res_done_ctr[1] = res_ns();                                      // (diagnostic: when the grid learnt of the step)
-            res_fence_sys();
+            seen = res_ns();
+            // (no system-scope fence on the way to the actions: the host ordered them before the command (sfence + one store), and
+            // every read of them is an uncached PCIe read issued after this one has returned)
             const unsigned g = (unsigned)(c >> 16) & 0xffffu, slot = (unsigned)c & (NCG_RES_SLOTS - 1);
             if (g != gen) { gen = g; valid = 0u; }
             if (!((valid >> slot) & 1u)) {
+                res_fence_sys();
                 for (int k = 0; k < 4; ++k) p.res_dev_tab[slot * 4 + k] = res_ld_sys(p.res_host_tab + slot * 4 + k);
                 valid |= 1u << slot;
             }
@@ -143,16 +155,20 @@ __device__ __noinline__ unsigned long long res_dispatch(const KParams& p, unsign
         }
     }
     res_st_rel(p.res_dev_cmd, c);
+    if (seen) p.res_done_ctr[1] = seen;                                        // (diagnostic: when the grid learnt of the step; after the relay, nothing waits for it)
     return c;
 }
 __device__ __noinline__ unsigned long long res_wait(const KParams& p, unsigned want) {
-    const unsigned long long t0 = res_ns();
-    for (;;) {
-        const unsigned long long c = res_ld_acq(p.res_dev_cmd);
-        if (((c >> 8) & 0xffu) != 0u || (unsigned)(c >> 32) == want) return c;
+    // (relaxed polls of the relay word in L2, one acquire fence when the word has changed; the clock is looked at every 4096 polls)
+    for (unsigned long long t0 = 0;;) {
+        for (int i = 0; i < 4096; ++i) {
+            const unsigned long long c = res_ld_gpu(p.res_dev_cmd);
+            if (((c >> 8) & 0xffu) != 0u || (unsigned)(c >> 32) == want) { res_fence_gpu(); return c; }
+        }
         // (never expected: CTA 0 relays every command and its own exit; a bound so that no CTA can spin for ever)
-        if (res_ns() - t0 > p.res_idle_ns + 10000000000ull) return ((unsigned long long)(want - 1u) << 32) | (NCG_RES_OP_EXIT << 8);
-        __nanosleep(32);
+        const unsigned long long now = res_ns();
+        if (!t0) t0 = now;
+        if (now - t0 > p.res_idle_ns + 10000000000ull) return ((unsigned long long)(want - 1u) << 32) | (NCG_RES_OP_EXIT << 8);
     }
 }
 
@@ -354,7 +370,12 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 // ---- the mailbox: wait for the command of this step (or for the word that ends the launch)
                 const unsigned want = p.res_seq0 + (unsigned)t + 1u;
                 unsigned long long c = 0;
-                if (lane == 0) c = blockIdx.x == 0 ? res_dispatch(p, want, res_gen, res_valid) : res_wait(p, want);
+                if (lane == 0) {
+                    c = blockIdx.x == 0 ? res_dispatch(p, want, res_gen, res_valid) : res_wait(p, want);
+#ifdef NCG_RES_TIMELINE2
+                    if (blockIdx.x == NCG_RES_TL_CTA) atomicAdd(p.res_done_ctr + 4 + 0, res_ns() - *(volatile unsigned long long*)(p.res_done_ctr + 1));
+#endif
+                }
                 c = __shfl_sync(0xffffffffu, c, 0);
                 if (((c >> 8) & 0xffu) != 0u) {
                     // leave: take the ray warps' outstanding "drained" arrivals, then wake them on the pose barrier with the exit flag up
@@ -375,10 +396,15 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 if (active) {
                     if (p.discrete) act_d = __ldcv((const int*)p.actions + gc); else act_c = __ldcv((const float2*)p.actions + gc);
                 }
+#ifdef NCG_RES_TIMELINE
+                if (active && act_c.x == 12345.0f && act_d == 77) s_res_exit = 2;      // (a use of the action before the stamp)
+                RTL(15);
+#endif
                 const unsigned long long* row = p.res_dev_tab + ((unsigned)c & (NCG_RES_SLOTS - 1)) * 4;
                 const unsigned long long q0 = __ldcg(row), q1 = __ldcg(row + 1), q2 = __ldcg(row + 2), q3 = __ldcg(row + 3);
                 if (lane == 0) s_res_obs[b] = reinterpret_cast<float*>(q0);
                 rew_out = reinterpret_cast<float*>(q1); term_out = reinterpret_cast<uint8_t*>(q2); trunc_out = reinterpret_cast<uint8_t*>(q3);
+                __syncwarp();       // the lanes go through the step together (lane 0 has been on its own in the mailbox)
             }
             float rew = 0.0f;
             StepCtx ctx;
@@ -426,6 +452,16 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                         cc_find_new_pairs(fat, p.C, PT);
                     }
                 }
+#ifdef NCG_RES_TIMELINE
+                if (RES && blockIdx.x == NCG_RES_TL_CTA) {      // per lane: when its own dynamics were done (slot 11: sum over lanes, 12: lanes counted, 13: lanes later than 1.5 x lane 0)
+                    long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) :: "memory");
+                    const long long d_ = c_ - *(volatile long long*)&s_res_t0;
+                    atomicAdd(p.res_done_ctr + 4 + 11, (unsigned long long)d_); atomicAdd(p.res_done_ctr + 4 + 12, 1ull);
+                    const long long d0_ = __shfl_sync(__activemask(), d_, 0);
+                    if (2 * d_ > 3 * d0_) atomicAdd(p.res_done_ctr + 4 + 13, 1ull);
+                    if (f2u(R[NCG_R_NCONTACT]) & 255u) atomicAdd(p.res_done_ctr + 4 + 14, 1ull);
+                }
+#endif
                 s_pose[b * SLOTS + slot] = make_float4(R[NCG_R_X], R[NCG_R_Y], R[NCG_R_ANGLE], 0.0f);
             }
             if (threadIdx.x == 0) s_ctr[b] = 32 * RW;           // ray queue: every ray lane starts on job = its index
@@ -536,6 +572,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
             if (RES) {
                 if (*(volatile int*)&s_res_exit) break;
                 obs_out = *(float* volatile*)&s_res_obs[b];
+                RTG(1);
             }
             if ((GROUPS == 2 || p.queue) && !(p.debug_skip & 1)) {
                 // every ray warp derives the cars' ray origins itself (same values to the same words: no barrier between
@@ -564,10 +601,12 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
             }
             TL(2);
             if (warp == PW) RTL(4);
+            RTG(4);
             TLWAIT(bar_sync(BAR_FULL + b, NT));
             TL(3);
             __syncwarp();
             if (warp == PW) RTL(5);
+            RTG(5);
             // ---- observation rows shared -> HBM: 38 consecutive floats per car, written as float2 (a row is 19 float2,
             // so a pair never straddles two cars and every store is 8-byte aligned).  Words 0..21 arrive raw from the
             // physics warp and are scaled and clipped here; the ray words are already in [0,1] (scale 1, lower bound 0
@@ -594,6 +633,7 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 // the step is complete for the host once every CTA's rows are on their way: the ray warps meet, one thread
                 // orders the CTA's writes before its count, and the grid's last arrival raises the host's done word
                 if (warp == PW) RTL(6);
+                RTG(6);
                 bar_sync(BAR_RES, 32 * RW);
                 if (warp == PW) RTL(7);
                 if (warp == PW && lane == 0) {

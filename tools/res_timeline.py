@@ -12,6 +12,11 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 n = 2000
 venv = NascarVectorEnv(num_envs=E, track_file="tracks/daytona.track")
 venv.reset()
+warm = int(os.environ.get("WARM", "0"))
+if warm:                                  # the random policy's dispersed steady state (device-side Philox actions, same distribution)
+    import torch
+    o = torch.empty((E, 38), device="cuda:0")
+    venv.engine.rollout(warm, seed=1, mode=0, obs_last=o.view(-1)); torch.cuda.synchronize()
 rng = np.random.default_rng(0)
 acts = [rng.uniform(-1, 1, (E, 2)).astype(np.float32) for _ in range(n + 50)]      # fresh actions every step (a short cycle of them drives the cars into the walls)
 for i in range(n): venv.step(acts[i])
@@ -21,7 +26,15 @@ lib = engine.load_library()
 lib.ncg_debug_resident_timeline.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 assert lib.ncg_debug_resident_timeline(venv.engine._h, out.ctypes.data_as(ctypes.c_void_p)) == 0
 names = ["actions arrived", "pose published", "rules done (before fence.sys)", "physics fence.sys done", "rays done", "FULL barrier passed",
-         "rows stored", "ray warps met", "signaller fence.sys done", "dynamics done (pose in shared memory)", "fence.cta before the pose barrier done"]
+         "rows stored", "ray warps met", "signaller fence.sys done", "dynamics done (pose in shared memory)", "fence.cta before the pose barrier done", "-", "-", "-", "-", "action load returned (before the slot pointers)"]
 print(st)
+scale = 1.965e3
+if "TIMELINE2" in os.environ.get("NCG_DEFINES", ""):           # globaltimer (ns) since CTA 0 saw the command, ray warp stamps only
+    names = ["command seen by this CTA (relay)", "pose barrier passed (ray warp)", "-", "-", "rays done", "FULL barrier passed", "rows stored"]
+    scale = 1e3
 for k, nm in enumerate(names):
-    print(f"  {nm:32s} {int(out[k]) / st['device_steps'] / 1.965e3:7.2f} us after the command was seen by CTA 0")
+    if nm == '-': continue
+    print(f"  {nm:32s} {int(out[k]) / st['device_steps'] / scale:7.2f} us after the command was seen by CTA 0")
+lanes = max(int(out[12]), 1)
+print(f"  per lane: dynamics done {int(out[11]) / lanes / 1.965e3:.2f} us on average, {int(out[13]) / lanes * 100:.1f} % of the lanes later than 1.5 x lane 0, "
+      f"{int(out[14]) / lanes * 100:.1f} % of the car-steps with broad-phase contacts")
