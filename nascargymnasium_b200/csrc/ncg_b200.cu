@@ -406,6 +406,7 @@ int res_start(NcgHandle* h, const void* h_actions, float* h_final_obs, float* h_
     p.res_host_cmd = h->p_res; p.res_host_done = reinterpret_cast<volatile unsigned*>(h->p_res + 16); p.res_host_tab = h->p_res + 64;
     p.res_dev_cmd = h->d_res; p.res_done_ctr = h->d_res + 16; p.res_dev_tab = h->d_res + 64;
     p.res_seq0 = h->res_seq; p.res_idle_ns = h->res_idle_ns;
+    { static const int fence_gpu = [] { const char* v = getenv("NCG_RESIDENT_FENCE"); return v && !strcmp(v, "gpu") ? 1 : 0; }(); p.res_fence_gpu = fence_gpu; }
     const unsigned long long idle_word = ((unsigned long long)h->res_seq << 32) | ((unsigned long long)(h->res_gen & 0xffffu) << 16);
     volatile unsigned* done = reinterpret_cast<volatile unsigned*>(h->p_res + 16);
     done[0] = h->res_seq; done[1] = 0;

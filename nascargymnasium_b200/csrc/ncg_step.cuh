@@ -84,6 +84,7 @@ struct KParams {
     unsigned long long* res_done_ctr;                      // CTAs that have finished a step, summed over the launch
     volatile unsigned* res_host_done;                      // mapped host: [0] last completed seq, [1] the kernel left by itself (idle)
     unsigned res_seq0; unsigned long long res_idle_ns;     // seq of the last step before this launch; idle time after which the kernel leaves
+    int res_fence_gpu;                                     // experiment (NCG_RESIDENT_FENCE=gpu): no system-scope fence before the done word
 };
 #define NCG_RES_SLOTS 16
 #define NCG_RES_OP_EXIT 1u
@@ -639,13 +640,27 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
                 if (warp == PW && lane == 0) {
                     // (release at GPU scope, cumulative over the barrier above: the CTA's writes are ordered before its count; the
                     // grid's last arrival, which has observed every count, is the one thread that pays for the system-scope fence)
+#ifdef NCG_RES_TIMELINE2
+                    const unsigned long long g0_ = res_ns();
+#endif
                     res_fence_gpu();
                     RTL(8);
+#ifdef NCG_RES_TIMELINE2
+                    const unsigned long long g1_ = res_ns();
+#endif
                     const unsigned long long old = atomicAdd(p.res_done_ctr, 1ull);
                     if (old + 1ull == (unsigned long long)gridDim.x * (unsigned long long)(t + 1)) {
-                        res_fence_sys();
+#ifdef NCG_RES_TIMELINE2
+                        const unsigned long long g2_ = res_ns();
+#endif
+                        if (p.res_fence_gpu) res_fence_gpu(); else res_fence_sys();
                         p.res_host_done[0] = p.res_seq0 + (unsigned)t + 1u;
                         p.res_done_ctr[2] += res_ns() - *(volatile unsigned long long*)(p.res_done_ctr + 1); p.res_done_ctr[3] += 1ull;   // (diagnostic: command seen -> done raised)
+#ifdef NCG_RES_TIMELINE2
+                        // the grid's last arrival: when its ray warps had met, its GPU-scope fence was done, it had counted itself
+                        { const unsigned long long ts_ = *(volatile unsigned long long*)(p.res_done_ctr + 1);
+                          p.res_done_ctr[4 + 8] += g0_ - ts_; p.res_done_ctr[4 + 9] += g1_ - ts_; p.res_done_ctr[4 + 10] += g2_ - ts_; }
+#endif
                     }
                 }
             }

@@ -30,7 +30,8 @@ names = ["actions arrived", "pose published", "rules done (before fence.sys)", "
 print(st)
 scale = 1.965e3
 if "TIMELINE2" in os.environ.get("NCG_DEFINES", ""):           # globaltimer (ns) since CTA 0 saw the command, ray warp stamps only
-    names = ["command seen by this CTA (relay)", "pose barrier passed (ray warp)", "-", "-", "rays done", "FULL barrier passed", "rows stored"]
+    names = ["command seen by this CTA (relay)", "pose barrier passed (ray warp)", "-", "-", "rays done", "FULL barrier passed", "rows stored", "-",
+             "last CTA: its ray warps had met", "last CTA: GPU-scope fence done", "last CTA: counted (atomicAdd returned)"]
     scale = 1e3
 for k, nm in enumerate(names):
     if nm == '-': continue
