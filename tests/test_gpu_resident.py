@@ -154,3 +154,44 @@ def test_a_slow_caller_falls_back_to_per_step_launches():
     assert vb.engine.launch_count - l0 >= 3 + 10
     assert vb.engine.resident_stats["steps"] == 3
     va.close(); vb.close()
+
+
+def test_post_and_wait_contract_through_the_c_abi():
+    """one wait per post; a second post, or a wait without a post, is refused; any other entry point completes a posted step first"""
+    import ctypes
+    from nascargymnasium_b200.engine import Engine, MappedBuffers, NcgError
+    E = 512
+    for resident in (True, False):
+        os.environ["NCG_RESIDENT"] = "1" if resident else "0"
+        try:
+            eng = Engine(E, 1, tracks=["daytona"], auto_reset=True)
+            ref = Engine(E, 1, tracks=["daytona"], auto_reset=True)
+        finally:
+            os.environ.pop("NCG_RESIDENT")
+        eng.reset_host(); ref.reset_host()
+        aux, res = eng.aux_block(), eng.result_block()
+        a, r = aux.ptrs, res.ptrs
+        buf = MappedBuffers(a["actions"].value, r["obs"].value, r["reward"].value, r["terminated"].value, r["truncated"].value,
+                            a["final_obs"].value, a["ep_return"].value, a["ep_length"].value)
+        lib, h = eng._lib, eng._h
+        done = ctypes.c_int32(0)
+        assert lib.ncg_step_mapped_wait(h, ctypes.byref(done)) != 0                      # nothing posted
+        rng = np.random.default_rng(3)
+        acts = rng.uniform(-1, 1, (3, E, 2)).astype(np.float32)
+        assert lib.ncg_step_mapped_post(h, acts[0].ctypes.data, 1, ctypes.byref(buf)) == 0
+        assert lib.ncg_step_mapped_post(h, acts[1].ctypes.data, 1, ctypes.byref(buf)) != 0   # one wait per post
+        assert lib.ncg_step_mapped_wait(h, ctypes.byref(done)) == 0
+        o_ref = ref.step_host(acts[0])[0]
+        assert np.array_equal(res.arrays["obs"], o_ref)
+        bad = acts[1].copy(); bad[7, 1] = np.nan
+        assert lib.ncg_step_mapped_post(h, bad.ctypes.data, 1, ctypes.byref(buf)) != 0 and lib.ncg_last_error() == b"Invalid action"
+        assert np.array_equal(res.arrays["obs"], o_ref)                                  # nothing was stepped
+        # a posted step that is never waited for: the state read completes it first (resident mode)
+        assert lib.ncg_step_mapped_post(h, acts[1].ctypes.data, 1, ctypes.byref(buf)) == 0
+        if resident:
+            s1 = eng.get_state_host()
+            ref.step_host(acts[1])
+            assert np.array_equal(s1.view(np.uint32), ref.get_state_host().view(np.uint32))
+        else:
+            assert lib.ncg_step_mapped_wait(h, ctypes.byref(done)) == 0
+        eng.close(); ref.close()
