@@ -356,9 +356,19 @@ int launch_step(NcgHandle* h, KParams& p, cudaStream_t s, bool resident = false)
         int& have = limit[std::make_pair((const void*)k, h->cfg.device)];
         if ((int)smem > have) { CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); have = (int)smem; }
     }
-    if (PW == 4) k<<<h->n_ctas, 32 * (4 + 8), smem, s>>>(p);
-    else if (PW == 2) k<<<h->n_pairs, pair_rw8 ? 320 : 256, smem, s>>>(p);
-    else k<<<h->n_ctas, 32 * (1 + 16 / RPL), smem, s>>>(p);
+    {
+        // single-step launches chain with programmatic dependent launch: the next launch's CTAs start as this one's leave their SMs
+        // and run their prologue in front of griddepcontrol.wait (NCG_PDL=0 switches it off)
+        static const int pdl_on = [] { const char* v = getenv("NCG_PDL"); return v ? atoi(v) != 0 : 1; }();
+        p.pdl = (pdl_on && p.T == 1) ? 1 : 0;
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(PW == 2 ? h->n_pairs : h->n_ctas); cfg.blockDim = dim3(PW == 4 ? 32 * (4 + 8) : PW == 2 ? (pair_rw8 ? 320 : 256) : 32 * (1 + 16 / RPL));
+        cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = p.pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k, p));
+    }
     CUDA_TRY(cudaGetLastError());
     ++h->launches;
     return NCG_OK;

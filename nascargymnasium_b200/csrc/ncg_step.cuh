@@ -85,6 +85,7 @@ struct KParams {
     volatile unsigned* res_host_done;                      // mapped host: [0] last completed seq, [1] the kernel left by itself (idle)
     unsigned res_seq0; unsigned long long res_idle_ns;     // seq of the last step before this launch; idle time after which the kernel leaves
     int res_fence_gpu;                                     // experiment (NCG_RESIDENT_FENCE=gpu): no system-scope fence before the done word
+    int pdl;                                               // launched with programmatic stream serialization (single-step launches)
 };
 #define NCG_RES_SLOTS 16
 #define NCG_RES_OP_EXIT 1u
@@ -291,6 +292,11 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
         }
         staged = s_track;
     }
+    // Programmatic dependent launch (launch_step sets cudaLaunchAttributeProgrammaticStreamSerialization): this kernel lets the NEXT
+    // launch of the stream start its CTAs as SMs free up, and does itself everything that does not depend on the launch before it
+    // (the table's bulk copy above, the slot table below) in front of griddepcontrol.wait -- in a loop of single-step launches a
+    // CTA's prologue then runs under the stragglers of the step before.  Without a programmatic predecessor both are no-ops.
+    if (!RES && p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // the groups of envs this CTA serves: n0 cars from global car cb0 in slots 0.., n1 cars from cb1 in slots 32..
     int2 g0, g1 = make_int2(0, 0);
     if (GROUPS == 1) g0 = p.cta_tab[blockIdx.x];
@@ -306,8 +312,8 @@ __global__ void __launch_bounds__(PW == 2 ? (RPL == 2 ? 320 : 256) : 32 * (PW + 
         s_gcar[SLOT_OF(ci)] = (p.slot_env ? p.slot_env[sl] : sl) * p.C + (k - le * p.C);
         NCG_CHECK(s_gcar[SLOT_OF(ci)] >= 0 && s_gcar[SLOT_OF(ci)] < N, "global car index");
     }
+    if (!RES && p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // records, actions and every output belong to the launch before until here
     __syncthreads();
-    const int cb0 = s_gcar[0];                                       // the CTA's first car: its record names the CTA's track
 
     // (the track table's bulk copy was issued at the top of the kernel)
     // the car slot this thread serves: its lane (physics warps) or, with the fixed ray mapping, the car its rays belong to
