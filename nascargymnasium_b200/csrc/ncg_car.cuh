@@ -240,7 +240,10 @@ NCG_HDN void w_find_new_contacts(World& W, const Track& T) {
     }
 }
 // ---- b2ContactSolver over the island {car} + isl[]
+// (`#pragma unroll 1` on the loops over contacts / manifold points of the contact path: their trip counts are 1-2 at run time, the
+// unrolled copies only made the code a contact step has to fetch larger -- 16 KB per kernel; the driving distribution gained 3 %)
 NCG_HDN void s_init(World& W, bool warm, float dtRatio) {
+#pragma unroll 1
     for (int i = 0; i < W.ni; ++i) {
         Contact& c = W.c[W.isl[i]]; VC& vc = W.vc[i]; PC& pc = W.pcs[i];
         vc.ci = W.isl[i]; vc.pc = c.m.pc;
@@ -256,12 +259,14 @@ NCG_HDN void s_init(World& W, bool warm, float dtRatio) {
 }
 NCG_HDN void s_init_velocity(World& W, const Track& T) {
     const float mA = NCG_INV_MASS, iA = NCG_INV_I, restitution = NCG_WALL_RESTITUTION;   // max(0.1, 0.25)
+#pragma unroll 1
     for (int i = 0; i < W.ni; ++i) {
         VC& vc = W.vc[i]; PC& pc = W.pcs[i]; Contact& c = W.c[vc.ci];
         Xf xfB; Box bB; wall_get(T, pc.wall, &xfB, &bB);
         V2 cA = W.pc_c; float aA = W.pc_a; V2 vA = W.pv; float wA = W.pw;
         Xf xfA; xfA.q = rot(aA); xfA.p = cA - mul(xfA.q, mk(0.0f, 0.0f));
         V2 pts[2]; world_manifold(&vc.normal, pts, c.m, xfA, xfB);
+#pragma unroll 1
         for (int j = 0; j < vc.pc; ++j) {
             VCPoint& p = vc.p[j];
             p.rA = pts[j] - cA;
@@ -290,9 +295,11 @@ NCG_HDN void s_init_velocity(World& W, const Track& T) {
 }
 NCG_HDN void s_warm_start(World& W) {
     const float mA = NCG_INV_MASS, iA = NCG_INV_I;
+#pragma unroll 1
     for (int i = 0; i < W.ni; ++i) {
         VC& vc = W.vc[i];
         V2 tangent = cross(vc.normal, 1.0f);
+#pragma unroll 1
         for (int j = 0; j < vc.pc; ++j) {
             V2 P = vc.p[j].ni * vc.normal + vc.p[j].ti * tangent;
             W.pw -= iA * cross(vc.p[j].rA, P);
@@ -308,10 +315,12 @@ NCG_HD void s_apply2(V2& vA, float& wA, const VC& vc, V2 x, V2 a) {
 NCG_HDN void s_solve_velocity(World& W) {
     const float mA = NCG_INV_MASS, iA = NCG_INV_I;
     const float friction = sqrtf(NCG_CAR_FRICTION * NCG_WALL_FRICTION);
+#pragma unroll 1
     for (int i = 0; i < W.ni; ++i) {
         VC& vc = W.vc[i];
         V2 vA = W.pv; float wA = W.pw;
         V2 normal = vc.normal, tangent = cross(normal, 1.0f);
+#pragma unroll 1
         for (int j = 0; j < vc.pc; ++j) {
             VCPoint& p = vc.p[j];
             V2 dv = (-vA) - cross(wA, p.rA);
@@ -360,6 +369,7 @@ NCG_HD void s_store_impulses(World& W) {
 NCG_HDN bool s_solve_position(World& W, const Track& T, float baumgarte, float okFactor) {
     const float mA = NCG_INV_MASS, iA = NCG_INV_I;
     float minSep = 0.0f;
+#pragma unroll 1
     for (int i = 0; i < W.ni; ++i) {
         PC& pc = W.pcs[i];
         Xf xfB; Box bB; wall_get(T, pc.wall, &xfB, &bB);
@@ -481,6 +491,7 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
     bool pristine = true;                                   // no TOI event has advanced the sweep or touched the contacts yet
     for (;;) {
         int minC = -1; float minAlpha = 1.0f;
+#pragma unroll 1
         for (int i = 0; i < W.nc; ++i) {
             Contact& c = W.c[i];
             if (!c.enabled) continue;
@@ -536,6 +547,7 @@ NCG_HDN void w_solve_toi(World& W, const Track& T, float stepDt) {
         if (!mc.enabled || !mc.touching) { mc.enabled = false; W.b.sweep = backup; W.wallAlpha[minC] = backupWall; w_sync_transform(W); continue; }
         w_set_awake(W, true);
         W.ni = 0; W.isl[W.ni++] = minC; mc.island = true;
+#pragma unroll 1
         for (int i = 0; i < W.nc; ++i) {
             Contact& c = W.c[i];
             if (c.island) continue;
@@ -593,6 +605,7 @@ NCG_HD void w_load_contacts(World& W, const float* R) {
     W.nc = (int)(ncw & 255u); W.na = (int)((ncw >> 8) & 255u);
     uint32_t tmask = (ncw >> 16) & 0xFFFu, pcw = f2u(R[NCG_R_MANIFOLD_PC]);
     int k = 0;
+#pragma unroll 1
     for (int i = 0; i < W.nc; ++i) {
         Contact& c = W.c[i];
         uint32_t ww = f2u(R[NCG_R_CONTACT_WALL + (i >> 1)]);
@@ -613,6 +626,7 @@ NCG_HD void w_load_contacts(World& W, const float* R) {
 NCG_HD void w_store_contacts(World& W, float* R) {
     uint32_t tmask = 0, pcw = 0; int k = 0;
     uint32_t ww[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
     for (int i = 0; i < W.nc; ++i) {
         const Contact& c = W.c[i];
         ww[i >> 1] |= ((uint32_t)c.wall & 0xFFFFu) << ((i & 1) * 16);
