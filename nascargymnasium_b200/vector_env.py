@@ -103,6 +103,7 @@ class NascarVectorEnv:
         self._aux, self._ring, self._ring_pos, self._spill = None, [], 0, None
         self._torch_bufs = None
         self._fast = None
+        self._posted = None
         self.closed = False
 
     # ------------------------------------------------------------------ numpy API
@@ -164,8 +165,62 @@ class NascarVectorEnv:
         """actions: (E[,C],2) float32 in [-1,1] or (E[,C]) ints.  Host buffers in, host buffers out.  The actions are
         checked and copied into a page-locked buffer the kernel reads directly (one pass, in the library); observations,
         rewards and flags are written by the kernel straight into page-locked result buffers, which are handed out without a
-        copy and not reused while the caller still references them.  The step is posted (ncg_step_mapped_post), the result
-        block of the NEXT step is chosen while the GPU works, then the results are waited for (ncg_step_mapped_wait)."""
+        copy and not reused while the caller still references them.  step() is step_async() + step_wait() in one body (the two
+        calls and the hand-over between them cost 0.7 us of a 35 us step)."""
+        if self._aux is None or self._posted is not None:
+            self.step_async(actions)                # (first call: buffers are made; or a misuse that step_async reports)
+            return self.step_wait()
+        aux = self._aux.arrays
+        a = actions if type(actions) is np.ndarray else np.asarray(actions)
+        if a.dtype != self._act_dtype or not a.flags.c_contiguous or a.size != aux["actions"].size:
+            if self.validate_actions:
+                if self.discrete:
+                    assert a.dtype.kind in "iu" and a.size == aux["actions"].size and a.min() >= 0 and a.max() < 5, "Invalid action"
+                else:
+                    assert a.dtype == np.float32 and a.size == aux["actions"].size, "Invalid action"
+            a = np.ascontiguousarray(a, dtype=self._act_dtype).reshape(aux["actions"].shape)
+        blk, self._next_blk = self._next_blk, None
+        if blk is None:
+            blk = self._next_result_block()
+        spill = blk is None
+        if spill:
+            if self._spill is None:
+                self._spill = self._new_result_block()
+            blk = self._spill
+        h = self.engine._h
+        rc = self._post_c(h, a.__array_interface__["data"][0], 1 if self.validate_actions else 0, blk.cref)
+        if rc:
+            if self.engine._lib.ncg_last_error() == b"Invalid action":
+                raise AssertionError("Invalid action")
+            from .engine import _check
+            _check(rc)
+        self._next_blk = self._free_result_block(exclude=blk)       # (while the GPU steps)
+        rc = self._wait_c(h, self._done_ref)
+        if rc:
+            from .engine import _check
+            _check(rc)
+        obs, rew, te, tr = blk.views
+        if spill:
+            obs, rew, te, tr = obs.copy(), rew.copy(), te.copy(), tr.copy()
+        if not self._done_flag.value:
+            return obs, rew, te, tr, {}
+        return obs, rew, te, tr, self._episode_info(te, tr)
+
+    def _episode_info(self, te, tr):
+        aux = self._aux.arrays
+        done = te | tr
+        idx = np.flatnonzero(done)
+        rows = aux["final_obs"].reshape(self._obs_shape)[idx]          # one gather-copy out of the mapped buffer
+        ep_r = np.zeros(self._rew_shape, dtype=np.float64)
+        ep_l = np.zeros(self.num_envs, dtype=np.int64)
+        ep_r[idx] = aux["ep_return"].reshape(self._rew_shape)[idx]
+        ep_l[idx] = aux["ep_length"][idx]
+        return StepInfo(done.copy(), idx, rows, self._obs_shape, {"r": ep_r, "l": ep_l})
+
+    def step_async(self, actions):
+        """Hand a step to the GPU and return at once (ncg_step_mapped_post; the interface of stable-baselines3's VecEnv, which
+        /root/reference/learn/ppo.py:65-78 drives).  Whatever the caller does before step_wait() overlaps the step.  `actions` is
+        copied before this returns.  Calling anything else of the env in between completes the step first."""
         if self._aux is None:
             import ctypes
             self._aux = self.engine.aux_block()
@@ -174,7 +229,9 @@ class NascarVectorEnv:
             self._done_flag = ctypes.c_int32(0)
             self._done_ref = ctypes.byref(self._done_flag)
             self._post_c, self._wait_c = self.engine._lib.ncg_step_mapped_post, self.engine._lib.ncg_step_mapped_wait
-            self._next_blk = None
+            self._next_blk, self._posted = None, None
+        if self._posted is not None:
+            raise RuntimeError("step_async() called twice without step_wait()")
         aux = self._aux.arrays
         a = actions if type(actions) is np.ndarray else np.asarray(actions)
         if a.dtype != self._act_dtype or not a.flags.c_contiguous or a.size != aux["actions"].size:
@@ -193,35 +250,30 @@ class NascarVectorEnv:
             if self._spill is None:
                 self._spill = self._new_result_block()
             blk = self._spill
-        h = self.engine._h
-        rc = self._post_c(h, a.__array_interface__["data"][0], 1 if self.validate_actions else 0, blk.cref)
+        rc = self._post_c(self.engine._h, a.__array_interface__["data"][0], 1 if self.validate_actions else 0, blk.cref)
         if rc:
             if self.engine._lib.ncg_last_error() == b"Invalid action":
                 raise AssertionError("Invalid action")
             from .engine import _check
             _check(rc)
+        self._posted = (blk, spill)
         # (while the GPU steps) the block of the next step, among those that exist: a block that is free now stays free, the caller
         # can only get hold of the one being filled
         self._next_blk = self._free_result_block(exclude=blk)
-        rc = self._wait_c(h, self._done_ref)
+
+    def step_wait(self):
+        """The results of the step handed over by step_async()."""
+        if getattr(self, "_posted", None) is None:
+            raise RuntimeError("step_wait() without step_async()")
+        (blk, spill), self._posted = self._posted, None
+        rc = self._wait_c(self.engine._h, self._done_ref)
         if rc:
             from .engine import _check
             _check(rc)
-        any_done = self._done_flag.value
         obs, rew, te, tr = blk.views
         if spill:
             obs, rew, te, tr = obs.copy(), rew.copy(), te.copy(), tr.copy()
-        info = {}
-        if any_done:
-            done = te | tr
-            idx = np.flatnonzero(done)
-            rows = aux["final_obs"].reshape(self._obs_shape)[idx]          # one gather-copy out of the mapped buffer
-            ep_r = np.zeros(self._rew_shape, dtype=np.float64)
-            ep_l = np.zeros(self.num_envs, dtype=np.int64)
-            ep_r[idx] = aux["ep_return"].reshape(self._rew_shape)[idx]
-            ep_l[idx] = aux["ep_length"][idx]
-            info = StepInfo(done.copy(), idx, rows, self._obs_shape, {"r": ep_r, "l": ep_l})
-        return obs, rew, te, tr, info
+        return obs, rew, te, tr, (self._episode_info(te, tr) if self._done_flag.value else {})
 
     # ------------------------------------------------------------------ torch API (device-resident)
     def _bufs(self):
@@ -313,10 +365,10 @@ def make_sb3_vec_env(num_envs: int, track_file=None, discrete_action_space: bool
             return venv.reset(seed=getattr(self, "_seed", None))[0]
 
         def step_async(self, actions):
-            self._actions = actions
+            venv.step_async(actions)          # the GPU starts on the step now; SB3 calls step_wait() next
 
         def step_wait(self):
-            obs, rew, te, tr, info = venv.step(self._actions)
+            obs, rew, te, tr, info = venv.step_wait()
             done = te | tr
             infos = [{} for _ in range(num_envs)]
             if info:

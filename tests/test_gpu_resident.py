@@ -195,3 +195,26 @@ def test_post_and_wait_contract_through_the_c_abi():
         else:
             assert lib.ncg_step_mapped_wait(h, ctypes.byref(done)) == 0
         eng.close(); ref.close()
+
+
+def test_step_async_and_step_wait_equal_step():
+    """SB3's VecEnv interface on the batched env: host work between the two halves overlaps the step, results are those of step()"""
+    va = _venv(True, num_envs=1024, track_file="tracks/daytona.track")
+    vb = _venv(True, num_envs=1024, track_file="tracks/daytona.track")
+    va.reset(); vb.reset()
+    rng = np.random.default_rng(9)
+    acts = [_actions(rng, va, True) for _ in range(300)]
+    keep = lambda r: tuple(np.array(x) for x in r[:4]) + (r[4],)
+    ra = [keep(va.step(a)) for a in acts]
+    rb = []
+    for a in acts:
+        vb.step_async(a)
+        a[...] = 0                                   # the actions were copied before step_async returned
+        with pytest.raises(RuntimeError):
+            vb.step_async(a)
+        rb.append(keep(vb.step_wait()))
+    with pytest.raises(RuntimeError):
+        vb.step_wait()
+    for x, y in zip(ra, rb):
+        _same(x, y)
+    va.close(); vb.close()
