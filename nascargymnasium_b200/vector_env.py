@@ -344,7 +344,7 @@ class NascarVectorEnv:
     def close(self):
         if not self.closed:
             # blocks the caller still references stay allocated until those arrays die (HostBlock.__del__ frees them)
-            self._ring, self._aux, self._spill = [], None, None
+            self._ring, self._aux, self._spill, self._next_blk, self._posted = [], None, None, None, None
             self.engine.close()
             self.closed = True
 
